@@ -1,0 +1,127 @@
+/*
+ * smjp_b200 -- C ABI of the B200-native engine for the gauenk/smjp hot path
+ * (Rao-Teh uniformization Gibbs sweep over semi-Markov jump process trajectories + the bootstrap
+ * particle filter behind pmcmc).
+ *
+ * The reference is pure Python: it has no FFI, so "the reference's FFI for this path" is the set
+ * of Python call sites listed below.  Each entry point names the reference function it replaces
+ * (paths relative to the reference root); INTEGRATION.md shows the ctypes stub a maintainer of the
+ * reference would add at each of those call sites.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - "dev" entry points take DEVICE pointers and enqueue work on the context's stream without
+ *     synchronising (except where a size must come back to the host, documented per call).
+ *   - "host" entry points take HOST pointers, stage through pinned buffers owned by the context,
+ *     run the same kernels and return after the results are in the caller's buffers.
+ *   - chains are ragged and batch-first: chain c owns elements [offs[c], offs[c+1]) of an array.
+ *     Grid arrays (W) hold n_c+1 times per chain (W[0]=0 ... W[n_c]=t_end); every per-grid-step
+ *     array (uniforms, logZ, aug_idx) and the path arrays reuse the SAME offsets (one spare slot).
+ *   - states are 0-based indices into the model's state space; the Python layer maps labels.
+ *   - every function returns 0 on success, a negative SMJP_E_* code otherwise;
+ *     smjp_last_error() gives the message.  Per-chain problems are reported in status[] (bit mask).
+ */
+#ifndef SMJP_B200_H
+#define SMJP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMJP_ABI_VERSION 1
+
+/* return codes */
+#define SMJP_OK 0
+#define SMJP_E_INVALID (-1)   /* bad argument (the reference raises ValueError / IndexError) */
+#define SMJP_E_CUDA (-2)      /* CUDA runtime failure, see smjp_last_error() */
+#define SMJP_E_NOMEM (-3)     /* workspace does not fit on the device */
+#define SMJP_E_UNSUPPORTED (-4)
+
+/* per-chain status bits */
+#define SMJP_ST_GRID_NOT_INCREASING 1 /* smjp_utils.py:398-399 "We can not have time_p >= time_c" */
+#define SMJP_ST_DEGENERATE 2          /* zero / non-finite normaliser (hidden_markov_model.py:170-185) */
+#define SMJP_ST_OVERFLOW 4            /* an output or workspace capacity was too small */
+
+/* message precision */
+#define SMJP_F64 0
+#define SMJP_F32 1
+
+/* candidate position law */
+#define SMJP_CAND_REFERENCE 0 /* unit-scale Weibull density truncated to the sojourn (distributions.py:295) */
+#define SMJP_CAND_EXACT 1     /* density proportional to the hazard: tau * U^(1/k) */
+
+/* particle-filter resampler */
+#define SMJP_RESAMPLE_MULTINOMIAL 0 /* utils.py:7-8 sampleDiscrete, pmcmc.py:302 */
+#define SMJP_RESAMPLE_SYSTEMATIC 1  /* new (north_star) */
+
+typedef struct smjp_ctx smjp_ctx_t;
+
+int smjp_abi_version(void);
+const char* smjp_last_error(void);
+
+/* One context per (device, stream).  `stream` is a cudaStream_t (NULL = legacy default stream). */
+smjp_ctx_t* smjp_ctx_create(int device, void* stream);
+void smjp_ctx_destroy(smjp_ctx_t* ctx);
+int smjp_ctx_sync(smjp_ctx_t* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t smjp_ctx_launch_count(smjp_ctx_t* ctx);
+/* tuning knobs: "ffbs_threads" (0 = auto, else threads per CTA of the FFBS kernel) */
+int smjp_ctx_set_option(smjp_ctx_t* ctx, const char* key, int64_t value);
+
+/*
+ * Model parameters (HOST pointers, copied).  Replaces the parameter reads the reference does through
+ * smjpHazardFunction.{shape_mat,scale_mat,omega} (smjp_utils.py:425-429), create_upperbound_scale
+ * (:180-187; B = omega*A and A_hat = (omega-1)*A are applied in-kernel), smjpEmission
+ * .{likelihood_power, final_grid_time} (:484-491) and its d_create table (:552-557), given here as a
+ * general row-stochastic emis[K*Kobs].  Call again after a parameter step (raoteh.py:173-193).
+ */
+int smjp_set_model(smjp_ctx_t* ctx, int K, int Kobs, const double* shape, const double* scale,
+                   double omega, const double* emis, double likelihood_power, double t_end);
+
+/*
+ * FFBS for C chains: forward filter over the augmented (v,l) states + backward sampling + path
+ * compaction + chain metrics.  Replaces smjp_ffbs / sample_smjp_trajectory_posterior
+ * (smjp_utils.py:261-330) = likelihood_and_decoding_hmm (fast_hmm.py:202-335) with
+ * smjpTransitionFunction (smjp_utils.py:382-416) and smjpEmission (:506-550) evaluated in-kernel,
+ * backward_sampling_hmm (fast_hmm.py:104-191), include_endpoint_in_thinned_samples
+ * (smjp_utils.py:338-348) and compute_evaluation_chain_metrics (mcmc_utils.py:40-56).
+ *
+ *   w_offs[C+1], W[w_offs[C]]           grids
+ *   obs_offs[C+1], obs_t[], obs_y[]     observations sorted by time per chain (sMJPDataWrapper)
+ *   uniforms[] or NULL                  u[w_offs[c]+i] drives the categorical draw at grid step i
+ *                                       (inverse CDF in the reference's state-major order
+ *                                       a = v*n + j); NULL = Philox stream (seed, sweep, chain)
+ *   precision                           SMJP_F64 | SMJP_F32 (arithmetic and message type)
+ *   messages or NULL, msg_offs[C+1]     optional export of the filtered messages: chain c, row i
+ *                                       (i = 0..n-1) starts at msg_offs[c] + K*i*(i+1)/2 and holds
+ *                                       alpha_i(v, W[j]) at [v*(i+1) + j], j <= i (normalised rows,
+ *                                       fast_hmm.py:231,321); element type per `precision`
+ *   logZ[] or NULL                      log row normalisers per grid step (discarded by the reference)
+ *   aug_idx[] or NULL                   sampled dense index a_i = v*n + j per grid step
+ *                                       (= `samples` of fast_hmm.py:191)
+ *   path_v[], path_t[], path_len[C]     compacted path (s_states, s_times of smjp_utils.py:327-329)
+ *   time_in_state[C*K], jumps[C*K]      or NULL
+ *   status[C]
+ */
+int smjp_ffbs_dev(smjp_ctx_t* ctx, int C, const int64_t* w_offs, const double* W,
+                  const int64_t* obs_offs, const double* obs_t, const int32_t* obs_y,
+                  const double* uniforms, uint64_t seed, uint32_t sweep, int precision,
+                  void* messages, const int64_t* msg_offs, double* logZ, int32_t* aug_idx,
+                  int32_t* path_v, double* path_t, int32_t* path_len, double* time_in_state,
+                  int32_t* jumps, int32_t* status,
+                  /* host copies of the ragged sizes, needed to size the workspace */
+                  int64_t n_max, int64_t total_w);
+
+/* Same call with HOST buffers (host<->device copies inside). messages/msg_offs may be NULL. */
+int smjp_ffbs_host(smjp_ctx_t* ctx, int C, const int64_t* w_offs, const double* W,
+                   const int64_t* obs_offs, const double* obs_t, const int32_t* obs_y,
+                   const double* uniforms, uint64_t seed, uint32_t sweep, int precision,
+                   void* messages, const int64_t* msg_offs, double* logZ, int32_t* aug_idx,
+                   int32_t* path_v, double* path_t, int32_t* path_len, double* time_in_state,
+                   int32_t* jumps, int32_t* status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMJP_B200_H */

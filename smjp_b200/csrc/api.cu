@@ -1,0 +1,465 @@
+// C ABI of the engine (include/smjp_b200.h): context, workspace, model upload, launchers.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/smjp_b200.h"
+#include "ffbs.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(x)                                                                        \
+    do {                                                                                   \
+        cudaError_t e_ = (x);                                                              \
+        if (e_ != cudaSuccess)                                                             \
+            return fail(SMJP_E_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                               \
+    } while (0)
+
+// growable device / pinned-host buffers owned by the context
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return SMJP_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(SMJP_E_NOMEM, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        }
+        cap = want;
+        return SMJP_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return SMJP_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(SMJP_E_NOMEM, "cudaMallocHost of %zu bytes failed: %s", want, cudaGetErrorString(e));
+        }
+        cap = want;
+        return SMJP_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct smjp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int num_sms = 0;
+    size_t smem_optin = 0;
+    int64_t launches = 0;
+    // model
+    int K = 0, Kobs = 0;
+    double omega = 0, power = 1, t_end = 0;
+    std::vector<double> h_model;
+    DevBuf d_model;
+    // workspaces
+    DevBuf d_queue, d_msg_scratch;
+    DevBuf d_in, d_out;  // staging for the host API
+    PinBuf h_in, h_out;
+    int ffbs_threads = 0;  // 0 = auto
+};
+
+using namespace smjp;
+
+extern "C" {
+
+int smjp_abi_version(void) { return SMJP_ABI_VERSION; }
+const char* smjp_last_error(void) { return g_err.c_str(); }
+
+smjp_ctx_t* smjp_ctx_create(int device, void* stream) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        fail(SMJP_E_CUDA, "no CUDA device: the smjp_b200 engine has no CPU path");
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) {
+        fail(SMJP_E_INVALID, "device %d out of range [0,%d)", device, ndev);
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) {
+        fail(SMJP_E_CUDA, "cudaSetDevice(%d) failed", device);
+        return nullptr;
+    }
+    smjp_ctx* c = new smjp_ctx();
+    c->device = device;
+    c->stream = (cudaStream_t)stream;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    c->num_sms = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    if (prop.major < 10) {
+        fail(SMJP_E_UNSUPPORTED, "device sm_%d%d: this library is built for sm_100a only", prop.major, prop.minor);
+        delete c;
+        return nullptr;
+    }
+    return c;
+}
+
+void smjp_ctx_destroy(smjp_ctx_t* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->d_model.release();
+    c->d_queue.release();
+    c->d_msg_scratch.release();
+    c->d_in.release();
+    c->d_out.release();
+    c->h_in.release();
+    c->h_out.release();
+    delete c;
+}
+
+int smjp_ctx_sync(smjp_ctx_t* c) {
+    if (!c) return fail(SMJP_E_INVALID, "null context");
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SMJP_OK;
+}
+
+int64_t smjp_ctx_launch_count(smjp_ctx_t* c) { return c ? c->launches : 0; }
+
+int smjp_ctx_set_option(smjp_ctx_t* c, const char* key, int64_t value) {
+    if (!c || !key) return fail(SMJP_E_INVALID, "null argument");
+    if (!strcmp(key, "ffbs_threads")) {
+        if (value != 0 && (value < 32 || value > 1024 || value % 32))
+            return fail(SMJP_E_INVALID, "ffbs_threads must be 0 (auto) or a multiple of 32 in [32,1024]");
+        c->ffbs_threads = (int)value;
+        return SMJP_OK;
+    }
+    return fail(SMJP_E_INVALID, "unknown option '%s'", key);
+}
+
+int smjp_set_model(smjp_ctx_t* c, int K, int Kobs, const double* shape, const double* scale,
+                   double omega, const double* emis, double likelihood_power, double t_end) {
+    if (!c) return fail(SMJP_E_INVALID, "null context");
+    if (K < 2 || K > 64) return fail(SMJP_E_INVALID, "K=%d outside [2,64]", K);
+    if (Kobs < 1 || Kobs > 4096) return fail(SMJP_E_INVALID, "Kobs=%d outside [1,4096]", Kobs);
+    if (!(omega > 1.0)) return fail(SMJP_E_INVALID, "omega must be > 1 (thinning needs B = omega*A > A)");
+    if (!(t_end > 0.0)) return fail(SMJP_E_INVALID, "t_end must be positive");
+    if (!shape || !scale || !emis) return fail(SMJP_E_INVALID, "null parameter array");
+    for (int t = 0; t < K * K; ++t)
+        if (!(shape[t] > 0.0) || !(scale[t] > 0.0) || !std::isfinite(shape[t]) || !std::isfinite(scale[t]))
+            return fail(SMJP_E_INVALID, "shape/scale entry %d is not positive finite", t);
+    for (int t = 0; t < K * Kobs; ++t)
+        if (!(emis[t] >= 0.0) || !std::isfinite(emis[t]))
+            return fail(SMJP_E_INVALID, "emission entry %d is negative or not finite", t);
+    CUDA_TRY(cudaSetDevice(c->device));
+    c->K = K;
+    c->Kobs = Kobs;
+    c->omega = omega;
+    c->power = likelihood_power;
+    c->t_end = t_end;
+    // device layout: shape[K*K], c2[K*K] = k*log2(lambda), emis[K*Kobs], scale[K*K]
+    c->h_model.assign((size_t)3 * K * K + (size_t)K * Kobs, 0.0);
+    for (int t = 0; t < K * K; ++t) {
+        c->h_model[t] = shape[t];
+        c->h_model[K * K + t] = shape[t] * std::log2(scale[t]);
+        c->h_model[2 * K * K + K * Kobs + t] = scale[t];
+    }
+    for (int t = 0; t < K * Kobs; ++t) c->h_model[2 * K * K + t] = emis[t];
+    int rc = c->d_model.reserve(c->h_model.size() * sizeof(double));
+    if (rc) return rc;
+    // stream-ordered with respect to kernels already enqueued that read the previous model
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpy(c->d_model.p, c->h_model.data(), c->h_model.size() * sizeof(double),
+                        cudaMemcpyHostToDevice));
+    return SMJP_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// FFBS launcher
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+template <typename Real, int K>
+int launch_ffbs_k(smjp_ctx* c, FfbsArgs& a, int threads, size_t smem, int grid) {
+    auto kern = ffbs_kernel<Real, K>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, threads, smem, c->stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    c->launches += 1;
+    return SMJP_OK;
+}
+
+template <typename Real, int K>
+int occupancy_k(int threads, size_t smem, int* per_sm) {
+    auto kern = ffbs_kernel<Real, K>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, kern, threads, smem));
+    return SMJP_OK;
+}
+
+#define SMJP_FOR_EACH_K(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10)
+
+template <typename Real>
+int occupancy(int K, int threads, size_t smem, int* per_sm) {
+    switch (K) {
+#define X(k) case k: return occupancy_k<Real, k>(threads, smem, per_sm);
+        SMJP_FOR_EACH_K(X)
+#undef X
+    }
+    return fail(SMJP_E_UNSUPPORTED, "sMJP FFBS kernel is instantiated for K in [2,10]; K=%d", K);
+}
+
+template <typename Real>
+int launch_ffbs(smjp_ctx* c, FfbsArgs& a, int threads, size_t smem, int grid) {
+    switch (c->K) {
+#define X(k) case k: return launch_ffbs_k<Real, k>(c, a, threads, smem, grid);
+        SMJP_FOR_EACH_K(X)
+#undef X
+    }
+    return fail(SMJP_E_UNSUPPORTED, "sMJP FFBS kernel is instantiated for K in [2,10]; K=%d", c->K);
+}
+
+template <typename Real>
+int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
+    const int K = c->K;
+    int threads = c->ffbs_threads;
+    if (threads == 0) {
+        // enough threads that a full row has ~2-4 grid points per thread, at least 2 warps
+        threads = 128;
+        if (n_max > 768) threads = 256;
+        if (n_max > 2048) threads = 512;
+        if (n_max <= 96) threads = 64;
+        if (n_max <= 32) threads = 32;
+    }
+    size_t smem = ffbs_smem_bytes<Real>(K, c->Kobs, (int)n_max, threads);
+    while (smem > c->smem_optin && threads > 32) {  // padding shrinks with fewer threads
+        threads /= 2;
+        smem = ffbs_smem_bytes<Real>(K, c->Kobs, (int)n_max, threads);
+    }
+    if (smem > c->smem_optin)
+        return fail(SMJP_E_UNSUPPORTED,
+                    "grid with %lld intervals x K=%d needs %zu B of shared memory (> %zu): "
+                    "chain state does not fit on chip", (long long)n_max, K, smem, c->smem_optin);
+    int per_sm = 0;
+    int rc = occupancy<Real>(K, threads, smem, &per_sm);
+    if (rc) return rc;
+    if (per_sm < 1) return fail(SMJP_E_UNSUPPORTED, "kernel cannot be resident (threads=%d smem=%zu)", threads, smem);
+    int grid = c->num_sms * per_sm;
+    if (grid > a.C) grid = a.C;
+    a.ncap = (int)n_max;
+    a.ncap_pad = (int)((n_max + threads - 1) / threads * threads);
+    if (!a.messages) {
+        const int64_t stride = (int64_t)K * n_max * (n_max + 1) / 2;
+        size_t bytes = (size_t)stride * sizeof(Real) * (size_t)grid;
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        size_t budget = free_b + c->d_msg_scratch.cap;
+        budget -= budget / 10;
+        if (bytes > budget) {  // fewer resident CTAs rather than failing
+            int g2 = (int)(budget / ((size_t)stride * sizeof(Real)));
+            if (g2 < 1)
+                return fail(SMJP_E_NOMEM, "message scratch for one chain (%zu B) does not fit", (size_t)stride * sizeof(Real));
+            grid = g2;
+            bytes = (size_t)stride * sizeof(Real) * (size_t)grid;
+        }
+        rc = c->d_msg_scratch.reserve(bytes);
+        if (rc) return rc;
+        a.msg_scratch = c->d_msg_scratch.p;
+        a.msg_scratch_stride = stride;
+    }
+    rc = c->d_queue.reserve(256);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(c->d_queue.p, 0, sizeof(unsigned int), c->stream));
+    a.queue = (unsigned int*)c->d_queue.p;
+    return launch_ffbs<Real>(c, a, threads, smem, grid);
+}
+
+}  // namespace
+
+extern "C" {
+
+int smjp_ffbs_dev(smjp_ctx_t* c, int C, const int64_t* w_offs, const double* W,
+                  const int64_t* obs_offs, const double* obs_t, const int32_t* obs_y,
+                  const double* uniforms, uint64_t seed, uint32_t sweep, int precision,
+                  void* messages, const int64_t* msg_offs, double* logZ, int32_t* aug_idx,
+                  int32_t* path_v, double* path_t, int32_t* path_len, double* time_in_state,
+                  int32_t* jumps, int32_t* status, int64_t n_max, int64_t total_w) {
+    if (!c) return fail(SMJP_E_INVALID, "null context");
+    if (c->K == 0) return fail(SMJP_E_INVALID, "smjp_set_model has not been called");
+    if (C < 0) return fail(SMJP_E_INVALID, "C < 0");
+    if (C == 0) return SMJP_OK;
+    if (!w_offs || !W || !obs_offs || !path_v || !path_t || !path_len || !status)
+        return fail(SMJP_E_INVALID, "null required pointer");
+    if (messages && !msg_offs) return fail(SMJP_E_INVALID, "messages given without msg_offs");
+    if (n_max < 1) return fail(SMJP_E_INVALID, "n_max < 1: every grid needs at least [0, t_end]");
+    if (total_w < (int64_t)C * 2) return fail(SMJP_E_INVALID, "total_w inconsistent with C");
+    if (precision != SMJP_F64 && precision != SMJP_F32) return fail(SMJP_E_INVALID, "bad precision");
+    CUDA_TRY(cudaSetDevice(c->device));
+    FfbsArgs a;
+    memset(&a, 0, sizeof a);
+    a.C = C;
+    a.w_offs = w_offs;
+    a.W = W;
+    a.obs_offs = obs_offs;
+    a.obs_t = obs_t;
+    a.obs_y = obs_y;
+    a.uniforms = uniforms;
+    a.seed = seed;
+    a.sweep = sweep;
+    a.chain_base = 0;
+    a.messages = messages;
+    a.msg_offs = msg_offs;
+    a.logZ = logZ;
+    a.aug_idx = aug_idx;
+    a.path_v = path_v;
+    a.path_t = path_t;
+    a.path_len = path_len;
+    a.time_in_state = time_in_state;
+    a.jumps = jumps;
+    a.status = status;
+    a.order = nullptr;
+    a.model = (const double*)c->d_model.p;
+    a.Kobs = c->Kobs;
+    a.omega = c->omega;
+    a.power = c->power;
+    a.t_end = c->t_end;
+    return precision == SMJP_F64 ? ffbs_dev_impl<double>(c, a, n_max) : ffbs_dev_impl<float>(c, a, n_max);
+}
+
+int smjp_ffbs_host(smjp_ctx_t* c, int C, const int64_t* w_offs, const double* W,
+                   const int64_t* obs_offs, const double* obs_t, const int32_t* obs_y,
+                   const double* uniforms, uint64_t seed, uint32_t sweep, int precision,
+                   void* messages, const int64_t* msg_offs, double* logZ, int32_t* aug_idx,
+                   int32_t* path_v, double* path_t, int32_t* path_len, double* time_in_state,
+                   int32_t* jumps, int32_t* status) {
+    if (!c) return fail(SMJP_E_INVALID, "null context");
+    if (c->K == 0) return fail(SMJP_E_INVALID, "smjp_set_model has not been called");
+    if (C < 0) return fail(SMJP_E_INVALID, "C < 0");
+    if (C == 0) return SMJP_OK;
+    if (!w_offs || !W || !obs_offs || !path_v || !path_t || !path_len || !status)
+        return fail(SMJP_E_INVALID, "null required pointer");
+    if (messages && !msg_offs) return fail(SMJP_E_INVALID, "messages given without msg_offs");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int K = c->K;
+    const int64_t total_w = w_offs[C], total_o = obs_offs[C];
+    if (w_offs[0] != 0 || obs_offs[0] != 0) return fail(SMJP_E_INVALID, "offsets must start at 0");
+    int64_t n_max = 0;
+    for (int i = 0; i < C; ++i) {
+        const int64_t len = w_offs[i + 1] - w_offs[i];
+        if (len < 2) return fail(SMJP_E_INVALID, "chain %d: a grid needs at least the two end points", i);
+        if (obs_offs[i + 1] < obs_offs[i]) return fail(SMJP_E_INVALID, "obs_offs not monotone at chain %d", i);
+        if (len - 1 > n_max) n_max = len - 1;
+    }
+    if (total_o > 0 && (!obs_t || !obs_y)) return fail(SMJP_E_INVALID, "observations missing");
+    const size_t esz = precision == SMJP_F64 ? 8 : 4;
+    const int64_t total_msg = messages ? msg_offs[C] : 0;
+
+    // ---- input staging layout (all 16-byte aligned) ----
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += smjp::align_up(bytes, 16); return o; };
+    const size_t o_woffs = take((C + 1) * 8), o_W = take(total_w * 8), o_ooffs = take((C + 1) * 8);
+    const size_t o_ot = take(total_o * 8), o_oy = take(total_o * 4);
+    const size_t o_u = uniforms ? take(total_w * 8) : 0;
+    const size_t o_moffs = messages ? take((C + 1) * 8) : 0;
+    const size_t in_bytes = off;
+    int rc = c->h_in.reserve(in_bytes);
+    if (rc) return rc;
+    rc = c->d_in.reserve(in_bytes);
+    if (rc) return rc;
+    char* hin = (char*)c->h_in.p;
+    memcpy(hin + o_woffs, w_offs, (C + 1) * 8);
+    memcpy(hin + o_W, W, total_w * 8);
+    memcpy(hin + o_ooffs, obs_offs, (C + 1) * 8);
+    if (total_o) {
+        memcpy(hin + o_ot, obs_t, total_o * 8);
+        memcpy(hin + o_oy, obs_y, total_o * 4);
+    }
+    if (uniforms) memcpy(hin + o_u, uniforms, total_w * 8);
+    if (messages) memcpy(hin + o_moffs, msg_offs, (C + 1) * 8);
+    CUDA_TRY(cudaMemcpyAsync(c->d_in.p, hin, in_bytes, cudaMemcpyHostToDevice, c->stream));
+
+    // ---- output staging layout ----
+    off = 0;
+    const size_t o_pv = take(total_w * 4), o_pt = take(total_w * 8), o_pl = take(C * 4), o_st = take(C * 4);
+    const size_t o_lz = logZ ? take(total_w * 8) : 0;
+    const size_t o_ai = aug_idx ? take(total_w * 4) : 0;
+    const size_t o_tis = time_in_state ? take((size_t)C * K * 8) : 0;
+    const size_t o_jm = jumps ? take((size_t)C * K * 4) : 0;
+    const size_t small_bytes = off;
+    const size_t o_msg = messages ? take(total_msg * esz) : 0;
+    const size_t out_bytes = off;
+    rc = c->d_out.reserve(out_bytes);
+    if (rc) return rc;
+    rc = c->h_out.reserve(small_bytes);
+    if (rc) return rc;
+    char* din = (char*)c->d_in.p;
+    char* dout = (char*)c->d_out.p;
+    if (aug_idx) CUDA_TRY(cudaMemsetAsync(dout + o_ai, 0, total_w * 4, c->stream));
+    if (logZ) CUDA_TRY(cudaMemsetAsync(dout + o_lz, 0, total_w * 8, c->stream));
+    rc = smjp_ffbs_dev(c, C, (const int64_t*)(din + o_woffs), (const double*)(din + o_W),
+                       (const int64_t*)(din + o_ooffs), (const double*)(din + o_ot),
+                       (const int32_t*)(din + o_oy), uniforms ? (const double*)(din + o_u) : nullptr,
+                       seed, sweep, precision, messages ? (void*)(dout + o_msg) : nullptr,
+                       messages ? (const int64_t*)(din + o_moffs) : nullptr,
+                       logZ ? (double*)(dout + o_lz) : nullptr, aug_idx ? (int32_t*)(dout + o_ai) : nullptr,
+                       (int32_t*)(dout + o_pv), (double*)(dout + o_pt), (int32_t*)(dout + o_pl),
+                       time_in_state ? (double*)(dout + o_tis) : nullptr,
+                       jumps ? (int32_t*)(dout + o_jm) : nullptr, (int32_t*)(dout + o_st), n_max, total_w);
+    if (rc) return rc;
+    char* hout = (char*)c->h_out.p;
+    CUDA_TRY(cudaMemcpyAsync(hout, dout, small_bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (messages)  // large: straight into the caller's (pageable) buffer
+        CUDA_TRY(cudaMemcpyAsync(messages, dout + o_msg, total_msg * esz, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    memcpy(path_v, hout + o_pv, total_w * 4);
+    memcpy(path_t, hout + o_pt, total_w * 8);
+    memcpy(path_len, hout + o_pl, C * 4);
+    memcpy(status, hout + o_st, C * 4);
+    if (logZ) memcpy(logZ, hout + o_lz, total_w * 8);
+    if (aug_idx) memcpy(aug_idx, hout + o_ai, total_w * 4);
+    if (time_in_state) memcpy(time_in_state, hout + o_tis, (size_t)C * K * 8);
+    if (jumps) memcpy(jumps, hout + o_jm, (size_t)C * K * 4);
+    return SMJP_OK;
+}
+
+}  // extern "C"

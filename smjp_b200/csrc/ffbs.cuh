@@ -1,0 +1,426 @@
+// FFBS over the augmented (v, l) state space of a semi-Markov jump process: one CTA per chain.
+//
+// Replaces (reference, paths relative to its root):
+//   likelihood_and_decoding_hmm   pkg/fast_hmm.py:202-335   forward filter, rows normalised
+//   compute_transition_matrix     pkg/fast_hmm.py:343-354   never materialised here
+//   smjpTransitionFunction        pkg/smjp_utils.py:382-416 jump A_vv'/B_v, thin 1 - A_v/B_v = 1 - 1/Omega
+//   smjpEmission.__call__         pkg/smjp_utils.py:506-550 + PoissonProcess.likelihood :104-133
+//   backward_sampling_hmm         pkg/fast_hmm.py:104-191   inverse CDF in state-major order
+//   smjp_ffbs tail                pkg/smjp_utils.py:319-330 path compaction (+ :338-348 endpoint)
+//   compute_evaluation_chain_metrics pkg/mcmc_utils.py:40-56
+//
+// Arithmetic: with tau = W[i+1] - W[j], H_vs = (tau/lambda_vs)^k_vs,
+// H_v = sum_s H_vs, D_v = sum_s k_vs H_vs (so A_v = D_v / tau):
+//   e_i(v,j)      = obs_i(v) * [Omega D_v / tau]^{not final} * exp(-Omega (H_v(tau) - H_v(tau_prev)))
+//   alpha_i(v,j)  ~ e_i(v,j) (1 - 1/Omega) alpha_{i-1}(v,j)                      j < i  (thinned)
+//   alpha_i(v',i) ~ e_i(v',i) J_i(v'),  J_i(v') = sum_{v,j<i} alpha_{i-1}(v,j) k_vv' H_vv' / (Omega D_v)
+// The K*K cumulative hazards computed for (i, j) serve e_i(v,j) AND the jump sums J_{i+1}: B_i is
+// generated in-kernel and never stored.  State carried per live (v,j): the unnormalised message and
+// H_v(tau) -- both in shared memory, indexed so that consecutive threads hit consecutive banks.
+// Normalisation is deferred by one step (row i-1 is scaled and streamed to HBM while row i is being
+// computed), so each grid step costs exactly one __syncthreads().
+#pragma once
+#include "../../include/smjp_b200.h"
+#include "common.cuh"
+
+namespace smjp {
+
+struct FfbsArgs {
+    int C;
+    const int64_t* w_offs;
+    const double* W;
+    const int64_t* obs_offs;
+    const double* obs_t;
+    const int32_t* obs_y;
+    const double* uniforms;  // may be null -> Philox
+    uint64_t seed;
+    uint32_t sweep;
+    uint32_t chain_base;  // global index of chain 0 (multi-GPU sharding keeps streams distinct)
+    void* messages;       // export buffer or null
+    const int64_t* msg_offs;
+    void* msg_scratch;  // per-CTA message scratch when not exporting
+    int64_t msg_scratch_stride;
+    double* logZ;
+    int32_t* aug_idx;
+    int32_t* path_v;
+    double* path_t;
+    int32_t* path_len;
+    double* time_in_state;
+    int32_t* jumps;
+    int32_t* status;
+    const int32_t* order;  // optional chain processing order (longest first)
+    unsigned int* queue;   // work counter, zeroed before launch
+    const double* model;   // device: shape[K*K], c2[K*K] (= k*log2(lambda)), emis[K*Kobs]
+    int Kobs;
+    double omega, power, t_end;
+    int ncap;      // max grid intervals any chain of this launch has (smem carve-up)
+    int ncap_pad;  // ncap rounded up to a multiple of blockDim.x
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// dynamic shared memory bytes for (Real, K, Kobs, ncap, threads)
+template <typename Real>
+__host__ __device__ inline size_t ffbs_smem_bytes(int K, int Kobs, int ncap, int threads) {
+    int ncap_pad = (ncap + threads - 1) / threads * threads;
+    size_t b = 0;
+    b += align_up((size_t)(ncap + 1) * sizeof(double), 16);            // Wd
+    b += align_up((size_t)(threads / 32 + 1) * sizeof(double) * 2, 16); // scan scratch (double)
+    b += align_up((size_t)2 * (ncap + 1) * sizeof(int), 16);           // sojourn list
+    b += align_up((size_t)K * ncap * sizeof(Real), 16);                // obsf
+    b += align_up((size_t)K * ncap_pad * sizeof(Real), 16);            // st_a / wbuf
+    b += align_up((size_t)K * ncap_pad * sizeof(Real), 16);            // st_h
+    b += align_up((size_t)2 * (threads / 32) * (K + 1) * sizeof(Real), 16);  // reduction scratch
+    b += align_up((size_t)(2 * K * K + K * Kobs) * sizeof(Real), 16);  // model
+    return b;
+}
+
+__device__ __forceinline__ bool np_isclose(double a, double b) {
+    // numpy.isclose(a, b): |a-b| <= atol + rtol*|b|, rtol=1e-5, atol=1e-8
+    return fabs(a - b) <= 1e-8 + 1e-5 * fabs(b);
+}
+
+template <typename Real, int K>
+__global__ void ffbs_kernel(const FfbsArgs a) {
+    using M = Math<Real>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, B = blockDim.x, lane = tid & 31, wid = tid >> 5, NW = B >> 5;
+    const int ncap = a.ncap, ncap_pad = a.ncap_pad, Kobs = a.Kobs;
+
+    unsigned char* sp = smem_raw;
+    double* Wd = (double*)sp;
+    sp += align_up((size_t)(ncap + 1) * sizeof(double), 16);
+    double* scan_s = (double*)sp;  // [NW + 1] warp totals, [NW+1..] spare
+    sp += align_up((size_t)(NW + 1) * sizeof(double) * 2, 16);
+    int* soj = (int*)sp;  // [2][ncap+1]: state, grid index of each sojourn found by the backward pass
+    sp += align_up((size_t)2 * (ncap + 1) * sizeof(int), 16);
+    Real* obsf = (Real*)sp;
+    sp += align_up((size_t)K * ncap * sizeof(Real), 16);
+    Real* st_a = (Real*)sp;
+    sp += align_up((size_t)K * ncap_pad * sizeof(Real), 16);
+    Real* st_h = (Real*)sp;
+    sp += align_up((size_t)K * ncap_pad * sizeof(Real), 16);
+    Real* red = (Real*)sp;
+    sp += align_up((size_t)2 * NW * (K + 1) * sizeof(Real), 16);
+    Real* sk = (Real*)sp;      // shape k_vs
+    Real* sc2 = sk + K * K;    // k_vs * log2(lambda_vs)
+    Real* sem = sc2 + K * K;   // emis[v*Kobs + y]
+
+    __shared__ int s_chain;
+    __shared__ int s_sel;
+    __shared__ int s_flag;
+
+    for (int t = tid; t < K * K; t += B) {
+        sk[t] = (Real)a.model[t];
+        sc2[t] = (Real)a.model[K * K + t];
+    }
+    for (int t = tid; t < K * Kobs; t += B) sem[t] = (Real)a.model[2 * K * K + t];
+
+    const Real thin = (Real)(1.0 - 1.0 / a.omega);
+    const Real inv_omega = (Real)(1.0 / a.omega);
+    const Real omega_r = (Real)a.omega;
+    const Real om_l2e = (Real)(a.omega * SMJP_LOG2E);
+    const Real power = (Real)a.power;
+
+    while (true) {
+        __syncthreads();
+        if (tid == 0) {
+            unsigned int q = atomicAdd(a.queue, 1u);
+            s_chain = (q < (unsigned)a.C) ? (a.order ? a.order[q] : (int)q) : -1;
+            s_flag = 0;
+        }
+        __syncthreads();
+        const int c = s_chain;
+        if (c < 0) break;
+        const int64_t w0 = a.w_offs[c];
+        const int n = (int)(a.w_offs[c + 1] - w0) - 1;
+        if (n < 1 || n > ncap) {
+            if (tid == 0) {
+                a.status[c] = (n < 1) ? SMJP_ST_GRID_NOT_INCREASING : SMJP_ST_OVERFLOW;
+                a.path_len[c] = 0;
+            }
+            continue;
+        }
+        // ---- stage the grid, validate it (smjp_utils.py:398-399) ----
+        for (int t = tid; t <= n; t += B) Wd[t] = a.W[w0 + t];
+        __syncthreads();
+        {
+            int bad = 0;
+            for (int t = tid; t < n; t += B) bad |= !(Wd[t + 1] > Wd[t]);
+            if (bad) atomicOr(&s_flag, 1);
+        }
+        // ---- observation factor per interval: (sum_{x in [W[i],W[i+1]]} P(x|v))^power ----
+        {
+            const int64_t o0 = a.obs_offs[c];
+            const int D = (int)(a.obs_offs[c + 1] - o0);
+            const double* ot = a.obs_t + o0;
+            const int32_t* oy = a.obs_y + o0;
+            for (int i = tid; i < n; i += B) {
+                const double wc = Wd[i], wn = Wd[i + 1];
+                int lo = 0, hi = D;  // first d with ot[d] >= wc
+                while (lo < hi) {
+                    int mid = (lo + hi) >> 1;
+                    if (ot[mid] < wc) lo = mid + 1; else hi = mid;
+                }
+                Real f[K];
+#pragma unroll
+                for (int v = 0; v < K; ++v) f[v] = 0;
+                int cnt = 0;
+                for (int d = lo; d < D && ot[d] <= wn; ++d, ++cnt) {
+                    const int y = oy[d];
+#pragma unroll
+                    for (int v = 0; v < K; ++v) f[v] += sem[v * Kobs + y];
+                }
+#pragma unroll
+                for (int v = 0; v < K; ++v)
+                    obsf[v * ncap + i] = (cnt == 0 || power == (Real)0) ? (Real)1 : (power == (Real)1 ? f[v] : M::pow(f[v], power));
+            }
+        }
+        __syncthreads();
+        if (s_flag) {
+            if (tid == 0) {
+                a.status[c] = SMJP_ST_GRID_NOT_INCREASING;
+                a.path_len[c] = 0;
+            }
+            continue;
+        }
+
+        Real* msg = a.messages ? (Real*)a.messages + a.msg_offs[c]
+                               : (Real*)a.msg_scratch + (int64_t)blockIdx.x * a.msg_scratch_stride;
+
+        // =========================== forward ===========================
+        Real invZ_prev = (Real)1;
+        Real J[K];
+#pragma unroll
+        for (int v = 0; v < K; ++v) J[v] = (Real)(1.0 / K);  // uniform prior on (v,0): smjp_utils.py:286-289
+        bool degenerate = false;
+        for (int i = 0; i < n; ++i) {
+            const double wn = Wd[i + 1];
+            const bool nonfinal = !np_isclose(a.t_end, wn);  // smjp_utils.py:544
+            Real of[K];
+#pragma unroll
+            for (int v = 0; v < K; ++v) of[v] = obsf[v * ncap + i];
+            Real Zp = 0;
+            Real Jp[K];
+#pragma unroll
+            for (int v = 0; v < K; ++v) Jp[v] = 0;
+            Real* row_prev = msg + (int64_t)K * (i - 1) * i / 2;  // row i-1: i entries per state
+            for (int j = tid; j <= i; j += B) {
+                const Real tau = (Real)(wn - Wd[j]);
+                const Real L2 = M::log2(tau);
+                const Real inv_tau = M::rcp(tau);
+#pragma unroll
+                for (int v = 0; v < K; ++v) {
+                    Real base, hprev;
+                    if (j < i) {
+                        const Real ap = st_a[v * ncap_pad + j] * invZ_prev;
+                        row_prev[(int64_t)v * i + j] = ap;
+                        base = ap * thin;
+                        hprev = st_h[v * ncap_pad + j];
+                    } else {
+                        base = J[v];
+                        hprev = 0;
+                    }
+                    Real Hs[K];
+                    Real hsum = 0, dsum = 0;
+#pragma unroll
+                    for (int s = 0; s < K; ++s) {
+                        Hs[s] = M::exp2(sk[v * K + s] * L2 - sc2[v * K + s]);
+                        hsum += Hs[s];
+                        dsum += sk[v * K + s] * Hs[s];
+                    }
+                    const Real surv = M::exp2(-om_l2e * (hsum - hprev));
+                    const Real front = nonfinal ? omega_r * dsum * inv_tau : (Real)1;
+                    const Real an = of[v] * front * surv * base;
+                    st_a[v * ncap_pad + j] = an;
+                    st_h[v * ncap_pad + j] = hsum;
+                    Zp += an;
+                    const Real g = dsum > (Real)0 ? an * inv_omega * M::rcp(dsum) : (Real)0;
+#pragma unroll
+                    for (int s = 0; s < K; ++s) Jp[s] += g * sk[v * K + s] * Hs[s];
+                }
+            }
+            // block reduction of (Z, J[0..K)) -- double-buffered scratch, one barrier per step
+            Real* rb = red + (i & 1) * NW * (K + 1);
+            Zp = warp_sum(Zp);
+#pragma unroll
+            for (int v = 0; v < K; ++v) Jp[v] = warp_sum(Jp[v]);
+            if (lane == 0) {
+                rb[wid * (K + 1)] = Zp;
+#pragma unroll
+                for (int v = 0; v < K; ++v) rb[wid * (K + 1) + 1 + v] = Jp[v];
+            }
+            __syncthreads();
+            Real Z = 0;
+#pragma unroll
+            for (int v = 0; v < K; ++v) J[v] = 0;
+            for (int w = 0; w < NW; ++w) {
+                Z += rb[w * (K + 1)];
+#pragma unroll
+                for (int v = 0; v < K; ++v) J[v] += rb[w * (K + 1) + 1 + v];
+            }
+            if (!(Z > (Real)0) || !(Z < (Real)INFINITY)) {
+                degenerate = true;
+                break;
+            }
+            invZ_prev = (Real)1 / Z;
+#pragma unroll
+            for (int v = 0; v < K; ++v) J[v] *= invZ_prev;
+            if (tid == 0 && a.logZ) a.logZ[w0 + i] = log((double)Z);
+        }
+        if (degenerate) {
+            if (tid == 0) {
+                a.status[c] = SMJP_ST_DEGENERATE;
+                a.path_len[c] = 0;
+            }
+            continue;
+        }
+        {   // last row: scale, store, and keep the normalised copy in st_a for the first draw
+            Real* row_last = msg + (int64_t)K * (n - 1) * n / 2;
+            for (int j = tid; j < n; j += B) {
+#pragma unroll
+                for (int v = 0; v < K; ++v) {
+                    const Real ap = st_a[v * ncap_pad + j] * invZ_prev;
+                    row_last[(int64_t)v * n + j] = ap;
+                }
+            }
+        }
+        __syncthreads();
+
+        // =========================== backward ===========================
+        Real* wbuf = st_a;  // [K][len] contiguous: the reference's state-major order a = v*len + j
+        int cur = n - 1, vplus = -1, cnt = 0;
+        while (true) {
+            const int len = cur + 1;
+            const Real* row = msg + (int64_t)K * cur * (cur + 1) / 2;
+            if (vplus < 0) {  // a_{n-1} ~ alpha_{n-1}  (fast_hmm.py:124-125)
+                for (int t = tid; t < K * len; t += B) wbuf[t] = row[t];
+            } else {  // jump at W[cur+1] into vplus: w = alpha_cur(v,j) A_{v,vplus}/B_v  (fast_hmm.py:153-171)
+                const double wn = Wd[cur + 1];
+                for (int j = tid; j < len; j += B) {
+                    const Real L2 = M::log2((Real)(wn - Wd[j]));
+#pragma unroll
+                    for (int v = 0; v < K; ++v) {
+                        Real dsum = 0, hto = 0;
+#pragma unroll
+                        for (int s = 0; s < K; ++s) {
+                            const Real h = M::exp2(sk[v * K + s] * L2 - sc2[v * K + s]);
+                            dsum += sk[v * K + s] * h;
+                            if (s == vplus) hto = sk[v * K + s] * h;
+                        }
+                        const Real r = dsum > (Real)0 ? hto * M::rcp(dsum) : (Real)0;
+                        wbuf[v * len + j] = row[(int64_t)v * len + j] * r;
+                    }
+                }
+            }
+            __syncthreads();
+            // inclusive scan over the flat weight vector, contiguous chunk per thread
+            const int L = K * len;
+            const int q = (L + B - 1) / B;
+            const int beg = min(tid * q, L), end = min(beg + q, L);
+            double loc = 0;
+            for (int t = beg; t < end; ++t) loc += (double)wbuf[t];
+            double incl = warp_inclusive_scan(loc, lane);
+            if (lane == 31) scan_s[wid + 1] = incl;
+            if (tid == 0) scan_s[0] = 0.0;
+            __syncthreads();
+            double off = 0;
+            for (int w = 1; w <= wid; ++w) off += scan_s[w];
+            incl += off;
+            double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) excl = off;
+            double total = 0;
+            for (int w = 1; w <= NW; ++w) total += scan_s[w];
+            if (!(total > 0.0) || !(total < (double)INFINITY)) {
+                degenerate = true;
+                break;
+            }
+            const double u = a.uniforms ? a.uniforms[w0 + cur]
+                                        : philox_u01(a.seed, TAG_BACKWARD, (uint64_t)cur, 0u, a.sweep,
+                                                     a.chain_base + (uint32_t)c);
+            const double target = u * total;
+            // owner: excl <= target < incl.  If rounding pushed target to >= total, the last
+            // thread with mass takes it.
+            const bool has = incl > excl;
+            if (has && target >= excl && target < incl) {
+                double acc = excl;
+                int sel = -1, lastpos = beg;
+                for (int t = beg; t < end; ++t) {
+                    const double wv = (double)wbuf[t];
+                    if (wv > 0.0) lastpos = t;
+                    acc += wv;
+                    if (acc > target) { sel = t; break; }
+                }
+                s_sel = sel >= 0 ? sel : lastpos;
+            }
+            if (target >= total && has) atomicMax(&s_flag, tid + 1);  // rare: u*total rounded up
+            __syncthreads();
+            if (target >= total) {  // block-uniform condition
+                if (tid + 1 == s_flag) {
+                    int lastpos = beg;
+                    for (int t = beg; t < end; ++t) if ((double)wbuf[t] > 0.0) lastpos = t;
+                    s_sel = lastpos;
+                }
+                __syncthreads();
+                if (tid == 0) s_flag = 0;
+            }
+            const int idx = s_sel;
+            const int v = idx / len, j = idx - v * len;
+            if (a.aug_idx)
+                for (int t = j + tid; t <= cur; t += B) a.aug_idx[w0 + t] = v * n + j;
+            if (tid == 0) {
+                soj[cnt] = v;
+                soj[(ncap + 1) + cnt] = j;
+            }
+            ++cnt;
+            if (j == 0) break;
+            vplus = v;
+            cur = j - 1;
+        }
+        __syncthreads();
+        if (degenerate) {
+            if (tid == 0) {
+                a.status[c] = SMJP_ST_DEGENERATE;
+                a.path_len[c] = 0;
+            }
+            continue;
+        }
+        // ---- path compaction (smjp_utils.py:319-330): sojourns were found last-to-first ----
+        for (int p = tid; p < cnt; p += B) {
+            a.path_v[w0 + p] = soj[cnt - 1 - p];
+            a.path_t[w0 + p] = Wd[soj[(ncap + 1) + cnt - 1 - p]];
+        }
+        const int v_last = soj[0];
+        const double t_last = Wd[soj[ncap + 1]];
+        const bool add_end = !np_isclose(t_last, a.t_end);  // smjp_utils.py:338-348
+        const int plen = cnt + (add_end ? 1 : 0);
+        if (tid == 0) {
+            if (add_end) {
+                a.path_v[w0 + cnt] = v_last;
+                a.path_t[w0 + cnt] = a.t_end;
+            }
+            a.path_len[c] = plen;
+            a.status[c] = 0;
+        }
+        // ---- chain metrics (mcmc_utils.py:40-56): one thread per state, fixed summation order ----
+        if (tid < K && (a.time_in_state || a.jumps)) {
+            double tsum = 0;
+            int jc = 0;
+            for (int p = 0; p < plen; ++p) {
+                const int vs = p < cnt ? soj[cnt - 1 - p] : v_last;
+                if (vs == tid) {
+                    ++jc;
+                    if (p + 1 < plen) {
+                        const double t0 = Wd[soj[(ncap + 1) + cnt - 1 - p]];
+                        const double t1 = (p + 1 < cnt) ? Wd[soj[(ncap + 1) + cnt - 2 - p]] : a.t_end;
+                        tsum += t1 - t0;
+                    }
+                }
+            }
+            if (a.time_in_state) a.time_in_state[(int64_t)c * K + tid] = tsum;
+            if (a.jumps) a.jumps[(int64_t)c * K + tid] = jc;
+        }
+    }
+}
+
+}  // namespace smjp

@@ -1,0 +1,187 @@
+"""Batched engine object: owns one C-ABI context (device + stream) and exposes the kernels on ragged
+batches of chains, with HOST (NumPy) buffers or DEVICE (torch) tensors.  This is the layer the
+reference-named drop-in functions (smjp_b200.smjp_utils, .fast_hmm, .raoteh, .pmcmc) call into.
+PyTorch is used only for device memory and streams."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import SMJP_F32, SMJP_F64, check
+
+PRECISIONS = {"f64": SMJP_F64, "fp64": SMJP_F64, "float64": SMJP_F64, np.float64: SMJP_F64,
+              "f32": SMJP_F32, "fp32": SMJP_F32, "float32": SMJP_F32, np.float32: SMJP_F32}
+
+
+def _ptr(a):
+    """address of a NumPy array / torch tensor / None"""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()  # torch tensor
+
+
+def ragged_offsets(lengths):
+    offs = np.zeros(len(lengths) + 1, dtype=np.int64)
+    np.cumsum(np.asarray(lengths, dtype=np.int64), out=offs[1:])
+    return offs
+
+
+def pack_ragged(arrays, dtype):
+    """list of 1-D arrays -> (flat, offsets)"""
+    lens = [len(a) for a in arrays]
+    offs = ragged_offsets(lens)
+    flat = np.zeros(int(offs[-1]), dtype=dtype)
+    for a, o in zip(arrays, offs[:-1]):
+        flat[o:o + len(a)] = a
+    return flat, offs
+
+
+def message_offsets(n_per_chain, K):
+    """element offsets of each chain's triangular message block: K*n*(n+1)/2 elements per chain"""
+    n = np.asarray(n_per_chain, dtype=np.int64)
+    return ragged_offsets(K * n * (n + 1) // 2)
+
+
+def triangular_to_dense(tri, n, K):
+    """one chain's exported messages -> the reference's dense [n, K*n] array (fast_hmm.py:209;
+    column a = v*n + j, zeros where the reference holds log 0)."""
+    dense = np.zeros((n, K, n), dtype=tri.dtype)
+    pos = 0
+    for i in range(n):
+        dense[i, :, : i + 1] = tri[pos: pos + K * (i + 1)].reshape(K, i + 1)
+        pos += K * (i + 1)
+    return dense.reshape(n, K * n)
+
+
+class Engine:
+    def __init__(self, device=0, stream=None):
+        self.lib = _lib.load()
+        self.device = int(device)
+        self.ctx = self.lib.smjp_ctx_create(self.device, stream)
+        if not self.ctx:
+            raise _lib.EngineError(self.lib.smjp_last_error().decode())
+        self.K = None
+        self.Kobs = None
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.smjp_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------
+    def set_option(self, key, value):
+        check(self.lib.smjp_ctx_set_option(self.ctx, key.encode(), int(value)))
+
+    def sync(self):
+        check(self.lib.smjp_ctx_sync(self.ctx))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.smjp_ctx_launch_count(self.ctx))
+
+    def set_model(self, shape, scale, omega, emis, likelihood_power, t_end):
+        shape = np.ascontiguousarray(shape, dtype=np.float64)
+        scale = np.ascontiguousarray(scale, dtype=np.float64)
+        emis = np.ascontiguousarray(emis, dtype=np.float64)
+        if shape.ndim != 2 or shape.shape[0] != shape.shape[1] or scale.shape != shape.shape:
+            raise ValueError("shape/scale must be [K,K]")
+        K = shape.shape[0]
+        if emis.ndim != 2 or emis.shape[0] != K:
+            raise ValueError("emis must be [K,Kobs]")
+        check(self.lib.smjp_set_model(self.ctx, K, emis.shape[1], _ptr(shape), _ptr(scale), float(omega),
+                                      _ptr(emis), float(likelihood_power), float(t_end)))
+        self.K, self.Kobs = K, emis.shape[1]
+        self.t_end = float(t_end)
+
+    # ------------------------------------------------------------------------------------------
+    def ffbs_host(self, W, obs_t, obs_y, uniforms=None, seed=0, sweep=0, precision="f64",
+                  want_messages=False, want_logZ=True, want_aug_idx=True, want_metrics=True):
+        """FFBS on HOST data.  W: list (per chain) of grids; obs_t/obs_y: list per chain, or one
+        array shared by all chains.  Returns a dict of NumPy results; ragged outputs as lists."""
+        if self.K is None:
+            raise ValueError("set_model first")
+        C = len(W)
+        prec = PRECISIONS[precision]
+        Wf, w_offs = pack_ragged([np.asarray(w, dtype=np.float64) for w in W], np.float64)
+        shared = (isinstance(obs_t, np.ndarray) and obs_t.dtype != object and obs_t.ndim == 1) or \
+                 (len(obs_t) == 0 or np.isscalar(obs_t[0]))
+        if shared:  # one observation record for every chain
+            obs_t = [obs_t] * C
+            obs_y = [obs_y] * C
+        if len(obs_t) != C or len(obs_y) != C:
+            raise ValueError("need one observation record per chain")
+        of, o_offs = pack_ragged([np.asarray(t, dtype=np.float64) for t in obs_t], np.float64)
+        oy, _ = pack_ragged([np.asarray(y, dtype=np.int32) for y in obs_y], np.int32)
+        if len(oy) and (oy.min() < 0 or oy.max() >= self.Kobs):
+            raise ValueError("observation symbol outside [0, Kobs)")
+        uf = None
+        if uniforms is not None:
+            uf = np.zeros(len(Wf), dtype=np.float64)
+            for c in range(C):
+                u = np.asarray(uniforms[c], dtype=np.float64)
+                n = w_offs[c + 1] - w_offs[c] - 1
+                if len(u) != n:
+                    raise ValueError("chain %d: need one uniform per grid interval (%d), got %d" % (c, n, len(u)))
+                uf[w_offs[c]: w_offs[c] + n] = u
+        n_per = np.diff(w_offs) - 1
+        K = self.K
+        rdt = np.float64 if prec == SMJP_F64 else np.float32
+        msgs = m_offs = None
+        if want_messages:
+            m_offs = message_offsets(n_per, K)
+            msgs = np.zeros(int(m_offs[-1]), dtype=rdt)
+        total = len(Wf)
+        logZ = np.zeros(total, dtype=np.float64) if want_logZ else None
+        aug = np.zeros(total, dtype=np.int32) if want_aug_idx else None
+        pv = np.zeros(total, dtype=np.int32)
+        pt = np.zeros(total, dtype=np.float64)
+        pl = np.zeros(C, dtype=np.int32)
+        tis = np.zeros((C, K), dtype=np.float64) if want_metrics else None
+        jm = np.zeros((C, K), dtype=np.int32) if want_metrics else None
+        st = np.zeros(C, dtype=np.int32)
+        check(self.lib.smjp_ffbs_host(self.ctx, C, _ptr(w_offs), _ptr(Wf), _ptr(o_offs), _ptr(of), _ptr(oy),
+                                      _ptr(uf), int(seed) & 0xFFFFFFFFFFFFFFFF, int(sweep), prec,
+                                      _ptr(msgs), _ptr(m_offs), _ptr(logZ), _ptr(aug), _ptr(pv), _ptr(pt),
+                                      _ptr(pl), _ptr(tis), _ptr(jm), _ptr(st)))
+        out = {"status": st, "path_len": pl, "n": n_per, "w_offs": w_offs}
+        out["V"] = [pv[w_offs[c]: w_offs[c] + pl[c]].copy() for c in range(C)]
+        out["T"] = [pt[w_offs[c]: w_offs[c] + pl[c]].copy() for c in range(C)]
+        if want_logZ:
+            out["logZ"] = [logZ[w_offs[c]: w_offs[c] + n_per[c]].copy() for c in range(C)]
+        if want_aug_idx:
+            out["aug_idx"] = [aug[w_offs[c]: w_offs[c] + n_per[c]].copy() for c in range(C)]
+        if want_metrics:
+            out["time_in_state"], out["jumps"] = tis, jm
+        if want_messages:
+            out["messages"] = [msgs[m_offs[c]: m_offs[c + 1]] for c in range(C)]
+        return out
+
+    def ffbs_dev(self, C, w_offs, W, obs_offs, obs_t, obs_y, path_v, path_t, path_len, status, n_max,
+                 total_w, uniforms=None, seed=0, sweep=0, precision="f64", messages=None, msg_offs=None,
+                 logZ=None, aug_idx=None, time_in_state=None, jumps=None):
+        """FFBS on DEVICE tensors (torch, already resident); asynchronous on the context's stream."""
+        check(self.lib.smjp_ffbs_dev(self.ctx, int(C), _ptr(w_offs), _ptr(W), _ptr(obs_offs), _ptr(obs_t),
+                                     _ptr(obs_y), _ptr(uniforms), int(seed) & 0xFFFFFFFFFFFFFFFF, int(sweep),
+                                     PRECISIONS[precision], _ptr(messages), _ptr(msg_offs), _ptr(logZ),
+                                     _ptr(aug_idx), _ptr(path_v), _ptr(path_t), _ptr(path_len),
+                                     _ptr(time_in_state), _ptr(jumps), _ptr(status), int(n_max), int(total_w)))
+
+
+def raise_for_status(status):
+    """Per-chain status bits -> the exceptions the reference raises at the same conditions."""
+    status = np.asarray(status)
+    if np.any(status & _lib.ST_GRID_NOT_INCREASING):
+        raise ValueError("We can not have time_p >= time_c")  # smjp_utils.py:398-399
+    if np.any(status & _lib.ST_DEGENERATE):
+        raise FloatingPointError("forward message / sampling vector is zero or not finite "
+                                 "(hidden_markov_model.py:170-185 exits here)")
+    if np.any(status & _lib.ST_OVERFLOW):
+        raise _lib.EngineError("engine capacity overflow (status %s)" % np.unique(status))

@@ -1,0 +1,158 @@
+"""GPU parity tests of the FFBS kernel, through the C ABI, against the reference golden fixtures
+and the oracle (run on the B200 box: pytest -m gpu)."""
+import numpy as np
+import pytest
+
+from conftest import ffbs_fixture_names, load_golden
+from oracle import smjp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+REL_F64 = 1e-6   # north_star tolerance for fp64 messages / log-likelihoods
+REL_F32 = 1e-4   # north_star tolerance for fp32
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from smjp_b200.engine import Engine
+    eng = Engine(0)
+    yield eng
+    eng.close()
+
+
+def run_fixture(engine, g, precision, **kw):
+    from smjp_b200.engine import triangular_to_dense
+    K = g["shape"].shape[0]
+    engine.set_model(g["shape"], g["scale"], float(g["omega"]), O.emission_matrix(K), float(g["power"]),
+                     float(g["t_end"]))
+    r = engine.ffbs_host([g["W"]], [g["obs_t"]], [g["obs_y"]], uniforms=[g["uniforms"]], precision=precision,
+                         want_messages=True, **kw)
+    n = len(g["W"]) - 1
+    r["dense"] = triangular_to_dense(r["messages"][0], n, K)
+    return r
+
+
+def rel_err(a, ref, floor):
+    """max relative error over entries that carry mass (> floor); absolute error elsewhere"""
+    big = ref > floor
+    rel = np.abs(a[big] - ref[big]) / ref[big]
+    ab = np.abs(a[~big] - ref[~big])
+    return (rel.max() if rel.size else 0.0), (ab.max() if ab.size else 0.0)
+
+
+@pytest.mark.parametrize("name", ffbs_fixture_names())
+def test_fp64_matches_reference_fixture(engine, name):
+    g = load_golden("ffbs_" + name)
+    r = run_fixture(engine, g, "f64")
+    assert r["status"][0] == 0
+    rel, ab = rel_err(r["dense"], g["alpha"], 1e-300)
+    assert rel < REL_F64, rel
+    assert rel < 1e-11  # what fp64 actually achieves
+    assert np.array_equal(r["dense"] > 0, g["alpha"] > 0)
+    # bit-exact backward path given identical host uniforms
+    assert np.array_equal(r["aug_idx"][0], g["samples"])
+    assert np.array_equal(r["V"][0], g["V"])
+    assert np.array_equal(r["T"][0], g["T"])
+    # log-normalisers: unpinned by the reference, compared with the oracle
+    K = g["shape"].shape[0]
+    ora = O.ffbs(g["W"], g["obs_t"], g["obs_y"], g["shape"], g["scale"], float(g["omega"]),
+                 O.emission_matrix(K), float(g["power"]), float(g["t_end"]), g["uniforms"])
+    assert np.allclose(r["logZ"][0], ora["logZ"], rtol=REL_F64, atol=1e-12)
+    t, j = O.chain_metrics(g["V"], g["T"], K)
+    assert np.array_equal(r["jumps"][0], j)
+    assert np.allclose(r["time_in_state"][0], t, rtol=0, atol=1e-14)
+
+
+@pytest.mark.parametrize("name", ffbs_fixture_names())
+def test_fp32_matches_reference_fixture(engine, name):
+    g = load_golden("ffbs_" + name)
+    r = run_fixture(engine, g, "f32")
+    assert r["status"][0] == 0
+    rel, ab = rel_err(r["dense"].astype(np.float64), g["alpha"], 1e-6)
+    assert rel < REL_F32, rel
+    assert ab < 1e-9
+    K = g["shape"].shape[0]
+    ora = O.ffbs(g["W"], g["obs_t"], g["obs_y"], g["shape"], g["scale"], float(g["omega"]),
+                 O.emission_matrix(K), float(g["power"]), float(g["t_end"]), g["uniforms"])
+    assert np.allclose(r["logZ"][0], ora["logZ"], rtol=REL_F32, atol=1e-5)
+
+
+def random_problem(rng, K, t_end, n, D, omega=2.0):
+    shape = rng.uniform(0.6, 3.0, (K, K))
+    scale = np.ones((K, K))
+    W = np.concatenate([[0.0], np.sort(rng.uniform(0, t_end, n - 1)), [t_end]])
+    obs_t = np.sort(rng.uniform(0, t_end, D))
+    obs_y = rng.integers(0, K, D)
+    return shape, scale, W, obs_t, obs_y
+
+
+@pytest.mark.parametrize("K,n,D", [(2, 40, 10), (3, 200, 150), (5, 130, 64), (10, 90, 30), (3, 700, 999)])
+def test_fp64_matches_oracle_random(engine, K, n, D):
+    from smjp_b200.engine import triangular_to_dense
+    rng = np.random.default_rng(100 * K + n)
+    t_end = n / 5.0
+    shape, scale, W, obs_t, obs_y = random_problem(rng, K, t_end, n, D)
+    emis = O.emission_matrix(K)
+    engine.set_model(shape, scale, 2.0, emis, 1.0, t_end)
+    C = 3
+    us = [rng.uniform(size=n) for _ in range(C)]
+    r = engine.ffbs_host([W] * C, obs_t, obs_y, uniforms=us, precision="f64", want_messages=True)
+    assert np.all(r["status"] == 0)
+    for c in range(C):
+        ora = O.ffbs(W, obs_t, obs_y, shape, scale, 2.0, emis, 1.0, t_end, us[c])
+        dense = triangular_to_dense(r["messages"][c], n, K)
+        rel, ab = rel_err(dense, ora["alpha"].reshape(n, K * n), 1e-250)
+        assert rel < 1e-9, rel
+        assert np.allclose(r["logZ"][c], ora["logZ"], rtol=1e-10, atol=1e-12)
+        assert np.array_equal(r["aug_idx"][c], ora["samples"])
+        assert np.array_equal(r["V"][c], ora["V"])
+        assert np.array_equal(r["T"][c], ora["T"])
+
+
+def test_ragged_batch_and_philox_backward(engine):
+    """chains of different lengths in one launch; device Philox uniforms reproduce the oracle's."""
+    from oracle import philox
+    rng = np.random.default_rng(7)
+    K, t_end = 3, 6.0
+    shape = rng.uniform(0.6, 3.0, (K, K)); scale = np.ones((K, K)); emis = O.emission_matrix(K)
+    engine.set_model(shape, scale, 2.0, emis, 1.0, t_end)
+    Ws, ots, oys = [], [], []
+    for c, n in enumerate([1, 2, 5, 33, 64, 65, 129, 17]):
+        Ws.append(np.concatenate([[0.0], np.sort(rng.uniform(0, t_end, n - 1)), [t_end]]))
+        D = int(rng.integers(0, 30))
+        ots.append(np.sort(rng.uniform(0, t_end, D))); oys.append(rng.integers(0, K, D))
+    r = engine.ffbs_host(Ws, ots, oys, uniforms=None, seed=1234, sweep=5, precision="f64")
+    assert np.all(r["status"] == 0)
+    for c, W in enumerate(Ws):
+        n = len(W) - 1
+        u = philox.u01(1234, philox.TAG_BACKWARD, np.arange(n), 0, 5, c)
+        ora = O.ffbs(W, ots[c], oys[c], shape, scale, 2.0, emis, 1.0, t_end, u)
+        assert np.array_equal(r["aug_idx"][c], ora["samples"])
+        assert np.array_equal(r["V"][c], ora["V"]) and np.array_equal(r["T"][c], ora["T"])
+        assert np.allclose(r["logZ"][c], ora["logZ"], rtol=1e-10, atol=1e-12)
+
+
+def test_non_increasing_grid_is_reported(engine):
+    from smjp_b200.engine import raise_for_status
+    K = 3
+    engine.set_model(np.full((K, K), 1.2), np.ones((K, K)), 2.0, O.emission_matrix(K), 1.0, 2.0)
+    r = engine.ffbs_host([np.array([0.0, 0.5, 0.5, 2.0]), np.array([0.0, 1.0, 2.0])], np.zeros(0), np.zeros(0, int),
+                         uniforms=[np.full(3, 0.5), np.full(2, 0.5)])
+    assert r["status"][0] == 1 and r["status"][1] == 0
+    with pytest.raises(ValueError):
+        raise_for_status(r["status"])
+
+
+def test_fp32_path_mismatches_only_near_cdf_boundaries(engine):
+    """fp32 messages differ by ~1e-5, so a sampled index may differ from the fp64 one only when the
+    uniform lands within that tolerance of a CDF boundary."""
+    rng = np.random.default_rng(11)
+    K, n, t_end = 3, 120, 24.0
+    shape, scale, W, obs_t, obs_y = random_problem(rng, K, t_end, n, 80)
+    engine.set_model(shape, scale, 2.0, O.emission_matrix(K), 1.0, t_end)
+    C = 64
+    us = [rng.uniform(size=n) for _ in range(C)]
+    r64 = engine.ffbs_host([W] * C, obs_t, obs_y, uniforms=us, precision="f64")
+    r32 = engine.ffbs_host([W] * C, obs_t, obs_y, uniforms=us, precision="f32")
+    same = sum(np.array_equal(a, b) for a, b in zip(r64["aug_idx"], r32["aug_idx"]))
+    assert same >= C - 2, same
