@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Benchmark of the Rao-Teh Gibbs sweep (candidates -> forward filter -> backward sample) on B200.
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): 4096 independent chains PER GPU of the 3-state Weibull sMJP of
+experiments.py:172-174, T=100, Omega=2, noisy discrete observations every 0.1 (D=999) simulated from a
+prior path per chain; chains start from an independent prior draw.  A "step" is one Gibbs sweep of
+every chain.  Metric: live augmented state-steps/s (K*n(n+1)/2 per chain-sweep),
+whole-job aggregate over all GPUs; chain-sweeps/s and grid-steps/s are reported beside it.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SHAPE = np.array([[1.606, 1.933, 0.865], [1.938, 0.869, 1.751], [1.69, 0.64, 0.696]])  # experiments.py:172-174
+K = 3
+OMEGA = 2.0
+T_END = 100.0
+OBS_DT = 0.1
+CHAINS_PER_GPU = 4096
+SEED = 20261019
+SWEEPS_PER_REF_STEP = 4
+METRIC = "ffbs_state_steps_per_sec"
+UNIT = "state-steps/s"
+
+
+def workload_name(chains):
+    return "cfg2: %d chains/GPU, K=3 Weibull sMJP (experiments.py:172-174), T=100, Omega=2, D=999 obs" % chains
+
+
+def algorithmic_bytes(n_per_chain, D, esz):
+    """per chain-sweep 2*sizeof(real) per live state-step (message written once by the
+    forward pass, read once by the backward pass) + 40 B per grid step (W, uniform, index, logZ, path)
+    + 12 B per observation."""
+    n = n_per_chain.astype(np.float64)
+    return float(np.sum(2 * esz * K * n * (n + 1) / 2 + 40 * n + 12 * D))
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = threading.Event()
+        self.sm, self.smmax, self.reasons = [], [], set()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.sm.append(float(f[0]))
+                self.smmax.append(float(f[1]))
+                for nm, val in zip(names, f[2:6]):
+                    if val.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(np.max(self.smmax)),
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """per-launch DRAM bytes of the FFBS kernel from the committed ncu --set full capture, if any"""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.isfile(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            pass
+    return None
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the ONLY place bench.py touches oracle/)
+# ------------------------------------------------------------------------------------------------
+def _cpu_chain_sweeps(args):
+    """one worker: run `sweeps` oracle sweeps on chain `c`; returns (state_steps, grid_steps, seconds)"""
+    c, sweeps, t_end = args
+    from oracle import philox, smjp_oracle as O
+    emis = O.emission_matrix(K)
+    scale = np.ones((K, K))
+    obs_t = np.arange(OBS_DT, t_end, OBS_DT)
+    V0, T0 = O.prior_path(SHAPE, scale, np.ones(K) / K, t_end, seed=SEED + 1, chain=c)
+    y = O.simulate_observations(V0, T0, obs_t, emis, seed=SEED + 2, chain=c)
+    V, T = O.prior_path(SHAPE, scale, np.ones(K) / K, t_end, seed=SEED + 3, chain=c)
+    ss = gs = 0.0
+    t0 = time.perf_counter()
+    for sw in range(sweeps):
+        W = O.candidates(V, T, SHAPE, scale, OMEGA, seed=SEED, sweep=sw, chain=c)
+        n = len(W) - 1
+        u = philox.u01(SEED, philox.TAG_BACKWARD, np.arange(n), 0, sw, c)
+        r = O.ffbs(W, obs_t, y, SHAPE, scale, OMEGA, emis, 1.0, t_end, u)
+        V, T = r["V"], r["T"]
+        ss += K * n * (n + 1) / 2
+        gs += n
+    return ss, gs, time.perf_counter() - t0
+
+
+def cpu_sample(n_chains, sweeps, t_end, procs):
+    """oracle port on `procs` host processes, one chain each at a time"""
+    import multiprocessing as mp
+    jobs = [(c, sweeps, t_end) for c in range(n_chains)]
+    t0 = time.perf_counter()
+    if procs <= 1:
+        res = [_cpu_chain_sweeps(j) for j in jobs]
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(_cpu_chain_sweeps, jobs)
+    wall = time.perf_counter() - t0
+    ss = sum(r[0] for r in res)
+    gs = sum(r[1] for r in res)
+    return ss, gs, wall
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the Python reference itself cannot
+    travel to the GPU box) on all host cores, on a bounded sample of the same workload per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 32))
+    t_end = T_END
+    sample_chains = procs  # one chain per worker per step
+    for _ in range(args.warmup):
+        cpu_sample(min(2, procs), 1, 10.0, min(2, procs))
+    tot_ss = tot_gs = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ss, gs, _ = cpu_sample(sample_chains, SWEEPS_PER_REF_STEP, t_end, procs)
+        tot_ss += ss
+        tot_gs += gs
+    wall = time.perf_counter() - t0
+    val = tot_ss / wall
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload_name(CHAINS_PER_GPU), "sample": "%d chains x %d sweeps per step" % (sample_chains, SWEEPS_PER_REF_STEP)},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": procs, "kind": "port",
+                             "sample": "%d full-size cfg2 chains (T=100, n~500) x %d sweeps per step, NumPy oracle, "
+                                       "%d processes" % (sample_chains, SWEEPS_PER_REF_STEP, procs)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "chain_sweeps_per_sec": sample_chains * SWEEPS_PER_REF_STEP * args.steps / wall, "grid_steps_per_sec": tot_gs / wall}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from smjp_b200.chains import DeviceChains
+    from smjp_b200.engine import Engine, sweep_host
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    C = args.chains
+    prec = args.precision
+    esz = 8 if prec == "f64" else 4
+
+    eng = Engine(local)
+    from smjp_b200.engine import _ptr  # noqa: F401
+    emis = np.ones((K, K)) + 9 * np.eye(K)
+    emis /= emis.sum(axis=1, keepdims=True)  # 10:1 emission, smjp_utils.py:552-557
+    eng.set_model(SHAPE, np.ones((K, K)), OMEGA, emis, 1.0, T_END)
+    obs_t = np.arange(OBS_DT, T_END, OBS_DT)
+    D = len(obs_t)
+    # ground-truth path -> observations; independent prior draw as the initial state
+    ch = DeviceChains(eng, C, obs_t, chain_base=rank * C)
+    ch.init_prior(np.ones(K) / K, seed=SEED + 1).simulate_observations(seed=SEED + 2)
+    ch.init_prior(np.ones(K) / K, seed=SEED + 3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for sw in range(args.warmup):
+        ch.sweep(seed=SEED, sweep=sw, precision=prec)
+    barrier()
+    eng.set_option("time_kernels", 1)
+    eng.kernel_time()
+    launches0 = eng.launch_count
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ss = gs = 0.0
+    alg_bytes = 0.0
+    n_snap = []
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        ch.sweep(seed=SEED, sweep=args.warmup + i, precision=prec)
+        n_snap.append(ch.cur["offs"])  # device tensor of this sweep's grid windows; reduced after timing
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    sampler.stop_flag.set()
+    sampler.join()
+    launches = eng.launch_count - launches0
+    k_ms, k_cnt = eng.kernel_time()
+    eng.set_option("time_kernels", 0)
+    for offs in n_snap:
+        n = (offs[1:] - offs[:-1] - 1).cpu().numpy()
+        ss += float(np.sum(K * n.astype(np.float64) * (n + 1) / 2))
+        gs += float(n.sum())
+        alg_bytes += algorithmic_bytes(n, D, esz)
+    status_bad = int((ch.status != 0).sum().item())
+
+    # ---- end to end through the host-buffer C-ABI call (smjp_sweep_host) ----
+    V, T = ch.paths_host()
+    Y = ch.obs_y.cpu().numpy().reshape(C, D)
+    e2e_steps = max(2, min(args.steps, 5))
+    r = sweep_host(eng, V, T, [obs_t] * C, list(Y), seed=SEED + 7, sweep=0, precision=prec)  # warm staging buffers
+    V, T = r["V"], r["T"]
+    barrier()
+    e_ss = 0.0
+    h2d = d2h = 0
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        r = sweep_host(eng, V, T, [obs_t] * C, list(Y), seed=SEED + 7, sweep=1 + i, precision=prec)
+        npts = sum(len(w) for w in r["W"])
+        h2d += sum(len(v) for v in V) * 12 + C * (4 + 16) + C * D * 12
+        d2h += npts * 20 + C * (8 + 4 + 4) + C * K * 12
+        n = np.array([len(w) - 1 for w in r["W"]], dtype=np.float64)
+        e_ss += float(np.sum(K * n * (n + 1) / 2))
+        V, T = r["V"], r["T"]
+    torch.cuda.synchronize()
+    e_wall = time.perf_counter() - t0
+
+    # ---- reduce over ranks: time = max, work = sum ----
+    stats = torch.tensor([ms, ss, gs, alg_bytes, float(launches), k_ms, float(k_cnt), e_wall, e_ss, float(status_bad)],
+                         dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        # gather posterior summaries the way a multi-GPU run reports them (NCCL all_gather of [C,2K])
+        summ = torch.cat([ch.time_in_state, ch.jumps.to(torch.float64)], dim=1)
+        out = [torch.empty_like(summ) for _ in range(world)]
+        dist.all_gather(out, summ)
+        ms, e_wall = float(mx[0]), float(mx[7])
+        ss, gs, alg_total, launches, e_ss = float(sm[1]), float(sm[2]), float(sm[3]), float(sm[4]), float(sm[8])
+        status_bad = int(sm[9])
+    else:
+        alg_total = alg_bytes
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    secs = ms / 1e3
+    value = ss / secs
+    peak, peak_src = measured_peak()
+    k_avg_s = (k_ms / max(k_cnt, 1)) / 1e3  # rank 0's FFBS kernel, average launch
+    achieved = (alg_bytes / max(k_cnt, 1)) / k_avg_s / 1e9
+    traffic = ncu_traffic()
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": prec, "data": "synthetic",
+        "config": {"workload": workload_name(C), "chains_total": C * world, "parallelism": "chains sharded x%d" % world,
+                   "l2": "message stream per sweep (%.1f GB/GPU) exceeds the 126 MB L2" % (alg_bytes / args.steps / 1e9),
+                   "mean_grid_intervals": gs / (C * world * args.steps), "candidates": "reference (Q5)"},
+        "chain_sweeps_per_sec": C * world * args.steps / secs, "grid_steps_per_sec": gs / secs,
+        "gpu_launches": int(launches), "failed_chains": status_bad,
+        "clocks": sampler.summary(),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
+                     "kernel": "ffbs_kernel<%s,3>" % ("double" if prec == "f64" else "float"),
+                     "kernel_ms_avg": k_ms / max(k_cnt, 1), "kernel_share_of_step": k_ms / ms,
+                     "algorithmic_bytes_per_launch": alg_bytes / max(k_cnt, 1)},
+        "e2e": {"value": e_ss / e_wall, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_steps,
+                "d2h_bytes_per_step": d2h // e2e_steps, "steps": e2e_steps,
+                "api": "smjp_sweep_host (host buffers in/out, pinned staging inside)"},
+    }
+    if world == 1 and not args.no_cpu:
+        ss_c, gs_c, wall_c = cpu_sample(16, 3, T_END, 1)  # ~10-20 s of CPU work
+        line["cpu_baseline"] = {"value": ss_c / wall_c, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": "16 full-size cfg2 chains (T=100, n~500) x 3 sweeps, NumPy oracle "
+                                          "(oracle/smjp_oracle.py), 1 process",
+                                "chain_sweeps_per_sec": 48 / wall_c}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -66,8 +66,14 @@ void smjp_ctx_destroy(smjp_ctx_t* ctx);
 int smjp_ctx_sync(smjp_ctx_t* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t smjp_ctx_launch_count(smjp_ctx_t* ctx);
-/* tuning knobs: "ffbs_threads" (0 = auto, else threads per CTA of the FFBS kernel) */
+/* knobs: "ffbs_threads" (0 = auto, else threads per CTA of the FFBS kernel);
+ *        "time_kernels" (0/1, see smjp_ctx_kernel_time);
+ *        "chain_base" (global index of chain 0 of this context's batches: keeps the Philox streams of
+ *        chains sharded over several GPUs distinct and independent of the sharding) */
 int smjp_ctx_set_option(smjp_ctx_t* ctx, const char* key, int64_t value);
+/* With option "time_kernels" = 1 every launch of the named kernel ("ffbs") is bracketed by CUDA events
+ * on the launching stream; this returns and resets their summed duration and count (synchronises). */
+int smjp_ctx_kernel_time(smjp_ctx_t* ctx, const char* kernel, double* total_ms, int64_t* count);
 
 /*
  * Model parameters (HOST pointers, copied).  Replaces the parameter reads the reference does through
@@ -120,6 +126,70 @@ int smjp_ffbs_host(smjp_ctx_t* ctx, int C, const int64_t* w_offs, const double* 
                    void* messages, const int64_t* msg_offs, double* logZ, int32_t* aug_idx,
                    int32_t* path_v, double* path_t, int32_t* path_len, double* time_in_state,
                    int32_t* jumps, int32_t* status);
+
+/*
+ * Prior trajectories, one per chain.  Replaces sample_smjp_trajectory_prior (smjp_utils.py:216-254):
+ * competing Weibull risks, argmin, last entry overwritten with (v_prev, t_end).  The reference draws
+ * unit-scale holding times (distributions.py:295) -- honour_scale != 0 multiplies by lambda.
+ * p_offs[C+1] are capacity windows of path_v/path_t (chain c may hold p_offs[c+1]-p_offs[c] entries;
+ * SMJP_ST_OVERFLOW if it needs more).  pi0 is a HOST array [K].
+ */
+int smjp_prior_dev(smjp_ctx_t* ctx, int C, const int64_t* p_offs, const double* pi0, int honour_scale,
+                   uint64_t seed, int32_t* path_v, double* path_t, int32_t* path_len, int32_t* status);
+
+/*
+ * Synthetic observations y_d ~ emis[v(t_d), :] at the given times.  Replaces sample_data_posterior
+ * (smjp_utils.py:350-364) + smjpEmission.sample (:559-563).
+ */
+int smjp_simulate_obs_dev(smjp_ctx_t* ctx, int C, const int64_t* p_offs, const int32_t* path_v,
+                          const double* path_t, const int32_t* path_len, const int64_t* obs_offs,
+                          const double* obs_t, uint64_t seed, int32_t* obs_y);
+
+/*
+ * Thinned-event candidates: W = sorted(thinned U T) per chain.  Replaces sample_smjp_event_times
+ * (smjp_utils.py:194-210) + PoissonProcess.sample (:61-99) with the A_hat = (omega-1)*A process.
+ * Two passes over the same counter-based draws:
+ *   count: writes w_offs[C+1] (device), soff[] (device scratch, int32, same windows as the path
+ *          arrays) and returns n_max / total_w to the HOST (synchronises the stream);
+ *   fill:  writes W[total_w] (device).
+ */
+int smjp_candidates_count_dev(smjp_ctx_t* ctx, int C, const int64_t* p_offs, const int32_t* path_v,
+                              const double* path_t, const int32_t* path_len, uint64_t seed,
+                              uint32_t sweep, int64_t* w_offs, int32_t* soff, int64_t* n_max_host,
+                              int64_t* total_w_host);
+int smjp_candidates_fill_dev(smjp_ctx_t* ctx, int C, const int64_t* p_offs, const int32_t* path_v,
+                             const double* path_t, const int32_t* path_len, uint64_t seed,
+                             uint32_t sweep, int mode, const int64_t* w_offs, const int32_t* soff,
+                             double* W);
+/* HOST buffers; W has room for w_capacity doubles. If the grids need more, returns SMJP_E_NOMEM with
+ * the required size in *total_w (w_offs is valid) so that the caller can retry. */
+int smjp_candidates_host(smjp_ctx_t* ctx, int C, const int64_t* p_offs, const int32_t* path_v,
+                         const double* path_t, const int32_t* path_len, uint64_t seed, uint32_t sweep,
+                         int mode, int64_t* w_offs, double* W, int64_t w_capacity, int64_t* total_w);
+
+/*
+ * One Rao-Teh Gibbs sweep for C chains, the loop body raoteh.py:58-59:
+ *     W = sample_smjp_event_times(A_hat, V, T);  V, T = smjp_ffbs(W, data, ...)
+ * DEVICE buffers.  The new grids/paths use windows w_offs (written here); W, path_v_out and
+ * path_t_out must have room for `capacity` elements, else SMJP_E_NOMEM is returned with the required
+ * size in *total_w_host (nothing else written).  Backward uniforms come from the Philox stream
+ * (seed, sweep, chain).  Synchronises once (sizes), then enqueues the FFBS kernel asynchronously.
+ */
+int smjp_sweep_dev(smjp_ctx_t* ctx, int C, const int64_t* p_offs, const int32_t* path_v,
+                   const double* path_t, const int32_t* path_len, const int64_t* obs_offs,
+                   const double* obs_t, const int32_t* obs_y, uint64_t seed, uint32_t sweep, int mode,
+                   int precision, int64_t capacity, int64_t* w_offs, int32_t* soff, double* W,
+                   int32_t* path_v_out, double* path_t_out, int32_t* path_len_out,
+                   double* time_in_state, int32_t* jumps, int32_t* status, int64_t* n_max_host,
+                   int64_t* total_w_host);
+/* Same sweep with HOST buffers (one call = H2D of paths+observations, kernels, D2H of W, V, T and
+ * metrics).  W / path outputs have room for `capacity` elements (retry protocol as above). */
+int smjp_sweep_host(smjp_ctx_t* ctx, int C, const int64_t* p_offs, const int32_t* path_v,
+                    const double* path_t, const int32_t* path_len, const int64_t* obs_offs,
+                    const double* obs_t, const int32_t* obs_y, uint64_t seed, uint32_t sweep, int mode,
+                    int precision, int64_t capacity, int64_t* w_offs, double* W, int32_t* path_v_out,
+                    double* path_t_out, int32_t* path_len_out, double* time_in_state, int32_t* jumps,
+                    int32_t* status, int64_t* total_w);
 
 #ifdef __cplusplus
 }

@@ -30,12 +30,27 @@ SIGNATURES = {
     "smjp_ctx_sync": (ctypes.c_int, [P]),
     "smjp_ctx_launch_count": (ctypes.c_int64, [P]),
     "smjp_ctx_set_option": (ctypes.c_int, [P, ctypes.c_char_p, ctypes.c_int64]),
+    "smjp_ctx_kernel_time": (ctypes.c_int, [P, ctypes.c_char_p, c_f64p, c_i64p]),
     "smjp_set_model": (ctypes.c_int, [P, ctypes.c_int, ctypes.c_int, P, P, ctypes.c_double, P,
                                       ctypes.c_double, ctypes.c_double]),
     "smjp_ffbs_dev": (ctypes.c_int, [P, ctypes.c_int, P, P, P, P, P, P, ctypes.c_uint64, ctypes.c_uint32,
                                      ctypes.c_int, P, P, P, P, P, P, P, P, P, P, ctypes.c_int64, ctypes.c_int64]),
     "smjp_ffbs_host": (ctypes.c_int, [P, ctypes.c_int, P, P, P, P, P, P, ctypes.c_uint64, ctypes.c_uint32,
                                       ctypes.c_int, P, P, P, P, P, P, P, P, P, P]),
+    "smjp_prior_dev": (ctypes.c_int, [P, ctypes.c_int, P, P, ctypes.c_int, ctypes.c_uint64, P, P, P, P]),
+    "smjp_simulate_obs_dev": (ctypes.c_int, [P, ctypes.c_int, P, P, P, P, P, P, ctypes.c_uint64, P]),
+    "smjp_candidates_count_dev": (ctypes.c_int, [P, ctypes.c_int, P, P, P, P, ctypes.c_uint64, ctypes.c_uint32,
+                                                 P, P, c_i64p, c_i64p]),
+    "smjp_candidates_fill_dev": (ctypes.c_int, [P, ctypes.c_int, P, P, P, P, ctypes.c_uint64, ctypes.c_uint32,
+                                                ctypes.c_int, P, P, P]),
+    "smjp_candidates_host": (ctypes.c_int, [P, ctypes.c_int, P, P, P, P, ctypes.c_uint64, ctypes.c_uint32,
+                                            ctypes.c_int, P, P, ctypes.c_int64, c_i64p]),
+    "smjp_sweep_dev": (ctypes.c_int, [P, ctypes.c_int, P, P, P, P, P, P, P, ctypes.c_uint64, ctypes.c_uint32,
+                                      ctypes.c_int, ctypes.c_int, ctypes.c_int64, P, P, P, P, P, P, P, P, P,
+                                      c_i64p, c_i64p]),
+    "smjp_sweep_host": (ctypes.c_int, [P, ctypes.c_int, P, P, P, P, P, P, P, ctypes.c_uint64, ctypes.c_uint32,
+                                       ctypes.c_int, ctypes.c_int, ctypes.c_int64, P, P, P, P, P, P, P, P,
+                                       c_i64p]),
 }
 
 

@@ -1,0 +1,158 @@
+"""Device-resident batch of independent chains: the batched Rao-Teh sweep the reference lacks.
+
+State per chain is its current trajectory (V, T) (raoteh.py:25, :58-59), kept in HBM as ragged
+arrays; one `sweep()` = candidates -> forward filter -> backward sample -> compaction -> metrics for
+every chain, entirely on the device (smjp_sweep_dev).  torch is used for device memory only.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+from .engine import PRECISIONS, Engine, _ptr, ragged_offsets
+
+CAND_MODES = {"reference": _lib.CAND_REFERENCE, "exact": _lib.CAND_EXACT}
+
+
+class DeviceChains:
+    def __init__(self, engine, C, obs_t, device=None, chain_base=0):
+        """obs_t: one 1-D array of observation times shared by all chains, or a list per chain."""
+        import torch
+        self.torch = torch
+        self.eng = engine
+        self.C = int(C)
+        self.dev = torch.device("cuda", engine.device) if device is None else device
+        self.chain_base = int(chain_base)
+        engine.set_option("chain_base", self.chain_base)
+        if isinstance(obs_t, np.ndarray) and obs_t.ndim == 1 and obs_t.dtype != object:
+            obs_t = [obs_t] * C
+        self.obs_offs_h = ragged_offsets([len(t) for t in obs_t])
+        flat = np.concatenate([np.asarray(t, dtype=np.float64) for t in obs_t]) if self.obs_offs_h[-1] else np.zeros(0)
+        self.obs_offs = torch.from_numpy(self.obs_offs_h).to(self.dev)
+        self.obs_t = torch.from_numpy(flat).to(self.dev)
+        self.obs_y = torch.zeros(len(flat), dtype=torch.int32, device=self.dev)
+        self.K = engine.K
+        self.time_in_state = torch.zeros((C, self.K), dtype=torch.float64, device=self.dev)
+        self.jumps = torch.zeros((C, self.K), dtype=torch.int32, device=self.dev)
+        self.status = torch.zeros(C, dtype=torch.int32, device=self.dev)
+        self.cur = None   # dict(offs, v, t, len) of the current paths
+        self.nxt = None
+        self.W = None
+        self.soff = None
+        self.n_max = 0
+        self.total_w = 0
+        self.sweeps_done = 0
+
+    # ------------------------------------------------------------------------------------------
+    def _alloc_paths(self, capacity, C=None):
+        t = self.torch
+        C = self.C if C is None else C
+        return {"offs": t.zeros(C + 1, dtype=t.int64, device=self.dev),
+                "v": t.zeros(capacity, dtype=t.int32, device=self.dev),
+                "t": t.zeros(capacity, dtype=t.float64, device=self.dev),
+                "len": t.zeros(C, dtype=t.int32, device=self.dev), "cap": capacity}
+
+    def init_prior(self, pi0, seed, honour_scale=False, cap_per_chain=None):
+        """sample_smjp_trajectory_prior for every chain (raoteh.py:25)."""
+        t = self.torch
+        pi0 = np.ascontiguousarray(pi0, dtype=np.float64)
+        cap = cap_per_chain or 64
+        while True:
+            p = self._alloc_paths(cap * self.C)
+            p["offs"].copy_(t.arange(self.C + 1, dtype=t.int64, device=self.dev) * cap)
+            check(self.eng.lib.smjp_prior_dev(self.eng.ctx, self.C, _ptr(p["offs"]), _ptr(pi0), int(honour_scale),
+                                              int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(p["v"]), _ptr(p["t"]),
+                                              _ptr(p["len"]), _ptr(self.status)))
+            if int((self.status != 0).sum().item()) == 0:
+                break
+            cap *= 2
+            if cap > (1 << 22):
+                raise _lib.EngineError("prior path does not terminate")
+        self.cur = p
+        return self
+
+    def set_paths(self, V, T):
+        """host lists of per-chain (state indices, times) -> device state"""
+        t = self.torch
+        offs = ragged_offsets([len(v) for v in V])
+        p = self._alloc_paths(int(offs[-1]))
+        p["offs"].copy_(t.from_numpy(offs))
+        p["v"].copy_(t.from_numpy(np.concatenate([np.asarray(v, dtype=np.int32) for v in V])))
+        p["t"].copy_(t.from_numpy(np.concatenate([np.asarray(x, dtype=np.float64) for x in T])))
+        p["len"].copy_(t.from_numpy(np.diff(offs).astype(np.int32)))
+        self.cur = p
+        return self
+
+    def simulate_observations(self, seed):
+        """y_d ~ emis[v(t_d)] from the current paths (sample_data_posterior, smjp_utils.py:350-364)."""
+        p = self.cur
+        check(self.eng.lib.smjp_simulate_obs_dev(self.eng.ctx, self.C, _ptr(p["offs"]), _ptr(p["v"]), _ptr(p["t"]),
+                                                 _ptr(p["len"]), _ptr(self.obs_offs), _ptr(self.obs_t),
+                                                 int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(self.obs_y)))
+        return self
+
+    def set_observations(self, obs_y):
+        t = self.torch
+        if isinstance(obs_y, np.ndarray) and obs_y.ndim == 1 and obs_y.dtype != object:
+            obs_y = [obs_y] * self.C
+        flat = np.concatenate([np.asarray(y, dtype=np.int32) for y in obs_y]) if self.obs_offs_h[-1] else np.zeros(0, np.int32)
+        if len(flat) != len(self.obs_y):
+            raise ValueError("observation count mismatch")
+        self.obs_y.copy_(t.from_numpy(flat))
+        return self
+
+    # ------------------------------------------------------------------------------------------
+    def sweep(self, seed, sweep=None, mode="reference", precision="f64"):
+        """One Gibbs sweep of every chain (raoteh.py:58-59).  Asynchronous after one size read-back."""
+        t = self.torch
+        sweep = self.sweeps_done if sweep is None else sweep
+        cur = self.cur
+        cap = max(int(cur["cap"] * 3), 1024) if self.nxt is None else self.nxt["cap"]
+        n_max = ctypes.c_int64(0)
+        total = ctypes.c_int64(0)
+        while True:
+            if self.nxt is None or self.nxt["cap"] < cap or self.W is None or self.W.numel() < cap:
+                self.nxt = self._alloc_paths(cap)
+                self.W = t.zeros(cap, dtype=t.float64, device=self.dev)
+            if self.soff is None or self.soff.numel() < cur["cap"]:
+                self.soff = t.zeros(cur["cap"], dtype=t.int32, device=self.dev)
+            nx = self.nxt
+            rc = self.eng.lib.smjp_sweep_dev(
+                self.eng.ctx, self.C, _ptr(cur["offs"]), _ptr(cur["v"]), _ptr(cur["t"]), _ptr(cur["len"]),
+                _ptr(self.obs_offs), _ptr(self.obs_t), _ptr(self.obs_y), int(seed) & 0xFFFFFFFFFFFFFFFF, int(sweep),
+                CAND_MODES[mode], PRECISIONS[precision], int(cap), _ptr(nx["offs"]), _ptr(self.soff), _ptr(self.W),
+                _ptr(nx["v"]), _ptr(nx["t"]), _ptr(nx["len"]), _ptr(self.time_in_state), _ptr(self.jumps),
+                _ptr(self.status), ctypes.byref(n_max), ctypes.byref(total))
+            if rc == -3 and total.value > cap:  # buffers too small for this sweep's grids: regrow, redo
+                cap = int(total.value * 1.25) + 1024
+                continue
+            check(rc)
+            break
+        self.n_max, self.total_w = int(n_max.value), int(total.value)
+        self.cur, self.nxt = nx, cur if cur["cap"] >= cap else None
+        self.sweeps_done += 1
+        return self
+
+    # ------------------------------------------------------------------------------------------
+    def paths_host(self):
+        """current trajectories as host lists (V state indices, T times)"""
+        p = self.cur
+        offs = p["offs"].cpu().numpy()
+        lens = p["len"].cpu().numpy()
+        v = p["v"].cpu().numpy()
+        tt = p["t"].cpu().numpy()
+        V = [v[offs[c]: offs[c] + lens[c]].copy() for c in range(self.C)]
+        T = [tt[offs[c]: offs[c] + lens[c]].copy() for c in range(self.C)]
+        return V, T
+
+    def grids_host(self):
+        """grids W of the last sweep"""
+        offs = self.cur["offs"].cpu().numpy()
+        w = self.W[: self.total_w].cpu().numpy()
+        return [w[offs[c]: offs[c + 1]].copy() for c in range(self.C)]
+
+    def state_steps_last_sweep(self):
+        """live augmented state-steps K*n(n+1)/2 summed over chains (SURVEY.md 8d unit)"""
+        n = (self.cur["offs"][1:] - self.cur["offs"][:-1] - 1).to(self.torch.float64)
+        return float((self.K * n * (n + 1) / 2).sum().item()), float(n.sum().item())

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/smjp_b200.h"
+#include "candidates.cuh"
 #include "ffbs.cuh"
 
 namespace {
@@ -103,6 +104,12 @@ struct smjp_ctx {
     DevBuf d_in, d_out;  // staging for the host API
     PinBuf h_in, h_out;
     int ffbs_threads = 0;  // 0 = auto
+    uint32_t chain_base = 0;
+    DevBuf d_stats, d_pi0, d_wlen, d_soff;
+    PinBuf h_stats;
+    // optional per-kernel timing (CUDA events on the launching stream)
+    bool time_kernels = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ffbs_events;
 };
 
 using namespace smjp;
@@ -153,6 +160,11 @@ void smjp_ctx_destroy(smjp_ctx_t* c) {
     c->d_out.release();
     c->h_in.release();
     c->h_out.release();
+    c->d_stats.release();
+    c->d_pi0.release();
+    c->d_wlen.release();
+    c->d_soff.release();
+    c->h_stats.release();
     delete c;
 }
 
@@ -164,12 +176,39 @@ int smjp_ctx_sync(smjp_ctx_t* c) {
 
 int64_t smjp_ctx_launch_count(smjp_ctx_t* c) { return c ? c->launches : 0; }
 
+int smjp_ctx_kernel_time(smjp_ctx_t* c, const char* kernel, double* total_ms, int64_t* count) {
+    if (!c || !kernel || !total_ms || !count) return fail(SMJP_E_INVALID, "null argument");
+    if (strcmp(kernel, "ffbs")) return fail(SMJP_E_INVALID, "unknown kernel '%s'", kernel);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    double ms = 0;
+    for (auto& ev : c->ffbs_events) {
+        float t = 0;
+        CUDA_TRY(cudaEventElapsedTime(&t, ev.first, ev.second));
+        ms += t;
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    *total_ms = ms;
+    *count = (int64_t)c->ffbs_events.size();
+    c->ffbs_events.clear();
+    return SMJP_OK;
+}
+
 int smjp_ctx_set_option(smjp_ctx_t* c, const char* key, int64_t value) {
     if (!c || !key) return fail(SMJP_E_INVALID, "null argument");
     if (!strcmp(key, "ffbs_threads")) {
         if (value != 0 && (value < 32 || value > 1024 || value % 32))
             return fail(SMJP_E_INVALID, "ffbs_threads must be 0 (auto) or a multiple of 32 in [32,1024]");
         c->ffbs_threads = (int)value;
+        return SMJP_OK;
+    }
+    if (!strcmp(key, "time_kernels")) {
+        c->time_kernels = value != 0;
+        return SMJP_OK;
+    }
+    if (!strcmp(key, "chain_base")) {
+        if (value < 0 || value > 0xFFFFFFFFll) return fail(SMJP_E_INVALID, "chain_base out of range");
+        c->chain_base = (uint32_t)value;
         return SMJP_OK;
     }
     return fail(SMJP_E_INVALID, "unknown option '%s'", key);
@@ -223,8 +262,18 @@ template <typename Real, int K>
 int launch_ffbs_k(smjp_ctx* c, FfbsArgs& a, int threads, size_t smem, int grid) {
     auto kern = ffbs_kernel<Real, K>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->time_kernels) {
+        CUDA_TRY(cudaEventCreate(&e0));
+        CUDA_TRY(cudaEventCreate(&e1));
+        CUDA_TRY(cudaEventRecord(e0, c->stream));
+    }
     kern<<<grid, threads, smem, c->stream>>>(a);
     CUDA_TRY(cudaGetLastError());
+    if (c->time_kernels) {
+        CUDA_TRY(cudaEventRecord(e1, c->stream));
+        c->ffbs_events.emplace_back(e0, e1);
+    }
     c->launches += 1;
     return SMJP_OK;
 }
@@ -346,7 +395,7 @@ int smjp_ffbs_dev(smjp_ctx_t* c, int C, const int64_t* w_offs, const double* W,
     a.uniforms = uniforms;
     a.seed = seed;
     a.sweep = sweep;
-    a.chain_base = 0;
+    a.chain_base = c->chain_base;
     a.messages = messages;
     a.msg_offs = msg_offs;
     a.logZ = logZ;
@@ -459,6 +508,345 @@ int smjp_ffbs_host(smjp_ctx_t* c, int C, const int64_t* w_offs, const double* W,
     if (aug_idx) memcpy(aug_idx, hout + o_ai, total_w * 4);
     if (time_in_state) memcpy(time_in_state, hout + o_tis, (size_t)C * K * 8);
     if (jumps) memcpy(jumps, hout + o_jm, (size_t)C * K * 4);
+    return SMJP_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// prior / observations / candidates / sweep
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+int model_ready(smjp_ctx* c) {
+    if (!c) return fail(SMJP_E_INVALID, "null context");
+    if (c->K == 0) return fail(SMJP_E_INVALID, "smjp_set_model has not been called");
+    return SMJP_OK;
+}
+
+CandArgs make_cand_args(smjp_ctx* c, int C, const int64_t* p_offs, const int32_t* path_v,
+                        const double* path_t, const int32_t* path_len, uint64_t seed, uint32_t sweep) {
+    CandArgs a;
+    memset(&a, 0, sizeof a);
+    a.C = C;
+    a.p_offs = p_offs;
+    a.path_v = path_v;
+    a.path_t = path_t;
+    a.path_len = path_len;
+    a.model = (const double*)c->d_model.p;
+    a.K = c->K;
+    a.Kobs = c->Kobs;
+    a.omega = c->omega;
+    a.seed = seed;
+    a.sweep = sweep;
+    a.chain_base = c->chain_base;
+    return a;
+}
+
+}  // namespace
+
+extern "C" {
+
+int smjp_prior_dev(smjp_ctx_t* c, int C, const int64_t* p_offs, const double* pi0, int honour_scale,
+                   uint64_t seed, int32_t* path_v, double* path_t, int32_t* path_len, int32_t* status) {
+    int rc = model_ready(c);
+    if (rc) return rc;
+    if (C <= 0) return C == 0 ? SMJP_OK : fail(SMJP_E_INVALID, "C < 0");
+    if (!p_offs || !pi0 || !path_v || !path_t || !path_len || !status)
+        return fail(SMJP_E_INVALID, "null required pointer");
+    double tot = 0;
+    for (int s = 0; s < c->K; ++s) {
+        if (!(pi0[s] >= 0)) return fail(SMJP_E_INVALID, "pi0[%d] negative", s);
+        tot += pi0[s];
+    }
+    if (!(tot > 0)) return fail(SMJP_E_INVALID, "pi0 has no mass");
+    CUDA_TRY(cudaSetDevice(c->device));
+    rc = c->d_pi0.reserve(64 * sizeof(double));
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpy(c->d_pi0.p, pi0, c->K * sizeof(double), cudaMemcpyHostToDevice));
+    PriorArgs a;
+    memset(&a, 0, sizeof a);
+    a.C = C;
+    a.p_offs = p_offs;
+    a.model = (const double*)c->d_model.p;
+    a.pi0 = (const double*)c->d_pi0.p;
+    a.K = c->K;
+    a.Kobs = c->Kobs;
+    a.t_end = c->t_end;
+    a.honour_scale = honour_scale;
+    a.seed = seed;
+    a.chain_base = c->chain_base;
+    a.path_v = path_v;
+    a.path_t = path_t;
+    a.path_len = path_len;
+    a.status = status;
+    prior_kernel<<<(C + 63) / 64, 64, 0, c->stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    c->launches += 1;
+    return SMJP_OK;
+}
+
+int smjp_simulate_obs_dev(smjp_ctx_t* c, int C, const int64_t* p_offs, const int32_t* path_v,
+                          const double* path_t, const int32_t* path_len, const int64_t* obs_offs,
+                          const double* obs_t, uint64_t seed, int32_t* obs_y) {
+    int rc = model_ready(c);
+    if (rc) return rc;
+    if (C <= 0) return C == 0 ? SMJP_OK : fail(SMJP_E_INVALID, "C < 0");
+    if (!p_offs || !path_v || !path_t || !path_len || !obs_offs || !obs_t || !obs_y)
+        return fail(SMJP_E_INVALID, "null required pointer");
+    CUDA_TRY(cudaSetDevice(c->device));
+    ObsSimArgs a;
+    memset(&a, 0, sizeof a);
+    a.C = C;
+    a.p_offs = p_offs;
+    a.path_v = path_v;
+    a.path_t = path_t;
+    a.path_len = path_len;
+    a.obs_offs = obs_offs;
+    a.obs_t = obs_t;
+    a.obs_y = obs_y;
+    a.model = (const double*)c->d_model.p;
+    a.K = c->K;
+    a.Kobs = c->Kobs;
+    a.seed = seed;
+    a.chain_base = c->chain_base;
+    int grid = C < c->num_sms * 8 ? C : c->num_sms * 8;
+    obs_sim_kernel<<<grid, 128, 0, c->stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    c->launches += 1;
+    return SMJP_OK;
+}
+
+int smjp_candidates_count_dev(smjp_ctx_t* c, int C, const int64_t* p_offs, const int32_t* path_v,
+                              const double* path_t, const int32_t* path_len, uint64_t seed,
+                              uint32_t sweep, int64_t* w_offs, int32_t* soff, int64_t* n_max_host,
+                              int64_t* total_w_host) {
+    int rc = model_ready(c);
+    if (rc) return rc;
+    if (C <= 0) return fail(SMJP_E_INVALID, "C <= 0");
+    if (!p_offs || !path_v || !path_t || !path_len || !w_offs || !soff || !n_max_host || !total_w_host)
+        return fail(SMJP_E_INVALID, "null required pointer");
+    CUDA_TRY(cudaSetDevice(c->device));
+    rc = c->d_wlen.reserve((size_t)C * sizeof(int64_t));
+    if (rc) return rc;
+    rc = c->d_stats.reserve(2 * sizeof(int64_t));
+    if (rc) return rc;
+    rc = c->h_stats.reserve(2 * sizeof(int64_t));
+    if (rc) return rc;
+    CandArgs a = make_cand_args(c, C, p_offs, path_v, path_t, path_len, seed, sweep);
+    a.soff = soff;
+    a.w_len = (int64_t*)c->d_wlen.p;
+    int grid = C < c->num_sms * 16 ? C : c->num_sms * 16;
+    cand_count_kernel<<<grid, 128, 0, c->stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    chain_scan_kernel<<<1, 1024, 0, c->stream>>>(C, (const int64_t*)c->d_wlen.p, w_offs, (int64_t*)c->d_stats.p);
+    CUDA_TRY(cudaGetLastError());
+    c->launches += 2;
+    CUDA_TRY(cudaMemcpyAsync(c->h_stats.p, c->d_stats.p, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *n_max_host = ((int64_t*)c->h_stats.p)[0];
+    *total_w_host = ((int64_t*)c->h_stats.p)[1];
+    return SMJP_OK;
+}
+
+int smjp_candidates_fill_dev(smjp_ctx_t* c, int C, const int64_t* p_offs, const int32_t* path_v,
+                             const double* path_t, const int32_t* path_len, uint64_t seed,
+                             uint32_t sweep, int mode, const int64_t* w_offs, const int32_t* soff,
+                             double* W) {
+    int rc = model_ready(c);
+    if (rc) return rc;
+    if (C <= 0) return fail(SMJP_E_INVALID, "C <= 0");
+    if (mode != SMJP_CAND_REFERENCE && mode != SMJP_CAND_EXACT) return fail(SMJP_E_INVALID, "bad candidate mode");
+    if (!p_offs || !path_v || !path_t || !path_len || !w_offs || !soff || !W)
+        return fail(SMJP_E_INVALID, "null required pointer");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CandArgs a = make_cand_args(c, C, p_offs, path_v, path_t, path_len, seed, sweep);
+    a.mode = mode;
+    a.soff = const_cast<int32_t*>(soff);
+    a.w_offs = w_offs;
+    a.W = W;
+    int grid = C < c->num_sms * 16 ? C : c->num_sms * 16;
+    cand_fill_kernel<<<grid, 128, 0, c->stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    c->launches += 1;
+    return SMJP_OK;
+}
+
+int smjp_sweep_dev(smjp_ctx_t* c, int C, const int64_t* p_offs, const int32_t* path_v,
+                   const double* path_t, const int32_t* path_len, const int64_t* obs_offs,
+                   const double* obs_t, const int32_t* obs_y, uint64_t seed, uint32_t sweep, int mode,
+                   int precision, int64_t capacity, int64_t* w_offs, int32_t* soff, double* W,
+                   int32_t* path_v_out, double* path_t_out, int32_t* path_len_out,
+                   double* time_in_state, int32_t* jumps, int32_t* status, int64_t* n_max_host,
+                   int64_t* total_w_host) {
+    int rc = smjp_candidates_count_dev(c, C, p_offs, path_v, path_t, path_len, seed, sweep, w_offs, soff,
+                                       n_max_host, total_w_host);
+    if (rc) return rc;
+    if (*total_w_host > capacity)
+        return fail(SMJP_E_NOMEM, "sweep needs %lld grid points, buffers hold %lld", (long long)*total_w_host,
+                    (long long)capacity);
+    rc = smjp_candidates_fill_dev(c, C, p_offs, path_v, path_t, path_len, seed, sweep, mode, w_offs, soff, W);
+    if (rc) return rc;
+    return smjp_ffbs_dev(c, C, w_offs, W, obs_offs, obs_t, obs_y, nullptr, seed, sweep, precision, nullptr,
+                         nullptr, nullptr, nullptr, path_v_out, path_t_out, path_len_out, time_in_state, jumps,
+                         status, *n_max_host, *total_w_host);
+}
+
+}  // extern "C"
+
+namespace {
+
+// stage the current paths (+ optionally the observations) of a host call into ctx->d_in
+struct StagedPaths {
+    const int64_t* p_offs;
+    const int32_t* path_v;
+    const double* path_t;
+    const int32_t* path_len;
+    const int64_t* obs_offs;
+    const double* obs_t;
+    const int32_t* obs_y;
+};
+
+int stage_paths(smjp_ctx* c, int C, const int64_t* p_offs, const int32_t* path_v, const double* path_t,
+                const int32_t* path_len, const int64_t* obs_offs, const double* obs_t, const int32_t* obs_y,
+                StagedPaths* out) {
+    if (p_offs[0] != 0) return fail(SMJP_E_INVALID, "offsets must start at 0");
+    const int64_t total_p = p_offs[C];
+    for (int i = 0; i < C; ++i) {
+        if (p_offs[i + 1] < p_offs[i]) return fail(SMJP_E_INVALID, "p_offs not monotone");
+        if (path_len[i] < 2 || path_len[i] > p_offs[i + 1] - p_offs[i])
+            return fail(SMJP_E_INVALID, "chain %d: path_len %d outside [2, window]", i, path_len[i]);
+    }
+    const int64_t total_o = obs_offs ? obs_offs[C] : 0;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += smjp::align_up(bytes, 16); return o; };
+    const size_t o_po = take((C + 1) * 8), o_pv = take(total_p * 4), o_pt = take(total_p * 8), o_pl = take(C * 4);
+    const size_t o_oo = take((C + 1) * 8), o_ot = take(total_o * 8), o_oy = take(total_o * 4);
+    int rc = c->h_in.reserve(off);
+    if (rc) return rc;
+    rc = c->d_in.reserve(off);
+    if (rc) return rc;
+    char* h = (char*)c->h_in.p;
+    memcpy(h + o_po, p_offs, (C + 1) * 8);
+    memcpy(h + o_pv, path_v, total_p * 4);
+    memcpy(h + o_pt, path_t, total_p * 8);
+    memcpy(h + o_pl, path_len, C * 4);
+    if (obs_offs) {
+        memcpy(h + o_oo, obs_offs, (C + 1) * 8);
+        if (total_o) {
+            memcpy(h + o_ot, obs_t, total_o * 8);
+            memcpy(h + o_oy, obs_y, total_o * 4);
+        }
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->d_in.p, h, off, cudaMemcpyHostToDevice, c->stream));
+    char* d = (char*)c->d_in.p;
+    out->p_offs = (const int64_t*)(d + o_po);
+    out->path_v = (const int32_t*)(d + o_pv);
+    out->path_t = (const double*)(d + o_pt);
+    out->path_len = (const int32_t*)(d + o_pl);
+    out->obs_offs = (const int64_t*)(d + o_oo);
+    out->obs_t = (const double*)(d + o_ot);
+    out->obs_y = (const int32_t*)(d + o_oy);
+    return SMJP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int smjp_candidates_host(smjp_ctx_t* c, int C, const int64_t* p_offs, const int32_t* path_v,
+                         const double* path_t, const int32_t* path_len, uint64_t seed, uint32_t sweep,
+                         int mode, int64_t* w_offs, double* W, int64_t w_capacity, int64_t* total_w) {
+    int rc = model_ready(c);
+    if (rc) return rc;
+    if (C <= 0) return fail(SMJP_E_INVALID, "C <= 0");
+    if (!p_offs || !path_v || !path_t || !path_len || !w_offs || !total_w)
+        return fail(SMJP_E_INVALID, "null required pointer");
+    CUDA_TRY(cudaSetDevice(c->device));
+    StagedPaths sp;
+    rc = stage_paths(c, C, p_offs, path_v, path_t, path_len, nullptr, nullptr, nullptr, &sp);
+    if (rc) return rc;
+    rc = c->d_soff.reserve((size_t)p_offs[C] * 4 + 16);
+    if (rc) return rc;
+    rc = c->d_out.reserve((size_t)(C + 1) * 8);
+    if (rc) return rc;
+    int64_t n_max = 0;
+    rc = smjp_candidates_count_dev(c, C, sp.p_offs, sp.path_v, sp.path_t, sp.path_len, seed, sweep,
+                                   (int64_t*)c->d_out.p, (int32_t*)c->d_soff.p, &n_max, total_w);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpy(w_offs, c->d_out.p, (size_t)(C + 1) * 8, cudaMemcpyDeviceToHost));
+    if (*total_w > w_capacity || !W)
+        return fail(SMJP_E_NOMEM, "grids need %lld doubles, W holds %lld", (long long)*total_w, (long long)w_capacity);
+    // d_out: [w_offs | W]
+    const size_t o_W = smjp::align_up((size_t)(C + 1) * 8, 16);
+    DevBuf tmp;  // keep w_offs alive while d_out may be regrown
+    rc = tmp.reserve(o_W + (size_t)*total_w * 8);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(tmp.p, c->d_out.p, (size_t)(C + 1) * 8, cudaMemcpyDeviceToDevice, c->stream));
+    rc = smjp_candidates_fill_dev(c, C, sp.p_offs, sp.path_v, sp.path_t, sp.path_len, seed, sweep, mode,
+                                  (const int64_t*)tmp.p, (const int32_t*)c->d_soff.p, (double*)((char*)tmp.p + o_W));
+    if (rc) { tmp.release(); return rc; }
+    cudaError_t e = cudaMemcpyAsync(W, (char*)tmp.p + o_W, (size_t)*total_w * 8, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    tmp.release();
+    if (e != cudaSuccess) return fail(SMJP_E_CUDA, "candidate copy-back failed: %s", cudaGetErrorString(e));
+    return SMJP_OK;
+}
+
+int smjp_sweep_host(smjp_ctx_t* c, int C, const int64_t* p_offs, const int32_t* path_v,
+                    const double* path_t, const int32_t* path_len, const int64_t* obs_offs,
+                    const double* obs_t, const int32_t* obs_y, uint64_t seed, uint32_t sweep, int mode,
+                    int precision, int64_t capacity, int64_t* w_offs, double* W, int32_t* path_v_out,
+                    double* path_t_out, int32_t* path_len_out, double* time_in_state, int32_t* jumps,
+                    int32_t* status, int64_t* total_w) {
+    int rc = model_ready(c);
+    if (rc) return rc;
+    if (C <= 0) return fail(SMJP_E_INVALID, "C <= 0");
+    if (!p_offs || !path_v || !path_t || !path_len || !obs_offs || !w_offs || !W || !path_v_out ||
+        !path_t_out || !path_len_out || !status || !total_w)
+        return fail(SMJP_E_INVALID, "null required pointer");
+    if (obs_offs[0] != 0) return fail(SMJP_E_INVALID, "offsets must start at 0");
+    if (obs_offs[C] > 0 && (!obs_t || !obs_y)) return fail(SMJP_E_INVALID, "observations missing");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int K = c->K;
+    StagedPaths sp;
+    rc = stage_paths(c, C, p_offs, path_v, path_t, path_len, obs_offs, obs_t, obs_y, &sp);
+    if (rc) return rc;
+    rc = c->d_soff.reserve((size_t)p_offs[C] * 4 + 16);
+    if (rc) return rc;
+    // output staging: fixed part sized by `capacity`
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += smjp::align_up(bytes, 16); return o; };
+    const size_t o_wo = take((C + 1) * 8), o_pl = take(C * 4), o_st = take(C * 4);
+    const size_t o_tis = take((size_t)C * K * 8), o_jm = take((size_t)C * K * 4);
+    const size_t o_W = take(capacity * 8), o_pv = take(capacity * 4), o_pt = take(capacity * 8);
+    rc = c->d_out.reserve(off);
+    if (rc) return rc;
+    rc = c->h_out.reserve(off);
+    if (rc) return rc;
+    char* d = (char*)c->d_out.p;
+    int64_t n_max = 0;
+    rc = smjp_sweep_dev(c, C, sp.p_offs, sp.path_v, sp.path_t, sp.path_len, sp.obs_offs, sp.obs_t, sp.obs_y,
+                        seed, sweep, mode, precision, capacity, (int64_t*)(d + o_wo), (int32_t*)c->d_soff.p,
+                        (double*)(d + o_W), (int32_t*)(d + o_pv), (double*)(d + o_pt), (int32_t*)(d + o_pl),
+                        (double*)(d + o_tis), (int32_t*)(d + o_jm), (int32_t*)(d + o_st), &n_max, total_w);
+    if (rc) return rc;
+    char* h = (char*)c->h_out.p;
+    const int64_t tw = *total_w;
+    CUDA_TRY(cudaMemcpyAsync(h, d, o_W, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(h + o_W, d + o_W, tw * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(h + o_pv, d + o_pv, tw * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(h + o_pt, d + o_pt, tw * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    memcpy(w_offs, h + o_wo, (C + 1) * 8);
+    memcpy(path_len_out, h + o_pl, C * 4);
+    memcpy(status, h + o_st, C * 4);
+    if (time_in_state) memcpy(time_in_state, h + o_tis, (size_t)C * K * 8);
+    if (jumps) memcpy(jumps, h + o_jm, (size_t)C * K * 4);
+    memcpy(W, h + o_W, tw * 8);
+    memcpy(path_v_out, h + o_pv, tw * 4);
+    memcpy(path_t_out, h + o_pt, tw * 8);
     return SMJP_OK;
 }
 

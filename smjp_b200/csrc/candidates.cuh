@@ -1,0 +1,307 @@
+// Candidate (thinned-event) sampler, prior trajectory sampler, observation simulator.
+//
+// Replaces (reference):
+//   sample_smjp_event_times        pkg/smjp_utils.py:194-210
+//   PoissonProcess.sample          pkg/smjp_utils.py:61-99   N ~ Poisson((Omega-1) H_vs(tau)) per target
+//   PoissonProcess.weibull_mean    pkg/smjp_utils.py:135-145
+//   WeibullDistribution.sample     pkg/distributions.py:292-306 (unit-scale draw)
+//   sample_smjp_trajectory_prior   pkg/smjp_utils.py:216-254
+//   sample_data_posterior          pkg/smjp_utils.py:350-364 + smjpEmission.sample :559-563
+//
+// Randomness is counter-based (Philox, common.cuh), so the count pass and the fill pass regenerate
+// the same draws and no RNG state or per-sojourn buffers ever touch HBM.  oracle/smjp_oracle.py
+// (candidates, prior_path, simulate_observations) is the bit-level CPU twin of this file.
+#pragma once
+#include "../../include/smjp_b200.h"
+#include "common.cuh"
+
+namespace smjp {
+
+#define SMJP_POISSON_CHUNK 32.0
+
+__device__ __forceinline__ int poisson_inv(double mu, double u) {
+    double p = exp(-mu), cdf = p;
+    int k = 0;
+    while (u > cdf && k < 1000) {
+        ++k;
+        p *= mu / k;
+        cdf += p;
+    }
+    return k;
+}
+
+struct CandArgs {
+    int C;
+    const int64_t* p_offs;  // path windows
+    const int32_t* path_v;
+    const double* path_t;
+    const int32_t* path_len;
+    const double* model;  // shape[K*K], c2[K*K], emis[K*Kobs], scale[K*K]
+    int K, Kobs;
+    double omega;
+    uint64_t seed;
+    uint32_t sweep, chain_base;
+    int mode;
+    int32_t* soff;    // per sojourn: offset of its first grid point inside the chain's W (same windows as path)
+    int64_t* w_len;   // per chain grid length (count pass) / w_offs (fill pass)
+    const int64_t* w_offs;
+    double* W;
+};
+
+// number of thinned events of sojourn q of chain c (all targets), optionally emitting them
+__device__ __forceinline__ int sojourn_events(const CandArgs& a, int c, int q, int v, double t0, double tau,
+                                              double* out) {
+    const int K = a.K;
+    const double* shape = a.model;
+    const double* scale = a.model + 2 * K * K + K * a.Kobs;
+    int total = 0;
+    for (int s = 0; s < K; ++s) {
+        const double k = shape[v * K + s];
+        const double mu = (a.omega - 1.0) * pow(tau / scale[v * K + s], k);
+        int m = (int)ceil(mu / SMJP_POISSON_CHUNK);
+        if (m < 1) m = 1;
+        const uint32_t aa = (uint32_t)(q * K + s);
+        int N = 0;
+        for (int cc = 0; cc < m; ++cc)
+            N += poisson_inv(mu / m, philox_u01(a.seed, TAG_CANDIDATES, (uint64_t)cc, aa, a.sweep,
+                                                a.chain_base + (uint32_t)c));
+        if (out) {
+            const double F = -expm1(-pow(tau, k));
+            for (int d = 0; d < N; ++d) {
+                const double u = philox_u01(a.seed, TAG_CANDIDATES, (uint64_t)(m + d), aa, a.sweep,
+                                            a.chain_base + (uint32_t)c);
+                double x = (a.mode == SMJP_CAND_REFERENCE) ? pow(-log1p(-u * F), 1.0 / k)
+                                                           : tau * pow(u, 1.0 / k);
+                x = fmin(x, tau);
+                // insertion into the sorted run out[0 .. total+d)
+                int pos = total + d;
+                const double val = t0 + x;
+                while (pos > 0 && out[pos - 1] > val) {
+                    out[pos] = out[pos - 1];
+                    --pos;
+                }
+                out[pos] = val;
+            }
+        }
+        total += N;
+    }
+    return total;
+}
+
+// one CTA per chain: per-sojourn counts -> offsets inside the chain's grid, chain grid length
+__global__ void cand_count_kernel(const CandArgs a) {
+    __shared__ int s_warp[33];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, B = blockDim.x, lane = tid & 31, wid = tid >> 5, NW = B >> 5;
+    for (int c = blockIdx.x; c < a.C; c += gridDim.x) {
+        const int64_t p0 = a.p_offs[c];
+        const int plen = a.path_len[c];
+        const int nsoj = plen - 1;
+        if (tid == 0) s_carry = 0;
+        __syncthreads();
+        for (int base = 0; base < nsoj; base += B) {
+            const int q = base + tid;
+            int cnt = 0;
+            if (q < nsoj) {
+                const double t0 = a.path_t[p0 + q], t1 = a.path_t[p0 + q + 1];
+                cnt = 1 + sojourn_events(a, c, q, a.path_v[p0 + q], t0, t1 - t0, nullptr);
+            }
+            int incl = warp_inclusive_scan(cnt, lane);
+            if (lane == 31) s_warp[wid] = incl;
+            __syncthreads();
+            int off = s_carry;
+            for (int w = 0; w < wid; ++w) off += s_warp[w];
+            if (q < nsoj) a.soff[p0 + q] = off + incl - cnt;
+            __syncthreads();
+            if (tid == B - 1) s_carry = off + incl;
+            __syncthreads();
+        }
+        if (tid == 0) a.w_len[c] = (plen >= 2) ? (int64_t)s_carry + 1 : 0;  // + the end point
+        __syncthreads();
+    }
+}
+
+// single CTA: exclusive scan of the chain grid lengths -> w_offs[C+1]; stats = {n_max, total}
+__global__ void chain_scan_kernel(int C, const int64_t* len, int64_t* offs, int64_t* stats) {
+    __shared__ long long s_warp[33];
+    __shared__ long long s_carry;
+    __shared__ long long s_max;
+    const int tid = threadIdx.x, B = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) { s_carry = 0; s_max = 0; }
+    __syncthreads();
+    long long mymax = 0;
+    for (int base = 0; base < C; base += B) {
+        const int c = base + tid;
+        long long v = c < C ? (long long)len[c] : 0;
+        mymax = v > mymax ? v : mymax;
+        long long incl = warp_inclusive_scan(v, lane);
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        long long off = s_carry;
+        for (int w = 0; w < wid; ++w) off += s_warp[w];
+        if (c < C) offs[c] = off + incl - v;
+        __syncthreads();
+        if (tid == B - 1) s_carry = off + incl;
+        __syncthreads();
+    }
+    atomicMax(&s_max, mymax);
+    __syncthreads();
+    if (tid == 0) {
+        offs[C] = s_carry;
+        stats[0] = s_max - 1;  // n_max (intervals)
+        stats[1] = s_carry;    // total grid points
+    }
+}
+
+// thread per sojourn: W[base] = T[q]; W[base+1 ..] = sorted thinned events
+__global__ void cand_fill_kernel(const CandArgs a) {
+    const int tid = threadIdx.x, B = blockDim.x;
+    for (int c = blockIdx.x; c < a.C; c += gridDim.x) {
+        const int64_t p0 = a.p_offs[c], w0 = a.w_offs[c];
+        const int plen = a.path_len[c];
+        const int nsoj = plen - 1;
+        for (int q = tid; q < nsoj; q += B) {
+            const double t0 = a.path_t[p0 + q], t1 = a.path_t[p0 + q + 1];
+            double* out = a.W + w0 + a.soff[p0 + q];
+            out[0] = t0;
+            sojourn_events(a, c, q, a.path_v[p0 + q], t0, t1 - t0, out + 1);
+        }
+        if (tid == 0 && plen >= 2) a.W[a.w_offs[c + 1] - 1] = a.path_t[p0 + plen - 1];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// prior trajectories: thread per chain (sequential competing risks)
+// ------------------------------------------------------------------------------------------------
+struct PriorArgs {
+    int C;
+    const int64_t* p_offs;  // capacity windows
+    const double* model;
+    const double* pi0;  // device [K]
+    int K, Kobs;
+    double t_end;
+    int honour_scale;
+    uint64_t seed;
+    uint32_t chain_base;
+    int32_t* path_v;
+    double* path_t;
+    int32_t* path_len;
+    int32_t* status;
+};
+
+__global__ void prior_kernel(const PriorArgs a) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.C) return;
+    const int K = a.K;
+    const double* shape = a.model;
+    const double* scale = a.model + 2 * K * K + K * a.Kobs;
+    const int64_t p0 = a.p_offs[c];
+    const int cap = (int)(a.p_offs[c + 1] - p0);
+    const uint32_t chain = a.chain_base + (uint32_t)c;
+    // v0 ~ pi0 by inverse CDF on the normalised vector
+    double tot = 0;
+    for (int s = 0; s < K; ++s) tot += a.pi0[s];
+    const double u0 = philox_u01(a.seed, TAG_PRIOR, 0, 0u, 0u, chain);
+    int v = K - 1;
+    {
+        double cdf = 0;
+        int lastpos = 0;
+        bool found = false;
+        for (int s = 0; s < K; ++s) {
+            const double p = a.pi0[s] / tot;
+            if (p > 0) lastpos = s;
+            cdf += p;
+            if (!found && cdf > u0) { v = s; found = true; }
+        }
+        if (!found) v = lastpos;
+    }
+    double w = 0.0;
+    int len = 0, vprev = v;
+    bool overflow = false;
+    if (cap < 2) overflow = true;
+    if (!overflow) {
+        a.path_v[p0] = v;
+        a.path_t[p0] = 0.0;
+        len = 1;
+    }
+    int step = 0;
+    while (!overflow && w < a.t_end) {
+        double best = INFINITY;
+        int arg = 0;
+        for (int s = 0; s < K; ++s) {
+            const double u = philox_u01(a.seed, TAG_PRIOR, (uint64_t)(1 + (int64_t)step * K + s), 0u, 0u, chain);
+            double h = pow(-log1p(-u), 1.0 / shape[v * K + s]);
+            if (a.honour_scale) h *= scale[v * K + s];
+            if (h < best) { best = h; arg = s; }
+        }
+        w += best;
+        vprev = v;
+        v = arg;
+        if (len >= cap) { overflow = true; break; }
+        a.path_v[p0 + len] = v;
+        a.path_t[p0 + len] = w;
+        ++len;
+        ++step;
+    }
+    if (overflow) {
+        a.status[c] = SMJP_ST_OVERFLOW;
+        a.path_len[c] = 0;
+        return;
+    }
+    // smjp_utils.py:251-252: last entry becomes (v_prev, t_end)
+    a.path_v[p0 + len - 1] = vprev;
+    a.path_t[p0 + len - 1] = a.t_end;
+    a.path_len[c] = len;
+    a.status[c] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// observations: thread per (chain, observation)
+// ------------------------------------------------------------------------------------------------
+struct ObsSimArgs {
+    int C;
+    const int64_t* p_offs;
+    const int32_t* path_v;
+    const double* path_t;
+    const int32_t* path_len;
+    const int64_t* obs_offs;
+    const double* obs_t;
+    int32_t* obs_y;
+    const double* model;
+    int K, Kobs;
+    uint64_t seed;
+    uint32_t chain_base;
+};
+
+__global__ void obs_sim_kernel(const ObsSimArgs a) {
+    const int K = a.K, Kobs = a.Kobs;
+    const double* emis = a.model + 2 * K * K;
+    for (int c = blockIdx.x; c < a.C; c += gridDim.x) {
+        const int64_t p0 = a.p_offs[c], o0 = a.obs_offs[c];
+        const int plen = a.path_len[c];
+        const int D = (int)(a.obs_offs[c + 1] - o0);
+        for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            const double t = a.obs_t[o0 + d];
+            int lo = 0, hi = plen;  // first q with T[q] > t
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (a.path_t[p0 + mid] <= t) lo = mid + 1; else hi = mid;
+            }
+            int q = lo - 1;
+            q = q < 0 ? 0 : (q > plen - 2 ? plen - 2 : q);
+            const int v = a.path_v[p0 + q];
+            const double u = philox_u01(a.seed, TAG_DATA, (uint64_t)d, 0u, 0u, a.chain_base + (uint32_t)c);
+            double cdf = 0;
+            int y = -1, lastpos = 0;
+            for (int x = 0; x < Kobs; ++x) {
+                const double p = emis[v * Kobs + x];
+                if (p > 0) lastpos = x;
+                cdf += p;
+                if (y < 0 && cdf > u) y = x;
+            }
+            a.obs_y[o0 + d] = y >= 0 ? y : lastpos;
+        }
+    }
+}
+
+}  // namespace smjp

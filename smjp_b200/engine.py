@@ -87,6 +87,12 @@ class Engine:
     def launch_count(self):
         return int(self.lib.smjp_ctx_launch_count(self.ctx))
 
+    def kernel_time(self, kernel="ffbs"):
+        """(total ms, launches) of the named kernel since the last call (needs option time_kernels=1)"""
+        ms, cnt = ctypes.c_double(0), ctypes.c_int64(0)
+        check(self.lib.smjp_ctx_kernel_time(self.ctx, kernel.encode(), ctypes.byref(ms), ctypes.byref(cnt)))
+        return ms.value, cnt.value
+
     def set_model(self, shape, scale, omega, emis, likelihood_power, t_end):
         shape = np.ascontiguousarray(shape, dtype=np.float64)
         scale = np.ascontiguousarray(scale, dtype=np.float64)
@@ -99,6 +105,8 @@ class Engine:
         check(self.lib.smjp_set_model(self.ctx, K, emis.shape[1], _ptr(shape), _ptr(scale), float(omega),
                                       _ptr(emis), float(likelihood_power), float(t_end)))
         self.K, self.Kobs = K, emis.shape[1]
+        self.omega = float(omega)
+        self.shape, self.scale, self.emis = shape.copy(), scale.copy(), emis.copy()
         self.t_end = float(t_end)
 
     # ------------------------------------------------------------------------------------------
@@ -173,6 +181,74 @@ class Engine:
                                      PRECISIONS[precision], _ptr(messages), _ptr(msg_offs), _ptr(logZ),
                                      _ptr(aug_idx), _ptr(path_v), _ptr(path_t), _ptr(path_len),
                                      _ptr(time_in_state), _ptr(jumps), _ptr(status), int(n_max), int(total_w)))
+
+
+def _pack_paths(V, T):
+    lens = [len(v) for v in V]
+    if any(len(t) != l for t, l in zip(T, lens)):
+        raise ValueError("V and T lengths differ")
+    offs = ragged_offsets(lens)
+    pv = np.concatenate([np.asarray(v, dtype=np.int32) for v in V]) if lens else np.zeros(0, np.int32)
+    pt = np.concatenate([np.asarray(t, dtype=np.float64) for t in T]) if lens else np.zeros(0)
+    return offs, np.ascontiguousarray(pv), np.ascontiguousarray(pt), np.asarray(lens, dtype=np.int32)
+
+
+def candidates_host(eng, V, T, seed, sweep=0, mode="reference"):
+    """Thinned-event grids for HOST paths (sample_smjp_event_times, smjp_utils.py:194-210).
+    V, T: lists per chain (state indices, times).  Returns the list of grids W."""
+    C = len(V)
+    offs, pv, pt, pl = _pack_paths(V, T)
+    w_offs = np.zeros(C + 1, dtype=np.int64)
+    total = ctypes.c_int64(0)
+    cap = int(len(pv) * max(2.0, float(getattr(eng, "omega", 2.0)) + 1) + 64)
+    modes = {"reference": _lib.CAND_REFERENCE, "exact": _lib.CAND_EXACT}
+    while True:
+        W = np.zeros(cap, dtype=np.float64)
+        rc = eng.lib.smjp_candidates_host(eng.ctx, C, _ptr(offs), _ptr(pv), _ptr(pt), _ptr(pl),
+                                          int(seed) & 0xFFFFFFFFFFFFFFFF, int(sweep), modes[mode], _ptr(w_offs),
+                                          _ptr(W), cap, ctypes.byref(total))
+        if rc == -3 and total.value > cap:
+            cap = int(total.value)
+            continue
+        check(rc)
+        break
+    return [W[w_offs[c]: w_offs[c + 1]].copy() for c in range(C)]
+
+
+def sweep_host(eng, V, T, obs_t, obs_y, seed, sweep=0, mode="reference", precision="f64"):
+    """One Rao-Teh sweep (raoteh.py:58-59) for HOST paths; returns dict(W, V, T, time_in_state, jumps, status)."""
+    C = len(V)
+    offs, pv, pt, pl = _pack_paths(V, T)
+    if isinstance(obs_t, np.ndarray) and obs_t.ndim == 1 and obs_t.dtype != object:
+        obs_t, obs_y = [obs_t] * C, [obs_y] * C
+    of, o_offs = pack_ragged([np.asarray(t, dtype=np.float64) for t in obs_t], np.float64)
+    oy, _ = pack_ragged([np.asarray(y, dtype=np.int32) for y in obs_y], np.int32)
+    K = eng.K
+    modes = {"reference": _lib.CAND_REFERENCE, "exact": _lib.CAND_EXACT}
+    cap = int(len(pv) * 3 + 1024)
+    total = ctypes.c_int64(0)
+    while True:
+        w_offs = np.zeros(C + 1, dtype=np.int64)
+        W = np.zeros(cap, dtype=np.float64)
+        nv = np.zeros(cap, dtype=np.int32)
+        nt = np.zeros(cap, dtype=np.float64)
+        nl = np.zeros(C, dtype=np.int32)
+        tis = np.zeros((C, K), dtype=np.float64)
+        jm = np.zeros((C, K), dtype=np.int32)
+        st = np.zeros(C, dtype=np.int32)
+        rc = eng.lib.smjp_sweep_host(eng.ctx, C, _ptr(offs), _ptr(pv), _ptr(pt), _ptr(pl), _ptr(o_offs), _ptr(of),
+                                     _ptr(oy), int(seed) & 0xFFFFFFFFFFFFFFFF, int(sweep), modes[mode],
+                                     PRECISIONS[precision], cap, _ptr(w_offs), _ptr(W), _ptr(nv), _ptr(nt), _ptr(nl),
+                                     _ptr(tis), _ptr(jm), _ptr(st), ctypes.byref(total))
+        if rc == -3 and total.value > cap:
+            cap = int(total.value * 1.25) + 1024
+            continue
+        check(rc)
+        break
+    return {"W": [W[w_offs[c]: w_offs[c + 1]].copy() for c in range(C)],
+            "V": [nv[w_offs[c]: w_offs[c] + nl[c]].copy() for c in range(C)],
+            "T": [nt[w_offs[c]: w_offs[c] + nl[c]].copy() for c in range(C)],
+            "time_in_state": tis, "jumps": jm, "status": st}
 
 
 def raise_for_status(status):

@@ -1,0 +1,178 @@
+"""GPU parity tests: candidates, prior sampler, observation simulator and the full sweep against the
+oracle's Philox-exact restatement (pytest -m gpu on the B200 box)."""
+import numpy as np
+import pytest
+
+from oracle import smjp_oracle as O
+from oracle import philox
+
+pytestmark = pytest.mark.gpu
+
+SHAPE3 = np.array([[1.606, 1.933, 0.865], [1.938, 0.869, 1.751], [1.69, 0.64, 0.696]])
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from smjp_b200.engine import Engine
+    eng = Engine(0)
+    yield eng
+    eng.close()
+
+
+def test_prior_paths_match_oracle(engine):
+    from smjp_b200.chains import DeviceChains
+    K, t_end = 3, 10.0
+    engine.set_model(SHAPE3, np.ones((K, K)), 2.0, O.emission_matrix(K), 1.0, t_end)
+    C = 64
+    pi0 = np.array([0.2, 0.5, 0.3])
+    ch = DeviceChains(engine, C, np.arange(0.1, t_end, 0.1)).init_prior(pi0, seed=42, cap_per_chain=8)
+    V, T = ch.paths_host()
+    for c in range(C):
+        v, w = O.prior_path(SHAPE3, np.ones((K, K)), pi0, t_end, seed=42, chain=c)
+        assert np.array_equal(V[c], v)
+        assert np.allclose(T[c], w, rtol=1e-13, atol=0)
+        assert T[c][0] == 0.0 and T[c][-1] == t_end
+
+
+def test_prior_honour_scale(engine):
+    from smjp_b200.chains import DeviceChains
+    rng = np.random.default_rng(1)
+    K, t_end = 4, 5.0
+    shape = rng.uniform(0.6, 3, (K, K)); scale = rng.uniform(0.5, 2, (K, K))
+    engine.set_model(shape, scale, 2.0, O.emission_matrix(K), 1.0, t_end)
+    ch = DeviceChains(engine, 16, np.zeros(0)).init_prior(np.ones(K), seed=3, honour_scale=True)
+    V, T = ch.paths_host()
+    for c in range(16):
+        v, w = O.prior_path(shape, scale, np.ones(K), t_end, seed=3, chain=c, honour_scale=True)
+        assert np.array_equal(V[c], v) and np.allclose(T[c], w, rtol=1e-13, atol=0)
+
+
+def test_simulated_observations_match_oracle(engine):
+    from smjp_b200.chains import DeviceChains
+    K, t_end = 3, 10.0
+    emis = O.emission_matrix(K)
+    engine.set_model(SHAPE3, np.ones((K, K)), 2.0, emis, 1.0, t_end)
+    obs_t = np.arange(0.1, t_end, 0.1)
+    ch = DeviceChains(engine, 32, obs_t).init_prior(np.ones(K) / K, seed=9).simulate_observations(seed=10)
+    V, T = ch.paths_host()
+    y = ch.obs_y.cpu().numpy().reshape(32, len(obs_t))
+    for c in range(32):
+        assert np.array_equal(y[c], O.simulate_observations(V[c], T[c], obs_t, emis, seed=10, chain=c))
+
+
+@pytest.mark.parametrize("mode", ["reference", "exact"])
+def test_candidates_match_oracle(engine, mode):
+    from smjp_b200.engine import candidates_host
+    K, t_end, omega = 3, 12.0, 2.0
+    engine.set_model(SHAPE3, np.ones((K, K)), omega, O.emission_matrix(K), 1.0, t_end)
+    V, T = [], []
+    for c in range(40):
+        v, w = O.prior_path(SHAPE3, np.ones((K, K)), np.ones(K) / K, t_end, seed=77, chain=c)
+        V.append(v); T.append(w)
+    Ws = candidates_host(engine, V, T, seed=123, sweep=4, mode=mode)
+    for c in range(40):
+        ora = O.candidates(V[c], T[c], SHAPE3, np.ones((K, K)), omega, seed=123, sweep=4, chain=c, mode=mode)
+        assert len(Ws[c]) == len(ora)
+        assert np.allclose(Ws[c], ora, rtol=1e-12, atol=1e-14)
+        assert np.all(np.diff(Ws[c]) > 0)
+
+
+def test_candidates_large_mean_and_omega3(engine):
+    """long sojourns -> Poisson means above the 32-chunk; non-unit scales; Omega = 3"""
+    from smjp_b200.engine import candidates_host
+    rng = np.random.default_rng(8)
+    K, t_end, omega = 3, 9.0, 3.0
+    shape = rng.uniform(0.6, 3, (K, K)); scale = rng.uniform(0.5, 2, (K, K))
+    engine.set_model(shape, scale, omega, O.emission_matrix(K), 1.0, t_end)
+    V = [np.array([0, 2, 2]), np.array([1, 1])]
+    T = [np.array([0.0, 6.5, 9.0]), np.array([0.0, 9.0])]
+    Ws = candidates_host(engine, V, T, seed=5, sweep=0)
+    for c in range(2):
+        ora = O.candidates(V[c], T[c], shape, scale, omega, seed=5, sweep=0, chain=c)
+        assert len(ora) > 60
+        assert len(Ws[c]) == len(ora) and np.allclose(Ws[c], ora, rtol=1e-12, atol=1e-14)
+
+
+def test_sweep_host_matches_oracle_composition(engine):
+    """sweep = candidates -> FFBS with Philox backward uniforms; compare every stage with the oracle."""
+    from smjp_b200.engine import sweep_host
+    K, t_end, omega = 3, 8.0, 2.0
+    emis = O.emission_matrix(K)
+    engine.set_model(SHAPE3, np.ones((K, K)), omega, emis, 1.0, t_end)
+    obs_t = np.arange(0.1, t_end, 0.1)
+    C = 12
+    V, T, Y = [], [], []
+    for c in range(C):
+        v, w = O.prior_path(SHAPE3, np.ones((K, K)), np.ones(K) / K, t_end, seed=1, chain=c)
+        V.append(v); T.append(w)
+        Y.append(O.simulate_observations(v, w, obs_t, emis, seed=2, chain=c))
+    for sw in range(3):
+        r = sweep_host(engine, V, T, [obs_t] * C, Y, seed=99, sweep=sw)
+        assert np.all(r["status"] == 0)
+        for c in range(C):
+            W = O.candidates(V[c], T[c], SHAPE3, np.ones((K, K)), omega, seed=99, sweep=sw, chain=c)
+            assert len(W) == len(r["W"][c]) and np.allclose(W, r["W"][c], rtol=1e-12, atol=1e-14)
+            n = len(W) - 1
+            u = philox.u01(99, philox.TAG_BACKWARD, np.arange(n), 0, sw, c)
+            ora = O.ffbs(r["W"][c], obs_t, Y[c], SHAPE3, np.ones((K, K)), omega, emis, 1.0, t_end, u)
+            assert np.array_equal(r["V"][c], ora["V"])
+            assert np.array_equal(r["T"][c], ora["T"])
+            t, j = O.chain_metrics(ora["V"], ora["T"], K)
+            assert np.array_equal(r["jumps"][c], j) and np.allclose(r["time_in_state"][c], t, atol=1e-13)
+        V, T = r["V"], r["T"]
+
+
+def test_device_chains_equal_host_sweeps(engine):
+    """the device-resident loop (DeviceChains.sweep) and the host-buffer call give identical chains"""
+    from smjp_b200.chains import DeviceChains
+    from smjp_b200.engine import sweep_host
+    K, t_end = 3, 8.0
+    emis = O.emission_matrix(K)
+    engine.set_model(SHAPE3, np.ones((K, K)), 2.0, emis, 1.0, t_end)
+    obs_t = np.arange(0.1, t_end, 0.1)
+    C = 50
+    ch = DeviceChains(engine, C, obs_t).init_prior(np.ones(K) / K, seed=4).simulate_observations(seed=5)
+    V, T = ch.paths_host()
+    Y = ch.obs_y.cpu().numpy().reshape(C, -1)
+    for sw in range(4):
+        ch.sweep(seed=6, sweep=sw)
+        r = sweep_host(engine, V, T, [obs_t] * C, list(Y), seed=6, sweep=sw)
+        V, T = r["V"], r["T"]
+        Vd, Td = ch.paths_host()
+        assert all(np.array_equal(a, b) for a, b in zip(V, Vd))
+        assert all(np.array_equal(a, b) for a, b in zip(T, Td))
+        assert np.array_equal(ch.jumps.cpu().numpy(), r["jumps"])
+        assert int(ch.status.abs().sum().item()) == 0
+
+
+def test_posterior_summaries_ks_vs_oracle_chain(engine):
+    """KS (reference acceptance rule, mcmc_utils.py:377-415: reject if D > 1.224 sqrt((n+m)/(nm)))
+    between time-in-state / jump counts of GPU chains and of oracle chains run with independent seeds."""
+    from scipy import stats
+    from smjp_b200.chains import DeviceChains
+    K, t_end, omega = 3, 2.0, 2.0
+    emis = O.emission_matrix(K)
+    engine.set_model(SHAPE3, np.ones((K, K)), omega, emis, 1.0, t_end)
+    obs_t = np.arange(0.1, 2.0, 0.1)
+    y = np.array([1, 1, 1, 1, 1, 1, 2, 2, 2, 1, 1, 1, 1, 3, 3, 2, 1, 1, 3]) - 1   # experiments.py:217
+    C, burn = 600, 12
+    ch = DeviceChains(engine, C, obs_t).init_prior(np.ones(K) / K, seed=21).set_observations(y)
+    for sw in range(burn):
+        ch.sweep(seed=22, sweep=sw)
+    g_t = ch.time_in_state.cpu().numpy(); g_j = ch.jumps.cpu().numpy()
+    Co = 300  # oracle: independent chains, same number of sweeps, different seed
+    o_t, o_j = [], []
+    for c in range(Co):
+        V, T = O.prior_path(SHAPE3, np.ones((K, K)), np.ones(K) / K, t_end, seed=31, chain=c)
+        for sw in range(burn):
+            W = O.candidates(V, T, SHAPE3, np.ones((K, K)), omega, seed=32, sweep=sw, chain=c)
+            u = philox.u01(32, philox.TAG_BACKWARD, np.arange(len(W) - 1), 0, sw, c)
+            r = O.ffbs(W, obs_t, y, SHAPE3, np.ones((K, K)), omega, emis, 1.0, t_end, u)
+            V, T = r["V"], r["T"]
+        t, j = O.chain_metrics(V, T, K)
+        o_t.append(t); o_j.append(j)
+    o_t, o_j = np.array(o_t), np.array(o_j)
+    ub = 1.224 * np.sqrt((C + Co) / (C * Co))
+    for s in range(K):
+        assert stats.ks_2samp(g_t[:, s], o_t[:, s]).statistic < ub
+        assert stats.ks_2samp(g_j[:, s], o_j[:, s]).statistic < ub
