@@ -43,6 +43,7 @@ class DeviceChains:
         self.n_max = 0
         self.total_w = 0
         self.sweeps_done = 0
+        self.cap = 0
 
     # ------------------------------------------------------------------------------------------
     def _alloc_paths(self, capacity, C=None):
@@ -108,29 +109,33 @@ class DeviceChains:
         t = self.torch
         sweep = self.sweeps_done if sweep is None else sweep
         cur = self.cur
-        cap = max(int(cur["cap"] * 3), 1024) if self.nxt is None else self.nxt["cap"]
+        if self.cap == 0:  # first sweep: size from the live path entries, grow on demand
+            self.cap = int(cur["len"].sum().item()) * 3 + 1024
         n_max = ctypes.c_int64(0)
         total = ctypes.c_int64(0)
         while True:
-            if self.nxt is None or self.nxt["cap"] < cap or self.W is None or self.W.numel() < cap:
-                self.nxt = self._alloc_paths(cap)
-                self.W = t.zeros(cap, dtype=t.float64, device=self.dev)
+            if self.nxt is None or self.nxt["cap"] < self.cap:
+                self.nxt = self._alloc_paths(self.cap)
+            if self.W is None or self.W.numel() < self.cap:
+                self.W = t.zeros(self.cap, dtype=t.float64, device=self.dev)
             if self.soff is None or self.soff.numel() < cur["cap"]:
                 self.soff = t.zeros(cur["cap"], dtype=t.int32, device=self.dev)
             nx = self.nxt
             rc = self.eng.lib.smjp_sweep_dev(
                 self.eng.ctx, self.C, _ptr(cur["offs"]), _ptr(cur["v"]), _ptr(cur["t"]), _ptr(cur["len"]),
                 _ptr(self.obs_offs), _ptr(self.obs_t), _ptr(self.obs_y), int(seed) & 0xFFFFFFFFFFFFFFFF, int(sweep),
-                CAND_MODES[mode], PRECISIONS[precision], int(cap), _ptr(nx["offs"]), _ptr(self.soff), _ptr(self.W),
-                _ptr(nx["v"]), _ptr(nx["t"]), _ptr(nx["len"]), _ptr(self.time_in_state), _ptr(self.jumps),
-                _ptr(self.status), ctypes.byref(n_max), ctypes.byref(total))
-            if rc == -3 and total.value > cap:  # buffers too small for this sweep's grids: regrow, redo
-                cap = int(total.value * 1.25) + 1024
+                CAND_MODES[mode], PRECISIONS[precision], int(nx["cap"]), _ptr(nx["offs"]), _ptr(self.soff),
+                _ptr(self.W), _ptr(nx["v"]), _ptr(nx["t"]), _ptr(nx["len"]), _ptr(self.time_in_state),
+                _ptr(self.jumps), _ptr(self.status), ctypes.byref(n_max), ctypes.byref(total))
+            if rc == -3 and total.value > nx["cap"]:  # buffers too small for this sweep's grids: regrow, redo
+                self.cap = int(total.value * 1.5) + 1024
+                self.nxt = None
+                self.W = None
                 continue
             check(rc)
             break
         self.n_max, self.total_w = int(n_max.value), int(total.value)
-        self.cur, self.nxt = nx, cur if cur["cap"] >= cap else None
+        self.cur, self.nxt = nx, (cur if cur["cap"] >= self.cap else None)
         self.sweeps_done += 1
         return self
 
