@@ -202,6 +202,7 @@ def run_ours(args):
     emis = np.ones((K, K)) + 9 * np.eye(K)
     emis /= emis.sum(axis=1, keepdims=True)  # 10:1 emission, smjp_utils.py:552-557
     eng.set_model(SHAPE, np.ones((K, K)), OMEGA, emis, 1.0, T_END)
+    eng.set_option("ffbs_threads", args.threads)
     obs_t = np.arange(OBS_DT, T_END, OBS_DT)
     D = len(obs_t)
     # ground-truth path -> observations; independent prior draw as the initial state
@@ -249,7 +250,7 @@ def run_ours(args):
     # ---- end to end through the host-buffer C-ABI call (smjp_sweep_host) ----
     V, T = ch.paths_host()
     Y = ch.obs_y.cpu().numpy().reshape(C, D)
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = 0 if args.no_e2e else max(2, min(args.steps, 5))
     r = sweep_host(eng, V, T, [obs_t] * C, list(Y), seed=SEED + 7, sweep=0, precision=prec)  # warm staging buffers
     V, T = r["V"], r["T"]
     barrier()
@@ -265,7 +266,7 @@ def run_ours(args):
         e_ss += float(np.sum(K * n * (n + 1) / 2))
         V, T = r["V"], r["T"]
     torch.cuda.synchronize()
-    e_wall = time.perf_counter() - t0
+    e_wall = max(time.perf_counter() - t0, 1e-9)
 
     # ---- reduce over ranks: time = max, work = sum ----
     stats = torch.tensor([ms, ss, gs, alg_bytes, float(launches), k_ms, float(k_cnt), e_wall, e_ss, float(status_bad)],
@@ -308,10 +309,12 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
                      "kernel": "ffbs_kernel<%s,3>" % ("double" if prec == "f64" else "float"),
-                     "kernel_ms_avg": k_ms / max(k_cnt, 1), "kernel_share_of_step": k_ms / ms,
+                     "kernel_ms_avg": k_ms / max(k_cnt, 1), "grid": eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_grid"),
+                     "threads": eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_threads"),
+                     "smem": eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_smem"), "kernel_share_of_step": k_ms / ms,
                      "algorithmic_bytes_per_launch": alg_bytes / max(k_cnt, 1)},
-        "e2e": {"value": e_ss / e_wall, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_steps,
-                "d2h_bytes_per_step": d2h // e2e_steps, "steps": e2e_steps,
+        "e2e": {"value": e_ss / e_wall, "unit": UNIT, "h2d_bytes_per_step": h2d // max(e2e_steps, 1),
+                "d2h_bytes_per_step": d2h // max(e2e_steps, 1), "steps": e2e_steps,
                 "api": "smjp_sweep_host (host buffers in/out, pinned staging inside)"},
     }
     if world == 1 and not args.no_cpu:
@@ -334,6 +337,8 @@ def main():
     ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (kernel experiments)")
+    ap.add_argument("--threads", type=int, default=0, help="threads per CTA of the FFBS kernel (0 = auto)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

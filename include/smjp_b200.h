@@ -66,6 +66,8 @@ void smjp_ctx_destroy(smjp_ctx_t* ctx);
 int smjp_ctx_sync(smjp_ctx_t* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t smjp_ctx_launch_count(smjp_ctx_t* ctx);
+/* launch geometry of the last FFBS kernel: "ffbs_grid", "ffbs_threads", "ffbs_smem"; "num_sms" */
+int64_t smjp_ctx_get_stat(smjp_ctx_t* ctx, const char* key);
 /* knobs: "ffbs_threads" (0 = auto, else threads per CTA of the FFBS kernel);
  *        "time_kernels" (0/1, see smjp_ctx_kernel_time);
  *        "chain_base" (global index of chain 0 of this context's batches: keeps the Philox streams of

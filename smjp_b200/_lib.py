@@ -29,6 +29,7 @@ SIGNATURES = {
     "smjp_ctx_destroy": (None, [P]),
     "smjp_ctx_sync": (ctypes.c_int, [P]),
     "smjp_ctx_launch_count": (ctypes.c_int64, [P]),
+    "smjp_ctx_get_stat": (ctypes.c_int64, [P, ctypes.c_char_p]),
     "smjp_ctx_set_option": (ctypes.c_int, [P, ctypes.c_char_p, ctypes.c_int64]),
     "smjp_ctx_kernel_time": (ctypes.c_int, [P, ctypes.c_char_p, c_f64p, c_i64p]),
     "smjp_set_model": (ctypes.c_int, [P, ctypes.c_int, ctypes.c_int, P, P, ctypes.c_double, P,

@@ -8,7 +8,7 @@
 
 #include "../../include/smjp_b200.h"
 #include "candidates.cuh"
-#include "ffbs.cuh"
+#include "ffbs_launch.cuh"
 
 namespace {
 
@@ -100,7 +100,9 @@ struct smjp_ctx {
     std::vector<double> h_model;
     DevBuf d_model;
     // workspaces
-    DevBuf d_queue, d_msg_scratch;
+    DevBuf d_queue, d_msg_scratch, d_obsf;
+    int last_grid = 0, last_threads = 0;
+    int64_t last_smem = 0;
     DevBuf d_in, d_out;  // staging for the host API
     PinBuf h_in, h_out;
     int ffbs_threads = 0;  // 0 = auto
@@ -156,6 +158,7 @@ void smjp_ctx_destroy(smjp_ctx_t* c) {
     c->d_model.release();
     c->d_queue.release();
     c->d_msg_scratch.release();
+    c->d_obsf.release();
     c->d_in.release();
     c->d_out.release();
     c->h_in.release();
@@ -175,6 +178,15 @@ int smjp_ctx_sync(smjp_ctx_t* c) {
 }
 
 int64_t smjp_ctx_launch_count(smjp_ctx_t* c) { return c ? c->launches : 0; }
+
+int64_t smjp_ctx_get_stat(smjp_ctx_t* c, const char* key) {
+    if (!c || !key) return -1;
+    if (!strcmp(key, "ffbs_grid")) return c->last_grid;
+    if (!strcmp(key, "ffbs_threads")) return c->last_threads;
+    if (!strcmp(key, "ffbs_smem")) return c->last_smem;
+    if (!strcmp(key, "num_sms")) return c->num_sms;
+    return -1;
+}
 
 int smjp_ctx_kernel_time(smjp_ctx_t* c, const char* kernel, double* total_ms, int64_t* count) {
     if (!c || !kernel || !total_ms || !count) return fail(SMJP_E_INVALID, "null argument");
@@ -197,8 +209,8 @@ int smjp_ctx_kernel_time(smjp_ctx_t* c, const char* kernel, double* total_ms, in
 int smjp_ctx_set_option(smjp_ctx_t* c, const char* key, int64_t value) {
     if (!c || !key) return fail(SMJP_E_INVALID, "null argument");
     if (!strcmp(key, "ffbs_threads")) {
-        if (value != 0 && (value < 32 || value > 1024 || value % 32))
-            return fail(SMJP_E_INVALID, "ffbs_threads must be 0 (auto) or a multiple of 32 in [32,1024]");
+        if (value != 0 && (value < 32 || value > 512 || value % 32))
+            return fail(SMJP_E_INVALID, "ffbs_threads must be 0 (auto) or a multiple of 32 in [32,512]");
         c->ffbs_threads = (int)value;
         return SMJP_OK;
     }
@@ -258,85 +270,43 @@ int smjp_set_model(smjp_ctx_t* c, int K, int Kobs, const double* shape, const do
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-template <typename Real, int K>
-int launch_ffbs_k(smjp_ctx* c, FfbsArgs& a, int threads, size_t smem, int grid) {
-    auto kern = ffbs_kernel<Real, K>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (c->time_kernels) {
-        CUDA_TRY(cudaEventCreate(&e0));
-        CUDA_TRY(cudaEventCreate(&e1));
-        CUDA_TRY(cudaEventRecord(e0, c->stream));
-    }
-    kern<<<grid, threads, smem, c->stream>>>(a);
-    CUDA_TRY(cudaGetLastError());
-    if (c->time_kernels) {
-        CUDA_TRY(cudaEventRecord(e1, c->stream));
-        c->ffbs_events.emplace_back(e0, e1);
-    }
-    c->launches += 1;
-    return SMJP_OK;
-}
-
-template <typename Real, int K>
-int occupancy_k(int threads, size_t smem, int* per_sm) {
-    auto kern = ffbs_kernel<Real, K>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, kern, threads, smem));
-    return SMJP_OK;
-}
-
-#define SMJP_FOR_EACH_K(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10)
-
 template <typename Real>
-int occupancy(int K, int threads, size_t smem, int* per_sm) {
-    switch (K) {
-#define X(k) case k: return occupancy_k<Real, k>(threads, smem, per_sm);
-        SMJP_FOR_EACH_K(X)
-#undef X
-    }
-    return fail(SMJP_E_UNSUPPORTED, "sMJP FFBS kernel is instantiated for K in [2,10]; K=%d", K);
-}
-
-template <typename Real>
-int launch_ffbs(smjp_ctx* c, FfbsArgs& a, int threads, size_t smem, int grid) {
-    switch (c->K) {
-#define X(k) case k: return launch_ffbs_k<Real, k>(c, a, threads, smem, grid);
-        SMJP_FOR_EACH_K(X)
-#undef X
-    }
-    return fail(SMJP_E_UNSUPPORTED, "sMJP FFBS kernel is instantiated for K in [2,10]; K=%d", c->K);
+cudaError_t ffbs_call(const FfbsArgs& a, FfbsLaunch& L, bool query) {
+    return sizeof(Real) == 8 ? ffbs_dispatch_f64(a, L, query) : ffbs_dispatch_f32(a, L, query);
 }
 
 template <typename Real>
 int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
     const int K = c->K;
+    if (K > 10) return fail(SMJP_E_UNSUPPORTED, "sMJP FFBS kernel is instantiated for K in [2,10]; K=%d", K);
     int threads = c->ffbs_threads;
     if (threads == 0) {
-        // enough threads that a full row has ~2-4 grid points per thread, at least 2 warps
+        // a full row should give every thread a few grid points; small grids use small CTAs
         threads = 128;
-        if (n_max > 768) threads = 256;
-        if (n_max > 2048) threads = 512;
+        if (n_max > 1024) threads = 256;
+        if (n_max > 3072) threads = 512;
         if (n_max <= 96) threads = 64;
         if (n_max <= 32) threads = 32;
     }
-    size_t smem = ffbs_smem_bytes<Real>(K, c->Kobs, (int)n_max, threads);
-    while (smem > c->smem_optin && threads > 32) {  // padding shrinks with fewer threads
-        threads /= 2;
-        smem = ffbs_smem_bytes<Real>(K, c->Kobs, (int)n_max, threads);
-    }
+    size_t smem = ffbs_smem_bytes<Real>(K, (int)n_max, threads);
     if (smem > c->smem_optin)
         return fail(SMJP_E_UNSUPPORTED,
                     "grid with %lld intervals x K=%d needs %zu B of shared memory (> %zu): "
                     "chain state does not fit on chip", (long long)n_max, K, smem, c->smem_optin);
-    int per_sm = 0;
-    int rc = occupancy<Real>(K, threads, smem, &per_sm);
-    if (rc) return rc;
+    FfbsLaunch L;
+    L.K = K;
+    L.threads = threads;
+    L.smem = smem;
+    L.grid = 0;
+    L.stream = c->stream;
+    CUDA_TRY(ffbs_call<Real>(a, L, true));
+    const int per_sm = L.grid;
     if (per_sm < 1) return fail(SMJP_E_UNSUPPORTED, "kernel cannot be resident (threads=%d smem=%zu)", threads, smem);
     int grid = c->num_sms * per_sm;
     if (grid > a.C) grid = a.C;
     a.ncap = (int)n_max;
-    a.ncap_pad = (int)((n_max + threads - 1) / threads * threads);
+    a.ncap_pad = ffbs_ncap_pad((int)n_max, threads);
+    int rc;
     if (!a.messages) {
         const int64_t stride = (int64_t)K * n_max * (n_max + 1) / 2;
         size_t bytes = (size_t)stride * sizeof(Real) * (size_t)grid;
@@ -356,11 +326,30 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
         a.msg_scratch = c->d_msg_scratch.p;
         a.msg_scratch_stride = stride;
     }
+    rc = c->d_obsf.reserve((size_t)grid * n_max * K * sizeof(Real));
+    if (rc) return rc;
+    a.obsf_scratch = c->d_obsf.p;
     rc = c->d_queue.reserve(256);
     if (rc) return rc;
     CUDA_TRY(cudaMemsetAsync(c->d_queue.p, 0, sizeof(unsigned int), c->stream));
     a.queue = (unsigned int*)c->d_queue.p;
-    return launch_ffbs<Real>(c, a, threads, smem, grid);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->time_kernels) {
+        CUDA_TRY(cudaEventCreate(&e0));
+        CUDA_TRY(cudaEventCreate(&e1));
+        CUDA_TRY(cudaEventRecord(e0, c->stream));
+    }
+    L.grid = grid;
+    CUDA_TRY(ffbs_call<Real>(a, L, false));
+    if (c->time_kernels) {
+        CUDA_TRY(cudaEventRecord(e1, c->stream));
+        c->ffbs_events.emplace_back(e0, e1);
+    }
+    c->launches += 1;
+    c->last_grid = grid;
+    c->last_threads = threads;
+    c->last_smem = (int64_t)smem;
+    return SMJP_OK;
 }
 
 }  // namespace

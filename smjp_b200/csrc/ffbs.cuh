@@ -9,12 +9,15 @@
 //   smjp_ffbs tail                pkg/smjp_utils.py:319-330 path compaction (+ :338-348 endpoint)
 //   compute_evaluation_chain_metrics pkg/mcmc_utils.py:40-56
 //
-// Arithmetic: with tau = W[i+1] - W[j], H_vs = (tau/lambda_vs)^k_vs,
-// H_v = sum_s H_vs, D_v = sum_s k_vs H_vs (so A_v = D_v / tau):
-//   e_i(v,j)      = obs_i(v) * [Omega D_v / tau]^{not final} * exp(-Omega (H_v(tau) - H_v(tau_prev)))
+// Arithmetic: with tau = W[i+1] - W[j],
+//   E_vs = (1/tau) (tau/lambda_vs)^k_vs = 2^((k_vs - 1) log2 tau - k_vs log2 lambda_vs)     [= H_vs / tau]
+//   A_v = sum_s k_vs E_vs (hazard of leaving v),   H_v = tau sum_s E_vs (cumulative hazard)
+//   e_i(v,j)      = obs_i(v) * [Omega A_v]^{not final} * exp(-Omega (H_v(tau) - H_v(tau_prev)))
 //   alpha_i(v,j)  ~ e_i(v,j) (1 - 1/Omega) alpha_{i-1}(v,j)                      j < i  (thinned)
-//   alpha_i(v',i) ~ e_i(v',i) J_i(v'),  J_i(v') = sum_{v,j<i} alpha_{i-1}(v,j) k_vv' H_vv' / (Omega D_v)
-// The K*K cumulative hazards computed for (i, j) serve e_i(v,j) AND the jump sums J_{i+1}: B_i is
+//   alpha_i(v',i) ~ e_i(v',i) J_i(v'),  J_i(v') = sum_{v,j<i} alpha_{i-1}(v,j) A_vv' / (Omega A_v)
+// The Omega A_v of the emission cancels the 1/(Omega A_v) of the jump term, so the forward pass needs
+// no division at all: with g = obs_i(v) surv base, alpha~_i = g Omega A_v and the contribution to
+// J_{i+1}(s) is g k_vs E_vs.  The K*K powers computed for (i, j) serve e_i(v,j) AND J_{i+1}: B_i is
 // generated in-kernel and never stored.  State carried per live (v,j): the unnormalised message and
 // H_v(tau) -- both in shared memory, indexed so that consecutive threads hit consecutive banks.
 // Normalisation is deferred by one step (row i-1 is scaled and streamed to HBM while row i is being
@@ -40,6 +43,7 @@ struct FfbsArgs {
     const int64_t* msg_offs;
     void* msg_scratch;  // per-CTA message scratch when not exporting
     int64_t msg_scratch_stride;
+    void* obsf_scratch;  // per-CTA observation factors [ncap][K]
     double* logZ;
     int32_t* aug_idx;
     int32_t* path_v;
@@ -50,28 +54,30 @@ struct FfbsArgs {
     int32_t* status;
     const int32_t* order;  // optional chain processing order (longest first)
     unsigned int* queue;   // work counter, zeroed before launch
-    const double* model;   // device: shape[K*K], c2[K*K] (= k*log2(lambda)), emis[K*Kobs]
+    const double* model;   // device: shape[K*K], c2[K*K] (= k*log2(lambda)), emis[K*Kobs], scale[K*K]
     int Kobs;
     double omega, power, t_end;
     int ncap;      // max grid intervals any chain of this launch has (smem carve-up)
-    int ncap_pad;  // ncap rounded up to a multiple of blockDim.x
+    int ncap_pad;  // ncap+1 rounded up to a multiple of blockDim.x
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// dynamic shared memory bytes for (Real, K, Kobs, ncap, threads)
+__host__ __device__ inline int ffbs_ncap_pad(int ncap, int threads) {
+    return (ncap + 1 + threads - 1) / threads * threads;
+}
+
+// dynamic shared memory bytes for (Real, K, ncap, threads)
 template <typename Real>
-__host__ __device__ inline size_t ffbs_smem_bytes(int K, int Kobs, int ncap, int threads) {
-    int ncap_pad = (ncap + threads - 1) / threads * threads;
+__host__ __device__ inline size_t ffbs_smem_bytes(int K, int ncap, int threads) {
+    const int ncap_pad = ffbs_ncap_pad(ncap, threads);
     size_t b = 0;
-    b += align_up((size_t)(ncap + 1) * sizeof(double), 16);            // Wd
-    b += align_up((size_t)(threads / 32 + 1) * sizeof(double) * 2, 16); // scan scratch (double)
-    b += align_up((size_t)2 * (ncap + 1) * sizeof(int), 16);           // sojourn list
-    b += align_up((size_t)K * ncap * sizeof(Real), 16);                // obsf
-    b += align_up((size_t)K * ncap_pad * sizeof(Real), 16);            // st_a / wbuf
-    b += align_up((size_t)K * ncap_pad * sizeof(Real), 16);            // st_h
+    b += align_up((size_t)(ncap + 1) * sizeof(double), 16);                  // Wd
+    b += align_up((size_t)(threads / 32 + 1) * sizeof(double) * 2, 16);      // scan scratch (double)
+    b += align_up((size_t)K * ncap_pad * sizeof(Real), 16);                  // st_a / wbuf
+    b += align_up((size_t)K * ncap_pad * sizeof(Real), 16);                  // st_h / sojourn list
     b += align_up((size_t)2 * (threads / 32) * (K + 1) * sizeof(Real), 16);  // reduction scratch
-    b += align_up((size_t)(2 * K * K + K * Kobs) * sizeof(Real), 16);  // model
+    b += align_up((size_t)(3 * K * K) * sizeof(Real), 16);                   // model
     return b;
 }
 
@@ -80,8 +86,46 @@ __device__ __forceinline__ bool np_isclose(double a, double b) {
     return fabs(a - b) <= 1e-8 + 1e-5 * fabs(b);
 }
 
-template <typename Real, int K>
-__global__ void ffbs_kernel(const FfbsArgs a) {
+// ------------------------------------------------------------------------------------------------
+// 2^x per precision.  fp64: table of 2^(i/256) in shared memory + degree-4 polynomial on
+// |r| <= 1/512 (truncation 4e-17): 8 DP operations against ~20 of the library exp2 -- the FP64
+// pipe is what bounds the fp64 kernel.  fp32: one SFU op.
+// ------------------------------------------------------------------------------------------------
+template <typename Real>
+struct Exp2;
+
+template <>
+struct Exp2<double> {
+    const double* tab;
+    static constexpr int TAB = 256;
+    __device__ __forceinline__ double operator()(double x) const {
+        const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
+        const double xc = fmin(fmax(x, -1022.0), 1023.5);
+        const double t = fma(xc, 256.0, MAGIC);
+        const int n = __double2loint(t);
+        const double nf = t - MAGIC;
+        const double r = fma(nf, -1.0 / 256.0, xc);
+        double q = fma(r, 9.618129107628477e-03, 5.550410866482158e-02);  // ln2^4/24, ln2^3/6
+        q = fma(r, q, 2.402265069591007e-01);                             // ln2^2/2
+        q = fma(r, q, 6.931471805599453e-01);                             // ln2
+        const double tv = tab[n & 255];
+        double res = fma(tv, r * q, tv);
+        res = __longlong_as_double(__double_as_longlong(res) + ((long long)(n >> 8) << 52));
+        res = x < -1022.0 ? 0.0 : res;  // flush instead of denormal; also x = -inf
+        res = x > 1023.5 ? INFINITY : res;
+        return res;
+    }
+};
+
+template <>
+struct Exp2<float> {
+    const double* tab;
+    static constexpr int TAB = 0;
+    __device__ __forceinline__ float operator()(float x) const { return Math<float>::exp2(x); }
+};
+
+template <typename Real, int K, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) ffbs_kernel(const FfbsArgs a) {
     using M = Math<Real>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, B = blockDim.x, lane = tid & 31, wid = tid >> 5, NW = B >> 5;
@@ -90,37 +134,39 @@ __global__ void ffbs_kernel(const FfbsArgs a) {
     unsigned char* sp = smem_raw;
     double* Wd = (double*)sp;
     sp += align_up((size_t)(ncap + 1) * sizeof(double), 16);
-    double* scan_s = (double*)sp;  // [NW + 1] warp totals, [NW+1..] spare
+    double* scan_s = (double*)sp;  // [NW + 1] warp totals
     sp += align_up((size_t)(NW + 1) * sizeof(double) * 2, 16);
-    int* soj = (int*)sp;  // [2][ncap+1]: state, grid index of each sojourn found by the backward pass
-    sp += align_up((size_t)2 * (ncap + 1) * sizeof(int), 16);
-    Real* obsf = (Real*)sp;
-    sp += align_up((size_t)K * ncap * sizeof(Real), 16);
-    Real* st_a = (Real*)sp;
+    Real* st_a = (Real*)sp;  // forward: unnormalised message; backward: weight vector
     sp += align_up((size_t)K * ncap_pad * sizeof(Real), 16);
-    Real* st_h = (Real*)sp;
+    Real* st_h = (Real*)sp;  // forward: H_v(tau); backward: sojourn list (int pairs)
     sp += align_up((size_t)K * ncap_pad * sizeof(Real), 16);
     Real* red = (Real*)sp;
     sp += align_up((size_t)2 * NW * (K + 1) * sizeof(Real), 16);
-    Real* sk = (Real*)sp;      // shape k_vs
-    Real* sc2 = sk + K * K;    // k_vs * log2(lambda_vs)
-    Real* sem = sc2 + K * K;   // emis[v*Kobs + y]
+    Real* sk = (Real*)sp;       // k_vs
+    Real* skm1 = sk + K * K;    // k_vs - 1
+    Real* sc2 = skm1 + K * K;   // k_vs * log2(lambda_vs)
+    int* soj = (int*)st_h;      // [2][ncap+1]: state, grid index of each sojourn (backward pass)
 
     __shared__ int s_chain;
     __shared__ int s_sel;
     __shared__ int s_flag;
+    __shared__ double s_tab[Exp2<Real>::TAB ? Exp2<Real>::TAB : 1];
 
     for (int t = tid; t < K * K; t += B) {
         sk[t] = (Real)a.model[t];
+        skm1[t] = (Real)(a.model[t] - 1.0);
         sc2[t] = (Real)a.model[K * K + t];
     }
-    for (int t = tid; t < K * Kobs; t += B) sem[t] = (Real)a.model[2 * K * K + t];
+    for (int t = tid; t < Exp2<Real>::TAB; t += B) s_tab[t] = ::exp2((double)t / 256.0);
+    Exp2<Real> ex2;
+    ex2.tab = s_tab;
+    const double* emis = a.model + 2 * K * K;
 
     const Real thin = (Real)(1.0 - 1.0 / a.omega);
-    const Real inv_omega = (Real)(1.0 / a.omega);
     const Real omega_r = (Real)a.omega;
     const Real om_l2e = (Real)(a.omega * SMJP_LOG2E);
     const Real power = (Real)a.power;
+    Real* obsf = (Real*)a.obsf_scratch + (int64_t)blockIdx.x * ncap * K;
 
     while (true) {
         __syncthreads();
@@ -169,11 +215,12 @@ __global__ void ffbs_kernel(const FfbsArgs a) {
                 for (int d = lo; d < D && ot[d] <= wn; ++d, ++cnt) {
                     const int y = oy[d];
 #pragma unroll
-                    for (int v = 0; v < K; ++v) f[v] += sem[v * Kobs + y];
+                    for (int v = 0; v < K; ++v) f[v] += (Real)emis[v * Kobs + y];
                 }
 #pragma unroll
                 for (int v = 0; v < K; ++v)
-                    obsf[v * ncap + i] = (cnt == 0 || power == (Real)0) ? (Real)1 : (power == (Real)1 ? f[v] : M::pow(f[v], power));
+                    obsf[i * K + v] = (cnt == 0 || power == (Real)0) ? (Real)1
+                                      : (power == (Real)1 ? f[v] : M::pow(f[v], power));
             }
         }
         __syncthreads();
@@ -190,54 +237,63 @@ __global__ void ffbs_kernel(const FfbsArgs a) {
 
         // =========================== forward ===========================
         Real invZ_prev = (Real)1;
-        Real J[K];
+        Real J[K], of[K];
 #pragma unroll
-        for (int v = 0; v < K; ++v) J[v] = (Real)(1.0 / K);  // uniform prior on (v,0): smjp_utils.py:286-289
+        for (int v = 0; v < K; ++v) {
+            J[v] = (Real)(1.0 / K);  // uniform prior on (v,0): smjp_utils.py:286-289
+            of[v] = obsf[v];
+        }
         bool degenerate = false;
         for (int i = 0; i < n; ++i) {
             const double wn = Wd[i + 1];
             const bool nonfinal = !np_isclose(a.t_end, wn);  // smjp_utils.py:544
-            Real of[K];
+            Real ofn[K];  // next step's observation factors, fetched under this step's arithmetic
 #pragma unroll
-            for (int v = 0; v < K; ++v) of[v] = obsf[v * ncap + i];
+            for (int v = 0; v < K; ++v) ofn[v] = (i + 1 < n) ? obsf[(i + 1) * K + v] : (Real)1;
             Real Zp = 0;
             Real Jp[K];
 #pragma unroll
             for (int v = 0; v < K; ++v) Jp[v] = 0;
             Real* row_prev = msg + (int64_t)K * (i - 1) * i / 2;  // row i-1: i entries per state
-            for (int j = tid; j <= i; j += B) {
-                const Real tau = (Real)(wn - Wd[j]);
-                const Real L2 = M::log2(tau);
-                const Real inv_tau = M::rcp(tau);
+            if (wid * 32 <= i) {
+                for (int j = tid; j <= i; j += B) {
+                    const Real tau = (Real)(wn - Wd[j]);
+                    const Real L2 = M::log2(tau);
 #pragma unroll
-                for (int v = 0; v < K; ++v) {
-                    Real base, hprev;
-                    if (j < i) {
-                        const Real ap = st_a[v * ncap_pad + j] * invZ_prev;
-                        row_prev[(int64_t)v * i + j] = ap;
-                        base = ap * thin;
-                        hprev = st_h[v * ncap_pad + j];
-                    } else {
-                        base = J[v];
-                        hprev = 0;
+                    for (int v = 0; v < K; ++v) {
+                        Real base, hprev;
+                        if (j < i) {
+                            const Real ap = st_a[v * ncap_pad + j] * invZ_prev;
+                            row_prev[(int64_t)v * i + j] = ap;
+                            base = ap * thin;
+                            hprev = st_h[v * ncap_pad + j];
+                        } else {
+                            base = J[v];
+                            hprev = 0;
+                        }
+                        Real kE[K];
+                        Real esum = 0, dsum = 0;
+#pragma unroll
+                        for (int s = 0; s < K; ++s) {
+                            const Real E = ex2(skm1[v * K + s] * L2 - sc2[v * K + s]);
+                            esum += E;
+                            kE[s] = sk[v * K + s] * E;
+                            dsum += kE[s];
+                        }
+                        const Real hsum = tau * esum;
+                        const Real g = of[v] * ex2(-om_l2e * (hsum - hprev)) * base;
+                        Real an;
+                        if (nonfinal) {
+                            an = g * omega_r * dsum;
+#pragma unroll
+                            for (int s = 0; s < K; ++s) Jp[s] += g * kE[s];
+                        } else {
+                            an = g;
+                        }
+                        st_a[v * ncap_pad + j] = an;
+                        st_h[v * ncap_pad + j] = hsum;
+                        Zp += an;
                     }
-                    Real Hs[K];
-                    Real hsum = 0, dsum = 0;
-#pragma unroll
-                    for (int s = 0; s < K; ++s) {
-                        Hs[s] = M::exp2(sk[v * K + s] * L2 - sc2[v * K + s]);
-                        hsum += Hs[s];
-                        dsum += sk[v * K + s] * Hs[s];
-                    }
-                    const Real surv = M::exp2(-om_l2e * (hsum - hprev));
-                    const Real front = nonfinal ? omega_r * dsum * inv_tau : (Real)1;
-                    const Real an = of[v] * front * surv * base;
-                    st_a[v * ncap_pad + j] = an;
-                    st_h[v * ncap_pad + j] = hsum;
-                    Zp += an;
-                    const Real g = dsum > (Real)0 ? an * inv_omega * M::rcp(dsum) : (Real)0;
-#pragma unroll
-                    for (int s = 0; s < K; ++s) Jp[s] += g * sk[v * K + s] * Hs[s];
                 }
             }
             // block reduction of (Z, J[0..K)) -- double-buffered scratch, one barrier per step
@@ -265,7 +321,10 @@ __global__ void ffbs_kernel(const FfbsArgs a) {
             }
             invZ_prev = (Real)1 / Z;
 #pragma unroll
-            for (int v = 0; v < K; ++v) J[v] *= invZ_prev;
+            for (int v = 0; v < K; ++v) {
+                J[v] *= invZ_prev;
+                of[v] = ofn[v];
+            }
             if (tid == 0 && a.logZ) a.logZ[w0 + i] = log((double)Z);
         }
         if (degenerate) {
@@ -275,14 +334,11 @@ __global__ void ffbs_kernel(const FfbsArgs a) {
             }
             continue;
         }
-        {   // last row: scale, store, and keep the normalised copy in st_a for the first draw
+        {   // last row: scale and store
             Real* row_last = msg + (int64_t)K * (n - 1) * n / 2;
             for (int j = tid; j < n; j += B) {
 #pragma unroll
-                for (int v = 0; v < K; ++v) {
-                    const Real ap = st_a[v * ncap_pad + j] * invZ_prev;
-                    row_last[(int64_t)v * n + j] = ap;
-                }
+                for (int v = 0; v < K; ++v) row_last[(int64_t)v * n + j] = st_a[v * ncap_pad + j] * invZ_prev;
             }
         }
         __syncthreads();
@@ -295,7 +351,7 @@ __global__ void ffbs_kernel(const FfbsArgs a) {
             const Real* row = msg + (int64_t)K * cur * (cur + 1) / 2;
             if (vplus < 0) {  // a_{n-1} ~ alpha_{n-1}  (fast_hmm.py:124-125)
                 for (int t = tid; t < K * len; t += B) wbuf[t] = row[t];
-            } else {  // jump at W[cur+1] into vplus: w = alpha_cur(v,j) A_{v,vplus}/B_v  (fast_hmm.py:153-171)
+            } else {  // jump at W[cur+1] into vplus: w = alpha_cur(v,j) A_{v,vplus}/A_v  (fast_hmm.py:153-171)
                 const double wn = Wd[cur + 1];
                 for (int j = tid; j < len; j += B) {
                     const Real L2 = M::log2((Real)(wn - Wd[j]));
@@ -304,9 +360,9 @@ __global__ void ffbs_kernel(const FfbsArgs a) {
                         Real dsum = 0, hto = 0;
 #pragma unroll
                         for (int s = 0; s < K; ++s) {
-                            const Real h = M::exp2(sk[v * K + s] * L2 - sc2[v * K + s]);
-                            dsum += sk[v * K + s] * h;
-                            if (s == vplus) hto = sk[v * K + s] * h;
+                            const Real kE = sk[v * K + s] * ex2(skm1[v * K + s] * L2 - sc2[v * K + s]);
+                            dsum += kE;
+                            hto = (s == vplus) ? kE : hto;
                         }
                         const Real r = dsum > (Real)0 ? hto * M::rcp(dsum) : (Real)0;
                         wbuf[v * len + j] = row[(int64_t)v * len + j] * r;
@@ -339,8 +395,7 @@ __global__ void ffbs_kernel(const FfbsArgs a) {
                                         : philox_u01(a.seed, TAG_BACKWARD, (uint64_t)cur, 0u, a.sweep,
                                                      a.chain_base + (uint32_t)c);
             const double target = u * total;
-            // owner: excl <= target < incl.  If rounding pushed target to >= total, the last
-            // thread with mass takes it.
+            // owner: excl <= target < incl (the intervals partition [0,total) exactly)
             const bool has = incl > excl;
             if (has && target >= excl && target < incl) {
                 double acc = excl;
