@@ -100,7 +100,8 @@ struct smjp_ctx {
     std::vector<double> h_model;
     DevBuf d_model;
     // workspaces
-    DevBuf d_queue, d_msg_scratch, d_obsf;
+    DevBuf d_queue, d_msg_scratch, d_obsf, d_order;
+    bool lpt_order = true;
     int last_grid = 0, last_threads = 0;
     int64_t last_smem = 0;
     DevBuf d_in, d_out;  // staging for the host API
@@ -159,6 +160,7 @@ void smjp_ctx_destroy(smjp_ctx_t* c) {
     c->d_queue.release();
     c->d_msg_scratch.release();
     c->d_obsf.release();
+    c->d_order.release();
     c->d_in.release();
     c->d_out.release();
     c->h_in.release();
@@ -212,6 +214,10 @@ int smjp_ctx_set_option(smjp_ctx_t* c, const char* key, int64_t value) {
         if (value != 0 && (value < 32 || value > 512 || value % 32))
             return fail(SMJP_E_INVALID, "ffbs_threads must be 0 (auto) or a multiple of 32 in [32,512]");
         c->ffbs_threads = (int)value;
+        return SMJP_OK;
+    }
+    if (!strcmp(key, "lpt_order")) {
+        c->lpt_order = value != 0;
         return SMJP_OK;
     }
     if (!strcmp(key, "time_kernels")) {
@@ -272,7 +278,8 @@ namespace {
 
 template <typename Real>
 cudaError_t ffbs_call(const FfbsArgs& a, FfbsLaunch& L, bool query) {
-    return sizeof(Real) == 8 ? ffbs_dispatch_f64(a, L, query) : ffbs_dispatch_f32(a, L, query);
+    if (sizeof(Real) == 8) return L.K <= 5 ? ffbs_dispatch_f64_lo(a, L, query) : ffbs_dispatch_f64_hi(a, L, query);
+    return L.K <= 5 ? ffbs_dispatch_f32_lo(a, L, query) : ffbs_dispatch_f32_hi(a, L, query);
 }
 
 template <typename Real>
@@ -288,6 +295,7 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
         if (n_max <= 96) threads = 64;
         if (n_max <= 32) threads = 32;
     }
+    threads = ffbs_round_threads(threads);
     size_t smem = ffbs_smem_bytes<Real>(K, (int)n_max, threads);
     if (smem > c->smem_optin)
         return fail(SMJP_E_UNSUPPORTED,
@@ -305,7 +313,7 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
     int grid = c->num_sms * per_sm;
     if (grid > a.C) grid = a.C;
     a.ncap = (int)n_max;
-    a.ncap_pad = ffbs_ncap_pad((int)n_max, threads);
+    a.nslot = ffbs_nslot((int)n_max, threads);
     int rc;
     if (!a.messages) {
         const int64_t stride = (int64_t)K * n_max * (n_max + 1) / 2;
@@ -333,6 +341,14 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
     if (rc) return rc;
     CUDA_TRY(cudaMemsetAsync(c->d_queue.p, 0, sizeof(unsigned int), c->stream));
     a.queue = (unsigned int*)c->d_queue.p;
+    if (a.C > grid && c->lpt_order) {  // more chains than resident CTAs: start the long grids first
+        rc = c->d_order.reserve((size_t)a.C * sizeof(int32_t));
+        if (rc) return rc;
+        chain_order_kernel<<<1, 1024, 0, c->stream>>>(a.C, a.w_offs, (int)n_max, (int32_t*)c->d_order.p);
+        CUDA_TRY(cudaGetLastError());
+        c->launches += 1;
+        a.order = (const int32_t*)c->d_order.p;
+    }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c->time_kernels) {
         CUDA_TRY(cudaEventCreate(&e0));

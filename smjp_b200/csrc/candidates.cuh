@@ -304,4 +304,39 @@ __global__ void obs_sim_kernel(const ObsSimArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Longest-first processing order (the persistent CTAs pull chains from a queue; work per chain is
+// ~n^2, so starting the long grids first trims the tail of the launch).  Counting sort by n into
+// 1024 bins, single CTA.
+// ------------------------------------------------------------------------------------------------
+__global__ void chain_order_kernel(int C, const int64_t* w_offs, int n_max, int32_t* order) {
+    __shared__ int hist[1024];
+    __shared__ int start[1024];
+    const int tid = threadIdx.x;
+    hist[tid] = 0;
+    __syncthreads();
+    const long long denom = n_max > 0 ? n_max : 1;
+    for (int c = tid; c < C; c += 1024) {
+        const long long n = w_offs[c + 1] - w_offs[c] - 1;
+        int b = (int)((n < 0 ? 0 : n) * 1023 / denom);
+        b = b > 1023 ? 1023 : b;
+        atomicAdd(&hist[1023 - b], 1);  // bin 0 = longest
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int b = 0; b < 1024; ++b) {
+            start[b] = acc;
+            acc += hist[b];
+        }
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += 1024) {
+        const long long n = w_offs[c + 1] - w_offs[c] - 1;
+        int b = (int)((n < 0 ? 0 : n) * 1023 / denom);
+        b = b > 1023 ? 1023 : b;
+        order[atomicAdd(&start[1023 - b], 1)] = c;
+    }
+}
+
 }  // namespace smjp

@@ -24,6 +24,8 @@
 // computed), so each grid step costs exactly one __syncthreads().
 #pragma once
 #include "../../include/smjp_b200.h"
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace smjp {
@@ -57,27 +59,27 @@ struct FfbsArgs {
     const double* model;   // device: shape[K*K], c2[K*K] (= k*log2(lambda)), emis[K*Kobs], scale[K*K]
     int Kobs;
     double omega, power, t_end;
-    int ncap;      // max grid intervals any chain of this launch has (smem carve-up)
-    int ncap_pad;  // ncap+1 rounded up to a multiple of blockDim.x
+    int ncap;   // max grid intervals any chain of this launch has (smem carve-up)
+    int nslot;  // grid slots per thread: ceil((ncap + 1) / blockDim.x)
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-__host__ __device__ inline int ffbs_ncap_pad(int ncap, int threads) {
-    return (ncap + 1 + threads - 1) / threads * threads;
-}
+// grid slots per thread: ceil((ncap + 1) / threads)
+__host__ __device__ inline int ffbs_nslot(int ncap, int threads) { return (ncap + threads) / threads; }
 
 // dynamic shared memory bytes for (Real, K, ncap, threads)
 template <typename Real>
 __host__ __device__ inline size_t ffbs_smem_bytes(int K, int ncap, int threads) {
-    const int ncap_pad = ffbs_ncap_pad(ncap, threads);
+    const size_t state = (size_t)ffbs_nslot(ncap, threads) * K * threads;
     size_t b = 0;
     b += align_up((size_t)(ncap + 1) * sizeof(double), 16);                  // Wd
-    b += align_up((size_t)(threads / 32 + 1) * sizeof(double) * 2, 16);      // scan scratch (double)
-    b += align_up((size_t)K * ncap_pad * sizeof(Real), 16);                  // st_a / wbuf
-    b += align_up((size_t)K * ncap_pad * sizeof(Real), 16);                  // st_h / sojourn list
+    b += align_up((size_t)threads * sizeof(double), 16);                     // buffered backward uniforms
+    b += align_up((size_t)(threads / 32 + 1) * sizeof(double), 16);          // scan scratch
+    b += align_up(state * sizeof(Real), 16);                                 // st_a / wbuf
+    b += align_up(state * sizeof(Real), 16);                                 // st_h / sojourn list
     b += align_up((size_t)2 * (threads / 32) * (K + 1) * sizeof(Real), 16);  // reduction scratch
-    b += align_up((size_t)(3 * K * K) * sizeof(Real), 16);                   // model
+    b += align_up((size_t)(4 * K * K) * sizeof(Real), 16);                   // model
     return b;
 }
 
@@ -124,28 +126,37 @@ struct Exp2<float> {
     __device__ __forceinline__ float operator()(float x) const { return Math<float>::exp2(x); }
 };
 
-template <typename Real, int K, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) ffbs_kernel(const FfbsArgs a) {
+template <typename Real> struct ScanAcc { typedef double type; };
+template <> struct ScanAcc<float> { typedef float type; };
+
+template <typename Real, int K, int B, int MINB>
+__global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
     using M = Math<Real>;
+    using Acc = typename ScanAcc<Real>::type;
+    constexpr int NW = B / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, B = blockDim.x, lane = tid & 31, wid = tid >> 5, NW = B >> 5;
-    const int ncap = a.ncap, ncap_pad = a.ncap_pad, Kobs = a.Kobs;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int ncap = a.ncap, Kobs = a.Kobs;
+    const size_t state = (size_t)a.nslot * K * B;
 
     unsigned char* sp = smem_raw;
     double* Wd = (double*)sp;
     sp += align_up((size_t)(ncap + 1) * sizeof(double), 16);
-    double* scan_s = (double*)sp;  // [NW + 1] warp totals
-    sp += align_up((size_t)(NW + 1) * sizeof(double) * 2, 16);
-    Real* st_a = (Real*)sp;  // forward: unnormalised message; backward: weight vector
-    sp += align_up((size_t)K * ncap_pad * sizeof(Real), 16);
-    Real* st_h = (Real*)sp;  // forward: H_v(tau); backward: sojourn list (int pairs)
-    sp += align_up((size_t)K * ncap_pad * sizeof(Real), 16);
+    double* ubuf = (double*)sp;  // backward uniforms of steps (u_hi - B, u_hi]
+    sp += align_up((size_t)B * sizeof(double), 16);
+    Acc* scan_s = (Acc*)sp;  // [NW + 1] warp totals
+    sp += align_up((size_t)(NW + 1) * sizeof(double), 16);
+    Real* st_a = (Real*)sp;  // forward: unnormalised message [slot][v][B]; backward: weights [K][len]
+    sp += align_up(state * sizeof(Real), 16);
+    Real* st_h = (Real*)sp;  // forward: H_v(tau) [slot][v][B]; backward: sojourn list (int pairs)
+    sp += align_up(state * sizeof(Real), 16);
     Real* red = (Real*)sp;
     sp += align_up((size_t)2 * NW * (K + 1) * sizeof(Real), 16);
-    Real* sk = (Real*)sp;       // k_vs
-    Real* skm1 = sk + K * K;    // k_vs - 1
-    Real* sc2 = skm1 + K * K;   // k_vs * log2(lambda_vs)
-    int* soj = (int*)st_h;      // [2][ncap+1]: state, grid index of each sojourn (backward pass)
+    Real* srk = (Real*)sp;       // 1 / k_vs
+    Real* skm1 = srk + K * K;    // k_vs - 1
+    Real* sc2p = skm1 + K * K;   // k_vs log2(lambda_vs) - log2(k_vs): 2^((k-1) L - c2p) = k E = A_vs
+    Real* sk = sc2p + K * K;     // k_vs
+    int* soj = (int*)st_h;       // [2][ncap+1]: state, grid index of each sojourn (backward pass)
 
     __shared__ int s_chain;
     __shared__ int s_sel;
@@ -153,9 +164,11 @@ __global__ void __launch_bounds__(MAXT, MINB) ffbs_kernel(const FfbsArgs a) {
     __shared__ double s_tab[Exp2<Real>::TAB ? Exp2<Real>::TAB : 1];
 
     for (int t = tid; t < K * K; t += B) {
-        sk[t] = (Real)a.model[t];
-        skm1[t] = (Real)(a.model[t] - 1.0);
-        sc2[t] = (Real)a.model[K * K + t];
+        const double k = a.model[t];
+        sk[t] = (Real)k;
+        srk[t] = (Real)(1.0 / k);
+        skm1[t] = (Real)(k - 1.0);
+        sc2p[t] = (Real)(a.model[K * K + t] - ::log2(k));
     }
     for (int t = tid; t < Exp2<Real>::TAB; t += B) s_tab[t] = ::exp2((double)t / 256.0);
     Exp2<Real> ex2;
@@ -254,48 +267,54 @@ __global__ void __launch_bounds__(MAXT, MINB) ffbs_kernel(const FfbsArgs a) {
             Real Jp[K];
 #pragma unroll
             for (int v = 0; v < K; ++v) Jp[v] = 0;
-            Real* row_prev = msg + (int64_t)K * (i - 1) * i / 2;  // row i-1: i entries per state
-            if (wid * 32 <= i) {
-                for (int j = tid; j <= i; j += B) {
-                    const Real tau = (Real)(wn - Wd[j]);
-                    const Real L2 = M::log2(tau);
+            const int mi = i / B, ti = i - mi * B;  // slot and owner thread of the new state (v, W[i])
+            Real* rowp = msg + (int64_t)K * (i - 1) * i / 2 + tid;  // row i-1: i entries per state
+            Real* pa = st_a + tid;
+            Real* ph = st_h + tid;
+            const double* pw = Wd + tid;
+            // one grid point (i, j): all K*K hazards, emission, thinned update, jump contributions
+            auto pair = [&](auto partial_tag, bool diag) {
+                constexpr bool PARTIAL = decltype(partial_tag)::value;
+                const Real tau = (Real)(wn - *pw);
+                const Real L2 = M::log2(tau);
 #pragma unroll
-                    for (int v = 0; v < K; ++v) {
-                        Real base, hprev;
-                        if (j < i) {
-                            const Real ap = st_a[v * ncap_pad + j] * invZ_prev;
-                            row_prev[(int64_t)v * i + j] = ap;
-                            base = ap * thin;
-                            hprev = st_h[v * ncap_pad + j];
-                        } else {
-                            base = J[v];
-                            hprev = 0;
-                        }
-                        Real kE[K];
-                        Real esum = 0, dsum = 0;
-#pragma unroll
-                        for (int s = 0; s < K; ++s) {
-                            const Real E = ex2(skm1[v * K + s] * L2 - sc2[v * K + s]);
-                            esum += E;
-                            kE[s] = sk[v * K + s] * E;
-                            dsum += kE[s];
-                        }
-                        const Real hsum = tau * esum;
-                        const Real g = of[v] * ex2(-om_l2e * (hsum - hprev)) * base;
-                        Real an;
-                        if (nonfinal) {
-                            an = g * omega_r * dsum;
-#pragma unroll
-                            for (int s = 0; s < K; ++s) Jp[s] += g * kE[s];
-                        } else {
-                            an = g;
-                        }
-                        st_a[v * ncap_pad + j] = an;
-                        st_h[v * ncap_pad + j] = hsum;
-                        Zp += an;
+                for (int v = 0; v < K; ++v) {
+                    const Real ap = pa[v * B] * invZ_prev;
+                    Real hprev = ph[v * B];
+                    Real base = ap * thin;
+                    if (PARTIAL) {
+                        if (!diag) rowp[(int64_t)v * i] = ap;
+                        base = diag ? J[v] : base;
+                        hprev = diag ? (Real)0 : hprev;
+                    } else {
+                        rowp[(int64_t)v * i] = ap;
                     }
+                    Real kE[K];
+                    Real esum = 0, dsum = 0;
+#pragma unroll
+                    for (int s = 0; s < K; ++s) {
+                        kE[s] = ex2(skm1[v * K + s] * L2 - sc2p[v * K + s]);  // A_vs(tau)
+                        esum += kE[s] * srk[v * K + s];
+                        dsum += kE[s];
+                    }
+                    const Real hsum = tau * esum;  // H_v(tau)
+                    const Real g = of[v] * ex2(-om_l2e * (hsum - hprev)) * base;
+#pragma unroll
+                    for (int s = 0; s < K; ++s) Jp[s] += g * kE[s];
+                    const Real an = g * (nonfinal ? omega_r * dsum : (Real)1);
+                    pa[v * B] = an;
+                    ph[v * B] = hsum;
+                    Zp += an;
                 }
+            };
+            for (int m = 0; m < mi; ++m) {  // full slots: every thread owns a live j < i
+                pair(std::false_type(), false);
+                pa += K * B;
+                ph += K * B;
+                pw += B;
+                rowp += B;
             }
+            if (tid <= ti) pair(std::true_type(), tid == ti);
             // block reduction of (Z, J[0..K)) -- double-buffered scratch, one barrier per step
             Real* rb = red + (i & 1) * NW * (K + 1);
             Zp = warp_sum(Zp);
@@ -310,6 +329,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ffbs_kernel(const FfbsArgs a) {
             Real Z = 0;
 #pragma unroll
             for (int v = 0; v < K; ++v) J[v] = 0;
+#pragma unroll
             for (int w = 0; w < NW; ++w) {
                 Z += rb[w * (K + 1)];
 #pragma unroll
@@ -325,7 +345,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ffbs_kernel(const FfbsArgs a) {
                 J[v] *= invZ_prev;
                 of[v] = ofn[v];
             }
-            if (tid == 0 && a.logZ) a.logZ[w0 + i] = log((double)Z);
+            if (a.logZ && tid == 0) a.logZ[w0 + i] = log((double)Z);
         }
         if (degenerate) {
             if (tid == 0) {
@@ -337,18 +357,25 @@ __global__ void __launch_bounds__(MAXT, MINB) ffbs_kernel(const FfbsArgs a) {
         {   // last row: scale and store
             Real* row_last = msg + (int64_t)K * (n - 1) * n / 2;
             for (int j = tid; j < n; j += B) {
+                const Real* p = st_a + (size_t)(j / B) * K * B + tid;
 #pragma unroll
-                for (int v = 0; v < K; ++v) row_last[(int64_t)v * n + j] = st_a[v * ncap_pad + j] * invZ_prev;
+                for (int v = 0; v < K; ++v) row_last[(int64_t)v * n + j] = p[v * B] * invZ_prev;
             }
         }
         __syncthreads();
 
         // =========================== backward ===========================
         Real* wbuf = st_a;  // [K][len] contiguous: the reference's state-major order a = v*len + j
-        int cur = n - 1, vplus = -1, cnt = 0;
+        int cur = n - 1, vplus = -1, cnt = 0, u_hi = -1;
         while (true) {
             const int len = cur + 1;
             const Real* row = msg + (int64_t)K * cur * (cur + 1) / 2;
+            if (!a.uniforms && (u_hi < 0 || cur <= u_hi - B)) {  // refill B uniforms: steps cur, cur-1, ...
+                if (cur - tid >= 0)
+                    ubuf[tid] = philox_u01(a.seed, TAG_BACKWARD, (uint64_t)(cur - tid), 0u, a.sweep,
+                                           a.chain_base + (uint32_t)c);
+                u_hi = cur;
+            }
             if (vplus < 0) {  // a_{n-1} ~ alpha_{n-1}  (fast_hmm.py:124-125)
                 for (int t = tid; t < K * len; t += B) wbuf[t] = row[t];
             } else {  // jump at W[cur+1] into vplus: w = alpha_cur(v,j) A_{v,vplus}/A_v  (fast_hmm.py:153-171)
@@ -360,7 +387,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ffbs_kernel(const FfbsArgs a) {
                         Real dsum = 0, hto = 0;
 #pragma unroll
                         for (int s = 0; s < K; ++s) {
-                            const Real kE = sk[v * K + s] * ex2(skm1[v * K + s] * L2 - sc2[v * K + s]);
+                            const Real kE = ex2(skm1[v * K + s] * L2 - sc2p[v * K + s]);
                             dsum += kE;
                             hto = (s == vplus) ? kE : hto;
                         }
@@ -374,35 +401,34 @@ __global__ void __launch_bounds__(MAXT, MINB) ffbs_kernel(const FfbsArgs a) {
             const int L = K * len;
             const int q = (L + B - 1) / B;
             const int beg = min(tid * q, L), end = min(beg + q, L);
-            double loc = 0;
-            for (int t = beg; t < end; ++t) loc += (double)wbuf[t];
-            double incl = warp_inclusive_scan(loc, lane);
+            Acc loc = 0;
+            for (int t = beg; t < end; ++t) loc += (Acc)wbuf[t];
+            Acc incl = warp_inclusive_scan(loc, lane);
             if (lane == 31) scan_s[wid + 1] = incl;
-            if (tid == 0) scan_s[0] = 0.0;
+            if (tid == 0) scan_s[0] = 0;
             __syncthreads();
-            double off = 0;
+            Acc off = 0;
             for (int w = 1; w <= wid; ++w) off += scan_s[w];
             incl += off;
-            double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            Acc excl = __shfl_up_sync(0xffffffffu, incl, 1);
             if (lane == 0) excl = off;
-            double total = 0;
+            Acc total = 0;
+#pragma unroll
             for (int w = 1; w <= NW; ++w) total += scan_s[w];
-            if (!(total > 0.0) || !(total < (double)INFINITY)) {
+            if (!(total > (Acc)0) || !(total < (Acc)INFINITY)) {
                 degenerate = true;
                 break;
             }
-            const double u = a.uniforms ? a.uniforms[w0 + cur]
-                                        : philox_u01(a.seed, TAG_BACKWARD, (uint64_t)cur, 0u, a.sweep,
-                                                     a.chain_base + (uint32_t)c);
-            const double target = u * total;
+            const double u = a.uniforms ? a.uniforms[w0 + cur] : ubuf[u_hi - cur];
+            const Acc target = (Acc)u * total;
             // owner: excl <= target < incl (the intervals partition [0,total) exactly)
             const bool has = incl > excl;
             if (has && target >= excl && target < incl) {
-                double acc = excl;
+                Acc acc = excl;
                 int sel = -1, lastpos = beg;
                 for (int t = beg; t < end; ++t) {
-                    const double wv = (double)wbuf[t];
-                    if (wv > 0.0) lastpos = t;
+                    const Acc wv = (Acc)wbuf[t];
+                    if (wv > (Acc)0) lastpos = t;
                     acc += wv;
                     if (acc > target) { sel = t; break; }
                 }
@@ -413,7 +439,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ffbs_kernel(const FfbsArgs a) {
             if (target >= total) {  // block-uniform condition
                 if (tid + 1 == s_flag) {
                     int lastpos = beg;
-                    for (int t = beg; t < end; ++t) if ((double)wbuf[t] > 0.0) lastpos = t;
+                    for (int t = beg; t < end; ++t) if ((Acc)wbuf[t] > (Acc)0) lastpos = t;
                     s_sel = lastpos;
                 }
                 __syncthreads();

@@ -13,40 +13,61 @@ struct FfbsLaunch {
     cudaStream_t stream;
 };
 
-#define SMJP_FOR_EACH_K(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10)
-
-template <typename Real, int K, int MAXT, int MINB>
+template <typename Real, int K, int B, int MINB>
 cudaError_t ffbs_do(const FfbsArgs& a, FfbsLaunch& L, bool query) {
-    auto kern = ffbs_kernel<Real, K, MAXT, MINB>;
+    auto kern = ffbs_kernel<Real, K, B, MINB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
     if (e != cudaSuccess) return e;
-    if (query) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&L.grid, kern, L.threads, L.smem);
-    kern<<<L.grid, L.threads, L.smem, L.stream>>>(a);
+    if (query) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&L.grid, kern, B, L.smem);
+    kern<<<L.grid, B, L.smem, L.stream>>>(a);
     return cudaGetLastError();
 }
+
+// block sizes the kernel is instantiated for
+inline int ffbs_round_threads(int t) { return t <= 32 ? 32 : t <= 64 ? 64 : t <= 128 ? 128 : t <= 256 ? 256 : 512; }
 
 template <typename Real, int K>
 cudaError_t ffbs_pick(const FfbsArgs& a, FfbsLaunch& L, bool query) {
     // resident CTAs per SM the register budget is tuned for: fp32 needs about half the registers of
     // fp64, K >= 6 about twice those of K <= 5 (K*K hazards per grid point are kept in flight)
-    constexpr int S = (sizeof(Real) == 8 ? 1 : 2);
-    constexpr int D = (K <= 5 ? 2 : 1);
-    if (L.threads <= 128) return ffbs_do<Real, K, 128, 2 * S * D>(a, L, query);
-    if (L.threads <= 256) return ffbs_do<Real, K, 256, S * D>(a, L, query);
-    return ffbs_do<Real, K, 512, (S * D) / 2 < 1 ? 1 : (S * D) / 2>(a, L, query);
-}
-
-template <typename Real>
-cudaError_t ffbs_dispatch(const FfbsArgs& a, FfbsLaunch& L, bool query) {
-    switch (L.K) {
-#define X(k) case k: return ffbs_pick<Real, k>(a, L, query);
-        SMJP_FOR_EACH_K(X)
-#undef X
+    constexpr int S = (sizeof(Real) == 8 ? 1 : 2) * (K <= 5 ? 2 : 1);  // 1, 2 or 4
+    switch (L.threads) {
+        case 32: return ffbs_do<Real, K, 32, 8 * S>(a, L, query);
+        case 64: return ffbs_do<Real, K, 64, 4 * S>(a, L, query);
+        case 128: return ffbs_do<Real, K, 128, 2 * S>(a, L, query);
+        case 256: return ffbs_do<Real, K, 256, S>(a, L, query);
+        case 512: return ffbs_do<Real, K, 512, (S + 1) / 2>(a, L, query);
     }
     return cudaErrorInvalidValue;
 }
 
-cudaError_t ffbs_dispatch_f64(const FfbsArgs& a, FfbsLaunch& L, bool query);
-cudaError_t ffbs_dispatch_f32(const FfbsArgs& a, FfbsLaunch& L, bool query);
+// K is split over two translation units per precision (compile time): lo = 2..5, hi = 6..10
+template <typename Real>
+cudaError_t ffbs_dispatch_lo(const FfbsArgs& a, FfbsLaunch& L, bool query) {
+    switch (L.K) {
+        case 2: return ffbs_pick<Real, 2>(a, L, query);
+        case 3: return ffbs_pick<Real, 3>(a, L, query);
+        case 4: return ffbs_pick<Real, 4>(a, L, query);
+        case 5: return ffbs_pick<Real, 5>(a, L, query);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <typename Real>
+cudaError_t ffbs_dispatch_hi(const FfbsArgs& a, FfbsLaunch& L, bool query) {
+    switch (L.K) {
+        case 6: return ffbs_pick<Real, 6>(a, L, query);
+        case 7: return ffbs_pick<Real, 7>(a, L, query);
+        case 8: return ffbs_pick<Real, 8>(a, L, query);
+        case 9: return ffbs_pick<Real, 9>(a, L, query);
+        case 10: return ffbs_pick<Real, 10>(a, L, query);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t ffbs_dispatch_f64_lo(const FfbsArgs& a, FfbsLaunch& L, bool query);
+cudaError_t ffbs_dispatch_f64_hi(const FfbsArgs& a, FfbsLaunch& L, bool query);
+cudaError_t ffbs_dispatch_f32_lo(const FfbsArgs& a, FfbsLaunch& L, bool query);
+cudaError_t ffbs_dispatch_f32_hi(const FfbsArgs& a, FfbsLaunch& L, bool query);
 
 }  // namespace smjp
