@@ -193,6 +193,36 @@ int smjp_sweep_host(smjp_ctx_t* ctx, int C, const int64_t* p_offs, const int32_t
                     double* path_t_out, int32_t* path_len_out, double* time_in_state, int32_t* jumps,
                     int32_t* status, int64_t* total_w);
 
+/*
+ * Dense S-state HMM: scaled forward filter + backward sampler, chains batched (ragged step windows
+ * t_offs[C+1]).  Replaces HiddenMarkovModel.likelihood / .backward_sampling
+ * (hidden_markov_model.py:213-313, :88-202) and is the K-state form of the sMJP filter when every
+ * shape is 1.  HOST buffers.
+ *   P          [S*S] when p_steps == 0, else [p_steps][S*S] with P[t] the transition into step t
+ *   E          dense emission likelihoods [total_steps][S], or NULL to use the table emis[S*Kobs]
+ *              with symbols y[total_steps]
+ *   uniforms   per step or NULL (Philox stream (seed, 0, chain))
+ *   alpha_hat  [total_steps][S] row-normalised messages (element type per `precision`), logc
+ *              [total_steps] log scale factors (log alpha_t = log alpha_hat_t + sum_{u<=t} logc[u]),
+ *              loglik[C] = log P(data), states[total_steps] sampled path (NULL = forward only)
+ */
+int smjp_hmm_dense_host(smjp_ctx_t* ctx, int C, int S, const int64_t* t_offs, const double* P, int p_steps,
+                        const double* E, const double* emis, int Kobs, const int32_t* y, const double* pi0,
+                        const double* uniforms, uint64_t seed, int precision, void* alpha_hat, double* logc,
+                        double* loglik, int32_t* states, int32_t* status);
+
+/*
+ * Bootstrap particle filter, one filter run of N particles per chain.  Replaces smjp_smc
+ * (pmcmc.py:224-310) with the two reference defects removed.  Uses the model of
+ * smjp_set_model (hazard A = shape/scale, emission table, t_end).  HOST buffers.
+ *   pi0[K], N particles, resampler SMJP_RESAMPLE_*
+ *   logZ[total_obs] per-observation log normalisers (or NULL), loglik[C] = sum_d Z_d
+ *   path of particle 0 after the last resampling, in capacity windows p_offs[C+1]
+ */
+int smjp_pf_host(smjp_ctx_t* ctx, int C, const int64_t* obs_offs, const double* obs_t, const int32_t* obs_y,
+                 const double* pi0, int N, uint64_t seed, int resampler, double* logZ, double* loglik,
+                 const int64_t* p_offs, int32_t* path_v, double* path_t, int32_t* path_len, int32_t* status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,6 +9,8 @@
 #include "../../include/smjp_b200.h"
 #include "candidates.cuh"
 #include "ffbs_launch.cuh"
+#include "hmm_dense.cuh"
+#include "pf.cuh"
 
 namespace {
 
@@ -41,7 +43,7 @@ struct DevBuf {
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
-        size_t want = bytes + bytes / 8 + 256;
+        size_t want = bytes + bytes / 4 + 256;  // headroom: grid sizes drift from sweep to sweep
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) {
             cudaGetLastError();
@@ -852,6 +854,235 @@ int smjp_sweep_host(smjp_ctx_t* c, int C, const int64_t* p_offs, const int32_t* 
     memcpy(W, h + o_W, tw * 8);
     memcpy(path_v_out, h + o_pv, tw * 4);
     memcpy(path_t_out, h + o_pt, tw * 8);
+    return SMJP_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// dense HMM and particle filter (host-buffer entry points)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+template <typename Real>
+int hmm_launch(smjp_ctx* c, const HmmArgs& a) {
+    const int S = a.S;
+    const int spl = (S + 31) / 32;
+    const int warps = 4;
+    const size_t smem = (size_t)S * S * sizeof(Real);
+    int grid = (a.C + warps - 1) / warps;
+    if (grid > c->num_sms * 8) grid = c->num_sms * 8;
+#define HMM_CASE(n)                                                                                      \
+    case n:                                                                                              \
+        CUDA_TRY(cudaFuncSetAttribute(hmm_dense_kernel<Real, n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        hmm_dense_kernel<Real, n><<<grid, warps * 32, smem, c->stream>>>(a);                            \
+        break;
+    switch (spl) {
+        HMM_CASE(1) HMM_CASE(2) HMM_CASE(3) HMM_CASE(4)
+        default: return fail(SMJP_E_UNSUPPORTED, "dense HMM kernel supports S <= 128 (S=%d)", S);
+    }
+#undef HMM_CASE
+    CUDA_TRY(cudaGetLastError());
+    c->launches += 1;
+    return SMJP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int smjp_hmm_dense_host(smjp_ctx_t* c, int C, int S, const int64_t* t_offs, const double* P, int p_steps,
+                        const double* E, const double* emis, int Kobs, const int32_t* y, const double* pi0,
+                        const double* uniforms, uint64_t seed, int precision, void* alpha_hat, double* logc,
+                        double* loglik, int32_t* states, int32_t* status) {
+    if (!c) return fail(SMJP_E_INVALID, "null context");
+    if (C <= 0) return C == 0 ? SMJP_OK : fail(SMJP_E_INVALID, "C < 0");
+    if (S < 1 || S > 128) return fail(SMJP_E_UNSUPPORTED, "dense HMM kernel supports 1 <= S <= 128 (S=%d)", S);
+    if (!t_offs || !P || !pi0 || !alpha_hat || !status) return fail(SMJP_E_INVALID, "null required pointer");
+    if (!E && (!emis || !y || Kobs < 1)) return fail(SMJP_E_INVALID, "need dense E or an emission table with symbols");
+    if (precision != SMJP_F64 && precision != SMJP_F32) return fail(SMJP_E_INVALID, "bad precision");
+    if (t_offs[0] != 0) return fail(SMJP_E_INVALID, "offsets must start at 0");
+    const int64_t total = t_offs[C];
+    for (int i = 0; i < C; ++i)
+        if (t_offs[i + 1] <= t_offs[i]) return fail(SMJP_E_INVALID, "chain %d has no steps", i);
+    if (!E)
+        for (int64_t t = 0; t < total; ++t)
+            if (y[t] < 0 || y[t] >= Kobs) return fail(SMJP_E_INVALID, "symbol %lld outside [0,Kobs)", (long long)t);
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t esz = precision == SMJP_F64 ? 8 : 4;
+    const size_t nP = (size_t)(p_steps > 0 ? p_steps : 1) * S * S;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += smjp::align_up(bytes, 16); return o; };
+    const size_t o_to = take((C + 1) * 8), o_P = take(nP * 8), o_pi = take(S * 8);
+    const size_t o_E = E ? take((size_t)total * S * 8) : 0;
+    const size_t o_em = E ? 0 : take((size_t)S * Kobs * 8), o_y = E ? 0 : take(total * 4);
+    const size_t o_u = uniforms ? take(total * 8) : 0;
+    const size_t in_bytes = off;
+    int rc = c->h_in.reserve(in_bytes);
+    if (rc) return rc;
+    rc = c->d_in.reserve(in_bytes);
+    if (rc) return rc;
+    char* h = (char*)c->h_in.p;
+    memcpy(h + o_to, t_offs, (C + 1) * 8);
+    memcpy(h + o_P, P, nP * 8);
+    memcpy(h + o_pi, pi0, S * 8);
+    if (E) memcpy(h + o_E, E, (size_t)total * S * 8);
+    else {
+        memcpy(h + o_em, emis, (size_t)S * Kobs * 8);
+        memcpy(h + o_y, y, total * 4);
+    }
+    if (uniforms) memcpy(h + o_u, uniforms, total * 8);
+    CUDA_TRY(cudaMemcpyAsync(c->d_in.p, h, in_bytes, cudaMemcpyHostToDevice, c->stream));
+    off = 0;
+    const size_t o_st = take(C * 4), o_ll = take(C * 8), o_lc = take(total * 8), o_s = take(total * 4);
+    const size_t o_ah = take((size_t)total * S * esz);
+    rc = c->d_out.reserve(off);
+    if (rc) return rc;
+    rc = c->h_out.reserve(o_ah);
+    if (rc) return rc;
+    char* d = (char*)c->d_in.p;
+    char* o = (char*)c->d_out.p;
+    HmmArgs a;
+    memset(&a, 0, sizeof a);
+    a.C = C;
+    a.S = S;
+    a.t_offs = (const int64_t*)(d + o_to);
+    a.P = (const double*)(d + o_P);
+    a.p_steps = p_steps > 0 ? p_steps : 0;
+    a.E = E ? (const double*)(d + o_E) : nullptr;
+    a.emis = E ? nullptr : (const double*)(d + o_em);
+    a.y = E ? nullptr : (const int32_t*)(d + o_y);
+    a.Kobs = Kobs;
+    a.pi0 = (const double*)(d + o_pi);
+    a.uniforms = uniforms ? (const double*)(d + o_u) : nullptr;
+    a.seed = seed;
+    a.sweep = 0;
+    a.chain_base = c->chain_base;
+    a.alpha_hat = o + o_ah;
+    a.logc = (double*)(o + o_lc);
+    a.loglik = (double*)(o + o_ll);
+    a.states = states ? (int32_t*)(o + o_s) : nullptr;
+    a.status = (int32_t*)(o + o_st);
+    rc = precision == SMJP_F64 ? hmm_launch<double>(c, a) : hmm_launch<float>(c, a);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->h_out.p, o, o_ah, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(alpha_hat, o + o_ah, (size_t)total * S * esz, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    char* ho = (char*)c->h_out.p;
+    memcpy(status, ho + o_st, C * 4);
+    if (loglik) memcpy(loglik, ho + o_ll, C * 8);
+    if (logc) memcpy(logc, ho + o_lc, total * 8);
+    if (states) memcpy(states, ho + o_s, total * 4);
+    return SMJP_OK;
+}
+
+int smjp_pf_host(smjp_ctx_t* c, int C, const int64_t* obs_offs, const double* obs_t, const int32_t* obs_y,
+                 const double* pi0, int N, uint64_t seed, int resampler, double* logZ, double* loglik,
+                 const int64_t* p_offs, int32_t* path_v, double* path_t, int32_t* path_len, int32_t* status) {
+    int rc = model_ready(c);
+    if (rc) return rc;
+    if (C <= 0) return C == 0 ? SMJP_OK : fail(SMJP_E_INVALID, "C < 0");
+    if (N < 1 || N > (1 << 24)) return fail(SMJP_E_INVALID, "N=%d outside [1, 2^24]", N);
+    if (resampler != SMJP_RESAMPLE_MULTINOMIAL && resampler != SMJP_RESAMPLE_SYSTEMATIC)
+        return fail(SMJP_E_INVALID, "bad resampler");
+    if (!obs_offs || !pi0 || !loglik || !p_offs || !path_v || !path_t || !path_len || !status)
+        return fail(SMJP_E_INVALID, "null required pointer");
+    if (obs_offs[0] != 0 || p_offs[0] != 0) return fail(SMJP_E_INVALID, "offsets must start at 0");
+    const int K = c->K;
+    const int64_t total_o = obs_offs[C], total_p = p_offs[C];
+    int64_t Dmax = 0;
+    for (int i = 0; i < C; ++i) {
+        const int64_t D = obs_offs[i + 1] - obs_offs[i];
+        if (D < 0) return fail(SMJP_E_INVALID, "obs_offs not monotone");
+        if (D > Dmax) Dmax = D;
+        if (p_offs[i + 1] - p_offs[i] < 2) return fail(SMJP_E_INVALID, "path window of chain %d smaller than 2", i);
+        for (int64_t d = obs_offs[i]; d < obs_offs[i + 1]; ++d) {
+            if (obs_y[d] < 0 || obs_y[d] >= c->Kobs) return fail(SMJP_E_INVALID, "observation symbol outside [0,Kobs)");
+            if (d > obs_offs[i] && !(obs_t[d] >= obs_t[d - 1])) return fail(SMJP_E_INVALID, "observation times not sorted");
+        }
+    }
+    double ptot = 0;
+    for (int s = 0; s < K; ++s) {
+        if (!(pi0[s] >= 0)) return fail(SMJP_E_INVALID, "pi0[%d] negative", s);
+        ptot += pi0[s];
+    }
+    if (!(ptot > 0)) return fail(SMJP_E_INVALID, "pi0 has no mass");
+    CUDA_TRY(cudaSetDevice(c->device));
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += smjp::align_up(bytes, 16); return o; };
+    const size_t o_oo = take((C + 1) * 8), o_ot = take(total_o * 8), o_oy = take(total_o * 4);
+    const size_t o_po = take((C + 1) * 8), o_pi = take(K * 8);
+    const size_t in_bytes = off;
+    rc = c->h_in.reserve(in_bytes);
+    if (rc) return rc;
+    rc = c->d_in.reserve(in_bytes);
+    if (rc) return rc;
+    char* h = (char*)c->h_in.p;
+    memcpy(h + o_oo, obs_offs, (C + 1) * 8);
+    if (total_o) {
+        memcpy(h + o_ot, obs_t, total_o * 8);
+        memcpy(h + o_oy, obs_y, total_o * 4);
+    }
+    memcpy(h + o_po, p_offs, (C + 1) * 8);
+    memcpy(h + o_pi, pi0, K * 8);
+    CUDA_TRY(cudaMemcpyAsync(c->d_in.p, h, in_bytes, cudaMemcpyHostToDevice, c->stream));
+    // outputs + workspaces
+    off = 0;
+    const size_t o_st = take(C * 4), o_pl = take(C * 4), o_ll = take(C * 8), o_lz = take(total_o * 8 + 8);
+    const size_t o_pv = take(total_p * 4), o_pt = take(total_p * 8);
+    const size_t out_bytes = off;
+    const size_t o_wv = take((size_t)C * 2 * N * 4), o_wl = take((size_t)C * 2 * N * 8), o_cdf = take((size_t)C * N * 8);
+    const size_t o_anc = take((size_t)C * (Dmax > 0 ? Dmax : 1) * N * 4), o_line = take((size_t)C * (Dmax > 0 ? Dmax : 1) * 4);
+    rc = c->d_out.reserve(off);
+    if (rc) return rc;
+    rc = c->h_out.reserve(out_bytes);
+    if (rc) return rc;
+    char* d = (char*)c->d_in.p;
+    char* o = (char*)c->d_out.p;
+    PfArgs a;
+    memset(&a, 0, sizeof a);
+    a.C = C;
+    a.N = N;
+    a.K = K;
+    a.Kobs = c->Kobs;
+    a.obs_offs = (const int64_t*)(d + o_oo);
+    a.obs_t = (const double*)(d + o_ot);
+    a.obs_y = (const int32_t*)(d + o_oy);
+    a.model = (const double*)c->d_model.p;
+    a.pi0 = (const double*)(d + o_pi);
+    a.t_end = c->t_end;
+    a.seed = seed;
+    a.chain_base = c->chain_base;
+    a.resampler = resampler;
+    a.max_iters = 4096;
+    a.pv = (int32_t*)(o + o_wv);
+    a.pl = (double*)(o + o_wl);
+    a.cdf = (double*)(o + o_cdf);
+    a.anc = (int32_t*)(o + o_anc);
+    a.anc_stride = (int64_t)(Dmax > 0 ? Dmax : 1) * N;
+    a.lineage = (int32_t*)(o + o_line);
+    a.lineage_stride = Dmax > 0 ? Dmax : 1;
+    a.logZ = (double*)(o + o_lz);
+    a.loglik = (double*)(o + o_ll);
+    a.p_offs = (const int64_t*)(d + o_po);
+    a.path_v = (int32_t*)(o + o_pv);
+    a.path_t = (double*)(o + o_pt);
+    a.path_len = (int32_t*)(o + o_pl);
+    a.status = (int32_t*)(o + o_st);
+    int grid = C < c->num_sms * 2 ? C : c->num_sms * 2;
+    if (N >= 4096) pf_kernel<1024><<<grid, 1024, 0, c->stream>>>(a);
+    else pf_kernel<256><<<grid, 256, 0, c->stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    c->launches += 1;
+    CUDA_TRY(cudaMemcpyAsync(c->h_out.p, o, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    char* ho = (char*)c->h_out.p;
+    memcpy(status, ho + o_st, C * 4);
+    memcpy(path_len, ho + o_pl, C * 4);
+    memcpy(loglik, ho + o_ll, C * 8);
+    if (logZ && total_o) memcpy(logZ, ho + o_lz, total_o * 8);
+    memcpy(path_v, ho + o_pv, total_p * 4);
+    memcpy(path_t, ho + o_pt, total_p * 8);
     return SMJP_OK;
 }
 

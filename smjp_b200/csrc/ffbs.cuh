@@ -89,41 +89,67 @@ __device__ __forceinline__ bool np_isclose(double a, double b) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// 2^x per precision.  fp64: table of 2^(i/256) in shared memory + degree-4 polynomial on
-// |r| <= 1/512 (truncation 4e-17): 8 DP operations against ~20 of the library exp2 -- the FP64
-// pipe is what bounds the fp64 kernel.  fp32: one SFU op.
+// 2^x and log2 x per precision.  The fp64 kernel is bound by the FP64 pipe (64 lanes/clk/SM), so
+// both are table driven to minimise FP64-pipe instructions (DSETP also issues there):
+//   2^x   : 2^(i/256) table + degree-4 polynomial on |r| <= 1/512 (truncation 4e-17), 8 DP ops,
+//           under/overflow resolved with integer compares on the exponent;
+//   log2 x: 128-entry {1/c, log2 c} table + degree-6 polynomial on |r| <= 1/256, 8 DP ops.
+// fp32: one SFU op each.
 // ------------------------------------------------------------------------------------------------
 template <typename Real>
 struct Exp2;
 
 template <>
 struct Exp2<double> {
-    const double* tab;
+    const double* tab;    // [256] 2^(i/256)
+    const double2* ltab;  // [128] {1/c_i, -log2(1/c_i)}, c_i = 1 + (i + 1/2)/128
     static constexpr int TAB = 256;
+    static constexpr int LTAB = 128;
+    // requires |x| < 2^22 (or NaN); flushes below 2^-1022 to 0, saturates above 2^1023 to inf
     __device__ __forceinline__ double operator()(double x) const {
         const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
-        const double xc = fmin(fmax(x, -1022.0), 1023.5);
-        const double t = fma(xc, 256.0, MAGIC);
+        const double t = fma(x, 256.0, MAGIC);
         const int n = __double2loint(t);
-        const double nf = t - MAGIC;
-        const double r = fma(nf, -1.0 / 256.0, xc);
+        const double r = fma(t - MAGIC, -1.0 / 256.0, x);
         double q = fma(r, 9.618129107628477e-03, 5.550410866482158e-02);  // ln2^4/24, ln2^3/6
         q = fma(r, q, 2.402265069591007e-01);                             // ln2^2/2
         q = fma(r, q, 6.931471805599453e-01);                             // ln2
         const double tv = tab[n & 255];
-        double res = fma(tv, r * q, tv);
-        res = __longlong_as_double(__double_as_longlong(res) + ((long long)(n >> 8) << 52));
-        res = x < -1022.0 ? 0.0 : res;  // flush instead of denormal; also x = -inf
-        res = x > 1023.5 ? INFINITY : res;
-        return res;
+        const double res = fma(tv, r * q, tv);  // [1, 2)
+        const int e = n >> 8;
+        int hi = __double2hiint(res) + (e << 20);
+        int lo = __double2loint(res);
+        const bool under = e < -1022, over = e > 1023;
+        hi = under ? 0 : (over ? 0x7ff00000 : hi);
+        lo = (under || over) ? 0 : lo;
+        return __hiloint2double(hi, lo);
+    }
+    // any x <= 0 including -inf (survival factors)
+    __device__ __forceinline__ double neg(double x) const { return (*this)(fmax(x, -4096.0)); }
+    __device__ __forceinline__ double log2(double x) const {
+        const int hi = __double2hiint(x);
+        if (hi < 0x00100000 || hi >= 0x7ff00000) return ::log2(x);  // zero / denormal / negative / inf / NaN
+        const double2 tv = ltab[(hi >> 13) & 127];
+        const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+        const double r = fma(m, tv.x, -1.0);  // |r| <= 2^-8
+        double p = fma(r, -2.404491734814939e-01, 2.885390081777927e-01);  // -1/(6 ln2), 1/(5 ln2)
+        p = fma(r, p, -3.606737602222409e-01);                             // -1/(4 ln2)
+        p = fma(r, p, 4.808983469629878e-01);                              //  1/(3 ln2)
+        p = fma(r, p, -7.213475204444817e-01);                             // -1/(2 ln2)
+        p = fma(r, p, 1.442695040888963e+00);                              //  1/ln2
+        return fma(r, p, (double)((hi >> 20) - 1023) + tv.y);
     }
 };
 
 template <>
 struct Exp2<float> {
     const double* tab;
+    const double2* ltab;
     static constexpr int TAB = 0;
+    static constexpr int LTAB = 0;
     __device__ __forceinline__ float operator()(float x) const { return Math<float>::exp2(x); }
+    __device__ __forceinline__ float neg(float x) const { return Math<float>::exp2(x); }
+    __device__ __forceinline__ float log2(float x) const { return Math<float>::log2(x); }
 };
 
 template <typename Real> struct ScanAcc { typedef double type; };
@@ -162,6 +188,7 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
     __shared__ int s_sel;
     __shared__ int s_flag;
     __shared__ double s_tab[Exp2<Real>::TAB ? Exp2<Real>::TAB : 1];
+    __shared__ double2 s_ltab[Exp2<Real>::LTAB ? Exp2<Real>::LTAB : 1];
 
     for (int t = tid; t < K * K; t += B) {
         const double k = a.model[t];
@@ -171,8 +198,13 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
         sc2p[t] = (Real)(a.model[K * K + t] - ::log2(k));
     }
     for (int t = tid; t < Exp2<Real>::TAB; t += B) s_tab[t] = ::exp2((double)t / 256.0);
+    for (int t = tid; t < Exp2<Real>::LTAB; t += B) {
+        const double rc = 1.0 / (1.0 + ((double)t + 0.5) / 128.0);
+        s_ltab[t] = make_double2(rc, -::log2(rc));
+    }
     Exp2<Real> ex2;
     ex2.tab = s_tab;
+    ex2.ltab = s_ltab;
     const double* emis = a.model + 2 * K * K;
 
     const Real thin = (Real)(1.0 - 1.0 / a.omega);
@@ -276,7 +308,7 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
             auto pair = [&](auto partial_tag, bool diag) {
                 constexpr bool PARTIAL = decltype(partial_tag)::value;
                 const Real tau = (Real)(wn - *pw);
-                const Real L2 = M::log2(tau);
+                const Real L2 = ex2.log2(tau);
 #pragma unroll
                 for (int v = 0; v < K; ++v) {
                     const Real ap = pa[v * B] * invZ_prev;
@@ -298,7 +330,7 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
                         dsum += kE[s];
                     }
                     const Real hsum = tau * esum;  // H_v(tau)
-                    const Real g = of[v] * ex2(-om_l2e * (hsum - hprev)) * base;
+                    const Real g = of[v] * ex2.neg(-om_l2e * (hsum - hprev)) * base;
 #pragma unroll
                     for (int s = 0; s < K; ++s) Jp[s] += g * kE[s];
                     const Real an = g * (nonfinal ? omega_r * dsum : (Real)1);
@@ -381,7 +413,7 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
             } else {  // jump at W[cur+1] into vplus: w = alpha_cur(v,j) A_{v,vplus}/A_v  (fast_hmm.py:153-171)
                 const double wn = Wd[cur + 1];
                 for (int j = tid; j < len; j += B) {
-                    const Real L2 = M::log2((Real)(wn - Wd[j]));
+                    const Real L2 = ex2.log2((Real)(wn - Wd[j]));
 #pragma unroll
                     for (int v = 0; v < K; ++v) {
                         Real dsum = 0, hto = 0;

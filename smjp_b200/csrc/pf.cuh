@@ -1,0 +1,238 @@
+// Bootstrap particle filter for the sMJP, one CTA per chain (filter run).
+//
+// Replaces smjp_smc (pkg/pmcmc.py:224-310):
+//   propagate  each particle (v, l) by competing conditional-Weibull risks until its next jump would
+//              pass the observation time (:261-289; WeibullDistribution.sample(hold_time=h),
+//              pkg/distributions.py:296-304, in the cancellation-free form
+//              tau = lambda ((h/lambda)^k - log(1-u))^(1/k));
+//   weight     w_p = P(y_d | v_p) (:279-281, smjpEmission.likelihood);
+//   normalise  Z_d = log sum_p w_p - log N (:294-297);
+//   resample   multinomial (:302-304, utils.py:7-8) or systematic (new) by inverse CDF: block-wide
+//              prefix scan of the weights into a CDF, then a binary search per offspring;
+//   output     the path of particle 0 after the last resampling + (v_last, t_final) (:307-309).
+// Deviations from the reference, both deliberate: resampled particles get copy
+// semantics (the reference aliases Python lists), and each particle's clock starts at the previous
+// observation time (the reference leaks t_curr from one particle into the next).
+// Paths are not stored per particle: only the ancestor table anc[d][p] is.  Every draw is
+// counter-based (Philox keyed by chain, observation, particle slot), so after the last step one
+// thread walks the lineage of particle 0 back through anc[][] and REPLAYS its propagation to emit
+// the jump times.  oracle/smjp_oracle.py::particle_filter is the CPU twin.
+#pragma once
+#include "../../include/smjp_b200.h"
+#include "common.cuh"
+
+namespace smjp {
+
+struct PfArgs {
+    int C, N, K, Kobs;
+    const int64_t* obs_offs;
+    const double* obs_t;
+    const int32_t* obs_y;
+    const double* model;  // shape[K*K], c2[K*K], emis[K*Kobs], scale[K*K]
+    const double* pi0;    // device [K]
+    double t_end;
+    uint64_t seed;
+    uint32_t chain_base;
+    int resampler;
+    int max_iters;        // cap on jumps per particle per observation interval
+    // per-chain workspaces, chain stride given
+    int32_t* pv;          // [C][2][N] particle state (double-buffered)
+    double* pl;           // [C][2][N] time of last jump
+    double* cdf;          // [C][N]
+    int32_t* anc;         // [C][Dmax][N] ancestors
+    int64_t anc_stride;   // Dmax * N
+    int32_t* lineage;     // [C][Dmax]
+    int64_t lineage_stride;
+    // outputs
+    double* logZ;         // [total_obs] or null
+    double* loglik;       // [C]
+    const int64_t* p_offs;  // path capacity windows
+    int32_t* path_v;
+    double* path_t;
+    int32_t* path_len;
+    int32_t* status;
+};
+
+// one propagation of a particle from clock t_cur towards t_obs; optionally records jumps
+__device__ __forceinline__ int pf_propagate(const PfArgs& a, uint32_t chain, uint32_t d, uint32_t slot, int& v,
+                                            double& l, double t_cur, double t_obs, int32_t* out_v, double* out_t,
+                                            int out_cap, int* out_n) {
+    const int K = a.K;
+    const double* shape = a.model;
+    const double* scale = a.model + 2 * K * K + K * a.Kobs;
+    int it = 0;
+    for (; it < a.max_iters; ++it) {
+        double best = INFINITY;
+        int arg = 0;
+        const double hold = t_cur - l;
+        for (int s = 0; s < K; ++s) {
+            const double k = shape[v * K + s], lam = scale[v * K + s];
+            const double u = philox_u01(a.seed, TAG_PF_PROPAGATE, (uint64_t)(it * K + s), slot, d, chain);
+            const double tau = lam * pow(pow(hold / lam, k) - log1p(-u), 1.0 / k);
+            if (tau < best) { best = tau; arg = s; }
+        }
+        const double w_next = l + best;
+        if (w_next >= t_obs) return 0;
+        t_cur = w_next;
+        l = w_next;
+        v = arg;
+        if (out_n) {
+            if (*out_n >= out_cap) return SMJP_ST_OVERFLOW;
+            out_v[*out_n] = v;
+            out_t[*out_n] = l;
+            ++*out_n;
+        }
+    }
+    return SMJP_ST_OVERFLOW;  // more than max_iters jumps inside one observation interval
+}
+
+template <int B>
+__global__ void __launch_bounds__(B) pf_kernel(const PfArgs a) {
+    constexpr int NW = B / 32;
+    __shared__ double s_warp[NW + 1];
+    __shared__ double s_carry;
+    __shared__ int s_flag;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int N = a.N, K = a.K;
+    const double* emis = a.model + 2 * K * K;
+    for (int c = blockIdx.x; c < a.C; c += gridDim.x) {
+        const uint32_t chain = a.chain_base + (uint32_t)c;
+        const int64_t o0 = a.obs_offs[c];
+        const int D = (int)(a.obs_offs[c + 1] - o0);
+        int32_t* pv = a.pv + (int64_t)c * 2 * N;
+        double* pl = a.pl + (int64_t)c * 2 * N;
+        double* cdf = a.cdf + (int64_t)c * N;
+        int32_t* anc = a.anc + (int64_t)c * a.anc_stride;
+        if (tid == 0) s_flag = 0;
+        // initial states v0 ~ pi0
+        double ptot = 0;
+        for (int s = 0; s < K; ++s) ptot += a.pi0[s];
+        for (int p = tid; p < N; p += B) {
+            const double u = philox_u01(a.seed, TAG_PF_PROPAGATE, 0, (uint32_t)p, 0xFFFFFFFFu, chain);
+            double acc = 0;
+            int v = -1, lastpos = 0;
+            for (int s = 0; s < K; ++s) {
+                const double pr = a.pi0[s] / ptot;
+                if (pr > 0) lastpos = s;
+                acc += pr;
+                if (v < 0 && acc > u) v = s;
+            }
+            pv[p] = v < 0 ? lastpos : v;
+            pl[p] = 0.0;
+        }
+        __syncthreads();
+        int cur = 0;
+        double loglik = 0;
+        for (int d = 0; d < D; ++d) {
+            const double t_prev = d == 0 ? 0.0 : a.obs_t[o0 + d - 1];
+            const double t_obs = a.obs_t[o0 + d];
+            const int y = a.obs_y[o0 + d];
+            int32_t* v_in = pv + cur * N;
+            double* l_in = pl + cur * N;
+            int32_t* v_out = pv + (cur ^ 1) * N;
+            double* l_out = pl + (cur ^ 1) * N;
+            // ---- propagate + weight: contiguous chunk per thread so that the scan is in particle order ----
+            const int q = (N + B - 1) / B;
+            const int beg = min(tid * q, N), end = min(beg + q, N);
+            double loc = 0;
+            for (int p = beg; p < end; ++p) {
+                int v = v_in[p];
+                double l = l_in[p];
+                const int rc = pf_propagate(a, chain, (uint32_t)d, (uint32_t)p, v, l, t_prev, t_obs, nullptr, nullptr, 0, nullptr);
+                if (rc) atomicOr(&s_flag, rc);
+                v_in[p] = v;
+                l_in[p] = l;
+                const double w = emis[v * a.Kobs + y];
+                loc += w;
+                cdf[p] = loc;  // chunk-local inclusive sums; offset added below
+            }
+            double incl = warp_inclusive_scan(loc, lane);
+            if (lane == 31) s_warp[wid] = incl;
+            __syncthreads();
+            double off = 0;
+            for (int w = 0; w < wid; ++w) off += s_warp[w];
+            double total = 0;
+            for (int w = 0; w < NW; ++w) total += s_warp[w];
+            const double excl = off + incl - loc;
+            for (int p = beg; p < end; ++p) cdf[p] += excl;
+            const double Zd = log(total) - log((double)N);
+            loglik += Zd;
+            if (tid == 0 && a.logZ) a.logZ[o0 + d] = Zd;
+            __syncthreads();
+            if (!(total > 0.0)) {  // every particle has zero weight
+                if (tid == 0) s_flag |= SMJP_ST_DEGENERATE;
+                __syncthreads();
+                break;
+            }
+            // ---- resample: inverse CDF per offspring ----
+            const double u_sys = philox_u01(a.seed, TAG_PF_RESAMPLE, 0, 0u, (uint32_t)d, chain);
+            for (int p = tid; p < N; p += B) {
+                const double pos = a.resampler == SMJP_RESAMPLE_SYSTEMATIC
+                                       ? (u_sys + (double)p) / (double)N
+                                       : philox_u01(a.seed, TAG_PF_RESAMPLE, (uint64_t)p, 0u, (uint32_t)d, chain);
+                const double target = pos * total;
+                int lo = 0, hi = N;  // first index with cdf > target
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (cdf[mid] > target) hi = mid; else lo = mid + 1;
+                }
+                const int an = lo < N ? lo : N - 1;
+                anc[(int64_t)d * N + p] = an;
+                v_out[p] = v_in[an];
+                l_out[p] = l_in[an];
+            }
+            cur ^= 1;
+            __syncthreads();
+        }
+        __syncthreads();
+        int flag = s_flag;
+        // ---- path of particle 0: lineage through the ancestor table, then replay ----
+        if (tid == 0) {
+            const int64_t p0 = a.p_offs[c];
+            const int cap = (int)(a.p_offs[c + 1] - p0);
+            int plen = 0;
+            if (!(flag & SMJP_ST_DEGENERATE) && cap >= 2) {
+                int32_t* line = a.lineage + (int64_t)c * a.lineage_stride;  // slot b_d of the surviving lineage
+                int b = 0;
+                for (int d = D - 1; d >= 0; --d) {
+                    b = anc[(int64_t)d * N + b];
+                    line[d] = b;
+                }
+                const int slot0 = D > 0 ? line[0] : 0;
+                const double u = philox_u01(a.seed, TAG_PF_PROPAGATE, 0, (uint32_t)slot0, 0xFFFFFFFFu, chain);
+                double acc = 0;
+                int v = -1, lastpos = 0;
+                for (int s = 0; s < K; ++s) {
+                    const double pr = a.pi0[s] / ptot;
+                    if (pr > 0) lastpos = s;
+                    acc += pr;
+                    if (v < 0 && acc > u) v = s;
+                }
+                v = v < 0 ? lastpos : v;
+                double l = 0.0;
+                int32_t* ov = a.path_v + p0;
+                double* ot = a.path_t + p0;
+                ov[0] = v;
+                ot[0] = 0.0;
+                int nout = 1;
+                for (int d = 0; d < D && !(flag & SMJP_ST_OVERFLOW); ++d) {
+                    const double t_prev = d == 0 ? 0.0 : a.obs_t[o0 + d - 1];
+                    const int rc = pf_propagate(a, chain, (uint32_t)d, (uint32_t)line[d], v, l, t_prev,
+                                                a.obs_t[o0 + d], ov, ot, cap - 1, &nout);
+                    if (rc) flag |= rc;
+                }
+                if (!(flag & SMJP_ST_OVERFLOW)) {
+                    ov[nout] = v;  // pmcmc.py:307-308: (v_last, t_final)
+                    ot[nout] = a.t_end;
+                    plen = nout + 1;
+                }
+            }
+            a.path_len[c] = plen;
+            a.loglik[c] = (flag & SMJP_ST_DEGENERATE) ? -INFINITY : loglik;
+            a.status[c] = flag;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace smjp

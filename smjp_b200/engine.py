@@ -251,6 +251,80 @@ def sweep_host(eng, V, T, obs_t, obs_y, seed, sweep=0, mode="reference", precisi
             "time_in_state": tis, "jumps": jm, "status": st}
 
 
+def hmm_dense_host(eng, P, pi0, E=None, emis=None, y=None, uniforms=None, seed=0, precision="f64", sample=True):
+    """Dense S-state HMM for a batch of chains (hidden_markov_model.py:213-313, :88-202).
+    P: [S,S] or [n,S,S]; per chain either E[c]: [n_c,S] likelihoods, or symbols y[c]: [n_c] with the
+    table emis [S,Kobs].  Returns dict(alpha_hat, logc, loglik, states, status) with ragged lists."""
+    P = np.ascontiguousarray(P, dtype=np.float64)
+    S = P.shape[-1]
+    p_steps = 0 if P.ndim == 2 else P.shape[0]
+    pi0 = np.ascontiguousarray(pi0, dtype=np.float64)
+    prec = PRECISIONS[precision]
+    if E is not None:
+        C = len(E)
+        lens = [len(e) for e in E]
+        Ef = np.ascontiguousarray(np.concatenate([np.asarray(e, dtype=np.float64).reshape(-1, S) for e in E]))
+        em, yf, Kobs = None, None, 0
+    else:
+        C = len(y)
+        lens = [len(v) for v in y]
+        Ef = None
+        em = np.ascontiguousarray(emis, dtype=np.float64)
+        Kobs = em.shape[1]
+        yf = np.ascontiguousarray(np.concatenate([np.asarray(v, dtype=np.int32) for v in y]))
+    offs = ragged_offsets(lens)
+    total = int(offs[-1])
+    uf = None
+    if uniforms is not None:
+        uf = np.ascontiguousarray(np.concatenate([np.asarray(u, dtype=np.float64) for u in uniforms]))
+        if len(uf) != total:
+            raise ValueError("need one uniform per step")
+    rdt = np.float64 if prec == SMJP_F64 else np.float32
+    ah = np.zeros((total, S), dtype=rdt)
+    logc = np.zeros(total, dtype=np.float64)
+    ll = np.zeros(C, dtype=np.float64)
+    st = np.zeros(C, dtype=np.int32)
+    states = np.zeros(total, dtype=np.int32) if sample else None
+    check(eng.lib.smjp_hmm_dense_host(eng.ctx, C, S, _ptr(offs), _ptr(P), p_steps, _ptr(Ef), _ptr(em), Kobs, _ptr(yf),
+                                      _ptr(pi0), _ptr(uf), int(seed) & 0xFFFFFFFFFFFFFFFF, prec, _ptr(ah), _ptr(logc),
+                                      _ptr(ll), _ptr(states), _ptr(st)))
+    sl = [slice(offs[c], offs[c + 1]) for c in range(C)]
+    return {"alpha_hat": [ah[x] for x in sl], "logc": [logc[x] for x in sl], "loglik": ll, "status": st,
+            "states": [states[x] for x in sl] if sample else None}
+
+
+def pf_host(eng, obs_t, obs_y, pi0, N, seed, resampler="systematic", C=None, path_cap=None):
+    """Bootstrap particle filter (smjp_smc, pmcmc.py:224-310) for C chains.  obs_t/obs_y: list per
+    chain, or one shared record with C given.  Returns dict(V, T, loglik, logZ, status)."""
+    if isinstance(obs_t, np.ndarray) and obs_t.ndim == 1 and obs_t.dtype != object:
+        C = 1 if C is None else C
+        obs_t, obs_y = [obs_t] * C, [obs_y] * C
+    C = len(obs_t)
+    of, o_offs = pack_ragged([np.asarray(t, dtype=np.float64) for t in obs_t], np.float64)
+    oy, _ = pack_ragged([np.asarray(v, dtype=np.int32) for v in obs_y], np.int32)
+    pi0 = np.ascontiguousarray(pi0, dtype=np.float64)
+    res = {"multinomial": _lib.RESAMPLE_MULTINOMIAL, "systematic": _lib.RESAMPLE_SYSTEMATIC}[resampler]
+    cap = path_cap or 256
+    while True:
+        p_offs = np.arange(C + 1, dtype=np.int64) * cap
+        pv = np.zeros(C * cap, dtype=np.int32)
+        pt = np.zeros(C * cap, dtype=np.float64)
+        pl = np.zeros(C, dtype=np.int32)
+        st = np.zeros(C, dtype=np.int32)
+        ll = np.zeros(C, dtype=np.float64)
+        lz = np.zeros(max(len(of), 1), dtype=np.float64)
+        check(eng.lib.smjp_pf_host(eng.ctx, C, _ptr(o_offs), _ptr(of), _ptr(oy), _ptr(pi0), int(N),
+                                   int(seed) & 0xFFFFFFFFFFFFFFFF, res, _ptr(lz), _ptr(ll), _ptr(p_offs), _ptr(pv),
+                                   _ptr(pt), _ptr(pl), _ptr(st)))
+        if np.any(st & _lib.ST_OVERFLOW) and cap < (1 << 20):
+            cap *= 4
+            continue
+        break
+    return {"V": [pv[c * cap: c * cap + pl[c]].copy() for c in range(C)],
+            "T": [pt[c * cap: c * cap + pl[c]].copy() for c in range(C)],
+            "loglik": ll, "logZ": [lz[o_offs[c]: o_offs[c + 1]].copy() for c in range(C)], "status": st}
+
+
 def raise_for_status(status):
     """Per-chain status bits -> the exceptions the reference raises at the same conditions."""
     status = np.asarray(status)

@@ -1,0 +1,124 @@
+"""GPU parity tests: dense K-state HMM (legacy hidden_markov_model API) and the bootstrap particle
+filter, against the reference fixture and the oracle (pytest -m gpu)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import smjp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from smjp_b200.engine import Engine
+    eng = Engine(0)
+    yield eng
+    eng.close()
+
+
+def test_dense_hmm_matches_reference_fixture(engine):
+    from smjp_b200.engine import hmm_dense_host
+    g = load_golden("hmm_dense")
+    r = hmm_dense_host(engine, g["P"], g["pi0"], emis=g["E"], y=[g["data"]], uniforms=[g["uniforms"]])
+    assert r["status"][0] == 0
+    log_alpha = np.log(r["alpha_hat"][0]) + np.cumsum(r["logc"][0])[:, None]  # the reference's unnormalised log messages
+    assert np.abs(log_alpha - g["log_alphas"]).max() < 1e-10
+    assert abs(np.exp(r["loglik"][0]) - float(g["prob"])) / float(g["prob"]) < 1e-10
+    assert np.array_equal(r["states"][0], g["samples"])
+
+
+@pytest.mark.parametrize("S,n,prec,tol", [(3, 50, "f64", 1e-10), (10, 300, "f64", 1e-10), (64, 200, "f64", 1e-10),
+                                          (100, 40, "f64", 1e-10), (64, 200, "f32", 1e-4)])
+def test_dense_hmm_matches_oracle(engine, S, n, prec, tol):
+    from smjp_b200.engine import hmm_dense_host
+    rng = np.random.default_rng(S * 1000 + n)
+    P = rng.dirichlet(np.ones(S), size=S)
+    pi0 = rng.dirichlet(np.ones(S))
+    C = 5
+    Es = [rng.uniform(0.05, 1.0, (n + c, S)) for c in range(C)]
+    us = [rng.uniform(size=n + c) for c in range(C)]
+    r = hmm_dense_host(engine, P, pi0, E=Es, uniforms=us, precision=prec)
+    assert np.all(r["status"] == 0)
+    for c in range(C):
+        la, ah, logc, ll = O.hmm_forward_dense(P, Es[c], pi0)
+        assert np.abs(r["alpha_hat"][c] - ah).max() < tol
+        assert abs(r["loglik"][c] - ll) < max(tol * abs(ll), 1e-9)
+        if prec == "f64":
+            assert np.array_equal(r["states"][c], O.hmm_backward_dense(ah, P, us[c]))
+
+
+def test_dense_hmm_time_varying_transition(engine):
+    from smjp_b200.engine import hmm_dense_host
+    rng = np.random.default_rng(3)
+    S, n = 6, 30
+    P = rng.dirichlet(np.ones(S), size=(n, S))
+    pi0 = np.ones(S) / S
+    E = rng.uniform(0.1, 1, (n, S)); u = rng.uniform(size=n)
+    r = hmm_dense_host(engine, P, pi0, E=[E], uniforms=[u])
+    la, ah, logc, ll = O.hmm_forward_dense(P, E, pi0)
+    assert np.abs(r["alpha_hat"][0] - ah).max() < 1e-12
+    assert np.array_equal(r["states"][0], O.hmm_backward_dense(ah, P, u))
+
+
+def test_collapsed_smjp_equals_augmented_filter_on_gpu(engine):
+    """shape == 1: marginalising the (v,l) FFBS messages over l equals the dense K-state filter (A.5)."""
+    from smjp_b200.engine import hmm_dense_host, triangular_to_dense
+    rng = np.random.default_rng(4)
+    K, n, omega, t_end = 5, 60, 2.0, 12.0
+    shape = np.ones((K, K)); scale = rng.uniform(0.5, 2.0, (K, K)); emis = O.emission_matrix(K)
+    W = np.concatenate([[0.0], np.sort(rng.uniform(0, t_end, n - 1)), [t_end]])
+    obs_t = np.sort(rng.uniform(0, t_end, 40)); obs_y = rng.integers(0, K, 40)
+    engine.set_model(shape, scale, omega, emis, 1.0, t_end)
+    r = engine.ffbs_host([W], [obs_t], [obs_y], uniforms=[rng.uniform(size=n)], want_messages=True)
+    marg = triangular_to_dense(r["messages"][0], n, K).reshape(n, K, n).sum(axis=2)
+    A_v = (1.0 / scale).sum(axis=1)
+    E = np.zeros((n, K))
+    for i in range(n):
+        lx = O.obs_factor(obs_t, obs_y, emis, 1.0, W[i], W[i + 1])
+        E[i] = lx * (omega * A_v if i < n - 1 else 1.0) * np.exp(-omega * A_v * (W[i + 1] - W[i]))
+    d = hmm_dense_host(engine, O.collapse_matrix(shape, scale, omega), np.ones(K) / K, E=[E], sample=False)
+    assert np.abs(d["alpha_hat"][0] - marg).max() < 1e-12
+    assert np.abs(d["logc"][0] - r["logZ"][0]).max() < 1e-10
+
+
+@pytest.mark.parametrize("resampler", ["systematic", "multinomial"])
+def test_particle_filter_matches_oracle(engine, resampler):
+    from smjp_b200.engine import pf_host
+    K, t_end, N = 3, 2.0, 96
+    shape = np.array([[1.606, 1.933, 0.865], [1.938, 0.869, 1.751], [1.69, 0.64, 0.696]])
+    scale = np.array([[1.0, 0.8, 1.3], [0.7, 1.0, 1.1], [1.2, 0.9, 1.0]])
+    emis = O.emission_matrix(K)
+    engine.set_model(shape, scale, 2.0, emis, 1.0, t_end)
+    obs_t = np.arange(0.1, 2.0, 0.1)
+    y = np.array([1, 1, 1, 1, 1, 1, 2, 2, 2, 1, 1, 1, 1, 3, 3, 2, 1, 1, 3]) - 1
+    C = 6
+    r = pf_host(engine, obs_t, y, np.ones(K) / K, N, seed=17, resampler=resampler, C=C)
+    assert np.all(r["status"] == 0)
+    for c in range(C):
+        V, T, ll, Z = O.particle_filter(obs_t, y, shape, scale, emis, np.ones(K) / K, t_end, N, seed=17, chain=c,
+                                        resampler=resampler)
+        assert np.allclose(r["logZ"][c], Z, rtol=1e-12, atol=1e-12)
+        assert abs(r["loglik"][c] - ll) < 1e-10
+        assert np.array_equal(r["V"][c], V)
+        assert np.allclose(r["T"][c], T, rtol=1e-12, atol=0)
+
+
+def test_particle_filter_large_and_unbiased(engine):
+    """65 536 particles (cfg3 scale): log-normaliser estimates from independent runs agree tightly and
+    match a small-N ensemble average (unbiasedness of exp(sum Z_d))."""
+    from smjp_b200.engine import pf_host
+    rng = np.random.default_rng(2)
+    K, t_end = 5, 10.0
+    shape = rng.uniform(0.6, 3.0, (K, K)); scale = np.ones((K, K)); emis = O.emission_matrix(K)
+    engine.set_model(shape, scale, 2.0, emis, 1.0, t_end)
+    obs_t = np.arange(0.1, t_end, 0.1); y = rng.integers(0, K, len(obs_t))
+    big = pf_host(engine, obs_t, y, np.ones(K) / K, 65536, seed=5, C=4)
+    assert np.all(big["status"] == 0)
+    assert np.ptp(big["loglik"]) < 0.2
+    small = pf_host(engine, obs_t, y, np.ones(K) / K, 512, seed=6, C=256)
+    m = np.max(small["loglik"])
+    avg = m + np.log(np.mean(np.exp(small["loglik"] - m)))
+    assert abs(avg - np.mean(big["loglik"])) < 0.35
+    for c in range(4):
+        assert big["T"][c][0] == 0.0 and big["T"][c][-1] == t_end and np.all(np.diff(big["T"][c]) > 0)
