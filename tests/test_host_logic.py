@@ -1,0 +1,156 @@
+"""CPU-only tests: host-side logic of the drop-in layer, ragged packing, and that the C-ABI library
+loads and exports every symbol include/smjp_b200.h declares (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+from smjp_b200 import _lib
+from smjp_b200.distributions import MultinomialDistribution, WeibullDistribution
+from smjp_b200.engine import message_offsets, pack_ragged, ragged_offsets, triangular_to_dense
+from smjp_b200 import mcmc_utils, smjp_utils as SU, utils
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "smjp_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(smjp_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    assert os.path.isfile(_lib.LIB_PATH), "build the library first (__graft_entry__.build())"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, missing
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert _lib.load().smjp_abi_version() == 1
+
+
+def test_engine_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from smjp_b200.engine import Engine
+    with pytest.raises(_lib.EngineError, match="no CUDA device"):
+        Engine(0)
+
+
+def test_ragged_helpers():
+    flat, offs = pack_ragged([np.arange(3), np.arange(0), np.arange(5)], np.float64)
+    assert offs.tolist() == [0, 3, 3, 8] and flat.tolist() == [0, 1, 2, 0, 1, 2, 3, 4]
+    assert ragged_offsets([2, 2]).tolist() == [0, 2, 4]
+    assert message_offsets([1, 2, 3], 3).tolist() == [0, 3, 12, 30]
+    n, K = 3, 2
+    tri = np.arange(K * n * (n + 1) // 2, dtype=np.float64) + 1
+    d = triangular_to_dense(tri, n, K).reshape(n, K, n)
+    assert d[0, 0, 0] == 1 and d[0, 1, 0] == 2 and d[0, 0, 1] == 0
+    assert d[1, 0].tolist() == [3, 4, 0] and d[1, 1].tolist() == [5, 6, 0]
+    assert d[2, 1].tolist() == [10, 11, 12]
+
+
+def test_state_space_enumeration_is_state_major():
+    aug = SU.enumerate_state_space([0.0, 0.5, 1.2, 2.0], [1, 2, 3])
+    assert aug.shape == (9, 2)
+    assert aug[:3].tolist() == [[1, 0.0], [1, 0.5], [1, 1.2]] and aug[3].tolist() == [2, 0.0]  # a = v*n + j
+
+
+def test_upperbound_scale_and_omega_inference():
+    shape = np.array([[1.5, 0.5], [2.0, 0.75]])
+    scale = np.array([[1.0, 2.0], [0.5, 1.0]])
+    A = SU.smjpHazardFunction([1, 2], shape, scale)
+    B = SU.smjpHazardFunction([1, 2], shape, SU.create_upperbound_scale(shape, scale, 3.0), omega=3.0)
+    assert abs(SU.infer_omega(A, B) - 3.0) < 1e-12
+    # hazards scale exactly by omega
+    assert abs(B(0.7, 1, 2) / A(0.7, 1, 2) - 3.0) < 1e-12
+    assert abs(B(0.7, 2, None) / A(0.7, 2, None) - 3.0) < 1e-12
+    with pytest.raises(ValueError):
+        SU.infer_omega(A, SU.smjpHazardFunction([1, 2], shape + 0.1, scale))
+    with pytest.raises(ValueError):
+        SU.infer_omega(A, SU.smjpHazardFunction([1, 2], shape, scale * np.array([[0.5, 0.4], [0.5, 0.5]])))
+    with pytest.raises(ValueError):
+        SU.infer_omega(A, SU.smjpHazardFunction([1, 2], shape, SU.create_upperbound_scale(shape, scale, 3.0), omega=2.0))
+
+
+def test_data_wrapper_and_label_mapping():
+    d = SU.sMJPDataWrapper(data=np.array([1, 3, 2, 2]), time=np.array([0.1, 0.2, 0.2, 0.5]))
+    assert d[0.2, 0.5].tolist() == [3, 2, 2]  # closed interval on both ends
+    assert d[0.3, 0.4].tolist() == []
+    with pytest.raises(NotImplementedError):
+        d[0.3]
+    with pytest.raises(IndexError):
+        d[0.1, 0.2, 0.3]
+    assert SU.state_index([10, 20, 30], [30.0, 10, 20.0]).tolist() == [2, 0, 1]  # float labels after a sweep (Q14)
+    with pytest.raises(ValueError):
+        SU.state_index([1, 2], [5])
+    t, y = SU.observation_arrays(SU.sMJPDataWrapper(data=[2, 1], time=[0.9, 0.3]), [1, 2])
+    assert t.tolist() == [0.3, 0.9] and y.tolist() == [0, 1]
+
+
+def test_emission_table_and_transition_accessor():
+    e = SU.smjpEmission([1, 2, 3], None, 2.0, 1.0)
+    E = e.matrix()
+    assert np.allclose(E.sum(axis=1), 1) and abs(E[0, 0] - 10 / 12) < 1e-15 and abs(E[0, 1] - 1 / 12) < 1e-15
+    assert abs(e.likelihood(0, 1) - 10 / 12) < 1e-15  # observation index 0 under state label 1
+    shape = np.array([[1.5, 0.5], [2.0, 0.75]]); scale = np.ones((2, 2))
+    A = SU.smjpHazardFunction([1, 2], shape, scale)
+    B = SU.smjpHazardFunction([1, 2], shape, SU.create_upperbound_scale(shape, scale, 2), omega=2)
+    aug = SU.enumerate_state_space([0.0, 1 / 3, 2 / 3, 1.0], [1, 2])
+    pi = SU.smjpTransitionFunction(aug, A, B)
+    assert abs(pi(0, 0, 0.0, 1 / 3) - np.log(0.5)) < 1e-12           # thinned: 1 - 1/omega
+    assert pi(0, 1, 0.0, 1 / 3) == pytest.approx(np.log(A(1 / 3, 1, 1) / B(1 / 3, 1, None)))  # jump incl. self
+    assert pi(1, 0, 1 / 3, 2 / 3) == -np.inf
+    with pytest.raises(ValueError):
+        pi(0, 0, 0.5, 0.5)
+    rows = np.exp([pi(0, c, 0.0, 1 / 3) for c in range(6)])
+    assert abs(rows.sum() - 1.0) < 1e-12  # K+1 non-zeros per row, already normalised
+
+
+def test_chain_metrics_match_reference_fixture():
+    g = load_golden("metrics")
+    agg = {"V": [g["V"][i, : g["lens"][i]] + 1.0 for i in range(len(g["lens"]))],
+           "T": [g["T"][i, : g["lens"][i]] for i in range(len(g["lens"]))]}
+    st, sj = mcmc_utils.compute_evaluation_chain_metrics(agg, [1, 2, 3])
+    assert np.array_equal(np.array([sj[s] for s in [1, 2, 3]]).T, g["state_jumps"])
+    assert np.allclose(np.array([st[s] for s in [1, 2, 3]]).T, g["state_times"], atol=1e-15)
+
+
+def test_ks_rule_and_pickle_roundtrip(tmp_path, monkeypatch):
+    rng = np.random.default_rng(0)
+    a = {s: list(rng.normal(size=900)) for s in [1, 2]}
+    b = {s: list(rng.normal(size=900)) for s in [1, 2]}
+    c = {s: list(rng.normal(loc=1.5, size=900)) for s in [1, 2]}
+    r = mcmc_utils.compute_ks_twosample_time_jump(a, b, a, b, [1, 2], verbose=False)
+    assert abs(r["ub"] - 1.224 * np.sqrt(60 / 900)) < 1e-12 and not r["reject_times"].any()
+    assert mcmc_utils.compute_ks_twosample_time_jump(a, c, a, c, [1, 2], verbose=False)["reject_times"].all()
+    monkeypatch.chdir(tmp_path)
+    fn = mcmc_utils.save_samples_in_pickle({"V": [[1, 2]]}, 2, "raoteh", "abc", 300)
+    assert fn == "results_raoteh_abc_300.pkl"
+    agg, u, om = mcmc_utils.load_samples_in_pickle(fn)
+    assert agg == {"V": [[1, 2]]} and u == "abc" and om == 2
+
+
+def test_numerics_helpers_and_distributions():
+    assert abs(utils.logsumexp(np.log([0.25, 0.75]))) < 1e-15
+    assert utils.np_log(0.0)[0] == -np.inf
+    assert utils.isiterable([1]) and not utils.isiterable(3)
+    w = WeibullDistribution({"shape": 1.5, "scale": 2.0}, is_hazard_rate=True)
+    assert abs(w.l(0.7) - (1.5 / 2.0) * (0.7 / 2.0) ** 0.5) < 1e-14
+    dens = WeibullDistribution({"shape": 1.5, "scale": 2.0})
+    assert abs(dens.l(0.7) - (1.5 / 2.0) * (0.7 / 2.0) ** 0.5 * np.exp(-(0.7 / 2.0) ** 1.5)) < 1e-14
+    import smjp_b200
+    smjp_b200.runtime.seed(1)
+    s = np.asarray(dens.sample(4000, hold_time=1.0))
+    assert s.min() >= 1.0  # conditional on tau > h
+    m = MultinomialDistribution({"prob_vector": [0.0, 1.0], "translation": ["a", "b"]})
+    assert m.sample(1) == "b" and m.ll(0) == -np.inf and m.l(1) == 1.0
+
+
+def test_raoteh_argument_checks():
+    from smjp_b200.raoteh import inference_error_checking
+    with pytest.raises(ValueError):
+        inference_error_checking([])
+    with pytest.raises(ValueError):
+        inference_error_checking(["parameters"])
+    inference_error_checking(["trajectory", "parameters"])
