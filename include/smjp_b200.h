@@ -70,6 +70,11 @@ int64_t smjp_ctx_launch_count(smjp_ctx_t* ctx);
 int64_t smjp_ctx_get_stat(smjp_ctx_t* ctx, const char* key);
 /* knobs: "ffbs_threads" (0 = auto, else threads per CTA of the FFBS kernel);
  *        "time_kernels" (0/1, see smjp_ctx_kernel_time);
+ *        "pf_extend" (0 = the particle-filter path is extended flat from the last observation to t_end
+ *        as the reference does, pmcmc.py:307-309; 1 = the segment is simulated);
+ *        "lpt_order" (0/1, default 1: the FFBS kernel starts the longest grids first);
+ *        "obs_product" (0 = observations that share a grid interval are summed, as the reference does
+ *        (smjp_utils.py:496-499); 1 = multiplied, the proper likelihood);
  *        "chain_base" (global index of chain 0 of this context's batches: keeps the Philox streams of
  *        chains sharded over several GPUs distinct and independent of the sharding) */
 int smjp_ctx_set_option(smjp_ctx_t* ctx, const char* key, int64_t value);

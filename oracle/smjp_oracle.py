@@ -79,20 +79,25 @@ def inv_cdf(p, u):
 # ----------------------------------------------------------------------------------------------
 
 
-def obs_factor(obs_t, obs_y, emis, power, wc, wn):
+def obs_factor(obs_t, obs_y, emis, power, wc, wn, combine="sum"):
     """(sum_{x in [wc,wn]} P(x|v))**power, 1 when the closed interval holds no observation
     (sMJPDataWrapper._slice_2d smjp_utils.py:40-48; compute_likelihood_obs :493-504; :538-542)."""
     K = emis.shape[0]
     sel = np.nonzero((obs_t >= wc) & (obs_t <= wn))[0]
     if len(sel) == 0:
         return np.ones(K)
+    if combine == "product":  # not the reference: the proper likelihood of several observations
+        lx = np.ones(K)
+        for d in sel:
+            lx = lx * emis[:, obs_y[d]]
+        return lx ** power
     lx = np.zeros(K)
-    for d in sel:  # the reference accumulates sample by sample
+    for d in sel:  # the reference accumulates sample by sample (SURVEY Q3)
         lx = lx + emis[:, obs_y[d]]
     return lx ** power
 
 
-def forward(W, obs_t, obs_y, shape, scale, omega, emis, power, t_end):
+def forward(W, obs_t, obs_y, shape, scale, omega, emis, power, t_end, obs_combine="sum"):
     """Normalised forward messages of likelihood_and_decoding_hmm (fast_hmm.py:202-335) for the
     sMJP transition (smjp_utils.py:382-416) and emission (smjp_utils.py:506-550, :104-133).
 
@@ -115,7 +120,7 @@ def forward(W, obs_t, obs_y, shape, scale, omega, emis, power, t_end):
         wc, wn = W[i], W[i + 1]
         if not (wn > wc):
             raise ValueError("We can not have time_p >= time_c")  # smjp_utils.py:398-399
-        lx = obs_factor(obs_t, obs_y, emis, power, wc, wn)
+        lx = obs_factor(obs_t, obs_y, emis, power, wc, wn, obs_combine)
         l = W[: i + 1]
         t_hold = wn - l
         t_hold_c = wc - l
@@ -196,11 +201,11 @@ def compact_path(samples, W, K, t_end):
     return np.asarray(states, dtype=np.int64), np.asarray(times, dtype=np.float64)
 
 
-def ffbs(W, obs_t, obs_y, shape, scale, omega, emis, power, t_end, uniforms):
+def ffbs(W, obs_t, obs_y, shape, scale, omega, emis, power, t_end, uniforms, obs_combine="sum"):
     """smjp_ffbs (smjp_utils.py:261-330) on state indices.  Returns dict."""
     shape = np.asarray(shape, dtype=np.float64)
     scale = np.asarray(scale, dtype=np.float64)
-    alpha, logZ = forward(W, obs_t, obs_y, shape, scale, omega, emis, power, t_end)
+    alpha, logZ = forward(W, obs_t, obs_y, shape, scale, omega, emis, power, t_end, obs_combine)
     samples = backward(alpha, W, shape, scale, omega, uniforms)
     V, T = compact_path(samples, W, shape.shape[0], t_end)
     return {"alpha": alpha, "logZ": logZ, "samples": samples, "V": V, "T": T}
@@ -412,14 +417,15 @@ def resample_ancestors(w, N, resampler, seed, d, chain):
 
 
 def particle_filter(obs_t, obs_y, shape, scale, emis, pi0, t_end, N, seed, chain,
-                    resampler="systematic", max_jumps=64):
+                    resampler="systematic", max_jumps=64, extend=False):
     """smjp_smc (pmcmc.py:224-310).  Per observation d: every particle (v, l) is propagated by
     competing conditional-Weibull risks (:261-289) until its next jump would pass obs_t[d]; weight
     log P(y_d | v) (:279-281); Z_d = logsumexp(logw) - log N (:294-297); resample (:302-304).
     Propagation stream (seed, TAG_PF_PROPAGATE, particle, d, chain), r = iteration*K + s; the
     initial states use d = 0xffffffff, r = 0.
-    Returns (path_states, path_times, loglik, Z [D]) -- path of particle 0 after the last resample
-    plus (v_last, t_end) (:307-309)."""
+    Returns (path_states, path_times, loglik, Z [D]) -- path of one particle after the last resample
+    (index 0 for multinomial as the reference, a uniformly drawn index for systematic) plus
+    (v_last, t_end) (:307-309)."""
     shape = np.asarray(shape, dtype=np.float64)
     scale = np.asarray(scale, dtype=np.float64)
     K = shape.shape[0]
@@ -431,6 +437,7 @@ def particle_filter(obs_t, obs_y, shape, scale, emis, pi0, t_end, N, seed, chain
     l = np.zeros(N)
     paths = [([int(v[p])], [0.0]) for p in range(N)]
     Z = np.zeros(D)
+    last_anc = np.arange(N)
     for d in range(D):
         t_obs = t[d + 1]
         t_cur = np.full(N, t[d])
@@ -455,8 +462,25 @@ def particle_filter(obs_t, obs_y, shape, scale, emis, pi0, t_end, N, seed, chain
         w = np.exp(logw - Zd)
         Z[d] = Zd - math.log(N)
         anc = resample_ancestors(w, N, resampler, seed, d, chain)
+        last_anc = anc
         v = v[anc]
         l = l[anc]
         paths = [(list(paths[a][0]), list(paths[a][1])) for a in anc]  # copy semantics (fixes Q9)
-    ps, pt = paths[0]
+    k = 0  # multinomial offspring are i.i.d.: the reference's index 0 (pmcmc.py:307) is a fair draw
+    if resampler == "systematic":  # offspring are ordered by ancestor: draw the index uniformly
+        k = min(int(float(philox.u01(seed, philox.TAG_PF_RESAMPLE, 1, 0, D, chain)) * N), N - 1)
+    ps, pt = paths[k]
+    if extend:  # simulate (t_last_obs, t_end] as well (the reference extends the path flat, pmcmc.py:307-309)
+        vp, lp, tc = int(v[k]), float(l[k]), float(t[D])
+        slot = int(last_anc[k]) if D > 0 else 0
+        for it in range(max_jumps):
+            us = philox.u01(seed, philox.TAG_PF_PROPAGATE, it * K + np.arange(K), slot, D, chain)
+            taus = cond_weibull(us, tc - lp, shape[vp], scale[vp])
+            s = int(np.argmin(taus))
+            if lp + float(taus[s]) >= t_end:
+                break
+            tc = lp = lp + float(taus[s])
+            vp = s
+            ps.append(vp)
+            pt.append(lp)
     return np.asarray(ps + [ps[-1]], dtype=np.int64), np.asarray(pt + [float(t_end)]), float(np.sum(Z)), Z

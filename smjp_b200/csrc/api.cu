@@ -104,6 +104,8 @@ struct smjp_ctx {
     // workspaces
     DevBuf d_queue, d_msg_scratch, d_obsf, d_order;
     bool lpt_order = true;
+    int obs_product = 0;
+    int pf_extend = 0;
     int last_grid = 0, last_threads = 0;
     int64_t last_smem = 0;
     DevBuf d_in, d_out;  // staging for the host API
@@ -216,6 +218,14 @@ int smjp_ctx_set_option(smjp_ctx_t* c, const char* key, int64_t value) {
         if (value != 0 && (value < 32 || value > 512 || value % 32))
             return fail(SMJP_E_INVALID, "ffbs_threads must be 0 (auto) or a multiple of 32 in [32,512]");
         c->ffbs_threads = (int)value;
+        return SMJP_OK;
+    }
+    if (!strcmp(key, "pf_extend")) {
+        c->pf_extend = value != 0;
+        return SMJP_OK;
+    }
+    if (!strcmp(key, "obs_product")) {
+        c->obs_product = value != 0;
         return SMJP_OK;
     }
     if (!strcmp(key, "lpt_order")) {
@@ -416,6 +426,7 @@ int smjp_ffbs_dev(smjp_ctx_t* c, int C, const int64_t* w_offs, const double* W,
     a.order = nullptr;
     a.model = (const double*)c->d_model.p;
     a.Kobs = c->Kobs;
+    a.obs_product = c->obs_product;
     a.omega = c->omega;
     a.power = c->power;
     a.t_end = c->t_end;
@@ -1055,6 +1066,7 @@ int smjp_pf_host(smjp_ctx_t* c, int C, const int64_t* obs_offs, const double* ob
     a.chain_base = c->chain_base;
     a.resampler = resampler;
     a.max_iters = 4096;
+    a.extend = c->pf_extend;
     a.pv = (int32_t*)(o + o_wv);
     a.pl = (double*)(o + o_wl);
     a.cdf = (double*)(o + o_cdf);

@@ -58,6 +58,7 @@ struct FfbsArgs {
     unsigned int* queue;   // work counter, zeroed before launch
     const double* model;   // device: shape[K*K], c2[K*K] (= k*log2(lambda)), emis[K*Kobs], scale[K*K]
     int Kobs;
+    int obs_product;  // 0: observations sharing a grid interval are SUMMED (reference); 1: multiplied
     double omega, power, t_end;
     int ncap;   // max grid intervals any chain of this launch has (smem carve-up)
     int nslot;  // grid slots per thread: ceil((ncap + 1) / blockDim.x)
@@ -255,12 +256,15 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
                 }
                 Real f[K];
 #pragma unroll
-                for (int v = 0; v < K; ++v) f[v] = 0;
+                for (int v = 0; v < K; ++v) f[v] = a.obs_product ? (Real)1 : (Real)0;
                 int cnt = 0;
                 for (int d = lo; d < D && ot[d] <= wn; ++d, ++cnt) {
                     const int y = oy[d];
 #pragma unroll
-                    for (int v = 0; v < K; ++v) f[v] += (Real)emis[v * Kobs + y];
+                    for (int v = 0; v < K; ++v) {
+                        const Real pe = (Real)emis[v * Kobs + y];
+                        f[v] = a.obs_product ? f[v] * pe : f[v] + pe;
+                    }
                 }
 #pragma unroll
                 for (int v = 0; v < K; ++v)

@@ -9,7 +9,9 @@
 //   normalise  Z_d = log sum_p w_p - log N (:294-297);
 //   resample   multinomial (:302-304, utils.py:7-8) or systematic (new) by inverse CDF: block-wide
 //              prefix scan of the weights into a CDF, then a binary search per offspring;
-//   output     the path of particle 0 after the last resampling + (v_last, t_final) (:307-309).
+//   output     the path of one particle after the last resampling + (v_last, t_final) (:307-309):
+//              particle 0 as in the reference for multinomial resampling, a uniformly drawn one for
+//              systematic resampling (whose offspring are ordered, index 0 would be biased).
 // Deviations from the reference, both deliberate: resampled particles get copy
 // semantics (the reference aliases Python lists), and each particle's clock starts at the previous
 // observation time (the reference leaks t_curr from one particle into the next).
@@ -35,6 +37,7 @@ struct PfArgs {
     uint32_t chain_base;
     int resampler;
     int max_iters;        // cap on jumps per particle per observation interval
+    int extend;           // 1: also simulate the returned path on (t_last_obs, t_end] (the reference does not)
     // per-chain workspaces, chain stride given
     int32_t* pv;          // [C][2][N] particle state (double-buffered)
     double* pl;           // [C][2][N] time of last jump
@@ -193,7 +196,14 @@ __global__ void __launch_bounds__(B) pf_kernel(const PfArgs a) {
             int plen = 0;
             if (!(flag & SMJP_ST_DEGENERATE) && cap >= 2) {
                 int32_t* line = a.lineage + (int64_t)c * a.lineage_stride;  // slot b_d of the surviving lineage
+                // which offspring of the last resampling to return: multinomial offspring are i.i.d., so the
+                // reference's index 0 (pmcmc.py:307) is a fair draw; systematic offspring are ordered by
+                // ancestor, so the index must itself be drawn uniformly
                 int b = 0;
+                if (a.resampler == SMJP_RESAMPLE_SYSTEMATIC) {
+                    const double uk = philox_u01(a.seed, TAG_PF_RESAMPLE, 1, 0u, (uint32_t)D, chain);
+                    b = min((int)(uk * (double)N), N - 1);
+                }
                 for (int d = D - 1; d >= 0; --d) {
                     b = anc[(int64_t)d * N + b];
                     line[d] = b;
@@ -219,6 +229,12 @@ __global__ void __launch_bounds__(B) pf_kernel(const PfArgs a) {
                     const double t_prev = d == 0 ? 0.0 : a.obs_t[o0 + d - 1];
                     const int rc = pf_propagate(a, chain, (uint32_t)d, (uint32_t)line[d], v, l, t_prev,
                                                 a.obs_t[o0 + d], ov, ot, cap - 1, &nout);
+                    if (rc) flag |= rc;
+                }
+                if (a.extend && !(flag & SMJP_ST_OVERFLOW)) {
+                    const double t_prev = D > 0 ? a.obs_t[o0 + D - 1] : 0.0;
+                    const int rc = pf_propagate(a, chain, (uint32_t)D, (uint32_t)(D > 0 ? line[D - 1] : 0), v, l, t_prev,
+                                                a.t_end, ov, ot, cap - 1, &nout);
                     if (rc) flag |= rc;
                 }
                 if (!(flag & SMJP_ST_OVERFLOW)) {

@@ -93,7 +93,7 @@ class Engine:
         check(self.lib.smjp_ctx_kernel_time(self.ctx, kernel.encode(), ctypes.byref(ms), ctypes.byref(cnt)))
         return ms.value, cnt.value
 
-    def set_model(self, shape, scale, omega, emis, likelihood_power, t_end):
+    def set_model(self, shape, scale, omega, emis, likelihood_power, t_end, obs_combine="sum"):
         shape = np.ascontiguousarray(shape, dtype=np.float64)
         scale = np.ascontiguousarray(scale, dtype=np.float64)
         emis = np.ascontiguousarray(emis, dtype=np.float64)
@@ -104,6 +104,7 @@ class Engine:
             raise ValueError("emis must be [K,Kobs]")
         check(self.lib.smjp_set_model(self.ctx, K, emis.shape[1], _ptr(shape), _ptr(scale), float(omega),
                                       _ptr(emis), float(likelihood_power), float(t_end)))
+        self.set_option("obs_product", {"sum": 0, "product": 1}[obs_combine])
         self.K, self.Kobs = K, emis.shape[1]
         self.omega = float(omega)
         self.shape, self.scale, self.emis = shape.copy(), scale.copy(), emis.copy()
@@ -293,7 +294,7 @@ def hmm_dense_host(eng, P, pi0, E=None, emis=None, y=None, uniforms=None, seed=0
             "states": [states[x] for x in sl] if sample else None}
 
 
-def pf_host(eng, obs_t, obs_y, pi0, N, seed, resampler="systematic", C=None, path_cap=None):
+def pf_host(eng, obs_t, obs_y, pi0, N, seed, resampler="systematic", C=None, path_cap=None, extend=False):
     """Bootstrap particle filter (smjp_smc, pmcmc.py:224-310) for C chains.  obs_t/obs_y: list per
     chain, or one shared record with C given.  Returns dict(V, T, loglik, logZ, status)."""
     if isinstance(obs_t, np.ndarray) and obs_t.ndim == 1 and obs_t.dtype != object:
@@ -304,6 +305,7 @@ def pf_host(eng, obs_t, obs_y, pi0, N, seed, resampler="systematic", C=None, pat
     oy, _ = pack_ragged([np.asarray(v, dtype=np.int32) for v in obs_y], np.int32)
     pi0 = np.ascontiguousarray(pi0, dtype=np.float64)
     res = {"multinomial": _lib.RESAMPLE_MULTINOMIAL, "systematic": _lib.RESAMPLE_SYSTEMATIC}[resampler]
+    eng.set_option("pf_extend", int(bool(extend)))  # False: path held flat after the last observation (reference)
     cap = path_cap or 256
     while True:
         p_offs = np.arange(C + 1, dtype=np.int64) * cap

@@ -44,7 +44,7 @@ def update_parameters(hazard_A, hazard_B, poisson_proc_A_hat, poisson_proc_B, th
 def raoteh(inference, number_of_samples, save_iter, state_space, time_final, emission,
            data, pi_0, hazard_A, hazard_B, poisson_process_A_hat, poisson_process_B,
            uuid_str, omega, obs_times, filename, load_file, *, seed=None, verbose=False, save=True,
-           candidate_mode="reference", precision="f64"):
+           candidate_mode="reference", precision="f64", obs_combine="sum"):
     """Returns (aggregate {'W','T','V','prob'[,'theta'][,'prior']}, uuid_str, omega)."""
     inference_error_checking(inference)
     if load_file:
@@ -65,7 +65,7 @@ def raoteh(inference, number_of_samples, save_iter, state_space, time_final, emi
             aggregate["data"].append(data)
         W = sample_smjp_event_times(poisson_process_A_hat, V, T, time_final, mode=candidate_mode)
         V, T, prob = smjp_ffbs(W, data, state_space, hazard_A, hazard_B, emission, time_final,
-                               "raoteh_{}_{}".format(uuid_str, i), precision=precision)
+                               "raoteh_{}_{}".format(uuid_str, i), precision=precision, obs_combine=obs_combine)
         aggregate["W"].append(W)
         aggregate["V"].append(V)
         aggregate["T"].append(T)
@@ -89,7 +89,7 @@ def raoteh(inference, number_of_samples, save_iter, state_space, time_final, emi
 
 def raoteh_batch(number_of_chains, number_of_sweeps, state_space, time_final, emission, data, pi_0, hazard_A,
                  hazard_B, *, seed=0, burn_in=0, candidate_mode="reference", precision="f64", engine=None,
-                 keep_paths=False, chain_base=0):
+                 keep_paths=False, chain_base=0, obs_combine="sum"):
     """`number_of_chains` independent Rao-Teh chains advanced together on one GPU; the paths never
     leave the device.  Returns dict(time_in_state [S,C,K], jumps [S,C,K] for the S kept sweeps,
     paths (last sweep, or every kept sweep when keep_paths), state_steps)."""
@@ -97,7 +97,7 @@ def raoteh_batch(number_of_chains, number_of_sweeps, state_space, time_final, em
     from .smjp_utils import load_model, observation_arrays
     eng = engine or runtime.get_engine()
     states = list(state_space)
-    load_model(eng, states, hazard_A, hazard_B, emission, time_final)
+    load_model(eng, states, hazard_A, hazard_B, emission, time_final, obs_combine)
     obs_t, obs_y = observation_arrays(data, states)
     ch = DeviceChains(eng, number_of_chains, obs_t, chain_base=chain_base)
     ch.init_prior(np.asarray(pi_0.prob_vector, dtype=np.float64), seed).set_observations(obs_y)

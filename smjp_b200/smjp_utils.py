@@ -264,13 +264,13 @@ def observation_arrays(data, state_space):
     return t[order], y[order]
 
 
-def load_model(engine, state_space, hazard_A, hazard_B, smjp_e, t_end):
+def load_model(engine, state_space, hazard_A, hazard_B, smjp_e, t_end, obs_combine="sum"):
     omega = infer_omega(hazard_A, hazard_B)
     fg = getattr(smjp_e, "final_grid_time", t_end)
     if not np.isclose(fg, t_end):
         raise ValueError("emission.final_grid_time (%r) and t_end (%r) differ" % (fg, t_end))
     engine.set_model(hazard_A.shape_mat, hazard_A.scale_mat, omega, emission_arrays(smjp_e),
-                     getattr(smjp_e, "likelihood_power", 1.0), float(t_end))
+                     getattr(smjp_e, "likelihood_power", 1.0), float(t_end), obs_combine=obs_combine)
     return omega
 
 
@@ -323,13 +323,16 @@ def smjp_ffbs(W, data, state_space, hazard_A, hazard_B, smjp_e, t_end, u_str, **
 
 
 def sample_smjp_trajectory_posterior(W, data, state_space, hazard_A, hazard_B, smjp_e, t_end, u_str, *,
-                                     uniforms=None, seed=None, precision="f64", engine=None, full_output=False):
+                                     uniforms=None, seed=None, precision="f64", engine=None, full_output=False,
+                                     obs_combine="sum"):
     """forward filter over the augmented states + backward sample + compaction (smjp_utils.py:261-330).
     Returns (s_states float64 labels, s_times, prob) with prob == 1.0 like the reference (SURVEY Q1);
-    full_output=True returns the result dict (messages, logZ, samples, ...) as a fourth item."""
+    full_output=True returns the result dict (messages, logZ, samples, ...) as a fourth item.
+    obs_combine='sum' mirrors the reference (several observations in one grid interval are summed,
+    SURVEY Q3); 'product' is the proper likelihood."""
     eng = engine or runtime.get_engine()
     states = list(state_space)
-    load_model(eng, states, hazard_A, hazard_B, smjp_e, t_end)
+    load_model(eng, states, hazard_A, hazard_B, smjp_e, t_end, obs_combine)
     obs_t, obs_y = observation_arrays(data, states)
     Wa = np.asarray(W, dtype=np.float64)
     if uniforms is not None:

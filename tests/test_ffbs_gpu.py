@@ -156,3 +156,21 @@ def test_fp32_path_mismatches_only_near_cdf_boundaries(engine):
     r32 = engine.ffbs_host([W] * C, obs_t, obs_y, uniforms=us, precision="f32")
     same = sum(np.array_equal(a, b) for a, b in zip(r64["aug_idx"], r32["aug_idx"]))
     assert same >= C - 2, same
+
+
+def test_product_observation_likelihood_matches_oracle(engine):
+    """obs_combine='product' (not the reference's sum) against the oracle's same switch"""
+    from smjp_b200.engine import triangular_to_dense
+    rng = np.random.default_rng(21)
+    K, n, t_end = 3, 30, 6.0
+    shape, scale, W, obs_t, obs_y = random_problem(rng, K, t_end, n, 120)
+    emis = O.emission_matrix(K)
+    engine.set_model(shape, scale, 2.0, emis, 0.7, t_end, obs_combine="product")
+    u = rng.uniform(size=n)
+    r = engine.ffbs_host([W], [obs_t], [obs_y], uniforms=[u], want_messages=True)
+    ora = O.ffbs(W, obs_t, obs_y, shape, scale, 2.0, emis, 0.7, t_end, u, obs_combine="product")
+    rel, ab = rel_err(triangular_to_dense(r["messages"][0], n, K), ora["alpha"].reshape(n, K * n), 1e-250)
+    assert rel < 1e-9 and np.array_equal(r["aug_idx"][0], ora["samples"])
+    engine.set_model(shape, scale, 2.0, emis, 0.7, t_end)  # back to the reference behaviour
+    r2 = engine.ffbs_host([W], [obs_t], [obs_y], uniforms=[u], want_messages=True)
+    assert np.abs(r2["messages"][0] - r["messages"][0]).max() > 1e-3  # the two targets really differ

@@ -82,8 +82,8 @@ def test_collapsed_smjp_equals_augmented_filter_on_gpu(engine):
     assert np.abs(d["logc"][0] - r["logZ"][0]).max() < 1e-10
 
 
-@pytest.mark.parametrize("resampler", ["systematic", "multinomial"])
-def test_particle_filter_matches_oracle(engine, resampler):
+@pytest.mark.parametrize("resampler,extend", [("systematic", False), ("multinomial", False), ("systematic", True)])
+def test_particle_filter_matches_oracle(engine, resampler, extend):
     from smjp_b200.engine import pf_host
     K, t_end, N = 3, 2.0, 96
     shape = np.array([[1.606, 1.933, 0.865], [1.938, 0.869, 1.751], [1.69, 0.64, 0.696]])
@@ -93,11 +93,11 @@ def test_particle_filter_matches_oracle(engine, resampler):
     obs_t = np.arange(0.1, 2.0, 0.1)
     y = np.array([1, 1, 1, 1, 1, 1, 2, 2, 2, 1, 1, 1, 1, 3, 3, 2, 1, 1, 3]) - 1
     C = 6
-    r = pf_host(engine, obs_t, y, np.ones(K) / K, N, seed=17, resampler=resampler, C=C)
+    r = pf_host(engine, obs_t, y, np.ones(K) / K, N, seed=17, resampler=resampler, C=C, extend=extend)
     assert np.all(r["status"] == 0)
     for c in range(C):
         V, T, ll, Z = O.particle_filter(obs_t, y, shape, scale, emis, np.ones(K) / K, t_end, N, seed=17, chain=c,
-                                        resampler=resampler)
+                                        resampler=resampler, extend=extend)
         assert np.allclose(r["logZ"][c], Z, rtol=1e-12, atol=1e-12)
         assert abs(r["loglik"][c] - ll) < 1e-10
         assert np.array_equal(r["V"][c], V)
@@ -122,3 +122,35 @@ def test_particle_filter_large_and_unbiased(engine):
     assert abs(avg - np.mean(big["loglik"])) < 0.35
     for c in range(4):
         assert big["T"][c][0] == 0.0 and big["T"][c][-1] == t_end and np.all(np.diff(big["T"][c]) > 0)
+
+
+def test_particle_filter_paths_follow_the_exact_posterior(engine):
+    """shape == 1 (a Markov jump process): posterior time-in-state has an exact answer from a fine-grid
+    forward-backward; the PF path sample means must match it for BOTH resamplers.  (Systematic
+    offspring are ordered by ancestor: returning particle 0, as the reference does after multinomial
+    resampling, would be biased -- the kernel draws the returned index uniformly in that mode.)"""
+    from scipy.linalg import expm
+    from smjp_b200.engine import pf_host
+    K, t_end = 3, 2.0
+    emis = O.emission_matrix(K)
+    engine.set_model(np.ones((K, K)), np.ones((K, K)), 2.0, emis, 1.0, t_end)
+    obs_t = np.arange(0.1, 2.0, 0.1)
+    y = np.array([1, 1, 1, 1, 1, 1, 2, 2, 2, 1, 1, 1, 1, 3, 3, 2, 1, 1, 3]) - 1
+    Q = np.ones((K, K)); np.fill_diagonal(Q, 0); Q -= np.diag(Q.sum(1))
+    dt = 0.001; n = int(round(t_end / dt)); P = expm(Q * dt)
+    oi = {int(round(t / dt)): v for t, v in zip(obs_t, y)}
+    al = np.zeros((n + 1, K)); a = np.ones(K) / K
+    for t in range(n + 1):
+        a = a @ P if t else a
+        a = a * emis[:, oi[t]] if t in oi else a
+        a /= a.sum(); al[t] = a
+    be = np.zeros((n + 1, K)); b = np.ones(K)
+    for t in range(n, -1, -1):
+        be[t] = b
+        b = P @ (b * (emis[:, oi[t]] if t in oi else 1.0)); b /= b.sum()
+    post = al * be; post /= post.sum(1, keepdims=True)
+    exact = post[:-1].sum(0) * dt
+    for res in ("systematic", "multinomial"):
+        r = pf_host(engine, obs_t, y, np.ones(K) / K, 4096, seed=31, resampler=res, C=3000)
+        tt = np.array([O.chain_metrics(V, T, K)[0] for V, T in zip(r["V"], r["T"])])
+        assert np.abs(tt.mean(0) - exact).max() < 0.02, (res, tt.mean(0), exact)
