@@ -176,3 +176,34 @@ def test_posterior_summaries_ks_vs_oracle_chain(engine):
     for s in range(K):
         assert stats.ks_2samp(g_t[:, s], o_t[:, s]).statistic < ub
         assert stats.ks_2samp(g_j[:, s], o_j[:, s]).statistic < ub
+
+
+def test_sharded_chains_equal_unsharded_bit_for_bit(engine):
+    """'sharded vs unsharded summaries bit-for-bit'.  The Philox streams are keyed by the GLOBAL
+    chain index (chain_base + local index), so splitting 64 chains into shards [0,40) and [40,64) -- what
+    two ranks would own -- reproduces the single-batch run exactly."""
+    from smjp_b200.chains import DeviceChains
+    from smjp_b200.engine import Engine
+    K, t_end = 3, 6.0
+    emis = O.emission_matrix(K)
+    obs_t = np.arange(0.1, t_end, 0.1)
+
+    def run(eng, C, base):
+        eng.set_model(SHAPE3, np.ones((K, K)), 2.0, emis, 1.0, t_end)
+        ch = DeviceChains(eng, C, obs_t, chain_base=base).init_prior(np.ones(K) / K, seed=4).simulate_observations(seed=5)
+        ch.init_prior(np.ones(K) / K, seed=6)
+        for sw in range(3):
+            ch.sweep(seed=7, sweep=sw)
+        V, T = ch.paths_host()
+        return V, T, ch.time_in_state.cpu().numpy(), ch.jumps.cpu().numpy()
+
+    full = run(engine, 64, 0)
+    eng2 = Engine(0)
+    a = run(eng2, 40, 0)
+    b = run(eng2, 24, 40)
+    eng2.close()
+    engine.set_option("chain_base", 0)
+    V = a[0] + b[0]; T = a[1] + b[1]
+    assert all(np.array_equal(x, y) for x, y in zip(V, full[0]))
+    assert all(np.array_equal(x, y) for x, y in zip(T, full[1]))
+    assert np.array_equal(np.concatenate([a[2], b[2]]), full[2]) and np.array_equal(np.concatenate([a[3], b[3]]), full[3])
