@@ -153,6 +153,39 @@ struct Exp2<float> {
     __device__ __forceinline__ float log2(float x) const { return Math<float>::log2(x); }
 };
 
+// Warp reduction of N (a power of two <= 16) values at once.  Plain butterflies cost 5*N shuffles; here
+// the value index is folded into the lane index: at lane distance D each lane keeps one half of its
+// values and trades the other half, so the live count halves per level (N/2 + N/4 + ... shuffles), and
+// the single remaining value finishes with ordinary butterflies.  On return lane L holds, in v[0], the
+// warp total of value number (L >> (5 - log2 N)).
+template <typename T, int N, int D>
+struct WarpHalve {
+    static __device__ __forceinline__ void run(T* v, int lane) {
+        constexpr int H = N / 2;
+        const bool up = (lane & D) != 0;
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+            const T send = up ? v[k] : v[k + H];
+            const T keep = up ? v[k + H] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, D);
+        }
+        WarpHalve<T, H, D / 2>::run(v, lane);
+    }
+};
+template <typename T, int D>
+struct WarpHalve<T, 1, D> {
+    static __device__ __forceinline__ void run(T* v, int) {
+#pragma unroll
+        for (int d = D; d >= 1; d >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], d);
+    }
+};
+template <typename T>
+struct WarpHalve<T, 1, 0> {
+    static __device__ __forceinline__ void run(T*, int) {}
+};
+constexpr int pow2_ceil(int x) { return x <= 1 ? 1 : x <= 2 ? 2 : x <= 4 ? 4 : x <= 8 ? 8 : 16; }
+constexpr int log2_of(int x) { return x <= 1 ? 0 : x <= 2 ? 1 : x <= 4 ? 2 : x <= 8 ? 3 : 4; }
+
 template <typename Real> struct ScanAcc { typedef double type; };
 template <> struct ScanAcc<float> { typedef float type; };
 
@@ -293,18 +326,25 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
             of[v] = obsf[v];
         }
         bool degenerate = false;
+        // intervals whose right end "is" t_end drop the Poisson-event term (smjp_utils.py:544): with an
+        // increasing grid these are the last ones, from i_final on (normally only n-1)
+        int i_final = n;
+        while (i_final > 0 && np_isclose(a.t_end, Wd[i_final])) --i_final;
+        Real* row_base = msg;  // start of row i-1 (row r holds K*(r+1) values)
+        const Real* obsf_next = obsf + K;
         for (int i = 0; i < n; ++i) {
             const double wn = Wd[i + 1];
-            const bool nonfinal = !np_isclose(a.t_end, wn);  // smjp_utils.py:544
+            const bool nonfinal = i < i_final;
             Real ofn[K];  // next step's observation factors, fetched under this step's arithmetic
 #pragma unroll
-            for (int v = 0; v < K; ++v) ofn[v] = (i + 1 < n) ? obsf[(i + 1) * K + v] : (Real)1;
+            for (int v = 0; v < K; ++v) ofn[v] = (i + 1 < n) ? obsf_next[v] : (Real)1;
+            obsf_next += K;
             Real Zp = 0;
             Real Jp[K];
 #pragma unroll
             for (int v = 0; v < K; ++v) Jp[v] = 0;
             const int mi = i / B, ti = i - mi * B;  // slot and owner thread of the new state (v, W[i])
-            Real* rowp = msg + (int64_t)K * (i - 1) * i / 2 + tid;  // row i-1: i entries per state
+            Real* rowp = row_base + tid;  // row i-1: i entries per state
             Real* pa = st_a + tid;
             Real* ph = st_h + tid;
             const double* pw = Wd + tid;
@@ -353,13 +393,17 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
             if (tid <= ti) pair(std::true_type(), tid == ti);
             // block reduction of (Z, J[0..K)) -- double-buffered scratch, one barrier per step
             Real* rb = red + (i & 1) * NW * (K + 1);
-            Zp = warp_sum(Zp);
+            {
+                constexpr int NVP = pow2_ceil(K + 1), SH = 5 - log2_of(NVP);
+                Real vals[NVP];
+                vals[0] = Zp;
 #pragma unroll
-            for (int v = 0; v < K; ++v) Jp[v] = warp_sum(Jp[v]);
-            if (lane == 0) {
-                rb[wid * (K + 1)] = Zp;
+                for (int v = 0; v < K; ++v) vals[1 + v] = Jp[v];
 #pragma unroll
-                for (int v = 0; v < K; ++v) rb[wid * (K + 1) + 1 + v] = Jp[v];
+                for (int v = K + 1; v < NVP; ++v) vals[v] = 0;
+                WarpHalve<Real, NVP, 16>::run(vals, lane);
+                const int idx = lane >> SH;
+                if ((lane & ((1 << SH) - 1)) == 0 && idx < K + 1) rb[wid * (K + 1) + idx] = vals[0];
             }
             __syncthreads();
             Real Z = 0;
@@ -382,6 +426,7 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
                 of[v] = ofn[v];
             }
             if (a.logZ && tid == 0) a.logZ[w0 + i] = log((double)Z);
+            if (i > 0) row_base += (int64_t)K * i;  // row i-1 done: advance to row i
         }
         if (degenerate) {
             if (tid == 0) {
