@@ -107,6 +107,7 @@ struct smjp_ctx {
     int obs_product = 0;
     int pf_extend = 0;
     int last_grid = 0, last_threads = 0;
+    int64_t ffbs_ncap_hint = 0;
     int64_t last_smem = 0;
     DevBuf d_in, d_out;  // staging for the host API
     PinBuf h_in, h_out;
@@ -259,6 +260,7 @@ int smjp_set_model(smjp_ctx_t* c, int K, int Kobs, const double* shape, const do
         if (!(emis[t] >= 0.0) || !std::isfinite(emis[t]))
             return fail(SMJP_E_INVALID, "emission entry %d is negative or not finite", t);
     CUDA_TRY(cudaSetDevice(c->device));
+    if (K != c->K) c->ffbs_ncap_hint = 0;
     c->K = K;
     c->Kobs = Kobs;
     c->omega = omega;
@@ -328,7 +330,12 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
     a.nslot = ffbs_nslot((int)n_max, threads);
     int rc;
     if (!a.messages) {
-        const int64_t stride = (int64_t)K * n_max * (n_max + 1) / 2;
+        // grid lengths drift from sweep to sweep: size the per-CTA scratch for a rounded-up, never
+        // shrinking length so that steady-state sweeps do not reallocate
+        int64_t hint = (n_max + n_max / 8 + 63) / 64 * 64;
+        if (hint < c->ffbs_ncap_hint) hint = c->ffbs_ncap_hint;
+        c->ffbs_ncap_hint = hint;
+        const int64_t stride = (int64_t)K * hint * (hint + 1) / 2;
         size_t bytes = (size_t)stride * sizeof(Real) * (size_t)grid;
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
@@ -741,23 +748,23 @@ int stage_paths(smjp_ctx* c, int C, const int64_t* p_offs, const int32_t* path_v
     auto take = [&](size_t bytes) { size_t o = off; off += smjp::align_up(bytes, 16); return o; };
     const size_t o_po = take((C + 1) * 8), o_pv = take(total_p * 4), o_pt = take(total_p * 8), o_pl = take(C * 4);
     const size_t o_oo = take((C + 1) * 8), o_ot = take(total_o * 8), o_oy = take(total_o * 4);
-    int rc = c->h_in.reserve(off);
+    // the caller's arrays go straight to the device: full PCIe rate when they are pinned, the driver's
+    // own staging when they are pageable -- no extra host copy here
+    int rc = c->d_in.reserve(off);
     if (rc) return rc;
-    rc = c->d_in.reserve(off);
-    if (rc) return rc;
-    char* h = (char*)c->h_in.p;
-    memcpy(h + o_po, p_offs, (C + 1) * 8);
-    memcpy(h + o_pv, path_v, total_p * 4);
-    memcpy(h + o_pt, path_t, total_p * 8);
-    memcpy(h + o_pl, path_len, C * 4);
+    char* dd = (char*)c->d_in.p;
+    auto put = [&](size_t o, const void* src, size_t bytes) -> cudaError_t {
+        return bytes ? cudaMemcpyAsync(dd + o, src, bytes, cudaMemcpyHostToDevice, c->stream) : cudaSuccess;
+    };
+    CUDA_TRY(put(o_po, p_offs, (C + 1) * 8));
+    CUDA_TRY(put(o_pv, path_v, total_p * 4));
+    CUDA_TRY(put(o_pt, path_t, total_p * 8));
+    CUDA_TRY(put(o_pl, path_len, C * 4));
     if (obs_offs) {
-        memcpy(h + o_oo, obs_offs, (C + 1) * 8);
-        if (total_o) {
-            memcpy(h + o_ot, obs_t, total_o * 8);
-            memcpy(h + o_oy, obs_y, total_o * 4);
-        }
+        CUDA_TRY(put(o_oo, obs_offs, (C + 1) * 8));
+        CUDA_TRY(put(o_ot, obs_t, total_o * 8));
+        CUDA_TRY(put(o_oy, obs_y, total_o * 4));
     }
-    CUDA_TRY(cudaMemcpyAsync(c->d_in.p, h, off, cudaMemcpyHostToDevice, c->stream));
     char* d = (char*)c->d_in.p;
     out->p_offs = (const int64_t*)(d + o_po);
     out->path_v = (const int32_t*)(d + o_pv);
@@ -841,8 +848,6 @@ int smjp_sweep_host(smjp_ctx_t* c, int C, const int64_t* p_offs, const int32_t* 
     const size_t o_W = take(capacity * 8), o_pv = take(capacity * 4), o_pt = take(capacity * 8);
     rc = c->d_out.reserve(off);
     if (rc) return rc;
-    rc = c->h_out.reserve(off);
-    if (rc) return rc;
     char* d = (char*)c->d_out.p;
     int64_t n_max = 0;
     rc = smjp_sweep_dev(c, C, sp.p_offs, sp.path_v, sp.path_t, sp.path_len, sp.obs_offs, sp.obs_t, sp.obs_y,
@@ -850,21 +855,19 @@ int smjp_sweep_host(smjp_ctx_t* c, int C, const int64_t* p_offs, const int32_t* 
                         (double*)(d + o_W), (int32_t*)(d + o_pv), (double*)(d + o_pt), (int32_t*)(d + o_pl),
                         (double*)(d + o_tis), (int32_t*)(d + o_jm), (int32_t*)(d + o_st), &n_max, total_w);
     if (rc) return rc;
-    char* h = (char*)c->h_out.p;
     const int64_t tw = *total_w;
-    CUDA_TRY(cudaMemcpyAsync(h, d, o_W, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(h + o_W, d + o_W, tw * 8, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(h + o_pv, d + o_pv, tw * 4, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(h + o_pt, d + o_pt, tw * 8, cudaMemcpyDeviceToHost, c->stream));
+    auto get = [&](void* dst, size_t o, size_t bytes) -> cudaError_t {
+        return (dst && bytes) ? cudaMemcpyAsync(dst, d + o, bytes, cudaMemcpyDeviceToHost, c->stream) : cudaSuccess;
+    };
+    CUDA_TRY(get(w_offs, o_wo, (C + 1) * 8));
+    CUDA_TRY(get(path_len_out, o_pl, C * 4));
+    CUDA_TRY(get(status, o_st, C * 4));
+    CUDA_TRY(get(time_in_state, o_tis, (size_t)C * K * 8));
+    CUDA_TRY(get(jumps, o_jm, (size_t)C * K * 4));
+    CUDA_TRY(get(W, o_W, tw * 8));
+    CUDA_TRY(get(path_v_out, o_pv, tw * 4));
+    CUDA_TRY(get(path_t_out, o_pt, tw * 8));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    memcpy(w_offs, h + o_wo, (C + 1) * 8);
-    memcpy(path_len_out, h + o_pl, C * 4);
-    memcpy(status, h + o_st, C * 4);
-    if (time_in_state) memcpy(time_in_state, h + o_tis, (size_t)C * K * 8);
-    if (jumps) memcpy(jumps, h + o_jm, (size_t)C * K * 4);
-    memcpy(W, h + o_W, tw * 8);
-    memcpy(path_v_out, h + o_pv, tw * 4);
-    memcpy(path_t_out, h + o_pt, tw * 8);
     return SMJP_OK;
 }
 

@@ -216,6 +216,93 @@ def candidates_host(eng, V, T, seed, sweep=0, mode="reference"):
     return [W[w_offs[c]: w_offs[c + 1]].copy() for c in range(C)]
 
 
+class PackedSweep:
+    """Reusable HOST buffers (pinned through torch when available) for smjp_sweep_host: the packed form
+    of one Rao-Teh sweep for C chains, with no per-chain Python work.  `inputs` are (offs, v, t, len) of
+    the current paths; after `run()` the outputs (w_offs, W, v, t, len, time_in_state, jumps, status)
+    hold the new grids and paths and `swap()` makes them the next inputs."""
+
+    def __init__(self, eng, C, obs_offs, obs_t, obs_y, capacity):
+        self.eng, self.C, self.K = eng, int(C), eng.K
+        self.obs_offs = self._buf(np.int64, C + 1, obs_offs)
+        self.obs_t = self._buf(np.float64, len(obs_t), obs_t)
+        self.obs_y = self._buf(np.int32, len(obs_y), obs_y)
+        self._alloc(int(capacity))
+        self.total_w = 0
+
+    @staticmethod
+    def _buf(dtype, n, init=None):
+        try:
+            import torch
+            t = torch.empty(max(int(n), 1), dtype={np.int64: torch.int64, np.int32: torch.int32, np.float64: torch.float64}[dtype],
+                            pin_memory=torch.cuda.is_available())
+            a = t.numpy()  # the view keeps the pinned tensor alive through .base
+        except Exception:
+            a = np.empty(max(int(n), 1), dtype=dtype)
+        if init is not None:
+            a[: len(init)] = init
+        return a
+
+    def _alloc(self, capacity):
+        C, K = self.C, self.K
+        self.cap = capacity
+        self.in_offs, self.in_len = self._buf(np.int64, C + 1), self._buf(np.int32, C)
+        self.in_v, self.in_t = self._buf(np.int32, capacity), self._buf(np.float64, capacity)
+        self.w_offs, self.out_len = self._buf(np.int64, C + 1), self._buf(np.int32, C)
+        self.W = self._buf(np.float64, capacity)
+        self.out_v, self.out_t = self._buf(np.int32, capacity), self._buf(np.float64, capacity)
+        self.tis, self.jumps = self._buf(np.float64, C * K), self._buf(np.int32, C * K)
+        self.status = self._buf(np.int32, C)
+
+    def set_paths(self, V, T):
+        offs, pv, pt, pl = _pack_paths(V, T)
+        if len(pv) > self.cap:
+            self._alloc(int(len(pv) * 3 + 1024))
+        self.in_offs[: self.C + 1] = offs
+        self.in_v[: len(pv)] = pv
+        self.in_t[: len(pt)] = pt
+        self.in_len[: self.C] = pl
+        return self
+
+    def run(self, seed, sweep, mode="reference", precision="f64"):
+        modes = {"reference": _lib.CAND_REFERENCE, "exact": _lib.CAND_EXACT}
+        total = ctypes.c_int64(0)
+        while True:
+            rc = self.eng.lib.smjp_sweep_host(
+                self.eng.ctx, self.C, _ptr(self.in_offs), _ptr(self.in_v), _ptr(self.in_t), _ptr(self.in_len),
+                _ptr(self.obs_offs), _ptr(self.obs_t), _ptr(self.obs_y), int(seed) & 0xFFFFFFFFFFFFFFFF, int(sweep),
+                modes[mode], PRECISIONS[precision], self.cap, _ptr(self.w_offs), _ptr(self.W), _ptr(self.out_v),
+                _ptr(self.out_t), _ptr(self.out_len), _ptr(self.tis), _ptr(self.jumps), _ptr(self.status),
+                ctypes.byref(total))
+            if rc == -3 and total.value > self.cap:
+                keep = (self.in_offs.copy(), self.in_v.copy(), self.in_t.copy(), self.in_len.copy())
+                self._alloc(int(total.value * 1.5) + 1024)
+                self.in_offs[: len(keep[0])] = keep[0]
+                self.in_v[: len(keep[1])] = keep[1]
+                self.in_t[: len(keep[2])] = keep[2]
+                self.in_len[: len(keep[3])] = keep[3]
+                continue
+            check(rc)
+            break
+        self.total_w = int(total.value)
+        return self
+
+    def swap(self):
+        """outputs of the last sweep become the inputs of the next (paths live in the grid windows)"""
+        self.in_offs, self.w_offs = self.w_offs, self.in_offs
+        self.in_v, self.out_v = self.out_v, self.in_v
+        self.in_t, self.out_t = self.out_t, self.in_t
+        self.in_len, self.out_len = self.out_len, self.in_len
+        return self
+
+    def h2d_bytes(self):
+        live = int(self.in_offs[self.C])
+        return live * 12 + self.C * 12 + 8 + (self.C + 1) * 8 + len(self.obs_t) * 12
+
+    def d2h_bytes(self):
+        return self.total_w * 20 + (self.C + 1) * 8 + self.C * 8 + self.C * self.K * 12
+
+
 def sweep_host(eng, V, T, obs_t, obs_y, seed, sweep=0, mode="reference", precision="f64"):
     """One Rao-Teh sweep (raoteh.py:58-59) for HOST paths; returns dict(W, V, T, time_in_state, jumps, status)."""
     C = len(V)

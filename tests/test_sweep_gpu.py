@@ -207,3 +207,30 @@ def test_sharded_chains_equal_unsharded_bit_for_bit(engine):
     assert all(np.array_equal(x, y) for x, y in zip(V, full[0]))
     assert all(np.array_equal(x, y) for x, y in zip(T, full[1]))
     assert np.array_equal(np.concatenate([a[2], b[2]]), full[2]) and np.array_equal(np.concatenate([a[3], b[3]]), full[3])
+
+
+def test_packed_sweep_equals_list_api(engine):
+    """PackedSweep (pinned, no per-chain Python work: the e2e path of bench.py) == sweep_host on lists"""
+    from smjp_b200.engine import PackedSweep, sweep_host, ragged_offsets
+    K, t_end = 3, 8.0
+    emis = O.emission_matrix(K)
+    engine.set_model(SHAPE3, np.ones((K, K)), 2.0, emis, 1.0, t_end)
+    obs_t = np.arange(0.1, t_end, 0.1)
+    C = 20
+    V, T, Y = [], [], []
+    for c in range(C):
+        v, w = O.prior_path(SHAPE3, np.ones((K, K)), np.ones(K) / K, t_end, seed=1, chain=c)
+        V.append(v); T.append(w); Y.append(O.simulate_observations(v, w, obs_t, emis, seed=2, chain=c))
+    ps = PackedSweep(engine, C, ragged_offsets([len(obs_t)] * C), np.tile(obs_t, C), np.concatenate(Y), 64)  # tiny: forces regrowth
+    ps.set_paths(V, T)
+    for sw in range(3):
+        r = sweep_host(engine, V, T, [obs_t] * C, Y, seed=5, sweep=sw)
+        ps.run(5, sw)
+        for c in range(C):
+            lo = ps.w_offs[c]
+            assert np.array_equal(ps.W[lo: ps.w_offs[c + 1]], r["W"][c])
+            assert np.array_equal(ps.out_v[lo: lo + ps.out_len[c]], r["V"][c])
+            assert np.array_equal(ps.out_t[lo: lo + ps.out_len[c]], r["T"][c])
+        assert np.array_equal(ps.jumps[: C * K].reshape(C, K), r["jumps"])
+        ps.swap()
+        V, T = r["V"], r["T"]
