@@ -100,44 +100,50 @@ __device__ __forceinline__ bool np_isclose(double a, double b) {
 template <typename Real>
 struct Exp2;
 
+// polynomial coefficients live in constant memory so that DFMA takes them as c[bank] operands
+__constant__ double c_exp2[4] = {6.931471805599453e-01, 2.402265069591007e-01, 5.550410866482158e-02,
+                                 9.618129107628477e-03};  // ln2^i / i!
+__constant__ double c_log2[6] = {1.442695040888963e+00, -7.213475204444817e-01, 4.808983469629878e-01,
+                                 -3.606737602222409e-01, 2.885390081777927e-01, -2.404491734814939e-01};  // (-1)^(i+1)/(i ln2)
+
 template <>
 struct Exp2<double> {
     const double* tab;    // [256] 2^(i/256)
     const double2* ltab;  // [128] {1/c_i, -log2(1/c_i)}, c_i = 1 + (i + 1/2)/128
     static constexpr int TAB = 256;
     static constexpr int LTAB = 128;
-    // requires |x| < 2^22 (or NaN); flushes below 2^-1022 to 0, saturates above 2^1023 to inf
+    // 2^x for |x| < 2^22.  The power of two is added to the exponent field of the TABLE value before the
+    // last fma, so the result needs no repacking; the exponent is clamped to the normal range with two
+    // integer min/max (results saturate at 2^-1022 / 2^1023 instead of 0 / inf).
     __device__ __forceinline__ double operator()(double x) const {
         const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
         const double t = fma(x, 256.0, MAGIC);
         const int n = __double2loint(t);
         const double r = fma(t - MAGIC, -1.0 / 256.0, x);
-        double q = fma(r, 9.618129107628477e-03, 5.550410866482158e-02);  // ln2^4/24, ln2^3/6
-        q = fma(r, q, 2.402265069591007e-01);                             // ln2^2/2
-        q = fma(r, q, 6.931471805599453e-01);                             // ln2
+        double q = fma(r, c_exp2[3], c_exp2[2]);
+        q = fma(r, q, c_exp2[1]);
+        q = fma(r, q, c_exp2[0]);
         const double tv = tab[n & 255];
-        const double res = fma(tv, r * q, tv);  // [1, 2)
-        const int e = n >> 8;
-        int hi = __double2hiint(res) + (e << 20);
-        int lo = __double2loint(res);
-        const bool under = e < -1022, over = e > 1023;
-        hi = under ? 0 : (over ? 0x7ff00000 : hi);
-        lo = (under || over) ? 0 : lo;
-        return __hiloint2double(hi, lo);
+        const int e = max(min(n >> 8, 1023), -1022);
+        const double ts = __hiloint2double(__double2hiint(tv) + (e << 20), __double2loint(tv));
+        return fma(ts, r * q, ts);
     }
-    // any x <= 0 including -inf (survival factors)
-    __device__ __forceinline__ double neg(double x) const { return (*this)(fmax(x, -4096.0)); }
+    // any x <= 0 including -inf (survival factors): exact 0 below 2^-1022
+    __device__ __forceinline__ double neg(double x) const {
+        const double y = (*this)(fmax(x, -2048.0));
+        return x < -1022.0 ? 0.0 : y;
+    }
     __device__ __forceinline__ double log2(double x) const {
         const int hi = __double2hiint(x);
         if (hi < 0x00100000 || hi >= 0x7ff00000) return ::log2(x);  // zero / denormal / negative / inf / NaN
         const double2 tv = ltab[(hi >> 13) & 127];
         const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
         const double r = fma(m, tv.x, -1.0);  // |r| <= 2^-8
-        double p = fma(r, -2.404491734814939e-01, 2.885390081777927e-01);  // -1/(6 ln2), 1/(5 ln2)
-        p = fma(r, p, -3.606737602222409e-01);                             // -1/(4 ln2)
-        p = fma(r, p, 4.808983469629878e-01);                              //  1/(3 ln2)
-        p = fma(r, p, -7.213475204444817e-01);                             // -1/(2 ln2)
-        p = fma(r, p, 1.442695040888963e+00);                              //  1/ln2
+        double p = fma(r, c_log2[5], c_log2[4]);
+        p = fma(r, p, c_log2[3]);
+        p = fma(r, p, c_log2[2]);
+        p = fma(r, p, c_log2[1]);
+        p = fma(r, p, c_log2[0]);
         return fma(r, p, (double)((hi >> 20) - 1023) + tv.y);
     }
 };
