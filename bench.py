@@ -314,7 +314,7 @@ def run_ours(args):
         "gpu_launches": int(launches), "failed_chains": status_bad,
         "clocks": sampler.summary(),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
+                     "traffic": ((traffic or {}).get(prec) or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
                      "kernel": "ffbs_kernel<%s,3>" % ("double" if prec == "f64" else "float"),
                      "kernel_ms_avg": k_ms / max(k_cnt, 1), "grid": eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_grid"),
                      "threads": eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_threads"),
