@@ -300,17 +300,31 @@ template <typename Real>
 int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
     const int K = c->K;
     if (K > 10) return fail(SMJP_E_UNSUPPORTED, "sMJP FFBS kernel is instantiated for K in [2,10]; K=%d", K);
-    int threads = c->ffbs_threads;
-    if (threads == 0) {
-        // a full row should give every thread a few grid points; small grids use small CTAs
-        threads = 128;
-        if (n_max > 1024) threads = 256;
-        if (n_max > 3072) threads = 512;
-        if (n_max <= 96) threads = 64;
-        if (n_max <= 32) threads = 32;
+    const bool item_kernel = K >= 4;  // thread per (v, j) for larger state spaces, thread per j for K <= 3
+    int threads;
+    size_t smem;
+    if (item_kernel) {
+        threads = ffbs_item_threads(K, n_max);
+        if (c->ffbs_threads == ffbs_item_base_threads(K) || c->ffbs_threads == 2 * ffbs_item_base_threads(K))
+            threads = c->ffbs_threads;
+        smem = ffbs_item_smem_bytes<Real>(K, (int)n_max, threads);
+        if (smem > c->smem_optin && threads == ffbs_item_base_threads(K)) {
+            threads *= 2;  // more threads never need more shared memory per slot; retry for the message
+            smem = ffbs_item_smem_bytes<Real>(K, (int)n_max, threads);
+        }
+    } else {
+        threads = c->ffbs_threads;
+        if (threads == 0) {
+            // a full row should give every thread a few grid points; small grids use small CTAs
+            threads = 128;
+            if (n_max > 1024) threads = 256;
+            if (n_max > 3072) threads = 512;
+            if (n_max <= 96) threads = 64;
+            if (n_max <= 32) threads = 32;
+        }
+        threads = ffbs_round_threads(threads);
+        smem = ffbs_smem_bytes<Real>(K, (int)n_max, threads);
     }
-    threads = ffbs_round_threads(threads);
-    size_t smem = ffbs_smem_bytes<Real>(K, (int)n_max, threads);
     if (smem > c->smem_optin)
         return fail(SMJP_E_UNSUPPORTED,
                     "grid with %lld intervals x K=%d needs %zu B of shared memory (> %zu): "
@@ -327,7 +341,7 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
     int grid = c->num_sms * per_sm;
     if (grid > a.C) grid = a.C;
     a.ncap = (int)n_max;
-    a.nslot = ffbs_nslot((int)n_max, threads);
+    a.nslot = item_kernel ? ffbs_item_nslot(K, (int)n_max, threads) : ffbs_nslot((int)n_max, threads);
     int rc;
     if (!a.messages) {
         // grid lengths drift from sweep to sweep: size the per-CTA scratch for a rounded-up, never

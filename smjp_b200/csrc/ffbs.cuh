@@ -84,6 +84,26 @@ __host__ __device__ inline size_t ffbs_smem_bytes(int K, int ncap, int threads) 
     return b;
 }
 
+// item-parallel kernel (ffbs_item.cuh): a slot holds threads/K grid points for all K states
+__host__ __device__ inline int ffbs_item_nslot(int K, int ncap, int threads) {
+    const int jps = threads / K;
+    return (ncap + jps) / jps;
+}
+
+template <typename Real>
+__host__ __device__ inline size_t ffbs_item_smem_bytes(int K, int ncap, int threads) {
+    const size_t state = (size_t)ffbs_item_nslot(K, ncap, threads) * threads;
+    size_t b = 0;
+    b += align_up((size_t)(ncap + 1) * sizeof(double), 16);
+    b += align_up((size_t)threads * sizeof(double), 16);
+    b += align_up((size_t)(threads / 32 + 1) * sizeof(double), 16);
+    b += align_up(state * sizeof(Real), 16);
+    b += align_up(state * sizeof(Real), 16);
+    b += align_up((size_t)2 * (threads / 32) * (K + 1) * sizeof(Real), 16);
+    b += align_up((size_t)(4 * K * K) * sizeof(Real), 16);
+    return b;
+}
+
 __device__ __forceinline__ bool np_isclose(double a, double b) {
     // numpy.isclose(a, b): |a-b| <= atol + rtol*|b|, rtol=1e-5, atol=1e-8
     return fabs(a - b) <= 1e-8 + 1e-5 * fabs(b);

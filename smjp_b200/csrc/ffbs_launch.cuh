@@ -2,6 +2,7 @@
 // ffbs_f64.cu / ffbs_f32.cu so that the two precisions compile in parallel.
 #pragma once
 #include "ffbs.cuh"
+#include "ffbs_item.cuh"
 
 namespace smjp {
 
@@ -42,14 +43,44 @@ cudaError_t ffbs_pick(const FfbsArgs& a, FfbsLaunch& L, bool query) {
     return cudaErrorInvalidValue;
 }
 
+// ---- K >= 4: item-parallel kernel, block size a multiple of K (two sizes per K) ----
+constexpr int ffbs_item_base_threads(int K) {
+    return K == 4 ? 128 : K == 5 ? 160 : K == 6 ? 192 : K == 7 ? 224 : K == 8 ? 128 : K == 9 ? 288 : 160;
+}
+inline int ffbs_item_threads(int K, long long n_max) {
+    const int b1 = ffbs_item_base_threads(K);
+    return (n_max * K > 32LL * b1) ? 2 * b1 : b1;  // keep a full row within ~32 items per thread
+}
+
+template <typename Real, int K, int B>
+cudaError_t ffbs_item_do(const FfbsArgs& a, FfbsLaunch& L, bool query) {
+    // register budget: ~64 per thread in fp32, ~128 in fp64
+    constexpr int fit = 1024 / B < 1 ? 1 : 1024 / B;
+    constexpr int MINB = sizeof(Real) == 8 ? (512 / B < 1 ? 1 : 512 / B) : fit;
+    auto kern = ffbs_item_kernel<Real, K, B, MINB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    if (e != cudaSuccess) return e;
+    if (query) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&L.grid, kern, B, L.smem);
+    kern<<<L.grid, B, L.smem, L.stream>>>(a);
+    return cudaGetLastError();
+}
+
+template <typename Real, int K>
+cudaError_t ffbs_item_pick(const FfbsArgs& a, FfbsLaunch& L, bool query) {
+    constexpr int B1 = ffbs_item_base_threads(K);
+    if (L.threads == B1) return ffbs_item_do<Real, K, B1>(a, L, query);
+    if (L.threads == 2 * B1) return ffbs_item_do<Real, K, 2 * B1>(a, L, query);
+    return cudaErrorInvalidValue;
+}
+
 // K is split over two translation units per precision (compile time): lo = 2..5, hi = 6..10
 template <typename Real>
 cudaError_t ffbs_dispatch_lo(const FfbsArgs& a, FfbsLaunch& L, bool query) {
     switch (L.K) {
         case 2: return ffbs_pick<Real, 2>(a, L, query);
         case 3: return ffbs_pick<Real, 3>(a, L, query);
-        case 4: return ffbs_pick<Real, 4>(a, L, query);
-        case 5: return ffbs_pick<Real, 5>(a, L, query);
+        case 4: return ffbs_item_pick<Real, 4>(a, L, query);
+        case 5: return ffbs_item_pick<Real, 5>(a, L, query);
     }
     return cudaErrorInvalidValue;
 }
@@ -57,11 +88,11 @@ cudaError_t ffbs_dispatch_lo(const FfbsArgs& a, FfbsLaunch& L, bool query) {
 template <typename Real>
 cudaError_t ffbs_dispatch_hi(const FfbsArgs& a, FfbsLaunch& L, bool query) {
     switch (L.K) {
-        case 6: return ffbs_pick<Real, 6>(a, L, query);
-        case 7: return ffbs_pick<Real, 7>(a, L, query);
-        case 8: return ffbs_pick<Real, 8>(a, L, query);
-        case 9: return ffbs_pick<Real, 9>(a, L, query);
-        case 10: return ffbs_pick<Real, 10>(a, L, query);
+        case 6: return ffbs_item_pick<Real, 6>(a, L, query);
+        case 7: return ffbs_item_pick<Real, 7>(a, L, query);
+        case 8: return ffbs_item_pick<Real, 8>(a, L, query);
+        case 9: return ffbs_item_pick<Real, 9>(a, L, query);
+        case 10: return ffbs_item_pick<Real, 10>(a, L, query);
     }
     return cudaErrorInvalidValue;
 }

@@ -1,0 +1,121 @@
+#!/usr/bin/env python
+"""Runs the BASELINE.json configurations that are not the bench line (configs[0], [2], [3], [4]) at
+representative sizes on one GPU and prints one JSON line each: they are parity-test configurations
+(tests/ cover their correctness); this script records what they cost on a B200.
+
+    python tools/run_configs.py [cfg1 cfg3 cfg4 cfg5]
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def emission(K):
+    E = np.ones((K, K)) + 9 * np.eye(K)
+    return E / E.sum(axis=1, keepdims=True)
+
+
+def cfg1():
+    """main.py default: single 3-state chain, T=2, 19 observations -- through the drop-in raoteh()"""
+    import experiments
+    from smjp_b200.raoteh import raoteh
+    m = experiments.build_experiment_2_model()
+    n = 300
+    t0 = time.perf_counter()
+    agg, _, _ = raoteh(["trajectory"], n, 300, m["state_space"], m["time_final"], m["emission"], m["data"], m["pi_0"],
+                       m["hazard_A"], m["hazard_B"], m["poisson_process_A_hat"], m["poisson_process_B"], "cfg1", m["omega"],
+                       m["obs_times"], None, False, seed=1, save=False)
+    dt = time.perf_counter() - t0
+    ss = sum(3 * (len(w) - 1) * len(w) / 2 for w in agg["W"])
+    return {"config": "cfg1 main.py default, 1 chain through the drop-in raoteh()", "sweeps_per_sec": n / dt,
+            "state_steps_per_sec": ss / dt, "reference_measured_sweeps_per_sec": 1.04, "note": "latency-bound: 2 host calls per sweep"}
+
+
+def cfg3(N=65536, C=8):
+    """pmcmc particle filter: 65536 particles per chain, 5-state sMJP, systematic resampling"""
+    import torch
+    from smjp_b200.engine import Engine, pf_host
+    rng = np.random.default_rng(3)
+    K, t_end = 5, 10.0
+    eng = Engine(0)
+    eng.set_model(rng.uniform(0.6, 3.0, (K, K)), np.ones((K, K)), 2.0, emission(K), 1.0, t_end)
+    obs_t = np.arange(0.1, t_end, 0.1)
+    y = rng.integers(0, K, len(obs_t))
+    pf_host(eng, obs_t, y, np.ones(K) / K, N, seed=1, C=C)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    r = pf_host(eng, obs_t, y, np.ones(K) / K, N, seed=2, C=C)
+    dt = time.perf_counter() - t0
+    eng.close()
+    return {"config": "cfg3 particle filter N=%d, K=5 Weibull hazards, D=%d, %d filter runs, systematic" % (N, len(obs_t), C),
+            "particle_steps_per_sec": N * len(obs_t) * C / dt, "seconds": dt, "loglik_spread": float(np.ptp(r["loglik"])),
+            "algorithmic_GBps": 68.0 * N * len(obs_t) * C / dt / 1e9, "status_ok": bool(np.all(r["status"] == 0))}
+
+
+def cfg4(C=1024, S=64, n=4000):
+    """large-state dense path: K=64 shared transition matrix (shape == 1 collapse), fp32"""
+    import torch
+    from smjp_b200.engine import Engine, hmm_dense_host
+    rng = np.random.default_rng(4)
+    scale = rng.uniform(0.5, 2.0, (S, S))
+    A = 1.0 / scale
+    B = 0.5 * np.eye(S) + A / (2.0 * A.sum(axis=1, keepdims=True))
+    emis = emission(S)
+    ys = [rng.integers(0, S, n).astype(np.int32) for _ in range(C)]
+    eng = Engine(0)
+    hmm_dense_host(eng, B, np.ones(S) / S, emis=emis, y=ys[:8], precision="f32", seed=1)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    r = hmm_dense_host(eng, B, np.ones(S) / S, emis=emis, y=ys, precision="f32", seed=2)
+    dt = time.perf_counter() - t0
+    eng.close()
+    return {"config": "cfg4 dense K=64 HMM (collapsed sMJP), %d chains x %d grid points, fp32, host API incl. copies" % (C, n),
+            "state_steps_per_sec": C * n * S / dt, "seconds": dt, "status_ok": bool(np.all(r["status"] == 0)),
+            "algorithmic_GBps": 2 * 4 * S * C * n / dt / 1e9}
+
+
+def cfg5(C=16384, T=20.0, sweeps=4, threads=0):
+    """10-state sMJP, many chains (one GPU's shard of the 65536-chain configuration)"""
+    import torch
+    from smjp_b200.chains import DeviceChains
+    from smjp_b200.engine import Engine
+    rng = np.random.default_rng(5)
+    K = 10
+    eng = Engine(0)
+    eng.set_model(rng.uniform(0.6, 3.0, (K, K)), np.ones((K, K)), 2.0, emission(K), 1.0, T)
+    eng.set_option("ffbs_threads", threads)
+    obs_t = np.arange(0.1, T, 0.1)
+    out = {"threads": threads}
+    for prec in ("f64", "f32"):
+        ch = DeviceChains(eng, C, obs_t).init_prior(np.ones(K) / K, seed=1).simulate_observations(seed=2)
+        ch.init_prior(np.ones(K) / K, seed=3)
+        for sw in range(3):
+            ch.sweep(seed=4, sweep=sw, precision=prec)
+        torch.cuda.synchronize()
+        ss = 0.0
+        t0 = time.perf_counter()
+        for sw in range(sweeps):
+            ch.sweep(seed=4, sweep=3 + sw, precision=prec)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        for _ in range(1):
+            s, g = ch.state_steps_last_sweep()
+        out[prec] = {"chain_sweeps_per_sec": C * sweeps / dt, "state_steps_per_sec": s * sweeps / dt, "mean_n": g / C,
+                     "ms_per_sweep": 1e3 * dt / sweeps, "failed": int((ch.status != 0).sum().item()),
+                     "algorithmic_GBps": (2 * (8 if prec == "f64" else 4) * s * sweeps / dt) / 1e9}
+    eng.close()
+    return {"config": "cfg5 shard: %d chains, K=10, T=%g" % (C, T), **out}
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["cfg1", "cfg3", "cfg4", "cfg5"]
+    for name in which:
+        if name.startswith("cfg5:"):
+            print(json.dumps(cfg5(threads=int(name[5:]))), flush=True)
+        else:
+            print(json.dumps(globals()[name]()), flush=True)
