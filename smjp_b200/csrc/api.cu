@@ -106,6 +106,7 @@ struct smjp_ctx {
     bool lpt_order = true;
     int obs_product = 0;
     int pf_extend = 0;
+    int item_k3 = 0;
     int last_grid = 0, last_threads = 0;
     int64_t ffbs_ncap_hint = 0;
     int64_t last_smem = 0;
@@ -221,6 +222,10 @@ int smjp_ctx_set_option(smjp_ctx_t* c, const char* key, int64_t value) {
         c->ffbs_threads = (int)value;
         return SMJP_OK;
     }
+    if (!strcmp(key, "item_k3")) {
+        c->item_k3 = value != 0;
+        return SMJP_OK;
+    }
     if (!strcmp(key, "pf_extend")) {
         c->pf_extend = value != 0;
         return SMJP_OK;
@@ -300,7 +305,8 @@ template <typename Real>
 int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
     const int K = c->K;
     if (K > 10) return fail(SMJP_E_UNSUPPORTED, "sMJP FFBS kernel is instantiated for K in [2,10]; K=%d", K);
-    const bool item_kernel = K >= 4;  // thread per (v, j) for larger state spaces, thread per j for K <= 3
+    const bool item_kernel = K >= 4 || (K == 3 && c->item_k3);
+    a.use_item = item_kernel;  // thread per (v, j) for larger state spaces, thread per j for K <= 3
     int threads;
     size_t smem;
     if (item_kernel) {

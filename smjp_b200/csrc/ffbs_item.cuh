@@ -279,6 +279,15 @@ __global__ void __launch_bounds__(B, MINB) ffbs_item_kernel(const FfbsArgs a) {
         while (true) {
             const int len = cur + 1;
             const Real* row = msg + (int64_t)K * cur * (cur + 1) / 2;
+            {   // The next draw reads row j*-1 where W[j*] starts the sojourn found now; sojourns are a few grid
+                // steps long, so rows cur-1 .. cur-3 (contiguous, just below this row) cover ~7/8 of the cases:
+                // pull them into L2 now, one draw ahead of the HBM round trip that would otherwise be exposed.
+                const int r0 = cur > 3 ? cur - 3 : 0;
+                const char* p0 = (const char*)(msg + (int64_t)K * r0 * (r0 + 1) / 2);
+                const char* p1 = (const char*)row;
+                for (const char* p = p0 + (size_t)tid * 128; p < p1; p += (size_t)B * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+            }
             if (!a.uniforms && (u_hi < 0 || cur <= u_hi - B)) {
                 if (cur - tid >= 0)
                     ubuf[tid] = philox_u01(a.seed, TAG_BACKWARD, (uint64_t)(cur - tid), 0u, a.sweep,

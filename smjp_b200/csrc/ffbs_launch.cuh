@@ -45,7 +45,7 @@ cudaError_t ffbs_pick(const FfbsArgs& a, FfbsLaunch& L, bool query) {
 
 // ---- K >= 4: item-parallel kernel, block size a multiple of K (two sizes per K) ----
 constexpr int ffbs_item_base_threads(int K) {
-    return K == 4 ? 128 : K == 5 ? 160 : K == 6 ? 192 : K == 7 ? 224 : K == 8 ? 128 : K == 9 ? 288 : 160;
+    return K == 3 ? 96 : K == 4 ? 128 : K == 5 ? 160 : K == 6 ? 192 : K == 7 ? 224 : K == 8 ? 128 : K == 9 ? 288 : 160;
 }
 inline int ffbs_item_threads(int K, long long n_max) {
     const int b1 = ffbs_item_base_threads(K);
@@ -78,7 +78,7 @@ template <typename Real>
 cudaError_t ffbs_dispatch_lo(const FfbsArgs& a, FfbsLaunch& L, bool query) {
     switch (L.K) {
         case 2: return ffbs_pick<Real, 2>(a, L, query);
-        case 3: return ffbs_pick<Real, 3>(a, L, query);
+        case 3: return a.use_item ? ffbs_item_pick<Real, 3>(a, L, query) : ffbs_pick<Real, 3>(a, L, query);
         case 4: return ffbs_item_pick<Real, 4>(a, L, query);
         case 5: return ffbs_item_pick<Real, 5>(a, L, query);
     }
