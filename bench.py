@@ -49,37 +49,64 @@ def algorithmic_bytes(n_per_chain, D, esz):
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons sampled DURING the timed region.  NVML in-process (a `nvidia-smi`
+    subprocess per sample holds the driver lock for ~0.2 s and was measured to stall the timed stream by
+    that much); nvidia-smi is only the fallback when pynvml is missing."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
         self.stop_flag = threading.Event()
         self.sm, self.smmax, self.reasons = [], [], set()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.smmax.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)))
+        except Exception:
+            self.nvml = None
 
-    def run(self):
+    def sample(self):
+        if self.nvml is not None:
+            n = self.nvml
+            self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+            try:
+                mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+            except Exception:
+                mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+            for bit, name in self.REASONS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+            return
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout
+        f = [x.strip() for x in out.strip().split(",")]
+        self.sm.append(float(f[0]))
+        self.smmax.append(float(f[1]))
+        for nm, val in zip(names, f[2:6]):
+            if val.lower().startswith("active"):
+                self.reasons.add(nm)
+
+    def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                self.sm.append(float(f[0]))
-                self.smmax.append(float(f[1]))
-                for nm, val in zip(names, f[2:6]):
-                    if val.lower().startswith("active"):
-                        self.reasons.add(nm)
+                self.sample()
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.02 if self.nvml is not None else 0.2)
 
     def summary(self):
         if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(np.max(self.smmax)),
-                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(np.max(self.smmax)) if self.smmax else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "via": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def measured_peak():
