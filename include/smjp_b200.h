@@ -51,6 +51,10 @@ extern "C" {
 #define SMJP_CAND_REFERENCE 0 /* unit-scale Weibull density truncated to the sojourn (distributions.py:295) */
 #define SMJP_CAND_EXACT 1     /* density proportional to the hazard: tau * U^(1/k) */
 
+/* holding-time family of the particle filter ("hazard_family" option; the filter kernels are Weibull only) */
+#define SMJP_HAZARD_WEIBULL 0 /* the reference: smjp_utils.py:419-423 "hazard function is weibull for now" */
+#define SMJP_HAZARD_GAMMA 1   /* new: shape = a, scale = theta (BASELINE configs[2]) */
+
 /* particle-filter resampler */
 #define SMJP_RESAMPLE_MULTINOMIAL 0 /* utils.py:7-8 sampleDiscrete, pmcmc.py:302 */
 #define SMJP_RESAMPLE_SYSTEMATIC 1  /* new (north_star) */
@@ -70,6 +74,8 @@ int64_t smjp_ctx_launch_count(smjp_ctx_t* ctx);
 int64_t smjp_ctx_get_stat(smjp_ctx_t* ctx, const char* key);
 /* knobs: "ffbs_threads" (0 = auto, else threads per CTA of the FFBS kernel);
  *        "time_kernels" (0/1, see smjp_ctx_kernel_time);
+ *        "hazard_family" (SMJP_HAZARD_*; gamma is honoured by smjp_pf_host only -- the FFBS / candidate /
+ *        prior entry points return SMJP_E_UNSUPPORTED for it);
  *        "pf_extend" (0 = the particle-filter path is extended flat from the last observation to t_end
  *        as the reference does, pmcmc.py:307-309; 1 = the segment is simulated);
  *        "lpt_order" (0/1, default 1: the FFBS kernel starts the longest grids first);

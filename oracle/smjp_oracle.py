@@ -394,6 +394,14 @@ def cond_weibull(u, hold, k, lam):
     return lam * np.power(np.power(hold / lam, k) - np.log1p(-u), 1.0 / k)
 
 
+def cond_gamma(u, hold, a, theta):
+    """Gamma(shape a, scale theta) holding time given tau > hold, by inverting the survival function
+    Q(a, tau/theta) = (1-u) Q(a, hold/theta).  Not in the reference (its hazards are Weibull only,
+    smjp_utils.py:419-423; distributions.py:179-217 has the gamma density); parity unpinned."""
+    from scipy import special
+    return theta * special.gammainccinv(a, (1.0 - u) * special.gammaincc(a, hold / theta))
+
+
 def logsumexp(x):
     """log sum exp; the reference's (utils.py:4-5) has no max shift -- identical wherever finite."""
     m = np.max(x)
@@ -417,7 +425,7 @@ def resample_ancestors(w, N, resampler, seed, d, chain):
 
 
 def particle_filter(obs_t, obs_y, shape, scale, emis, pi0, t_end, N, seed, chain,
-                    resampler="systematic", max_jumps=64, extend=False):
+                    resampler="systematic", max_jumps=64, extend=False, family="weibull"):
     """smjp_smc (pmcmc.py:224-310).  Per observation d: every particle (v, l) is propagated by
     competing conditional-Weibull risks (:261-289) until its next jump would pass obs_t[d]; weight
     log P(y_d | v) (:279-281); Z_d = logsumexp(logw) - log N (:294-297); resample (:302-304).
@@ -446,7 +454,7 @@ def particle_filter(obs_t, obs_y, shape, scale, emis, pi0, t_end, N, seed, chain
             pv, pt = paths[p]
             for it in range(max_jumps):
                 us = philox.u01(seed, philox.TAG_PF_PROPAGATE, it * K + np.arange(K), p, d, chain)
-                taus = cond_weibull(us, tc - lp, shape[vp], scale[vp])
+                taus = (cond_gamma if family == "gamma" else cond_weibull)(us, tc - lp, shape[vp], scale[vp])
                 s = int(np.argmin(taus))
                 w_next = lp + float(taus[s])
                 if w_next >= t_obs:
@@ -475,7 +483,7 @@ def particle_filter(obs_t, obs_y, shape, scale, emis, pi0, t_end, N, seed, chain
         slot = int(last_anc[k]) if D > 0 else 0
         for it in range(max_jumps):
             us = philox.u01(seed, philox.TAG_PF_PROPAGATE, it * K + np.arange(K), slot, D, chain)
-            taus = cond_weibull(us, tc - lp, shape[vp], scale[vp])
+            taus = (cond_gamma if family == "gamma" else cond_weibull)(us, tc - lp, shape[vp], scale[vp])
             s = int(np.argmin(taus))
             if lp + float(taus[s]) >= t_end:
                 break

@@ -106,6 +106,7 @@ struct smjp_ctx {
     bool lpt_order = true;
     int obs_product = 0;
     int pf_extend = 0;
+    int hazard_family = SMJP_HAZARD_WEIBULL;
     int item_k3 = 0;
     int last_grid = 0, last_threads = 0;
     int64_t ffbs_ncap_hint = 0;
@@ -122,6 +123,15 @@ struct smjp_ctx {
 };
 
 using namespace smjp;
+
+namespace {
+int weibull_only(smjp_ctx* c, const char* what) {
+    if (c->hazard_family != SMJP_HAZARD_WEIBULL)
+        return fail(SMJP_E_UNSUPPORTED, "%s is implemented for Weibull hazards only (hazard_family = gamma is a "
+                    "particle-filter option)", what);
+    return SMJP_OK;
+}
+}  // namespace
 
 extern "C" {
 
@@ -224,6 +234,11 @@ int smjp_ctx_set_option(smjp_ctx_t* c, const char* key, int64_t value) {
     }
     if (!strcmp(key, "item_k3")) {
         c->item_k3 = value != 0;
+        return SMJP_OK;
+    }
+    if (!strcmp(key, "hazard_family")) {
+        if (value != SMJP_HAZARD_WEIBULL && value != SMJP_HAZARD_GAMMA) return fail(SMJP_E_INVALID, "bad hazard family");
+        c->hazard_family = (int)value;
         return SMJP_OK;
     }
     if (!strcmp(key, "pf_extend")) {
@@ -427,6 +442,10 @@ int smjp_ffbs_dev(smjp_ctx_t* c, int C, const int64_t* w_offs, const double* W,
     if (n_max < 1) return fail(SMJP_E_INVALID, "n_max < 1: every grid needs at least [0, t_end]");
     if (total_w < (int64_t)C * 2) return fail(SMJP_E_INVALID, "total_w inconsistent with C");
     if (precision != SMJP_F64 && precision != SMJP_F32) return fail(SMJP_E_INVALID, "bad precision");
+    {
+        const int rcw = weibull_only(c, "the FFBS kernel");
+        if (rcw) return rcw;
+    }
     CUDA_TRY(cudaSetDevice(c->device));
     FfbsArgs a;
     memset(&a, 0, sizeof a);
@@ -569,6 +588,7 @@ int model_ready(smjp_ctx* c) {
     return SMJP_OK;
 }
 
+
 CandArgs make_cand_args(smjp_ctx* c, int C, const int64_t* p_offs, const int32_t* path_v,
                         const double* path_t, const int32_t* path_len, uint64_t seed, uint32_t sweep) {
     CandArgs a;
@@ -595,6 +615,8 @@ extern "C" {
 int smjp_prior_dev(smjp_ctx_t* c, int C, const int64_t* p_offs, const double* pi0, int honour_scale,
                    uint64_t seed, int32_t* path_v, double* path_t, int32_t* path_len, int32_t* status) {
     int rc = model_ready(c);
+    if (rc) return rc;
+    rc = weibull_only(c, "the prior sampler");
     if (rc) return rc;
     if (C <= 0) return C == 0 ? SMJP_OK : fail(SMJP_E_INVALID, "C < 0");
     if (!p_offs || !pi0 || !path_v || !path_t || !path_len || !status)
@@ -668,6 +690,8 @@ int smjp_candidates_count_dev(smjp_ctx_t* c, int C, const int64_t* p_offs, const
                               uint32_t sweep, int64_t* w_offs, int32_t* soff, int64_t* n_max_host,
                               int64_t* total_w_host) {
     int rc = model_ready(c);
+    if (rc) return rc;
+    rc = weibull_only(c, "the candidate sampler");
     if (rc) return rc;
     if (C <= 0) return fail(SMJP_E_INVALID, "C <= 0");
     if (!p_offs || !path_v || !path_t || !path_len || !w_offs || !soff || !n_max_host || !total_w_host)
@@ -1090,6 +1114,7 @@ int smjp_pf_host(smjp_ctx_t* c, int C, const int64_t* obs_offs, const double* ob
     a.resampler = resampler;
     a.max_iters = 4096;
     a.extend = c->pf_extend;
+    a.family = c->hazard_family;
     a.pv = (int32_t*)(o + o_wv);
     a.pl = (double*)(o + o_wl);
     a.cdf = (double*)(o + o_cdf);

@@ -37,6 +37,7 @@ struct PfArgs {
     uint32_t chain_base;
     int resampler;
     int max_iters;        // cap on jumps per particle per observation interval
+    int family;           // SMJP_HAZARD_WEIBULL | SMJP_HAZARD_GAMMA (shape = a, scale = theta)
     int extend;           // 1: also simulate the returned path on (t_last_obs, t_end] (the reference does not)
     // per-chain workspaces, chain stride given
     int32_t* pv;          // [C][2][N] particle state (double-buffered)
@@ -56,6 +57,73 @@ struct PfArgs {
     int32_t* status;
 };
 
+// ------------------------------------------------------------------------------------------------
+// Gamma holding times (not in the reference, whose hazards are "weibull for now", smjp_utils.py:419-423;
+// BASELINE configs[2] asks for a gamma-hazard sMJP).  tau ~ Gamma(shape a, scale theta) given tau > h is
+// drawn by inverting the survival function: Q(a, tau/theta) = (1 - u) Q(a, h/theta), Q the regularised
+// upper incomplete gamma function (series / continued fraction, inverse by Halley steps from a
+// Wilson-Hilferty start).  Twin: oracle cond_gamma (scipy.special.gammaincc / gammainccinv).
+// ------------------------------------------------------------------------------------------------
+__device__ inline double igamc(double a, double x) {
+    if (!(x > 0.0)) return 1.0;
+    const double lax = a * log(x) - x - lgamma(a);
+    if (lax < -745.0) return x < a + 1.0 ? 1.0 : 0.0;
+    const double ax = exp(lax);
+    if (x < a + 1.0) {  // P(a,x) by series
+        double r = a, c = 1.0, ans = 1.0;
+        for (int it = 0; it < 500; ++it) {
+            r += 1.0;
+            c *= x / r;
+            ans += c;
+            if (c <= 1e-17 * ans) break;
+        }
+        return 1.0 - ans * ax / a;
+    }
+    const double tiny = 1e-300;  // Q(a,x) by continued fraction (modified Lentz)
+    double b = x + 1.0 - a, c = 1.0 / tiny, d = 1.0 / b, h = d;
+    for (int i = 1; i < 500; ++i) {
+        const double an = -(double)i * ((double)i - a);
+        b += 2.0;
+        d = an * d + b;
+        if (fabs(d) < tiny) d = tiny;
+        c = b + an / c;
+        if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        const double delta = d * c;
+        h *= delta;
+        if (fabs(delta - 1.0) < 1e-16) break;
+    }
+    return ax * h;
+}
+
+__device__ inline double igamci(double a, double q) {  // x with Q(a, x) = q
+    if (q >= 1.0) return 0.0;
+    if (!(q > 0.0)) return INFINITY;
+    const double t = -normcdfinv(q), d = 1.0 / (9.0 * a), y = 1.0 - d + t * sqrt(d);
+    double x = a * y * y * y;
+    if (x <= 0.0 || a < 1.0) {
+        const double p = 1.0 - q;
+        const double x0 = exp((log(fmax(p, 1e-300)) + lgamma(a + 1.0)) / a);
+        if (x <= 0.0) x = x0;
+        else if (p < 0.5) x = x0;
+        else x = fmax(x, x0);
+    }
+    for (int it = 0; it < 60; ++it) {
+        const double f = igamc(a, x) - q;
+        const double fp = -exp((a - 1.0) * log(x) - x - lgamma(a));
+        if (fp == 0.0) break;
+        double dx = f / fp;
+        const double den = 1.0 - 0.5 * dx * ((a - 1.0) / x - 1.0);
+        if (den > 0.2) dx /= den;
+        double xn = x - dx;
+        if (!(xn > 0.0)) xn = 0.5 * x;
+        const bool done = fabs(xn - x) <= 1e-15 * xn;
+        x = xn;
+        if (done) break;
+    }
+    return x;
+}
+
 // one propagation of a particle from clock t_cur towards t_obs; optionally records jumps
 __device__ __forceinline__ int pf_propagate(const PfArgs& a, uint32_t chain, uint32_t d, uint32_t slot, int& v,
                                             double& l, double t_cur, double t_obs, int32_t* out_v, double* out_t,
@@ -71,7 +139,9 @@ __device__ __forceinline__ int pf_propagate(const PfArgs& a, uint32_t chain, uin
         for (int s = 0; s < K; ++s) {
             const double k = shape[v * K + s], lam = scale[v * K + s];
             const double u = philox_u01(a.seed, TAG_PF_PROPAGATE, (uint64_t)(it * K + s), slot, d, chain);
-            const double tau = lam * pow(pow(hold / lam, k) - log1p(-u), 1.0 / k);
+            const double tau = a.family == SMJP_HAZARD_GAMMA
+                                   ? lam * igamci(k, (1.0 - u) * igamc(k, hold / lam))
+                                   : lam * pow(pow(hold / lam, k) - log1p(-u), 1.0 / k);
             if (tau < best) { best = tau; arg = s; }
         }
         const double w_next = l + best;

@@ -381,7 +381,8 @@ def hmm_dense_host(eng, P, pi0, E=None, emis=None, y=None, uniforms=None, seed=0
             "states": [states[x] for x in sl] if sample else None}
 
 
-def pf_host(eng, obs_t, obs_y, pi0, N, seed, resampler="systematic", C=None, path_cap=None, extend=False):
+def pf_host(eng, obs_t, obs_y, pi0, N, seed, resampler="systematic", C=None, path_cap=None, extend=False,
+            family="weibull"):
     """Bootstrap particle filter (smjp_smc, pmcmc.py:224-310) for C chains.  obs_t/obs_y: list per
     chain, or one shared record with C given.  Returns dict(V, T, loglik, logZ, status)."""
     if isinstance(obs_t, np.ndarray) and obs_t.ndim == 1 and obs_t.dtype != object:
@@ -393,6 +394,7 @@ def pf_host(eng, obs_t, obs_y, pi0, N, seed, resampler="systematic", C=None, pat
     pi0 = np.ascontiguousarray(pi0, dtype=np.float64)
     res = {"multinomial": _lib.RESAMPLE_MULTINOMIAL, "systematic": _lib.RESAMPLE_SYSTEMATIC}[resampler]
     eng.set_option("pf_extend", int(bool(extend)))  # False: path held flat after the last observation (reference)
+    eng.set_option("hazard_family", {"weibull": 0, "gamma": 1}[family])  # gamma: shape = a, scale = theta
     cap = path_cap or 256
     while True:
         p_offs = np.arange(C + 1, dtype=np.int64) * cap
@@ -409,6 +411,7 @@ def pf_host(eng, obs_t, obs_y, pi0, N, seed, resampler="systematic", C=None, pat
             cap *= 4
             continue
         break
+    eng.set_option("hazard_family", 0)
     return {"V": [pv[c * cap: c * cap + pl[c]].copy() for c in range(C)],
             "T": [pt[c * cap: c * cap + pl[c]].copy() for c in range(C)],
             "loglik": ll, "logZ": [lz[o_offs[c]: o_offs[c + 1]].copy() for c in range(C)], "status": st}

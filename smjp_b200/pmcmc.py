@@ -14,7 +14,8 @@ from .utils import np_log
 
 def smjp_smc(*args, **kwargs):
     """keywords as the reference: pi_0, time_final, N, data, A, emission, states, uuid; extras:
-    seed, resampler ('multinomial' = reference, 'systematic'), engine.
+    seed, resampler ('multinomial' = reference, 'systematic'), family ('weibull' = reference, 'gamma': shape_mat
+    holds the gamma shapes and scale_mat the gamma scales), extend, engine.
     Returns (path_states, path_times, log_likelihood)."""
     states = list(kwargs["states"])
     hazard_A, emission = kwargs["A"], kwargs["emission"]
@@ -24,7 +25,8 @@ def smjp_smc(*args, **kwargs):
     obs_t, obs_y = observation_arrays(kwargs["data"], states)
     seed = kwargs.get("seed")
     r = pf_host(eng, obs_t, obs_y, np.asarray(kwargs["pi_0"].prob_vector, dtype=np.float64), int(kwargs["N"]),
-                runtime.next_seed() if seed is None else seed, resampler=kwargs.get("resampler", "multinomial"), C=1)
+                runtime.next_seed() if seed is None else seed, resampler=kwargs.get("resampler", "multinomial"), C=1,
+                family=kwargs.get("family", "weibull"), extend=kwargs.get("extend", False))
     raise_for_status(r["status"])
     return [states[i] for i in r["V"][0]], list(r["T"][0]), float(r["loglik"][0])
 

@@ -154,3 +154,33 @@ def test_particle_filter_paths_follow_the_exact_posterior(engine):
         r = pf_host(engine, obs_t, y, np.ones(K) / K, 4096, seed=31, resampler=res, C=3000)
         tt = np.array([O.chain_metrics(V, T, K)[0] for V, T in zip(r["V"], r["T"])])
         assert np.abs(tt.mean(0) - exact).max() < 0.02, (res, tt.mean(0), exact)
+
+
+def test_gamma_hazard_particle_filter_matches_oracle(engine):
+    """BASELINE configs[2]: gamma holding times (new; the reference has Weibull hazards only).  Same Philox
+    streams as the oracle, whose conditional gamma draw inverts scipy's regularised incomplete gamma."""
+    from smjp_b200.engine import pf_host
+    rng = np.random.default_rng(33)
+    K, t_end, N = 5, 3.0, 64
+    shape = rng.uniform(0.6, 3.0, (K, K)); scale = rng.uniform(0.5, 1.5, (K, K))
+    emis = O.emission_matrix(K)
+    engine.set_model(shape, scale, 2.0, emis, 1.0, t_end)
+    obs_t = np.arange(0.1, t_end, 0.1); y = rng.integers(0, K, len(obs_t))
+    r = pf_host(engine, obs_t, y, np.ones(K) / K, N, seed=3, C=4, family="gamma")
+    assert np.all(r["status"] == 0)
+    for c in range(4):
+        V, T, ll, Z = O.particle_filter(obs_t, y, shape, scale, emis, np.ones(K) / K, t_end, N, seed=3, chain=c,
+                                        family="gamma")
+        assert np.allclose(r["logZ"][c], Z, rtol=1e-10, atol=1e-10)
+        assert np.array_equal(r["V"][c], V) and np.allclose(r["T"][c], T, rtol=1e-9, atol=0)
+    # and the draws really are gamma: exponential special case a = 1 equals the Weibull k = 1 filter
+    engine.set_model(np.ones((K, K)), scale, 2.0, emis, 1.0, t_end)
+    g = pf_host(engine, obs_t, y, np.ones(K) / K, 256, seed=4, C=2, family="gamma")
+    w = pf_host(engine, obs_t, y, np.ones(K) / K, 256, seed=4, C=2, family="weibull")
+    assert np.allclose(g["loglik"], w["loglik"], rtol=1e-9) and all(np.array_equal(a, b) for a, b in zip(g["V"], w["V"]))
+    with pytest.raises(Exception):
+        engine.set_option("hazard_family", 1)
+        try:
+            engine.ffbs_host([np.array([0.0, 1.0, t_end])], np.zeros(0), np.zeros(0, int), uniforms=[np.array([0.5, 0.5])])
+        finally:
+            engine.set_option("hazard_family", 0)
