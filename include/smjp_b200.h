@@ -70,12 +70,13 @@ void smjp_ctx_destroy(smjp_ctx_t* ctx);
 int smjp_ctx_sync(smjp_ctx_t* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t smjp_ctx_launch_count(smjp_ctx_t* ctx);
-/* launch geometry of the last FFBS kernel: "ffbs_grid", "ffbs_threads", "ffbs_smem"; "num_sms" */
+/* launch geometry of the last FFBS kernel: "ffbs_grid", "ffbs_threads", "ffbs_smem"; "num_sms"; "pf_cluster" */
 int64_t smjp_ctx_get_stat(smjp_ctx_t* ctx, const char* key);
 /* knobs: "ffbs_threads" (0 = auto, else threads per CTA of the FFBS kernel);
  *        "time_kernels" (0/1, see smjp_ctx_kernel_time);
  *        "hazard_family" (SMJP_HAZARD_*; gamma is honoured by smjp_pf_host only -- the FFBS / candidate /
  *        prior entry points return SMJP_E_UNSUPPORTED for it);
+ *        "pf_cluster" (thread-block-cluster size of one particle-filter run: 0 = auto, 1, 2, 4, 8, 16);
  *        "pf_extend" (0 = the particle-filter path is extended flat from the last observation to t_end
  *        as the reference does, pmcmc.py:307-309; 1 = the segment is simulated);
  *        "lpt_order" (0/1, default 1: the FFBS kernel starts the longest grids first);
@@ -84,7 +85,7 @@ int64_t smjp_ctx_get_stat(smjp_ctx_t* ctx, const char* key);
  *        "chain_base" (global index of chain 0 of this context's batches: keeps the Philox streams of
  *        chains sharded over several GPUs distinct and independent of the sharding) */
 int smjp_ctx_set_option(smjp_ctx_t* ctx, const char* key, int64_t value);
-/* With option "time_kernels" = 1 every launch of the named kernel ("ffbs") is bracketed by CUDA events
+/* With option "time_kernels" = 1 every launch of the named kernel ("ffbs", "hmm", "pf") is bracketed by CUDA events
  * on the launching stream; this returns and resets their summed duration and count (synchronises). */
 int smjp_ctx_kernel_time(smjp_ctx_t* ctx, const char* kernel, double* total_ms, int64_t* count);
 

@@ -107,6 +107,7 @@ struct smjp_ctx {
     int obs_product = 0;
     int pf_extend = 0;
     int hazard_family = SMJP_HAZARD_WEIBULL;
+    int pf_cluster = 0, last_pf_cluster = 0;
     int item_k3 = 0;
     int last_grid = 0, last_threads = 0;
     int64_t ffbs_ncap_hint = 0;
@@ -119,7 +120,7 @@ struct smjp_ctx {
     PinBuf h_stats;
     // optional per-kernel timing (CUDA events on the launching stream)
     bool time_kernels = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ffbs_events;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ffbs_events, hmm_events, pf_events;
 };
 
 using namespace smjp;
@@ -203,15 +204,20 @@ int64_t smjp_ctx_get_stat(smjp_ctx_t* c, const char* key) {
     if (!strcmp(key, "ffbs_threads")) return c->last_threads;
     if (!strcmp(key, "ffbs_smem")) return c->last_smem;
     if (!strcmp(key, "num_sms")) return c->num_sms;
+    if (!strcmp(key, "pf_cluster")) return c->last_pf_cluster;
     return -1;
 }
 
 int smjp_ctx_kernel_time(smjp_ctx_t* c, const char* kernel, double* total_ms, int64_t* count) {
     if (!c || !kernel || !total_ms || !count) return fail(SMJP_E_INVALID, "null argument");
-    if (strcmp(kernel, "ffbs")) return fail(SMJP_E_INVALID, "unknown kernel '%s'", kernel);
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>>* evs = nullptr;
+    if (!strcmp(kernel, "ffbs")) evs = &c->ffbs_events;
+    else if (!strcmp(kernel, "hmm")) evs = &c->hmm_events;
+    else if (!strcmp(kernel, "pf")) evs = &c->pf_events;
+    else return fail(SMJP_E_INVALID, "unknown kernel '%s'", kernel);
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     double ms = 0;
-    for (auto& ev : c->ffbs_events) {
+    for (auto& ev : *evs) {
         float t = 0;
         CUDA_TRY(cudaEventElapsedTime(&t, ev.first, ev.second));
         ms += t;
@@ -219,8 +225,8 @@ int smjp_ctx_kernel_time(smjp_ctx_t* c, const char* kernel, double* total_ms, in
         cudaEventDestroy(ev.second);
     }
     *total_ms = ms;
-    *count = (int64_t)c->ffbs_events.size();
-    c->ffbs_events.clear();
+    *count = (int64_t)evs->size();
+    evs->clear();
     return SMJP_OK;
 }
 
@@ -234,6 +240,12 @@ int smjp_ctx_set_option(smjp_ctx_t* c, const char* key, int64_t value) {
     }
     if (!strcmp(key, "item_k3")) {
         c->item_k3 = value != 0;
+        return SMJP_OK;
+    }
+    if (!strcmp(key, "pf_cluster")) {
+        if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8 && value != 16)
+            return fail(SMJP_E_INVALID, "pf_cluster must be 0 (auto), 1, 2, 4, 8 or 16");
+        c->pf_cluster = (int)value;
         return SMJP_OK;
     }
     if (!strcmp(key, "hazard_family")) {
@@ -935,12 +947,22 @@ int hmm_launch(smjp_ctx* c, const HmmArgs& a) {
         CUDA_TRY(cudaFuncSetAttribute(hmm_dense_kernel<Real, n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         hmm_dense_kernel<Real, n><<<grid, warps * 32, smem, c->stream>>>(a);                            \
         break;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->time_kernels) {
+        CUDA_TRY(cudaEventCreate(&e0));
+        CUDA_TRY(cudaEventCreate(&e1));
+        CUDA_TRY(cudaEventRecord(e0, c->stream));
+    }
     switch (spl) {
         HMM_CASE(1) HMM_CASE(2) HMM_CASE(3) HMM_CASE(4)
         default: return fail(SMJP_E_UNSUPPORTED, "dense HMM kernel supports S <= 128 (S=%d)", S);
     }
 #undef HMM_CASE
     CUDA_TRY(cudaGetLastError());
+    if (c->time_kernels) {
+        CUDA_TRY(cudaEventRecord(e1, c->stream));
+        c->hmm_events.emplace_back(e0, e1);
+    }
     c->launches += 1;
     return SMJP_OK;
 }
@@ -1129,10 +1151,58 @@ int smjp_pf_host(smjp_ctx_t* c, int C, const int64_t* obs_offs, const double* ob
     a.path_t = (double*)(o + o_pt);
     a.path_len = (int32_t*)(o + o_pl);
     a.status = (int32_t*)(o + o_st);
-    int grid = C < c->num_sms * 2 ? C : c->num_sms * 2;
-    if (N >= 4096) pf_kernel<1024><<<grid, 1024, 0, c->stream>>>(a);
-    else pf_kernel<256><<<grid, 256, 0, c->stream>>>(a);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->time_kernels) {
+        CUDA_TRY(cudaEventCreate(&e0));
+        CUDA_TRY(cudaEventCreate(&e1));
+        CUDA_TRY(cudaEventRecord(e0, c->stream));
+    }
+    {
+        // cluster size: spread one filter run over as many SMs as the chain count leaves free
+        int cs = 1;
+        if (N >= 4096) {
+            while (cs < 16 && (int64_t)C * cs * 2 <= c->num_sms && N / (cs * 2) >= 2048) cs *= 2;
+        }
+        if (c->pf_cluster > 0) cs = c->pf_cluster;
+        const int threads = N / cs >= 4096 ? 1024 : 256;
+        int n_clusters = C;
+        if ((int64_t)n_clusters * cs > (int64_t)c->num_sms * 2) n_clusters = (c->num_sms * 2) / cs;
+        if (n_clusters < 1) n_clusters = 1;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3((unsigned)(n_clusters * cs));
+        cfg.blockDim = dim3((unsigned)threads);
+        cfg.stream = c->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)cs;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+#define PF_LAUNCH(BT, CSV)                                                                                        \
+    do {                                                                                                          \
+        if (CSV > 8) CUDA_TRY(cudaFuncSetAttribute(pf_kernel<BT, CSV>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)); \
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, pf_kernel<BT, CSV>, a));                                                \
+    } while (0)
+#define PF_PICK(CSV)                                   \
+    case CSV:                                          \
+        if (threads == 1024) PF_LAUNCH(1024, CSV);     \
+        else PF_LAUNCH(256, CSV);                      \
+        break;
+        switch (cs) {
+            PF_PICK(1) PF_PICK(2) PF_PICK(4) PF_PICK(8) PF_PICK(16)
+            default: return fail(SMJP_E_INVALID, "pf_cluster must be 1, 2, 4, 8 or 16");
+        }
+#undef PF_PICK
+#undef PF_LAUNCH
+        c->last_pf_cluster = cs;
+    }
     CUDA_TRY(cudaGetLastError());
+    if (c->time_kernels) {
+        CUDA_TRY(cudaEventRecord(e1, c->stream));
+        c->pf_events.emplace_back(e0, e1);
+    }
     c->launches += 1;
     CUDA_TRY(cudaMemcpyAsync(c->h_out.p, o, out_bytes, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));

@@ -21,6 +21,8 @@
 // the jump times.  oracle/smjp_oracle.py::particle_filter is the CPU twin.
 #pragma once
 #include "../../include/smjp_b200.h"
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace smjp {
@@ -159,16 +161,26 @@ __device__ __forceinline__ int pf_propagate(const PfArgs& a, uint32_t chain, uin
     return SMJP_ST_OVERFLOW;  // more than max_iters jumps inside one observation interval
 }
 
-template <int B>
+// One thread-block CLUSTER of CS CTAs per filter run: the N particles are split over the CTAs of the
+// cluster, per-CTA weight totals are exchanged through distributed shared memory, and two cluster
+// barriers per observation order the shared CDF / particle arrays in global memory.  CS = 1 is the
+// single-CTA filter.
+template <int B, int CS>
 __global__ void __launch_bounds__(B) pf_kernel(const PfArgs a) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
     constexpr int NW = B / 32;
     __shared__ double s_warp[NW + 1];
-    __shared__ double s_carry;
+    __shared__ double s_total;  // this CTA's weight total, read by the whole cluster
     __shared__ int s_flag;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int rank = CS > 1 ? (int)cluster.block_rank() : 0;
+    const int cluster_id = blockIdx.x / CS, n_clusters = gridDim.x / CS;
     const int N = a.N, K = a.K;
+    const int Np = (N + CS - 1) / CS;
+    const int p_lo = min(rank * Np, N), p_hi = min(p_lo + Np, N);
     const double* emis = a.model + 2 * K * K;
-    for (int c = blockIdx.x; c < a.C; c += gridDim.x) {
+    for (int c = cluster_id; c < a.C; c += n_clusters) {
         const uint32_t chain = a.chain_base + (uint32_t)c;
         const int64_t o0 = a.obs_offs[c];
         const int D = (int)(a.obs_offs[c + 1] - o0);
@@ -180,7 +192,7 @@ __global__ void __launch_bounds__(B) pf_kernel(const PfArgs a) {
         // initial states v0 ~ pi0
         double ptot = 0;
         for (int s = 0; s < K; ++s) ptot += a.pi0[s];
-        for (int p = tid; p < N; p += B) {
+        for (int p = p_lo + tid; p < p_hi; p += B) {
             const double u = philox_u01(a.seed, TAG_PF_PROPAGATE, 0, (uint32_t)p, 0xFFFFFFFFu, chain);
             double acc = 0;
             int v = -1, lastpos = 0;
@@ -196,6 +208,7 @@ __global__ void __launch_bounds__(B) pf_kernel(const PfArgs a) {
         __syncthreads();
         int cur = 0;
         double loglik = 0;
+        bool dead = false;
         for (int d = 0; d < D; ++d) {
             const double t_prev = d == 0 ? 0.0 : a.obs_t[o0 + d - 1];
             const double t_obs = a.obs_t[o0 + d];
@@ -205,8 +218,8 @@ __global__ void __launch_bounds__(B) pf_kernel(const PfArgs a) {
             int32_t* v_out = pv + (cur ^ 1) * N;
             double* l_out = pl + (cur ^ 1) * N;
             // ---- propagate + weight: contiguous chunk per thread so that the scan is in particle order ----
-            const int q = (N + B - 1) / B;
-            const int beg = min(tid * q, N), end = min(beg + q, N);
+            const int q = (p_hi - p_lo + B - 1) / B;
+            const int beg = min(p_lo + tid * q, p_hi), end = min(beg + q, p_hi);
             double loc = 0;
             for (int p = beg; p < end; ++p) {
                 int v = v_in[p];
@@ -217,29 +230,40 @@ __global__ void __launch_bounds__(B) pf_kernel(const PfArgs a) {
                 l_in[p] = l;
                 const double w = emis[v * a.Kobs + y];
                 loc += w;
-                cdf[p] = loc;  // chunk-local inclusive sums; offset added below
+                cdf[p] = loc;  // chunk-local inclusive sums; offsets added below
             }
             double incl = warp_inclusive_scan(loc, lane);
             if (lane == 31) s_warp[wid] = incl;
             __syncthreads();
             double off = 0;
             for (int w = 0; w < wid; ++w) off += s_warp[w];
-            double total = 0;
-            for (int w = 0; w < NW; ++w) total += s_warp[w];
-            const double excl = off + incl - loc;
+            double cta_total = 0;
+            for (int w = 0; w < NW; ++w) cta_total += s_warp[w];
+            if (tid == 0) s_total = cta_total;
+            double cta_excl = 0, total = cta_total;
+            if (CS > 1) {
+                cluster.sync();  // every CTA's s_total is written
+                total = 0;
+                for (int r = 0; r < CS; ++r) {
+                    const double tr = *cluster.map_shared_rank(&s_total, r);
+                    if (r < rank) cta_excl += tr;
+                    total += tr;
+                }
+            }
+            const double excl = cta_excl + off + incl - loc;
             for (int p = beg; p < end; ++p) cdf[p] += excl;
             const double Zd = log(total) - log((double)N);
             loglik += Zd;
-            if (tid == 0 && a.logZ) a.logZ[o0 + d] = Zd;
-            __syncthreads();
-            if (!(total > 0.0)) {  // every particle has zero weight
-                if (tid == 0) s_flag |= SMJP_ST_DEGENERATE;
-                __syncthreads();
+            if (rank == 0 && tid == 0 && a.logZ) a.logZ[o0 + d] = Zd;
+            if (CS > 1) cluster.sync();  // CDF and propagated particles of all CTAs are in global memory
+            else __syncthreads();
+            if (!(total > 0.0)) {  // every particle has zero weight (uniform over the cluster)
+                dead = true;
                 break;
             }
             // ---- resample: inverse CDF per offspring ----
             const double u_sys = philox_u01(a.seed, TAG_PF_RESAMPLE, 0, 0u, (uint32_t)d, chain);
-            for (int p = tid; p < N; p += B) {
+            for (int p = p_lo + tid; p < p_hi; p += B) {
                 const double pos = a.resampler == SMJP_RESAMPLE_SYSTEMATIC
                                        ? (u_sys + (double)p) / (double)N
                                        : philox_u01(a.seed, TAG_PF_RESAMPLE, (uint64_t)p, 0u, (uint32_t)d, chain);
@@ -257,10 +281,16 @@ __global__ void __launch_bounds__(B) pf_kernel(const PfArgs a) {
             cur ^= 1;
             __syncthreads();
         }
-        __syncthreads();
-        int flag = s_flag;
+        // combine the per-CTA flags on rank 0 and make the last resampling visible to it
+        __shared__ int s_flag_pub;
+        if (tid == 0) s_flag_pub = s_flag | (dead ? SMJP_ST_DEGENERATE : 0);
+        if (CS > 1) cluster.sync();
+        else __syncthreads();
+        int flag = 0;
+        if (rank == 0 && tid == 0)
+            for (int r = 0; r < CS; ++r) flag |= CS > 1 ? *cluster.map_shared_rank(&s_flag_pub, r) : s_flag_pub;
         // ---- path of particle 0: lineage through the ancestor table, then replay ----
-        if (tid == 0) {
+        if (rank == 0 && tid == 0) {
             const int64_t p0 = a.p_offs[c];
             const int cap = (int)(a.p_offs[c + 1] - p0);
             int plen = 0;
@@ -317,7 +347,8 @@ __global__ void __launch_bounds__(B) pf_kernel(const PfArgs a) {
             a.loglik[c] = (flag & SMJP_ST_DEGENERATE) ? -INFINITY : loglik;
             a.status[c] = flag;
         }
-        __syncthreads();
+        if (CS > 1) cluster.sync();  // nobody leaves (or reuses its shared memory) while rank 0 reads the flags
+        else __syncthreads();
     }
 }
 

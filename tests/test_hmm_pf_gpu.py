@@ -184,3 +184,27 @@ def test_gamma_hazard_particle_filter_matches_oracle(engine):
             engine.ffbs_host([np.array([0.0, 1.0, t_end])], np.zeros(0), np.zeros(0, int), uniforms=[np.array([0.5, 0.5])])
         finally:
             engine.set_option("hazard_family", 0)
+
+
+@pytest.mark.parametrize("cs", [1, 2, 8, 16])
+def test_particle_filter_cluster_sizes_agree(engine, cs):
+    """the filter run split over a thread-block cluster (DSMEM totals + cluster barriers) is the same
+    filter: identical ancestors and paths for every cluster size, equal to the oracle"""
+    from smjp_b200.engine import pf_host
+    K, t_end, N = 3, 2.0, 4096
+    shape = np.array([[1.606, 1.933, 0.865], [1.938, 0.869, 1.751], [1.69, 0.64, 0.696]])
+    emis = O.emission_matrix(K)
+    engine.set_model(shape, np.ones((K, K)), 2.0, emis, 1.0, t_end)
+    obs_t = np.arange(0.1, 2.0, 0.1)
+    y = np.array([1, 1, 1, 1, 1, 1, 2, 2, 2, 1, 1, 1, 1, 3, 3, 2, 1, 1, 3]) - 1
+    engine.set_option("pf_cluster", 1)
+    ref = pf_host(engine, obs_t, y, np.ones(K) / K, N, seed=8, C=3)
+    engine.set_option("pf_cluster", cs)
+    try:
+        r = pf_host(engine, obs_t, y, np.ones(K) / K, N, seed=8, C=3)
+    finally:
+        engine.set_option("pf_cluster", 0)
+    assert np.all(r["status"] == 0)
+    assert np.allclose(r["loglik"], ref["loglik"], rtol=0, atol=1e-10)
+    for c in range(3):
+        assert np.array_equal(r["V"][c], ref["V"][c]) and np.array_equal(r["T"][c], ref["T"][c])

@@ -48,12 +48,15 @@ def cfg3(N=65536, C=8):
     y = rng.integers(0, K, len(obs_t))
     pf_host(eng, obs_t, y, np.ones(K) / K, N, seed=1, C=C)
     torch.cuda.synchronize()
+    eng.set_option("time_kernels", 1)
     t0 = time.perf_counter()
     r = pf_host(eng, obs_t, y, np.ones(K) / K, N, seed=2, C=C)
     dt = time.perf_counter() - t0
+    kms, _ = eng.kernel_time("pf")
     eng.close()
     return {"config": "cfg3 particle filter N=%d, K=5 Weibull hazards, D=%d, %d filter runs, systematic" % (N, len(obs_t), C),
-            "particle_steps_per_sec": N * len(obs_t) * C / dt, "seconds": dt, "loglik_spread": float(np.ptp(r["loglik"])),
+            "particle_steps_per_sec": N * len(obs_t) * C / dt, "seconds": dt, "kernel_ms": kms,
+            "kernel_particle_steps_per_sec": N * len(obs_t) * C / (kms / 1e3), "loglik_spread": float(np.ptp(r["loglik"])),
             "algorithmic_GBps": 68.0 * N * len(obs_t) * C / dt / 1e9, "status_ok": bool(np.all(r["status"] == 0))}
 
 
@@ -70,12 +73,16 @@ def cfg4(C=1024, S=64, n=4000):
     eng = Engine(0)
     hmm_dense_host(eng, B, np.ones(S) / S, emis=emis, y=ys[:8], precision="f32", seed=1)
     torch.cuda.synchronize()
+    eng.set_option("time_kernels", 1)
     t0 = time.perf_counter()
     r = hmm_dense_host(eng, B, np.ones(S) / S, emis=emis, y=ys, precision="f32", seed=2)
     dt = time.perf_counter() - t0
+    kms, _ = eng.kernel_time("hmm")
     eng.close()
     return {"config": "cfg4 dense K=64 HMM (collapsed sMJP), %d chains x %d grid points, fp32, host API incl. copies" % (C, n),
-            "state_steps_per_sec": C * n * S / dt, "seconds": dt, "status_ok": bool(np.all(r["status"] == 0)),
+            "state_steps_per_sec": C * n * S / dt, "seconds": dt, "kernel_ms": kms,
+            "kernel_state_steps_per_sec": C * n * S / (kms / 1e3), "kernel_algorithmic_GBps": 2 * 4 * S * C * n / (kms / 1e3) / 1e9,
+            "status_ok": bool(np.all(r["status"] == 0)),
             "algorithmic_GBps": 2 * 4 * S * C * n / dt / 1e9}
 
 
