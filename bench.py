@@ -304,8 +304,8 @@ def run_ours(args):
         assert int(np.count_nonzero(ps.status[:C])) == 0
 
     # ---- reduce over ranks: time = max, work = sum ----
-    stats = torch.tensor([ms, ss, gs, alg_bytes, float(launches), k_ms, float(k_cnt), e_wall, e_ss, float(status_bad)],
-                         dtype=torch.float64, device=dev)
+    stats = torch.tensor([ms, ss, gs, alg_bytes, float(launches), k_ms, float(k_cnt), e_wall, e_ss, float(status_bad),
+                          float(h2d), float(d2h)], dtype=torch.float64, device=dev)
     if world > 1:
         mx = stats.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -318,6 +318,7 @@ def run_ours(args):
         ms, e_wall = float(mx[0]), float(mx[7])
         ss, gs, alg_total, launches, e_ss = float(sm[1]), float(sm[2]), float(sm[3]), float(sm[4]), float(sm[8])
         status_bad = int(sm[9])
+        h2d, d2h = int(sm[10]), int(sm[11])
     else:
         alg_total = alg_bytes
     if rank != 0:
@@ -352,6 +353,38 @@ def run_ours(args):
                 "d2h_bytes_per_step": d2h // max(e2e_steps, 1), "steps": e2e_steps,
                 "api": "smjp_sweep_host (pinned host buffers in/out, H2D + D2H inside the timed call)"},
     }
+    if world == 1 and prec == "f64" and not args.no_alt:
+        # the same workload in the engine's fp32 mode (north_star: messages within 1e-4), reported beside the
+        # fp64 headline: device-resident sweeps only
+        for sw in range(3):
+            ch.sweep(seed=SEED + 11, sweep=sw, precision="f32")
+        torch.cuda.synchronize()
+        eng.set_option("time_kernels", 1)
+        eng.kernel_time()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        snaps = []
+        a0.record()
+        for sw in range(args.steps):
+            ch.sweep(seed=SEED + 11, sweep=3 + sw, precision="f32")
+            snaps.append(ch.cur["offs"])
+        a1.record()
+        torch.cuda.synchronize()
+        ms32 = a0.elapsed_time(a1)
+        k32, c32 = eng.kernel_time()
+        eng.set_option("time_kernels", 0)
+        ss32 = b32 = 0.0
+        for offs in snaps:
+            n = (offs[1:] - offs[:-1] - 1).cpu().numpy()
+            ss32 += float(np.sum(K * n.astype(np.float64) * (n + 1) / 2))
+            b32 += algorithmic_bytes(n, D, 4)
+        line["f32"] = {"value": ss32 / (ms32 / 1e3), "unit": UNIT, "ms_per_step": ms32 / args.steps,
+                       "chain_sweeps_per_sec": C * args.steps / (ms32 / 1e3),
+                       "roofline": {"bound": "hbm", "achieved": (b32 / max(c32, 1)) / (k32 / max(c32, 1) / 1e3) / 1e9,
+                                    "peak": peak, "unit": "GB/s",
+                                    "frac": (b32 / max(c32, 1)) / (k32 / max(c32, 1) / 1e3) / 1e9 / peak,
+                                    "traffic": ((traffic or {}).get("f32") or {}).get("dram_bytes_per_launch"),
+                                    "kernel": "ffbs_kernel<float,3>", "kernel_ms_avg": k32 / max(c32, 1)},
+                       "tolerance": "messages within 1e-4 of the reference (tests/test_ffbs_gpu.py)"}
     if world == 1 and not args.no_cpu:
         ss_c, gs_c, wall_c = cpu_sample(16, 3, T_END, 1)  # ~10-20 s of CPU work
         line["cpu_baseline"] = {"value": ss_c / wall_c, "unit": UNIT, "cores": 1, "kind": "port",
@@ -372,6 +405,7 @@ def main():
     ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-alt", action="store_true", help="skip the secondary fp32 measurement")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (kernel experiments)")
     ap.add_argument("--threads", type=int, default=0, help="threads per CTA of the FFBS kernel (0 = auto)")
     ap.add_argument("--item-k3", type=int, default=0, help="experiment: item-parallel kernel for K=3")
