@@ -235,6 +235,29 @@ int smjp_pf_host(smjp_ctx_t* ctx, int C, const int64_t* obs_offs, const double* 
                  const double* pi0, int N, uint64_t seed, int resampler, double* logZ, double* loglik,
                  const int64_t* p_offs, int32_t* path_v, double* path_t, int32_t* path_len, int32_t* status);
 
+/*
+ * FFBS on the dense K-state path: the shape == 1 collapse of the sMJP, K <= 128.
+ * Same inputs and path outputs as smjp_ffbs_dev; requires every Weibull shape of the model to be 1
+ * (SMJP_E_INVALID otherwise).  m_i ~ e_i o (m_{i-1} B) with the constant
+ * B = (1 - 1/omega) I + diag(1/(omega A_v)) A; the backward pass draws the state with u_state[] and,
+ * when the state repeats, thinned-vs-self-jump with u_jump[] (both per grid step, same offsets as W;
+ * NULL = Philox).  Replaces the same reference lines as smjp_ffbs_dev for exponential holding times and is
+ * the K-state form of hidden_markov_model.py:213-313 / :88-202.  DEVICE buffers, asynchronous.
+ */
+int smjp_ffbs_dense_dev(smjp_ctx_t* ctx, int C, const int64_t* w_offs, const double* W,
+                        const int64_t* obs_offs, const double* obs_t, const int32_t* obs_y,
+                        const double* u_state, const double* u_jump, uint64_t seed, uint32_t sweep,
+                        int precision, double* logZ, int32_t* path_v, double* path_t, int32_t* path_len,
+                        double* time_in_state, int32_t* jumps, int32_t* status, int64_t total_w);
+/* Rao-Teh sweep (candidates + dense FFBS) for shape == 1 models; arguments as smjp_sweep_dev. */
+int smjp_sweep_dense_dev(smjp_ctx_t* ctx, int C, const int64_t* p_offs, const int32_t* path_v,
+                         const double* path_t, const int32_t* path_len, const int64_t* obs_offs,
+                         const double* obs_t, const int32_t* obs_y, uint64_t seed, uint32_t sweep, int mode,
+                         int precision, int64_t capacity, int64_t* w_offs, int32_t* soff, double* W,
+                         int32_t* path_v_out, double* path_t_out, int32_t* path_len_out,
+                         double* time_in_state, int32_t* jumps, int32_t* status, int64_t* n_max_host,
+                         int64_t* total_w_host);
+
 #ifdef __cplusplus
 }
 #endif

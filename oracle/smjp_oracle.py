@@ -382,6 +382,55 @@ def collapse_matrix(shape, scale, omega):
     return (1.0 - 1.0 / omega) * np.eye(K) + A / (omega * A.sum(axis=1, keepdims=True))
 
 
+def dense_ffbs_collapsed(W, obs_t, obs_y, scale, omega, emis, power, t_end, u_state, u_jump, obs_combine="sum"):
+    """FFBS of the shape == 1 sMJP on its K-state collapse (Appendix A.5): the marginal over l of
+    forward() above, m_i ~ e_i o (m_{i-1} B) with B = collapse_matrix(), e_i(v) = obs_i(v)
+    [Omega A_v]^{W[i+1] != t_end} exp(-Omega A_v (W[i+1]-W[i])) (smjp_utils.py:506-550 with constant hazards).
+    Backward: v_i ~ m_i(v) B[v, v_{i+1}] by inverse CDF of u_state[i]; when v_i == v_{i+1} the step was a
+    self-jump with probability [A_vv/(Omega A_v)] / B[v,v] (u_jump[i] below it), else the thinned continuation.
+    A jump at W[i+1] starts a sojourn there.  Returns dict(m [n,K], logZ [n], V, T) in compact_path() format."""
+    W = np.asarray(W, dtype=np.float64)
+    obs_t = np.asarray(obs_t, dtype=np.float64)
+    obs_y = np.asarray(obs_y, dtype=np.int64)
+    scale = np.asarray(scale, dtype=np.float64)
+    K = scale.shape[0]
+    n = len(W) - 1
+    A = 1.0 / scale
+    Av = A.sum(axis=1)
+    B = collapse_matrix(np.ones_like(scale), scale, omega)
+    self_jump = np.diag(A) / (omega * Av)
+    pself = self_jump / ((1.0 - 1.0 / omega) + self_jump)
+    m = np.zeros((n, K))
+    logZ = np.zeros(n)
+    for i in range(n):
+        wc, wn = W[i], W[i + 1]
+        if not (wn > wc):
+            raise ValueError("We can not have time_p >= time_c")
+        e = obs_factor(obs_t, obs_y, emis, power, wc, wn, obs_combine) * np.exp(-omega * Av * (wn - wc))
+        if not np.isclose(t_end, wn):
+            e = e * omega * Av
+        a = e / K if i == 0 else e * (m[i - 1] @ B)
+        Z = a.sum()
+        logZ[i] = math.log(Z)
+        m[i] = a / Z
+    starts = []
+    v_next = -1
+    for i in range(n - 1, -1, -1):
+        w = m[i] if v_next < 0 else m[i] * B[:, v_next]
+        v = inv_cdf(w / w.sum(), float(u_state[i]))
+        if v_next >= 0 and (v != v_next or float(u_jump[i]) < pself[v]):
+            starts.append((float(W[i + 1]), v_next))
+        v_next = v
+    starts.append((0.0, v_next))
+    starts.reverse()
+    V = [p[1] for p in starts]
+    T = [p[0] for p in starts]
+    if not np.isclose(T[-1], t_end):
+        V.append(V[-1])
+        T.append(float(t_end))
+    return {"m": m, "logZ": logZ, "V": np.asarray(V, dtype=np.int64), "T": np.asarray(T, dtype=np.float64)}
+
+
 # ----------------------------------------------------------------------------------------------
 # Bootstrap particle filter (Appendix A.6; pmcmc.py:224-310 with the Q9/Q10 defects removed)
 # ----------------------------------------------------------------------------------------------

@@ -104,8 +104,9 @@ class DeviceChains:
         return self
 
     # ------------------------------------------------------------------------------------------
-    def sweep(self, seed, sweep=None, mode="reference", precision="f64"):
-        """One Gibbs sweep of every chain (raoteh.py:58-59).  Asynchronous after one size read-back."""
+    def sweep(self, seed, sweep=None, mode="reference", precision="f64", dense=False):
+        """One Gibbs sweep of every chain (raoteh.py:58-59).  Asynchronous after one size read-back.
+        dense=True runs the K-state collapse (shape == 1 models only, any K <= 128)."""
         t = self.torch
         sweep = self.sweeps_done if sweep is None else sweep
         cur = self.cur
@@ -121,7 +122,7 @@ class DeviceChains:
             if self.soff is None or self.soff.numel() < cur["cap"]:
                 self.soff = t.zeros(cur["cap"], dtype=t.int32, device=self.dev)
             nx = self.nxt
-            rc = self.eng.lib.smjp_sweep_dev(
+            rc = (self.eng.lib.smjp_sweep_dense_dev if dense else self.eng.lib.smjp_sweep_dev)(
                 self.eng.ctx, self.C, _ptr(cur["offs"]), _ptr(cur["v"]), _ptr(cur["t"]), _ptr(cur["len"]),
                 _ptr(self.obs_offs), _ptr(self.obs_t), _ptr(self.obs_y), int(seed) & 0xFFFFFFFFFFFFFFFF, int(sweep),
                 CAND_MODES[mode], PRECISIONS[precision], int(nx["cap"]), _ptr(nx["offs"]), _ptr(self.soff),

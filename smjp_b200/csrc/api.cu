@@ -9,6 +9,7 @@
 #include "../../include/smjp_b200.h"
 #include "candidates.cuh"
 #include "ffbs_launch.cuh"
+#include "dense_smjp.cuh"
 #include "hmm_dense.cuh"
 #include "pf.cuh"
 
@@ -102,7 +103,7 @@ struct smjp_ctx {
     std::vector<double> h_model;
     DevBuf d_model;
     // workspaces
-    DevBuf d_queue, d_msg_scratch, d_obsf, d_order;
+    DevBuf d_queue, d_msg_scratch, d_obsf, d_order, d_dense_msg;
     bool lpt_order = true;
     int obs_product = 0;
     int pf_extend = 0;
@@ -178,6 +179,7 @@ void smjp_ctx_destroy(smjp_ctx_t* c) {
     c->d_msg_scratch.release();
     c->d_obsf.release();
     c->d_order.release();
+    c->d_dense_msg.release();
     c->d_in.release();
     c->d_out.release();
     c->h_in.release();
@@ -1214,6 +1216,124 @@ int smjp_pf_host(smjp_ctx_t* c, int C, const int64_t* obs_offs, const double* ob
     memcpy(path_v, ho + o_pv, total_p * 4);
     memcpy(path_t, ho + o_pt, total_p * 8);
     return SMJP_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// dense K-state FFBS (shape == 1 collapse)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+template <typename Real>
+int dense_launch(smjp_ctx* c, const DenseArgs& a) {
+    const int K = a.K, spl = (K + 31) / 32, warps = 4;
+    const DensePlan plan = dense_plan(K, a.Kobs, sizeof(Real));
+    const size_t smem = plan.bytes;
+    int grid = (a.C + warps - 1) / warps;
+    if (grid > c->num_sms * 8) grid = c->num_sms * 8;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->time_kernels) {
+        CUDA_TRY(cudaEventCreate(&e0));
+        CUDA_TRY(cudaEventCreate(&e1));
+        CUDA_TRY(cudaEventRecord(e0, c->stream));
+    }
+#define DENSE_CASE(n)                                                                                       \
+    case n:                                                                                                 \
+        CUDA_TRY(cudaFuncSetAttribute(dense_smjp_kernel<Real, n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        dense_smjp_kernel<Real, n><<<grid, warps * 32, smem, c->stream>>>(a, plan.has_bt, plan.has_em);                              \
+        break;
+    switch (spl) {
+        DENSE_CASE(1) DENSE_CASE(2) DENSE_CASE(3) DENSE_CASE(4)
+        default: return fail(SMJP_E_UNSUPPORTED, "dense sMJP kernel supports K <= 128 (K=%d)", K);
+    }
+#undef DENSE_CASE
+    CUDA_TRY(cudaGetLastError());
+    if (c->time_kernels) {
+        CUDA_TRY(cudaEventRecord(e1, c->stream));
+        c->hmm_events.emplace_back(e0, e1);
+    }
+    c->launches += 1;
+    return SMJP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int smjp_ffbs_dense_dev(smjp_ctx_t* c, int C, const int64_t* w_offs, const double* W,
+                        const int64_t* obs_offs, const double* obs_t, const int32_t* obs_y,
+                        const double* u_state, const double* u_jump, uint64_t seed, uint32_t sweep,
+                        int precision, double* logZ, int32_t* path_v, double* path_t, int32_t* path_len,
+                        double* time_in_state, int32_t* jumps, int32_t* status, int64_t total_w) {
+    int rc = model_ready(c);
+    if (rc) return rc;
+    rc = weibull_only(c, "the dense FFBS kernel");
+    if (rc) return rc;
+    if (C <= 0) return C == 0 ? SMJP_OK : fail(SMJP_E_INVALID, "C < 0");
+    if (!w_offs || !W || !obs_offs || !path_v || !path_t || !path_len || !status)
+        return fail(SMJP_E_INVALID, "null required pointer");
+    if (precision != SMJP_F64 && precision != SMJP_F32) return fail(SMJP_E_INVALID, "bad precision");
+    if (total_w < (int64_t)C * 2) return fail(SMJP_E_INVALID, "total_w inconsistent with C");
+    if ((u_state == nullptr) != (u_jump == nullptr)) return fail(SMJP_E_INVALID, "give both u_state and u_jump, or neither");
+    const int K = c->K;
+    for (int t = 0; t < K * K; ++t)
+        if (c->h_model[t] != 1.0)
+            return fail(SMJP_E_INVALID, "the dense K-state path needs every Weibull shape to be 1 (entry %d is %g)", t,
+                        c->h_model[t]);
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t esz = precision == SMJP_F64 ? 8 : 4;
+    rc = c->d_dense_msg.reserve((size_t)total_w * K * esz);
+    if (rc) return rc;
+    DenseArgs a;
+    memset(&a, 0, sizeof a);
+    a.C = C;
+    a.K = K;
+    a.Kobs = c->Kobs;
+    a.w_offs = w_offs;
+    a.W = W;
+    a.obs_offs = obs_offs;
+    a.obs_t = obs_t;
+    a.obs_y = obs_y;
+    a.u_state = u_state;
+    a.u_jump = u_jump;
+    a.seed = seed;
+    a.sweep = sweep;
+    a.chain_base = c->chain_base;
+    a.model = (const double*)c->d_model.p;
+    a.obs_product = c->obs_product;
+    a.omega = c->omega;
+    a.power = c->power;
+    a.t_end = c->t_end;
+    a.msg = c->d_dense_msg.p;
+    a.logZ = logZ;
+    a.path_v = path_v;
+    a.path_t = path_t;
+    a.path_len = path_len;
+    a.time_in_state = time_in_state;
+    a.jumps = jumps;
+    a.status = status;
+    return precision == SMJP_F64 ? dense_launch<double>(c, a) : dense_launch<float>(c, a);
+}
+
+int smjp_sweep_dense_dev(smjp_ctx_t* c, int C, const int64_t* p_offs, const int32_t* path_v,
+                         const double* path_t, const int32_t* path_len, const int64_t* obs_offs,
+                         const double* obs_t, const int32_t* obs_y, uint64_t seed, uint32_t sweep, int mode,
+                         int precision, int64_t capacity, int64_t* w_offs, int32_t* soff, double* W,
+                         int32_t* path_v_out, double* path_t_out, int32_t* path_len_out,
+                         double* time_in_state, int32_t* jumps, int32_t* status, int64_t* n_max_host,
+                         int64_t* total_w_host) {
+    int rc = smjp_candidates_count_dev(c, C, p_offs, path_v, path_t, path_len, seed, sweep, w_offs, soff,
+                                       n_max_host, total_w_host);
+    if (rc) return rc;
+    if (*total_w_host > capacity)
+        return fail(SMJP_E_NOMEM, "sweep needs %lld grid points, buffers hold %lld", (long long)*total_w_host,
+                    (long long)capacity);
+    rc = smjp_candidates_fill_dev(c, C, p_offs, path_v, path_t, path_len, seed, sweep, mode, w_offs, soff, W);
+    if (rc) return rc;
+    return smjp_ffbs_dense_dev(c, C, w_offs, W, obs_offs, obs_t, obs_y, nullptr, nullptr, seed, sweep, precision,
+                               nullptr, path_v_out, path_t_out, path_len_out, time_in_state, jumps, status,
+                               *total_w_host);
 }
 
 }  // extern "C"

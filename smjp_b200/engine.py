@@ -173,6 +173,59 @@ class Engine:
             out["messages"] = [msgs[m_offs[c]: m_offs[c + 1]] for c in range(C)]
         return out
 
+    def ffbs_dense(self, W, obs_t, obs_y, u_state=None, u_jump=None, seed=0, sweep=0, precision="f64"):
+        """FFBS of a shape == 1 model on its K-state collapse (smjp_ffbs_dense_dev; any K <= 128).
+        Host lists in, host lists out (staged through torch device tensors); uniforms per grid interval."""
+        import torch as t
+        if self.K is None:
+            raise ValueError("set_model first")
+        C = len(W)
+        dev = t.device("cuda", self.device)
+        Wf, w_offs = pack_ragged([np.asarray(w, dtype=np.float64) for w in W], np.float64)
+        if (isinstance(obs_t, np.ndarray) and obs_t.dtype != object and obs_t.ndim == 1) or len(obs_t) == 0 or np.isscalar(obs_t[0]):
+            obs_t, obs_y = [obs_t] * C, [obs_y] * C
+        of, o_offs = pack_ragged([np.asarray(x, dtype=np.float64) for x in obs_t], np.float64)
+        oy, _ = pack_ragged([np.asarray(y, dtype=np.int32) for y in obs_y], np.int32)
+        if len(oy) and (oy.min() < 0 or oy.max() >= self.Kobs):
+            raise ValueError("observation symbol outside [0, Kobs)")
+
+        def flat(us):
+            if us is None:
+                return None
+            f = np.zeros(len(Wf), dtype=np.float64)
+            for c in range(C):
+                n = w_offs[c + 1] - w_offs[c] - 1
+                u = np.asarray(us[c], dtype=np.float64)
+                if len(u) != n:
+                    raise ValueError("chain %d: need one uniform per grid interval (%d), got %d" % (c, n, len(u)))
+                f[w_offs[c]: w_offs[c] + n] = u
+            return t.from_numpy(f).to(dev)
+
+        d = lambda a: t.from_numpy(a).to(dev)
+        total = len(Wf)
+        dW, dwo, doo, dot, doy = d(Wf), d(w_offs), d(o_offs), d(of), d(oy)
+        dus, duj = flat(u_state), flat(u_jump)
+        logZ = t.zeros(total, dtype=t.float64, device=dev)
+        pv = t.zeros(total, dtype=t.int32, device=dev)
+        pt = t.zeros(total, dtype=t.float64, device=dev)
+        pl = t.zeros(C, dtype=t.int32, device=dev)
+        tis = t.zeros((C, self.K), dtype=t.float64, device=dev)
+        jm = t.zeros((C, self.K), dtype=t.int32, device=dev)
+        st = t.zeros(C, dtype=t.int32, device=dev)
+        t.cuda.synchronize(dev)
+        check(self.lib.smjp_ffbs_dense_dev(self.ctx, C, _ptr(dwo), _ptr(dW), _ptr(doo), _ptr(dot), _ptr(doy),
+                                           _ptr(dus), _ptr(duj), int(seed) & 0xFFFFFFFFFFFFFFFF, int(sweep),
+                                           PRECISIONS[precision], _ptr(logZ), _ptr(pv), _ptr(pt), _ptr(pl),
+                                           _ptr(tis), _ptr(jm), _ptr(st), total))
+        self.sync()
+        pl_h, pv_h, pt_h, lz = pl.cpu().numpy(), pv.cpu().numpy(), pt.cpu().numpy(), logZ.cpu().numpy()
+        n_per = np.diff(w_offs) - 1
+        return {"status": st.cpu().numpy(), "path_len": pl_h, "n": n_per,
+                "V": [pv_h[w_offs[c]: w_offs[c] + pl_h[c]].copy() for c in range(C)],
+                "T": [pt_h[w_offs[c]: w_offs[c] + pl_h[c]].copy() for c in range(C)],
+                "logZ": [lz[w_offs[c]: w_offs[c] + n_per[c]].copy() for c in range(C)],
+                "time_in_state": tis.cpu().numpy(), "jumps": jm.cpu().numpy()}
+
     def ffbs_dev(self, C, w_offs, W, obs_offs, obs_t, obs_y, path_v, path_t, path_len, status, n_max,
                  total_w, uniforms=None, seed=0, sweep=0, precision="f64", messages=None, msg_offs=None,
                  logZ=None, aug_idx=None, time_in_state=None, jumps=None):

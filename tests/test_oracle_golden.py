@@ -182,3 +182,18 @@ def test_particle_filter_lognormaliser_is_unbiased_for_exact_likelihood():
     mc = np.mean(tot); mc_se = np.std(tot) / np.sqrt(len(tot))
     pf = np.mean(ests); pf_se = np.std(ests) / np.sqrt(len(ests))
     assert abs(pf - mc) < 4 * np.hypot(mc_se, pf_se)
+
+
+def test_collapsed_oracle_is_the_marginal_of_the_augmented_filter():
+    """shape == 1 (A.5): dense_ffbs_collapsed's messages equal forward() summed over l, step by step"""
+    rng = np.random.default_rng(77)
+    K, n, omega, t_end = 4, 25, 2.0, 5.0
+    scale = rng.uniform(0.5, 2.0, (K, K)); emis = O.emission_matrix(K)
+    W = np.concatenate([[0.0], np.sort(rng.uniform(0, t_end, n - 1)), [t_end]])
+    obs_t = np.sort(rng.uniform(0, t_end, 15)); obs_y = rng.integers(0, K, 15)
+    alpha, logZ = O.forward(W, obs_t, obs_y, np.ones((K, K)), scale, omega, emis, 1.0, t_end)
+    d = O.dense_ffbs_collapsed(W, obs_t, obs_y, scale, omega, emis, 1.0, t_end, rng.uniform(size=n), rng.uniform(size=n))
+    assert np.abs(alpha.sum(axis=2) - d["m"]).max() < 1e-12
+    assert np.abs(logZ - d["logZ"]).max() < 1e-10
+    assert d["T"][0] == 0.0 and d["T"][-1] == t_end and np.all(np.diff(d["T"]) > 0)
+    assert set(d["T"]) <= set(W)

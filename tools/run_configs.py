@@ -60,30 +60,38 @@ def cfg3(N=65536, C=8):
             "algorithmic_GBps": 68.0 * N * len(obs_t) * C / dt / 1e9, "status_ok": bool(np.all(r["status"] == 0))}
 
 
-def cfg4(C=1024, S=64, n=4000):
-    """large-state dense path: K=64 shared transition matrix (shape == 1 collapse), fp32"""
+def cfg4(C=1024, K=64, T=2000.0, sweeps=3):
+    """large-state dense path: K=64 exponential sMJP (shape == 1 collapse), Rao-Teh sweeps on the device"""
     import torch
-    from smjp_b200.engine import Engine, hmm_dense_host
+    from smjp_b200.chains import DeviceChains
+    from smjp_b200.engine import Engine
     rng = np.random.default_rng(4)
-    scale = rng.uniform(0.5, 2.0, (S, S))
-    A = 1.0 / scale
-    B = 0.5 * np.eye(S) + A / (2.0 * A.sum(axis=1, keepdims=True))
-    emis = emission(S)
-    ys = [rng.integers(0, S, n).astype(np.int32) for _ in range(C)]
     eng = Engine(0)
-    hmm_dense_host(eng, B, np.ones(S) / S, emis=emis, y=ys[:8], precision="f32", seed=1)
-    torch.cuda.synchronize()
-    eng.set_option("time_kernels", 1)
-    t0 = time.perf_counter()
-    r = hmm_dense_host(eng, B, np.ones(S) / S, emis=emis, y=ys, precision="f32", seed=2)
-    dt = time.perf_counter() - t0
-    kms, _ = eng.kernel_time("hmm")
+    # total leaving rate A_v ~ 1 per unit time: about 2*T grid points per chain at omega = 2
+    eng.set_model(np.ones((K, K)), rng.uniform(0.5 * K, 1.5 * K, (K, K)), 2.0, emission(K), 1.0, T)
+    obs_t = np.arange(0.5, T, 1.0)
+    out = {}
+    for prec in ("f64", "f32"):
+        ch = DeviceChains(eng, C, obs_t).init_prior(np.ones(K) / K, seed=1, honour_scale=True).simulate_observations(seed=2)
+        ch.init_prior(np.ones(K) / K, seed=3, honour_scale=True)
+        for sw in range(2):
+            ch.sweep(seed=4, sweep=sw, precision=prec, dense=True)
+        torch.cuda.synchronize()
+        eng.set_option("time_kernels", 1)
+        t0 = time.perf_counter()
+        for sw in range(sweeps):
+            ch.sweep(seed=4, sweep=2 + sw, precision=prec, dense=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        kms, nk = eng.kernel_time("hmm")
+        eng.set_option("time_kernels", 0)
+        _, g = ch.state_steps_last_sweep()
+        esz = 8 if prec == "f64" else 4
+        out[prec] = {"ms_per_sweep": 1e3 * dt / sweeps, "kernel_ms": kms / max(nk, 1), "mean_n": g / C,
+                     "state_steps_per_sec": K * g * sweeps / dt, "failed": int((ch.status != 0).sum().item()),
+                     "kernel_algorithmic_GBps": 2 * esz * K * g / (kms / max(nk, 1) / 1e3) / 1e9}
     eng.close()
-    return {"config": "cfg4 dense K=64 HMM (collapsed sMJP), %d chains x %d grid points, fp32, host API incl. copies" % (C, n),
-            "state_steps_per_sec": C * n * S / dt, "seconds": dt, "kernel_ms": kms,
-            "kernel_state_steps_per_sec": C * n * S / (kms / 1e3), "kernel_algorithmic_GBps": 2 * 4 * S * C * n / (kms / 1e3) / 1e9,
-            "status_ok": bool(np.all(r["status"] == 0)),
-            "algorithmic_GBps": 2 * 4 * S * C * n / dt / 1e9}
+    return {"config": "cfg4 dense K=%d exponential sMJP, %d chains, T=%g, Rao-Teh sweeps (candidates + dense FFBS)" % (K, C, T), **out}
 
 
 def cfg5(C=16384, T=20.0, sweeps=4, threads=0):
