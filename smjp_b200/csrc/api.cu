@@ -1227,7 +1227,7 @@ namespace {
 
 template <typename Real>
 int dense_launch(smjp_ctx* c, const DenseArgs& a) {
-    const int K = a.K, spl = (K + 31) / 32, warps = 4;
+    const int K = a.K, spl = (K + 31) / 32, warps = DENSE_WARPS;
     const DensePlan plan = dense_plan(K, a.Kobs, sizeof(Real));
     const size_t smem = plan.bytes;
     int grid = (a.C + warps - 1) / warps;

@@ -10,7 +10,7 @@
 // v_i ~ m_i(v) B[v, v_{i+1}] and, when v_i == v_{i+1}, a Bernoulli between the thinned continuation
 // (1 - 1/Omega) and the self-jump A_vv/(Omega A_v): jumps delimit the sojourns of the returned path.
 // This is the path BASELINE configs[3] (K = 64, long horizon) runs on: the (v,l) kernels stop at K = 10.
-// Lane s owns states s, s+32, ...; B (and its transpose, and the emission table) live in shared memory; the
+// Lane s owns the SPL adjacent states SPL*s ..; B (and its transpose, and the emission table) live in shared memory; the
 // message stream m_i goes to HBM (2 K sizeof(real) bytes per grid step) for the backward pass.  Grid steps
 // are staged 32 at a time: lane L loads W, finds the observations and draws the Philox block of step i0 + L,
 // so the serial recursion itself only sees shuffles, shared memory and the (prefetched) message row.
@@ -46,7 +46,9 @@ struct DenseArgs {
 };
 
 // shared-memory plan: Bs [Kr][KV] (rows = source state, zero padded), optional BT [K][KV] (B transposed, for
-// the backward column reads) and emT [Kobs][KV] (emission, transposed) when they fit, rate [KV], pself [KV]
+// the backward column reads) and emT [Kobs][KV] (emission, transposed) when they fit, rate [KV], pself [KV],
+// and one message row [KV] per warp (the forward matvec reads it back as broadcast vectors)
+constexpr int DENSE_WARPS = 4;
 struct DensePlan {
     int KV, Kr, has_bt, has_em;
     size_t bytes;
@@ -56,7 +58,7 @@ inline DensePlan dense_plan(int K, int Kobs, size_t esz) {
     p.KV = ((K + 31) / 32) * 32;
     p.Kr = (K + 3) & ~3;
     const size_t budget = 200 * 1024;
-    size_t b = ((size_t)p.Kr * p.KV + 2 * p.KV) * esz;
+    size_t b = ((size_t)p.Kr * p.KV + (2 + DENSE_WARPS) * p.KV) * esz;
     p.has_bt = b + (size_t)K * p.KV * esz <= budget;
     if (p.has_bt) b += (size_t)K * p.KV * esz;
     p.has_em = b + (size_t)Kobs * p.KV * esz <= budget;
@@ -65,18 +67,40 @@ inline DensePlan dense_plan(int K, int Kobs, size_t esz) {
     return p;
 }
 
+// SPL consecutive reals at a 16-byte-friendly shared address (p is SPL*sizeof(Real) aligned)
 template <typename Real, int SPL>
-__global__ void __launch_bounds__(128) dense_smjp_kernel(const DenseArgs a, const int has_bt, const int has_em) {
+__device__ __forceinline__ void lds_vec(const Real* p, Real (&o)[SPL]) {
+    if constexpr (sizeof(Real) == 4 && SPL == 2) {
+        const float2 t = *reinterpret_cast<const float2*>(p);
+        o[0] = t.x; o[1] = t.y;
+    } else if constexpr (sizeof(Real) == 4 && SPL == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+    } else if constexpr (sizeof(Real) == 8 && (SPL == 2 || SPL == 4)) {
+#pragma unroll
+        for (int k = 0; k < SPL; k += 2) {
+            const double2 t = *reinterpret_cast<const double2*>(p + k);
+            o[k] = t.x; o[k + 1] = t.y;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) o[k] = p[k];
+    }
+}
+
+template <typename Real, int SPL>
+__global__ void __launch_bounds__(DENSE_WARPS * 32, 1) dense_smjp_kernel(const DenseArgs a, const int has_bt, const int has_em) {
     extern __shared__ __align__(16) unsigned char dsm[];
     constexpr int KV = 32 * SPL;
     constexpr unsigned FULL = 0xffffffffu;
     const int K = a.K, Kobs = a.Kobs, Kr = (K + 3) & ~3;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, NW = blockDim.x >> 5;
     Real* Bs = (Real*)dsm;                          // [Kr][KV]  B[v'][v]
     Real* rate_s = Bs + Kr * KV;                    // [KV] Omega A_v
     Real* pself_s = rate_s + KV;                    // [KV] P(self-jump | stayed in v)
-    Real* BT = pself_s + KV;                        // [K][KV]   B[v][v_next] stored as BT[v_next][v]
+    Real* mrow = pself_s + KV + wid * KV;           // [KV] this warp's current (unnormalised) message
+    Real* BT = pself_s + KV + DENSE_WARPS * KV;     // [K][KV]   B[v][v_next] stored as BT[v_next][v]
     Real* emT = BT + (has_bt ? K * KV : 0);         // [Kobs][KV]
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, NW = blockDim.x >> 5;
     const double* scale = a.model + 2 * K * K + K * Kobs;
     const double* emis = a.model + 2 * K * K;
     __shared__ double Av_d[128];
@@ -97,7 +121,7 @@ __global__ void __launch_bounds__(128) dense_smjp_kernel(const DenseArgs a, cons
         double b = 0;
         if (vp < K && v < K) b = (vp == v ? 1.0 - 1.0 / a.omega : 0.0) + (1.0 / scale[vp * K + v]) / (a.omega * Av_d[vp]);
         Bs[t] = (Real)b;
-        if (has_bt && vp < K && v < K) BT[v * KV + vp] = (Real)b;  // BT[v_next][v]; pad columns v >= K are set below
+        if (has_bt && vp < K && v < K) BT[v * KV + vp] = (Real)b;  // BT[v_next][v]; pad columns are zeroed below
     }
     if (has_bt)
         for (int t = threadIdx.x; t < K * (KV - K); t += blockDim.x) BT[(t / (KV - K)) * KV + K + t % (KV - K)] = (Real)0;
@@ -111,15 +135,28 @@ __global__ void __launch_bounds__(128) dense_smjp_kernel(const DenseArgs a, cons
     for (int v = 0; v < K; ++v) rmin_d = fmin(rmin_d, a.omega * Av_d[v]);
     const Real power = (Real)a.power;
     using M = Math<Real>;
-    // per-lane constants of the owned states v = lane + 32 k
+    // per-lane constants of the owned states v = SPL * lane + k (adjacent: vector shared loads, one warp scan)
+    const int vbase = SPL * lane;
     Real rt[SPL], fin[SPL], rd[SPL];
 #pragma unroll
     for (int k = 0; k < SPL; ++k) {
-        const int v = lane + 32 * k;
+        const int v = vbase + k;
         rt[k] = v < K ? rate_s[v] : (Real)0;
         fin[k] = v < K ? (Real)1 : (Real)0;
         // exponent relative to the slowest state keeps fp32 away from underflow; rmin goes back into logZ
         rd[k] = v < K ? (Real)(-(double)SMJP_LOG2E * (a.omega * Av_d[v] - rmin_d)) : (Real)0;
+    }
+
+    // fp32, K <= 64: the lane's columns of B stay in registers (32 SPL^2 of them), so the recursion reads only
+    // the broadcast message row from shared memory; otherwise every warp streams all of B per grid step
+    constexpr bool REGB = sizeof(Real) == 4 && SPL <= 2;
+    Real Breg[REGB ? KV : 1][SPL];
+    if constexpr (REGB) {
+#pragma unroll
+        for (int vp = 0; vp < KV; ++vp) {
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) Breg[vp][k] = vp < Kr ? Bs[vp * KV + vbase + k] : (Real)0;
+        }
     }
 
     for (int c = blockIdx.x * NW + wid; c < a.C; c += gridDim.x * NW) {
@@ -138,9 +175,9 @@ __global__ void __launch_bounds__(128) dense_smjp_kernel(const DenseArgs a, cons
         int i_final = n;
         while (i_final > 0 && np_isclose(a.t_end, W[i_final])) --i_final;
         // ---------------- forward, 32 grid steps per block: lane L stages step i0 + L ----------------
-        Real al[SPL];
-#pragma unroll
-        for (int k = 0; k < SPL; ++k) al[k] = 0;
+        // The row kept in shared memory and HBM is r_i = z_i m_i (normalised by the PREVIOUS step's sum only):
+        // sum(r_i) is exactly the reference's normaliser z_i, and its warp reduction overlaps the next matvec.
+        Real iz = 1;  // 1 / sum(r_{i-1})
         int flag = 0, dbase = 0;
         for (int i0 = 0; i0 < n && !flag; i0 += 32) {
             const int il = i0 + lane;
@@ -182,17 +219,22 @@ __global__ void __launch_bounds__(128) dense_smjp_kernel(const DenseArgs a, cons
                 if (cnt > 0) {
                     const int y0 = __shfl_sync(FULL, y_l, s);
                     const int dlo = __shfl_sync(FULL, dlo_l, s);
+                    Real f[SPL];
 #pragma unroll
-                    for (int k = 0; k < SPL; ++k) {
-                        const int v = lane + 32 * k;
-                        Real f = a.obs_product ? (Real)1 : (Real)0;
-                        for (int d = 0; d < cnt; ++d) {
-                            const int y = d == 0 ? y0 : oy[dlo + d];
-                            const Real pe = has_em ? emT[y * KV + v] : (v < K ? (Real)emis[v * Kobs + y] : (Real)0);
-                            f = a.obs_product ? f * pe : f + pe;
+                    for (int k = 0; k < SPL; ++k) f[k] = a.obs_product ? (Real)1 : (Real)0;
+                    for (int d = 0; d < cnt; ++d) {
+                        const int y = d == 0 ? y0 : oy[dlo + d];
+                        Real pe[SPL];
+                        if (has_em) lds_vec<Real, SPL>(emT + y * KV + vbase, pe);
+#pragma unroll
+                        for (int k = 0; k < SPL; ++k) {
+                            if (!has_em) pe[k] = vbase + k < K ? (Real)emis[(vbase + k) * Kobs + y] : (Real)0;
+                            f[k] = a.obs_product ? f[k] * pe[k] : f[k] + pe[k];
                         }
-                        nw[k] *= power == (Real)0 ? (Real)1 : (power == (Real)1 ? f : M::pow(f, power));
                     }
+#pragma unroll
+                    for (int k = 0; k < SPL; ++k)
+                        nw[k] *= power == (Real)0 ? (Real)1 : (power == (Real)1 ? f[k] : M::pow(f[k], power));
                 }
                 if (i == 0) {
 #pragma unroll
@@ -201,32 +243,58 @@ __global__ void __launch_bounds__(128) dense_smjp_kernel(const DenseArgs a, cons
                     Real acc[SPL][2];
 #pragma unroll
                     for (int k = 0; k < SPL; ++k) acc[k][0] = acc[k][1] = 0;
+                    if constexpr (REGB) {
 #pragma unroll
-                    for (int kb = 0; kb < SPL; ++kb) {
-                        const int lim = min(32, Kr - 32 * kb);  // multiple of 4; rows >= K are zero
-                        const Real* brow = Bs + (32 * kb) * KV + lane;
+                        for (int vp = 0; vp < KV; vp += 4) {  // entries >= K of mrow are zero
+                            Real m4[4];
+                            lds_vec<Real, 4>(mrow + vp, m4);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                                for (int k = 0; k < SPL; ++k) acc[k][q & 1] += m4[q] * Breg[vp + q][k];
+                            }
+                        }
+                    } else {
+                        const Real* bcol = Bs + vbase;
 #pragma unroll 4
-                        for (int sl = 0; sl < lim; ++sl) {
-                            const Real av = __shfl_sync(FULL, al[kb], sl);
+                        for (int vp = 0; vp < Kr; vp += 4) {  // rows >= K of Bs and entries >= K of mrow are zero
+                            Real m4[4];
+                            lds_vec<Real, 4>(mrow + vp, m4);
 #pragma unroll
-                            for (int k = 0; k < SPL; ++k) acc[k][sl & 1] += av * brow[sl * KV + 32 * k];
+                            for (int q = 0; q < 4; ++q) {
+                                Real b[SPL];
+                                lds_vec<Real, SPL>(bcol + (vp + q) * KV, b);
+#pragma unroll
+                                for (int k = 0; k < SPL; ++k) acc[k][q & 1] += m4[q] * b[k];
+                            }
                         }
                     }
 #pragma unroll
-                    for (int k = 0; k < SPL; ++k) nw[k] *= acc[k][0] + acc[k][1];
+                    for (int k = 0; k < SPL; ++k) nw[k] *= (acc[k][0] + acc[k][1]) * iz;
+                    __syncwarp();  // every lane has read mrow before it is overwritten
                 }
+                {
+                    if constexpr (SPL == 2 || SPL == 4) {
+#pragma unroll
+                        for (int k = 0; k < SPL; k += 2) {
+                            if constexpr (sizeof(Real) == 4) *reinterpret_cast<float2*>(mrow + vbase + k) = make_float2(nw[k], nw[k + 1]);
+                            else *reinterpret_cast<double2*>(mrow + vbase + k) = make_double2(nw[k], nw[k + 1]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < SPL; ++k) mrow[vbase + k] = nw[k];
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < SPL; ++k)
+                    if (vbase + k < K) mh[(int64_t)i * K + vbase + k] = nw[k];
                 Real z = 0;
 #pragma unroll
                 for (int k = 0; k < SPL; ++k) z += nw[k];
-                z = warp_sum(z);
+                z = warp_sum(z);  // also orders the mrow stores before the next step's loads (shuffles synchronise)
+                __syncwarp();
                 if (!(z > (Real)0) || !(z < (Real)INFINITY)) { flag = SMJP_ST_DEGENERATE; break; }
-                const Real iz = (Real)1 / z;
-#pragma unroll
-                for (int k = 0; k < SPL; ++k) {
-                    al[k] = nw[k] * iz;
-                    const int v = lane + 32 * k;
-                    if (v < K) mh[(int64_t)i * K + v] = al[k];
-                }
+                iz = (Real)1 / z;
                 if (lane == s) z_l = z;
             }
             if (a.logZ && live && !flag) a.logZ[w0 + il] = log((double)z_l) - rmin_d * (wn_l - wc_l);
@@ -244,8 +312,7 @@ __global__ void __launch_bounds__(128) dense_smjp_kernel(const DenseArgs a, cons
         Real cur[SPL], nxt[SPL];
 #pragma unroll
         for (int k = 0; k < SPL; ++k) {
-            const int v = lane + 32 * k;
-            cur[k] = v < K ? mh[(int64_t)(n - 1) * K + v] : (Real)0;
+            cur[k] = vbase + k < K ? mh[(int64_t)(n - 1) * K + vbase + k] : (Real)0;
             nxt[k] = 0;
         }
         for (int i0 = ((n - 1) >> 5) << 5; i0 >= 0 && !flag; i0 -= 32) {
@@ -256,7 +323,7 @@ __global__ void __launch_bounds__(128) dense_smjp_kernel(const DenseArgs a, cons
             if (live) {
                 if (a.u_state) {
                     us_l = a.u_state[w0 + il];
-                    uj_l = a.u_jump ? a.u_jump[w0 + il] : 0.0;
+                    uj_l = a.u_jump[w0 + il];
                 } else {  // one Philox block per grid step: words 0,1 -> state draw (r = 2i), 2,3 -> jump draw (r = 2i+1)
                     const Philox4 o = philox4x32_10((uint32_t)il, 0u, a.sweep, chain, (uint32_t)a.seed,
                                                     (uint32_t)(a.seed >> 32) ^ TAG_BACKWARD);
@@ -264,39 +331,44 @@ __global__ void __launch_bounds__(128) dense_smjp_kernel(const DenseArgs a, cons
                     uj_l = uniform53(o.x[2], o.x[3]);
                 }
             }
+            const Real usr_l = (Real)us_l;
             for (int s = min(31, n - 1 - i0); s >= 0; --s) {
                 const int i = i0 + s;
                 if (i > 0) {
 #pragma unroll
-                    for (int k = 0; k < SPL; ++k) {
-                        const int v = lane + 32 * k;
-                        nxt[k] = v < K ? mh[(int64_t)(i - 1) * K + v] : (Real)0;
-                    }
+                    for (int k = 0; k < SPL; ++k) nxt[k] = vbase + k < K ? mh[(int64_t)(i - 1) * K + vbase + k] : (Real)0;
                 }
                 Real w[SPL];
 #pragma unroll
-                for (int k = 0; k < SPL; ++k) {
-                    const int v = lane + 32 * k;
-                    w[k] = cur[k];
-                    if (v_next >= 0) w[k] *= has_bt ? BT[v_next * KV + v] : (v < K ? Bs[v * KV + v_next] : (Real)0);
-                }
-                Real incl[SPL], carry = 0;
+                for (int k = 0; k < SPL; ++k) w[k] = cur[k];
+                if (v_next >= 0) {
+                    Real bt[SPL];
+                    if (has_bt) lds_vec<Real, SPL>(BT + v_next * KV + vbase, bt);
 #pragma unroll
-                for (int k = 0; k < SPL; ++k) {
-                    incl[k] = warp_inclusive_scan(w[k], lane) + carry;
-                    carry = __shfl_sync(FULL, incl[k], 31);
+                    for (int k = 0; k < SPL; ++k) {
+                        if (!has_bt) bt[k] = vbase + k < K ? Bs[(vbase + k) * KV + v_next] : (Real)0;
+                        w[k] *= bt[k];
+                    }
                 }
-                const Real target = (Real)__shfl_sync(FULL, us_l, s) * carry;
-                int pick = -1, lastpos = -1;
+                Real pre[SPL];  // inclusive prefix over the lane's own states, then one warp scan of lane totals
+                pre[0] = w[0];
 #pragma unroll
-                for (int k = 0; k < SPL; ++k) {
-                    const unsigned pos = __ballot_sync(FULL, w[k] > (Real)0);
-                    const unsigned hit = __ballot_sync(FULL, w[k] > (Real)0 && incl[k] > target);
-                    if (pick < 0 && hit) pick = 32 * k + __ffs(hit) - 1;
-                    if (pos) lastpos = 32 * k + 31 - __clz(pos);
+                for (int k = 1; k < SPL; ++k) pre[k] = pre[k - 1] + w[k];
+                const Real incl_lane = warp_inclusive_scan(pre[SPL - 1], lane);
+                const Real excl = incl_lane - pre[SPL - 1];
+                const Real target = __shfl_sync(FULL, usr_l, s) * __shfl_sync(FULL, incl_lane, 31);
+                int cand_l = -1, last_l = -1;
+#pragma unroll
+                for (int k = SPL - 1; k >= 0; --k) {
+                    if (w[k] > (Real)0) {
+                        if (last_l < 0) last_l = vbase + k;
+                        if (excl + pre[k] > target) cand_l = vbase + k;
+                    }
                 }
-                if (pick < 0) pick = lastpos;
-                if (pick < 0) { flag = SMJP_ST_DEGENERATE; break; }
+                const unsigned hit = __ballot_sync(FULL, cand_l >= 0);
+                const unsigned pos = __ballot_sync(FULL, last_l >= 0);
+                if (!pos) { flag = SMJP_ST_DEGENERATE; break; }
+                const int pick = hit ? __shfl_sync(FULL, cand_l, __ffs(hit) - 1) : __shfl_sync(FULL, last_l, 31 - __clz(pos));
                 // did the transition i -> i+1 jump?  (a jump at W[i+1] starts a sojourn in v_next there)
                 if (v_next >= 0) {
                     bool jump = pick != v_next;
@@ -339,23 +411,24 @@ __global__ void __launch_bounds__(128) dense_smjp_kernel(const DenseArgs a, cons
             a.status[c] = 0;
         }
         __syncwarp();
-        // chain metrics (mcmc_utils.py:40-56): lanes stride the path, per-state totals by shared atomics-free
-        // reduction: lane s accumulates states s, s+32, ... in path order
+        // chain metrics (mcmc_utils.py:40-56): each lane accumulates its own states in path order
         if (a.time_in_state || a.jumps) {
+            double tsum[SPL];
+            int jc[SPL];
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) { tsum[k] = 0; jc[k] = 0; }
+            for (int p = 0; p < plen; ++p) {
+                const int k = pv[p] - vbase;
+                const double dt = p + 1 < plen ? pt[p + 1] - pt[p] : 0.0;
+#pragma unroll
+                for (int q = 0; q < SPL; ++q)
+                    if (k == q) { ++jc[q]; tsum[q] += dt; }
+            }
 #pragma unroll
             for (int k = 0; k < SPL; ++k) {
-                const int v = lane + 32 * k;
-                if (v >= K) continue;
-                double tsum = 0;
-                int jc = 0;
-                for (int p = 0; p < plen; ++p) {
-                    if (pv[p] == v) {
-                        ++jc;
-                        if (p + 1 < plen) tsum += pt[p + 1] - pt[p];
-                    }
-                }
-                if (a.time_in_state) a.time_in_state[(int64_t)c * K + v] = tsum;
-                if (a.jumps) a.jumps[(int64_t)c * K + v] = jc;
+                if (vbase + k >= K) continue;
+                if (a.time_in_state) a.time_in_state[(int64_t)c * K + vbase + k] = tsum[k];
+                if (a.jumps) a.jumps[(int64_t)c * K + vbase + k] = jc[k];
             }
         }
     }

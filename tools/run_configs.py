@@ -72,8 +72,8 @@ def cfg4(C=1024, K=64, T=2000.0, sweeps=3):
     obs_t = np.arange(0.5, T, 1.0)
     out = {}
     for prec in ("f64", "f32"):
-        ch = DeviceChains(eng, C, obs_t).init_prior(np.ones(K) / K, seed=1, honour_scale=True).simulate_observations(seed=2)
-        ch.init_prior(np.ones(K) / K, seed=3, honour_scale=True)
+        ch = DeviceChains(eng, C, obs_t).init_prior(np.ones(K) / K, seed=1, honour_scale=True, cap_per_chain=4096).simulate_observations(seed=2)
+        ch.init_prior(np.ones(K) / K, seed=3, honour_scale=True, cap_per_chain=4096)
         for sw in range(2):
             ch.sweep(seed=4, sweep=sw, precision=prec, dense=True)
         torch.cuda.synchronize()
