@@ -124,6 +124,9 @@ struct Exp2;
 // polynomial coefficients live in constant memory so that DFMA takes them as c[bank] operands
 __constant__ double c_exp2[4] = {6.931471805599453e-01, 2.402265069591007e-01, 5.550410866482158e-02,
                                  9.618129107628477e-03};  // ln2^i / i!
+// the same, for an argument pre-multiplied by 256 (Exp2<double>::SCALE): ln2^i / (i! 256^i), exact rescalings
+__constant__ double c_exp2s[4] = {6.931471805599453e-01 / 256.0, 2.402265069591007e-01 / 65536.0,
+                                  5.550410866482158e-02 / 16777216.0, 9.618129107628477e-03 / 4294967296.0};
 __constant__ double c_log2[6] = {1.442695040888963e+00, -7.213475204444817e-01, 4.808983469629878e-01,
                                  -3.606737602222409e-01, 2.885390081777927e-01, -2.404491734814939e-01};  // (-1)^(i+1)/(i ln2)
 
@@ -133,26 +136,27 @@ struct Exp2<double> {
     const double2* ltab;  // [128] {1/c_i, -log2(1/c_i)}, c_i = 1 + (i + 1/2)/128
     static constexpr int TAB = 256;
     static constexpr int LTAB = 128;
-    // 2^x for |x| < 2^22.  The power of two is added to the exponent field of the TABLE value before the
-    // last fma, so the result needs no repacking; the exponent is clamped to the normal range with two
-    // integer min/max (results saturate at 2^-1022 / 2^1023 instead of 0 / inf).
-    __device__ __forceinline__ double operator()(double x) const {
-        const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
-        const double t = fma(x, 256.0, MAGIC);
-        const int n = __double2loint(t);
-        const double r = fma(t - MAGIC, -1.0 / 256.0, x);
-        double q = fma(r, c_exp2[3], c_exp2[2]);
-        q = fma(r, q, c_exp2[1]);
-        q = fma(r, q, c_exp2[0]);
+    // Arguments arrive PRE-SCALED by SCALE = 256 (the callers fold it into their constants): xs = 256 x.
+    // 2^x for |xs| < 2^31: n = round(xs) and r = xs - n go through the conversion unit (F2I/I2F, XU pipe) so
+    // that range reduction costs one FP64-pipe instruction; the power of two is added to the exponent field
+    // of the TABLE value before the last fma, so the result needs no repacking; the exponent is clamped to
+    // the normal range with two integer min/max (results saturate at 2^-1022 / 2^1023 instead of 0 / inf).
+    static constexpr double SCALE = 256.0;
+    __device__ __forceinline__ double operator()(double xs) const {
+        const int n = __double2int_rn(xs);
+        const double r = xs - (double)n;
+        double q = fma(r, c_exp2s[3], c_exp2s[2]);
+        q = fma(r, q, c_exp2s[1]);
+        q = fma(r, q, c_exp2s[0]);
         const double tv = tab[n & 255];
         const int e = max(min(n >> 8, 1023), -1022);
         const double ts = __hiloint2double(__double2hiint(tv) + (e << 20), __double2loint(tv));
         return fma(ts, r * q, ts);
     }
-    // any x <= 0 including -inf (survival factors): exact 0 below 2^-1022
-    __device__ __forceinline__ double neg(double x) const {
-        const double y = (*this)(fmax(x, -2048.0));
-        return x < -1022.0 ? 0.0 : y;
+    // any xs <= 0 including -inf (survival factors): exact 0 below 2^-1022
+    __device__ __forceinline__ double neg(double xs) const {
+        const double y = (*this)(fmax(xs, -2048.0 * SCALE));
+        return xs < -1022.0 * SCALE ? 0.0 : y;
     }
     __device__ __forceinline__ double log2(double x) const {
         const int hi = __double2hiint(x);
@@ -175,6 +179,7 @@ struct Exp2<float> {
     const double2* ltab;
     static constexpr int TAB = 0;
     static constexpr int LTAB = 0;
+    static constexpr float SCALE = 1.0f;
     __device__ __forceinline__ float operator()(float x) const { return Math<float>::exp2(x); }
     __device__ __forceinline__ float neg(float x) const { return Math<float>::exp2(x); }
     __device__ __forceinline__ float log2(float x) const { return Math<float>::log2(x); }
@@ -240,8 +245,8 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
     Real* red = (Real*)sp;
     sp += align_up((size_t)2 * NW * (K + 1) * sizeof(Real), 16);
     Real* srk = (Real*)sp;       // 1 / k_vs
-    Real* skm1 = srk + K * K;    // k_vs - 1
-    Real* sc2p = skm1 + K * K;   // k_vs log2(lambda_vs) - log2(k_vs): 2^((k-1) L - c2p) = k E = A_vs
+    Real* skm1 = srk + K * K;    // (k_vs - 1) * SCALE
+    Real* sc2p = skm1 + K * K;   // (k_vs log2(lambda_vs) - log2(k_vs)) * SCALE: 2^(((k-1) L - c2p)/SCALE) = k E = A_vs
     Real* sk = sc2p + K * K;     // k_vs
     int* soj = (int*)st_h;       // [2][ncap+1]: state, grid index of each sojourn (backward pass)
 
@@ -255,8 +260,8 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
         const double k = a.model[t];
         sk[t] = (Real)k;
         srk[t] = (Real)(1.0 / k);
-        skm1[t] = (Real)(k - 1.0);
-        sc2p[t] = (Real)(a.model[K * K + t] - ::log2(k));
+        skm1[t] = (Real)((k - 1.0) * (double)Exp2<Real>::SCALE);  // exponent arguments carry Exp2's scale
+        sc2p[t] = (Real)((a.model[K * K + t] - ::log2(k)) * (double)Exp2<Real>::SCALE);
     }
     for (int t = tid; t < Exp2<Real>::TAB; t += B) s_tab[t] = ::exp2((double)t / 256.0);
     for (int t = tid; t < Exp2<Real>::LTAB; t += B) {
@@ -270,7 +275,7 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
 
     const Real thin = (Real)(1.0 - 1.0 / a.omega);
     const Real omega_r = (Real)a.omega;
-    const Real om_l2e = (Real)(a.omega * SMJP_LOG2E);
+    const Real om_l2e = (Real)(a.omega * SMJP_LOG2E * (double)Exp2<Real>::SCALE);
     const Real power = (Real)a.power;
     Real* obsf = (Real*)a.obsf_scratch + (int64_t)blockIdx.x * ncap * K;
 

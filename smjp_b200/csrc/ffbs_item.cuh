@@ -55,8 +55,8 @@ __global__ void __launch_bounds__(B, MINB) ffbs_item_kernel(const FfbsArgs a) {
     for (int t = tid; t < K * K; t += B) {
         const double k = a.model[t];
         srk[t] = (Real)(1.0 / k);
-        skm1[t] = (Real)(k - 1.0);
-        sc2p[t] = (Real)(a.model[K * K + t] - ::log2(k));
+        skm1[t] = (Real)((k - 1.0) * (double)Exp2<Real>::SCALE);
+        sc2p[t] = (Real)((a.model[K * K + t] - ::log2(k)) * (double)Exp2<Real>::SCALE);
     }
     for (int t = tid; t < Exp2<Real>::TAB; t += B) s_tab[t] = ::exp2((double)t / 256.0);
     for (int t = tid; t < Exp2<Real>::LTAB; t += B) {
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(B, MINB) ffbs_item_kernel(const FfbsArgs a) {
 
     const Real thin = (Real)(1.0 - 1.0 / a.omega);
     const Real omega_r = (Real)a.omega;
-    const Real om_l2e = (Real)(a.omega * SMJP_LOG2E);
+    const Real om_l2e = (Real)(a.omega * SMJP_LOG2E * (double)Exp2<Real>::SCALE);
     const Real power = (Real)a.power;
     Real* obsf = (Real*)a.obsf_scratch + (int64_t)blockIdx.x * ncap * K;
     const bool exporting = a.messages != nullptr;
