@@ -304,6 +304,7 @@ def run_ours(args):
         assert int(np.count_nonzero(ps.status[:C])) == 0
 
     # ---- reduce over ranks: time = max, work = sum ----
+    ss_rank0 = ss  # this rank's own state-steps (the kernel figures below are rank 0's)
     stats = torch.tensor([ms, ss, gs, alg_bytes, float(launches), k_ms, float(k_cnt), e_wall, e_ss, float(status_bad),
                           float(h2d), float(d2h)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -332,6 +333,24 @@ def run_ours(args):
     k_avg_s = (k_ms / max(k_cnt, 1)) / 1e3  # rank 0's FFBS kernel, average launch
     achieved = (alg_bytes / max(k_cnt, 1)) / k_avg_s / 1e9
     traffic = ncu_traffic()
+
+    def compute_ceiling(precision, pairs_per_launch, kernel_s, sm_mhz):
+        """second ceiling: the arithmetic pipe the hazard generation runs on.  Instructions per
+        (i, j) pair and issue utilisation come from the committed ncu capture; the pipe fraction is live:
+        pairs x thread-instructions per pair / (pipe lanes per clock x SMs x measured SM clock x kernel time)."""
+        t = ((traffic or {}).get(precision) or {})
+        if "pipe_thread_inst_per_pair" not in t or not sm_mhz:
+            return None
+        lanes = float(t["pipe_lanes_per_clk_sm"])
+        sms = torch.cuda.get_device_properties(0).multi_processor_count
+        peak = lanes * sms * float(sm_mhz) * 1e6
+        need = pairs_per_launch * float(t["pipe_thread_inst_per_pair"])
+        return {"pipe": t["pipe"], "thread_inst_per_pair": t["pipe_thread_inst_per_pair"], "lanes_per_clk_sm": lanes,
+                "peak_thread_inst_per_s": peak, "frac": need / (peak * kernel_s),
+                "kernel_ms_at_pipe_peak": 1e3 * need / peak, "warp_inst_per_pair_all_pipes": t.get("warp_inst_per_warp_pair"),
+                "issue_active_pct_ncu": t.get("issue_active_pct"), "source": "profiles/roofline_traffic.json (ncu --set full)"}
+
+    clk = sampler.summary()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -341,14 +360,15 @@ def run_ours(args):
                    "mean_grid_intervals": gs / (C * world * args.steps), "candidates": "reference (Q5)"},
         "chain_sweeps_per_sec": C * world * args.steps / secs, "grid_steps_per_sec": gs / secs,
         "gpu_launches": int(launches), "failed_chains": status_bad,
-        "clocks": sampler.summary(),
+        "clocks": clk,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ((traffic or {}).get(prec) or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
                      "kernel": "ffbs_kernel<%s,3>" % ("double" if prec == "f64" else "float"),
                      "kernel_ms_avg": k_ms / max(k_cnt, 1), "grid": eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_grid"),
                      "threads": eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_threads"),
                      "smem": eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_smem"), "kernel_share_of_step": k_ms / ms,
-                     "algorithmic_bytes_per_launch": alg_bytes / max(k_cnt, 1)},
+                     "algorithmic_bytes_per_launch": alg_bytes / max(k_cnt, 1),
+                     "compute": compute_ceiling(prec, ss_rank0 / K / max(k_cnt, 1), k_avg_s, clk.get("sm_mhz"))},
         "e2e": {"value": e_ss / e_wall, "unit": UNIT, "h2d_bytes_per_step": h2d // max(e2e_steps, 1),
                 "d2h_bytes_per_step": d2h // max(e2e_steps, 1), "steps": e2e_steps,
                 "api": "smjp_sweep_host (pinned host buffers in/out, H2D + D2H inside the timed call)"},
@@ -383,7 +403,9 @@ def run_ours(args):
                                     "peak": peak, "unit": "GB/s",
                                     "frac": (b32 / max(c32, 1)) / (k32 / max(c32, 1) / 1e3) / 1e9 / peak,
                                     "traffic": ((traffic or {}).get("f32") or {}).get("dram_bytes_per_launch"),
-                                    "kernel": "ffbs_kernel<float,3>", "kernel_ms_avg": k32 / max(c32, 1)},
+                                    "kernel": "ffbs_kernel<float,3>", "kernel_ms_avg": k32 / max(c32, 1),
+                                    "compute": compute_ceiling("f32", ss32 / K / max(c32, 1), k32 / max(c32, 1) / 1e3,
+                                                               clk.get("sm_mhz"))},
                        "tolerance": "messages within 1e-4 of the reference (tests/test_ffbs_gpu.py)"}
     if world == 1 and not args.no_cpu:
         ss_c, gs_c, wall_c = cpu_sample(16, 3, T_END, 1)  # ~10-20 s of CPU work

@@ -258,6 +258,20 @@ int smjp_sweep_dense_dev(smjp_ctx_t* ctx, int C, const int64_t* p_offs, const in
                          double* time_in_state, int32_t* jumps, int32_t* status, int64_t* n_max_host,
                          int64_t* total_w_host);
 
+/*
+ * Parameter step: per-transition holding-time statistics of the current trajectories
+ * and the reference's Weibull shape estimate, for every (v, v') and every group -- a group is one chain
+ * (pooled = 0, G = C) or all chains together (pooled = 1, G = 1).  Replaces filter_T_by_state
+ * (pkg/raoteh.py:136-151), esimtate_weibull_shape (:153-167: the FIRST k of arange(grid, grid_max, grid)
+ * minimising |sum T^k ln T / sum T^k - 1/k - mean ln T|; reference defaults grid = 0.001, grid_max = 5) and
+ * esimtate_weibull_shape_mat (:119-134).  khat / gval are NaN where count == 0 (the reference then draws
+ * U(0.6, 3) on the host).  Paths in the layout of smjp_sweep_dev; outputs [G, K, K]; DEVICE buffers,
+ * asynchronous on the context's stream.  K is passed explicitly (no model needed): path_v holds indices in [0, K).
+ */
+int smjp_shape_mle_dev(smjp_ctx_t* ctx, int C, int K, const int64_t* p_offs, const int32_t* path_v,
+                       const double* path_t, const int32_t* path_len, int pooled, double grid, double grid_max,
+                       double* khat, double* gval, int32_t* count, double* sum_log, double* sum_t);
+
 #ifdef __cplusplus
 }
 #endif

@@ -432,6 +432,54 @@ def dense_ffbs_collapsed(W, obs_t, obs_y, scale, omega, emis, power, t_end, u_st
 
 
 # ----------------------------------------------------------------------------------------------
+# Parameter step helpers (raoteh.py:119-167)
+# ----------------------------------------------------------------------------------------------
+
+
+def hold_times(V, T, v0, v1):
+    """filter_T_by_state (raoteh.py:136-151): T[j+1]-T[j] over consecutive entries (V[j],V[j+1]) == (v0,v1)."""
+    V = np.asarray(V)
+    T = np.asarray(T, dtype=np.float64)
+    sel = np.nonzero((V[:-1] == v0) & (V[1:] == v1))[0]
+    return T[sel + 1] - T[sel]
+
+
+def weibull_shape_grid(h, grid=0.001, grid_max=5.0):
+    """esimtate_weibull_shape (raoteh.py:153-167): the first k of arange(grid, grid_max, grid) minimising
+    |sum T^k ln T / sum T^k - 1/k - mean ln T|; returns (k, g(k)) -- (-1, inf) if every g is NaN."""
+    h = np.asarray(h, dtype=np.float64)
+    ks = np.arange(grid, grid_max, grid)
+    lt = np.log(h)
+    tk = np.power(h[None, :], ks[:, None])
+    g = (tk * lt).sum(axis=1) / tk.sum(axis=1) - 1.0 / ks - lt.mean()
+    a = np.abs(g)
+    if np.all(np.isnan(a)):
+        return -1.0, math.inf
+    m = int(np.nanargmin(a))
+    return float(ks[m]), float(g[m])
+
+
+def shape_mle_matrix(paths, K, grid=0.001, grid_max=5.0):
+    """esimtate_weibull_shape_mat (raoteh.py:119-134) on the holding times of one or several paths pooled in
+    order; NaN where a transition never occurs (the reference draws U(0.6,3) there).
+    Returns (khat [K,K], g [K,K], count [K,K], sum_log [K,K], sum_t [K,K])."""
+    khat = np.full((K, K), np.nan)
+    g = np.full((K, K), np.nan)
+    cnt = np.zeros((K, K), dtype=np.int64)
+    sl = np.zeros((K, K))
+    st = np.zeros((K, K))
+    for a in range(K):
+        for b in range(K):
+            h = np.concatenate([hold_times(V, T, a, b) for V, T in paths]) if len(paths) else np.zeros(0)
+            cnt[a, b] = len(h)
+            if len(h):
+                khat[a, b], g[a, b] = weibull_shape_grid(h, grid, grid_max)
+                sl[a, b] = np.log(h).sum()
+                st[a, b] = h.sum()
+    return khat, g, cnt, sl, st
+
+
+# ----------------------------------------------------------------------------------------------
 # Bootstrap particle filter (Appendix A.6; pmcmc.py:224-310 with the Q9/Q10 defects removed)
 # ----------------------------------------------------------------------------------------------
 

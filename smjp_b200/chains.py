@@ -141,6 +141,29 @@ class DeviceChains:
         return self
 
     # ------------------------------------------------------------------------------------------
+    def shape_mle(self, pooled=True, grid=0.001, grid_max=5.0):
+        """Parameter-step statistics of the current trajectories (raoteh.py:119-167) on the device: for every
+        (v, v') the number of holding times, sum ln T, sum T and the reference's grid-search Weibull shape
+        estimate, per chain (pooled=False -> arrays [C,K,K]) or over all chains (pooled=True -> [K,K]).
+        khat / g are NaN where the transition never occurs."""
+        t = self.torch
+        G = 1 if pooled else self.C
+        K = self.K
+        khat = t.empty((G, K, K), dtype=t.float64, device=self.dev)
+        g = t.empty_like(khat)
+        sl = t.empty_like(khat)
+        st = t.empty_like(khat)
+        cnt = t.empty((G, K, K), dtype=t.int32, device=self.dev)
+        p = self.cur
+        check(self.eng.lib.smjp_shape_mle_dev(self.eng.ctx, self.C, K, _ptr(p["offs"]), _ptr(p["v"]), _ptr(p["t"]),
+                                              _ptr(p["len"]), int(bool(pooled)), float(grid), float(grid_max),
+                                              _ptr(khat), _ptr(g), _ptr(cnt), _ptr(sl), _ptr(st)))
+        self.eng.sync()
+        out = {"khat": khat.cpu().numpy(), "g": g.cpu().numpy(), "count": cnt.cpu().numpy(),
+               "sum_log": sl.cpu().numpy(), "sum_t": st.cpu().numpy()}
+        return {k: (v[0] if pooled else v) for k, v in out.items()}
+
+    # ------------------------------------------------------------------------------------------
     def paths_host(self):
         """current trajectories as host lists (V state indices, T times)"""
         p = self.cur

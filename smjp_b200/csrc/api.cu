@@ -11,6 +11,7 @@
 #include "ffbs_launch.cuh"
 #include "dense_smjp.cuh"
 #include "hmm_dense.cuh"
+#include "params.cuh"
 #include "pf.cuh"
 
 namespace {
@@ -1337,3 +1338,42 @@ int smjp_sweep_dense_dev(smjp_ctx_t* c, int C, const int64_t* p_offs, const int3
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// parameter step: holding-time statistics + Weibull shape estimate
+// ------------------------------------------------------------------------------------------------
+extern "C" int smjp_shape_mle_dev(smjp_ctx_t* c, int C, int K, const int64_t* p_offs, const int32_t* path_v,
+                                  const double* path_t, const int32_t* path_len, int pooled, double grid,
+                                  double grid_max, double* khat, double* gval, int32_t* count, double* sum_log,
+                                  double* sum_t) {
+    if (!c) return fail(SMJP_E_INVALID, "null context");
+    if (K < 1 || K > 1024) return fail(SMJP_E_INVALID, "K=%d outside [1,1024]", K);
+    if (C <= 0) return C == 0 ? SMJP_OK : fail(SMJP_E_INVALID, "C < 0");
+    if (!p_offs || !path_v || !path_t || !path_len || !khat || !gval || !count || !sum_log || !sum_t)
+        return fail(SMJP_E_INVALID, "null required pointer");
+    if (!(grid > 0) || !(grid_max > grid)) return fail(SMJP_E_INVALID, "need 0 < grid < grid_max");
+    if ((grid_max - grid) / grid > 1e8) return fail(SMJP_E_INVALID, "shape grid has more than 1e8 points");
+    CUDA_TRY(cudaSetDevice(c->device));
+    ShapeMleArgs a;
+    memset(&a, 0, sizeof a);
+    a.C = C;
+    a.K = K;
+    a.pooled = pooled ? 1 : 0;
+    a.p_offs = p_offs;
+    a.path_v = path_v;
+    a.path_t = path_t;
+    a.path_len = path_len;
+    a.grid = grid;
+    a.grid_max = grid_max;
+    a.khat = khat;
+    a.gval = gval;
+    a.count = count;
+    a.sum_log = sum_log;
+    a.sum_t = sum_t;
+    const int64_t blocks = (int64_t)(pooled ? 1 : C) * K * K;
+    if (blocks > 0x7fffffff) return fail(SMJP_E_INVALID, "too many (chain, v, v') groups");
+    shape_mle_kernel<<<(unsigned)blocks, MLE_THREADS, 0, c->stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    c->launches += 1;
+    return SMJP_OK;
+}

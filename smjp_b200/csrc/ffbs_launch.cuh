@@ -32,7 +32,8 @@ cudaError_t ffbs_pick(const FfbsArgs& a, FfbsLaunch& L, bool query) {
     // resident CTAs per SM the register budget is tuned for: fp32 needs about half the registers of
     // fp64, K >= 6 about twice those of K <= 5 (K*K hazards per grid point are kept in flight)
     constexpr int S = (sizeof(Real) == 8 ? 1 : 2) * (K <= 5 ? 2 : 1);  // 1, 2 or 4
-    // (fp64, K <= 3 at 128 threads: 5 CTAs/SM = 96 registers measured 9 % faster than 4 CTAs/SM = 128)
+    // (fp64, K <= 3 at 128 threads: 5 CTAs/SM = 96 registers measured 9 % faster than 4 CTAs/SM = 128 and
+    //  5 % faster than 6 CTAs/SM = 80)
     switch (L.threads) {
         case 32: return ffbs_do<Real, K, 32, 8 * S>(a, L, query);
         case 64: return ffbs_do<Real, K, 64, 4 * S>(a, L, query);

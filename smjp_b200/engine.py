@@ -470,6 +470,30 @@ def pf_host(eng, obs_t, obs_y, pi0, N, seed, resampler="systematic", C=None, pat
             "loglik": ll, "logZ": [lz[o_offs[c]: o_offs[c + 1]].copy() for c in range(C)], "status": st}
 
 
+def shape_mle_host(eng, V, T, K, pooled=True, grid=0.001, grid_max=5.0):
+    """smjp_shape_mle_dev on HOST paths (lists of index arrays V and time arrays T): the parameter-step
+    statistics of raoteh.py:119-167.  Returns dict(khat, g, count, sum_log, sum_t), [K,K] when pooled else [C,K,K]."""
+    import torch as t
+    C = len(V)
+    dev = t.device("cuda", eng.device)
+    offs, pv, pt, pl = _pack_paths(V, T)
+    if len(pv) and (pv.min() < 0 or pv.max() >= K):
+        raise ValueError("state index outside [0, K)")
+    G = 1 if pooled else C
+    d = lambda a: t.from_numpy(a).to(dev)
+    dv, do, dt, dl = d(pv), d(offs), d(pt), d(pl)
+    khat = t.empty((G, K, K), dtype=t.float64, device=dev)
+    g, sl, st = t.empty_like(khat), t.empty_like(khat), t.empty_like(khat)
+    cnt = t.empty((G, K, K), dtype=t.int32, device=dev)
+    t.cuda.synchronize(dev)
+    check(eng.lib.smjp_shape_mle_dev(eng.ctx, C, int(K), _ptr(do), _ptr(dv), _ptr(dt), _ptr(dl), int(bool(pooled)),
+                                     float(grid), float(grid_max), _ptr(khat), _ptr(g), _ptr(cnt), _ptr(sl), _ptr(st)))
+    eng.sync()
+    out = {"khat": khat.cpu().numpy(), "g": g.cpu().numpy(), "count": cnt.cpu().numpy(),
+           "sum_log": sl.cpu().numpy(), "sum_t": st.cpu().numpy()}
+    return {k: (v[0] if pooled else v) for k, v in out.items()}
+
+
 def raise_for_status(status):
     """Per-chain status bits -> the exceptions the reference raises at the same conditions."""
     status = np.asarray(status)

@@ -28,6 +28,40 @@ def sample_smjp_parameters(data, V, T, state_space, sigma=1.0):
     return {"shape": runtime.rng().uniform(0.6, 3.0, K * K).reshape(K, K)}
 
 
+def filter_T_by_state(T, V, curr_s, next_s):
+    """holding times of the consecutive path entries (curr_s, next_s) (raoteh.py:136-151), as a list"""
+    V = np.asarray(V)
+    T = np.asarray(T, dtype=np.float64)
+    sel = np.nonzero((V[:-1] == curr_s) & (V[1:] == next_s))[0]
+    return list(T[sel + 1] - T[sel])
+
+
+def esimtate_weibull_shape(T, grid=0.001, grid_max=5):
+    """(k-hat, g(k-hat)) of the reference's grid search (raoteh.py:153-167) -- on the device: the holding
+    times are laid out as one single-state path, whose only transition (0, 0) carries them"""
+    from .engine import shape_mle_host
+    h = np.asarray(T, dtype=np.float64)
+    if len(h) == 0:
+        raise ValueError("no holding times")
+    r = shape_mle_host(runtime.get_engine(), [np.zeros(len(h) + 1, np.int32)], [np.concatenate([[0.0], np.cumsum(h)])],
+                       1, True, grid, grid_max)
+    return float(r["khat"][0, 0]), float(r["g"][0, 0])
+
+
+def esimtate_weibull_shape_mat(V, T, state_space):
+    """K x K shape estimates from the holding times of one trajectory (raoteh.py:119-134): one kernel launch
+    for all (v, v'); transitions that never occur get the reference's U(0.6, 3) draw (hold_times.txt is not
+    written)"""
+    from .engine import shape_mle_host
+    labels = list(state_space)
+    idx = np.asarray([labels.index(x) for x in np.asarray(V).tolist()], dtype=np.int32)
+    r = shape_mle_host(runtime.get_engine(), [idx], [np.asarray(T, dtype=np.float64)], len(labels), True)
+    shapes = r["khat"].copy()
+    empty = r["count"] == 0
+    shapes[empty] = runtime.rng().uniform(0.6, 3.0, int(empty.sum()))
+    return shapes
+
+
 def update_parameters(hazard_A, hazard_B, poisson_proc_A_hat, poisson_proc_B, theta):
     """push new shapes into A, B = omega*A, A_hat = (omega-1)*A and the B process (raoteh.py:173-193)"""
     omega = hazard_B.omega

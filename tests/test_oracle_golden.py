@@ -197,3 +197,23 @@ def test_collapsed_oracle_is_the_marginal_of_the_augmented_filter():
     assert np.abs(logZ - d["logZ"]).max() < 1e-10
     assert d["T"][0] == 0.0 and d["T"][-1] == t_end and np.all(np.diff(d["T"]) > 0)
     assert set(d["T"]) <= set(W)
+
+
+def _golden_paths(g):
+    offs = np.concatenate([[0], np.cumsum(g["lens"])])
+    return [(g["V"][offs[c]: offs[c + 1]], g["T"][offs[c]: offs[c + 1]]) for c in range(len(g["lens"]))]
+
+
+def test_shape_mle_oracle_matches_reference_fixture():
+    """hold_times / weibull_shape_grid restate raoteh.py:136-167: same counts, same grid point, same g"""
+    g = load_golden("shape_mle")
+    paths = _golden_paths(g)
+    K, C = int(g["K"]), len(paths)
+    for c in range(C + 1):
+        sel = paths if c == C else [paths[c]]
+        khat, gv, cnt, _, _ = O.shape_mle_matrix(sel, K)
+        assert np.array_equal(cnt, g["count"][c])
+        assert np.array_equal(np.isnan(khat), np.isnan(g["khat"][c]))
+        ok = ~np.isnan(khat)
+        assert np.abs(khat[ok] - g["khat"][c][ok]).max() < 1e-12
+        assert np.abs(gv[ok] - g["gval"][c][ok]).max() < 1e-9
