@@ -67,6 +67,9 @@ class ClockSampler(threading.Thread):
             self.nvml = pynvml
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.smmax.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)))
+            self.sample()  # first queries of each kind are slow (they were seen to hold up the first timed launch)
+            self.sm.clear()
+            self.reasons.clear()
         except Exception:
             self.nvml = None
 
@@ -100,7 +103,7 @@ class ClockSampler(threading.Thread):
                 self.sample()
             except Exception:
                 pass
-            self.stop_flag.wait(0.02 if self.nvml is not None else 0.2)
+            self.stop_flag.wait(0.05 if self.nvml is not None else 0.2)
 
     def summary(self):
         if not self.sm:
@@ -256,13 +259,18 @@ def run_ours(args):
     alg_bytes = 0.0
     n_snap = []
     barrier()
+    step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)] if os.environ.get("SMJP_BENCH_DEBUG") else None
     ev0.record()
     for i in range(args.steps):
         ch.sweep(seed=SEED, sweep=args.warmup + i, precision=prec)
         n_snap.append(ch.cur["offs"])  # device tensor of this sweep's grid windows; reduced after timing
+        if step_ev:
+            step_ev[i].record()
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
+    if step_ev and rank == 0:
+        print("per-step ms:", [round(ev0.elapsed_time(e), 2) for e in step_ev], file=sys.stderr)
     sampler.stop_flag.set()
     sampler.join()
     launches = eng.launch_count - launches0

@@ -346,8 +346,9 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
             continue;
         }
 
-        Real* msg = a.messages ? (Real*)a.messages + a.msg_offs[c]
-                               : (Real*)a.msg_scratch + (int64_t)blockIdx.x * a.msg_scratch_stride;
+        const bool exporting = a.messages != nullptr;  // exported rows are the reference's alpha, deferred one step
+        Real* msg = exporting ? (Real*)a.messages + a.msg_offs[c]
+                              : (Real*)a.msg_scratch + (int64_t)blockIdx.x * a.msg_scratch_stride;
 
         // =========================== forward ===========================
         Real invZ_prev = (Real)1;
@@ -391,11 +392,11 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
                     Real hprev = ph[v * B];
                     Real base = ap * thin;
                     if (PARTIAL) {
-                        if (!diag) rowp[(int64_t)v * i] = ap;
+                        if (exporting && !diag) rowp[(int64_t)v * i] = ap;
                         base = diag ? J[v] : base;
                         hprev = diag ? (Real)0 : hprev;
                     } else {
-                        rowp[(int64_t)v * i] = ap;
+                        if (exporting) rowp[(int64_t)v * i] = ap;
                     }
                     Real kE[K];
                     Real esum = 0, dsum = 0;
@@ -407,6 +408,9 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
                     }
                     const Real hsum = tau * esum;  // H_v(tau)
                     const Real g = of[v] * ex2.neg(-om_l2e * (hsum - hprev)) * base;
+                    // scratch rows hold g = alpha / (Omega A_v) of row i itself (row i starts K*i past row i-1):
+                    // the backward jump weight alpha A_{v,v+} / (Omega A_v) is then g A_{v,v+}, one hazard per entry
+                    if (!exporting) rowp[(int64_t)K * i + (int64_t)v * (i + 1)] = g;
 #pragma unroll
                     for (int s = 0; s < K; ++s) Jp[s] += g * kE[s];
                     const Real an = g * (nonfinal ? omega_r * dsum : (Real)1);
@@ -415,6 +419,11 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
                     Zp += an;
                 }
             };
+#ifndef SMJP_PAIR_UNROLL
+#define SMJP_PAIR_UNROLL 1
+#endif
+            constexpr int PAIR_UNROLL = SMJP_PAIR_UNROLL;
+#pragma unroll PAIR_UNROLL
             for (int m = 0; m < mi; ++m) {  // full slots: every thread owns a live j < i
                 pair(std::false_type(), false);
                 pa += K * B;
@@ -467,7 +476,7 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
             }
             continue;
         }
-        {   // last row: scale and store
+        if (exporting) {  // last row: scale and store (scratch rows were complete when their step ended)
             Real* row_last = msg + (int64_t)K * (n - 1) * n / 2;
             for (int j = tid; j < n; j += B) {
                 const Real* p = st_a + (size_t)(j / B) * K * B + tid;
@@ -500,6 +509,18 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
             }
             if (vplus < 0) {  // a_{n-1} ~ alpha_{n-1}  (fast_hmm.py:124-125)
                 for (int t = tid; t < K * len; t += B) wbuf[t] = row[t];
+            } else if (!exporting && cur < i_final) {  // scratch row holds g: w = g_cur(v,j) A_{v,vplus}(tau)
+                const double wn = Wd[cur + 1];
+#pragma unroll 2
+                for (int j = tid; j < len; j += B) {
+                    Real rv[K];
+#pragma unroll
+                    for (int v = 0; v < K; ++v) rv[v] = row[(int64_t)v * len + j];
+                    const Real L2 = ex2.log2((Real)(wn - Wd[j]));
+#pragma unroll
+                    for (int v = 0; v < K; ++v)
+                        wbuf[v * len + j] = rv[v] * ex2(skm1[v * K + vplus] * L2 - sc2p[v * K + vplus]);
+                }
             } else {  // jump at W[cur+1] into vplus: w = alpha_cur(v,j) A_{v,vplus}/A_v  (fast_hmm.py:153-171)
                 const double wn = Wd[cur + 1];
                 for (int j = tid; j < len; j += B) {

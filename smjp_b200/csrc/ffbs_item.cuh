@@ -190,11 +190,7 @@ __global__ void __launch_bounds__(B, MINB) ffbs_item_kernel(const FfbsArgs a) {
                 const Real ap = *pa * invZ_prev;
                 Real hprev = *ph;
                 Real base = ap * thin;
-                if (!PARTIAL || !diag) {
-                    // row i-1: scratch rows are [j][v] (this thread's item order), exported rows [v][j]
-                    const int64_t pos = exporting ? (int64_t)v * i + j : (int64_t)j * K + v;
-                    row_base[pos] = ap;
-                }
+                if (exporting && (!PARTIAL || !diag)) row_base[(int64_t)v * i + j] = ap;  // row i-1, [v][j]
                 if (PARTIAL) {
                     base = diag ? Jv : base;
                     hprev = diag ? (Real)0 : hprev;
@@ -209,6 +205,9 @@ __global__ void __launch_bounds__(B, MINB) ffbs_item_kernel(const FfbsArgs a) {
                 }
                 const Real hsum = tau * esum;
                 const Real g = of_v * ex2.neg(-om_l2e * (hsum - hprev)) * base;
+                // scratch rows hold g = alpha / (Omega A_v) of row i itself, [j][v] (this thread's item order):
+                // the backward jump weight alpha A_{v,v+} / (Omega A_v) is then g A_{v,v+}, one hazard per entry
+                if (!exporting) row_base[(int64_t)K * i + (int64_t)j * K + v] = g;
 #pragma unroll
                 for (int s = 0; s < K; ++s) Jp[s] += g * kE[s];
                 const Real an = g * (nonfinal ? omega_r * dsum : (Real)1);
@@ -264,12 +263,10 @@ __global__ void __launch_bounds__(B, MINB) ffbs_item_kernel(const FfbsArgs a) {
             }
             continue;
         }
-        {   // last row
+        if (exporting) {  // last row (scratch rows were complete when their step ended)
             Real* row_last = msg + (int64_t)K * (n - 1) * n / 2;
-            for (int j = jt, m = 0; j < n; j += JPS, ++m) {
-                const int64_t pos = exporting ? (int64_t)v * n + j : (int64_t)j * K + v;
-                row_last[pos] = st_a[(size_t)m * B + tid] * invZ_prev;
-            }
+            for (int j = jt, m = 0; j < n; j += JPS, ++m)
+                row_last[(int64_t)v * n + j] = st_a[(size_t)m * B + tid] * invZ_prev;
         }
         __syncthreads();
 
@@ -295,21 +292,33 @@ __global__ void __launch_bounds__(B, MINB) ffbs_item_kernel(const FfbsArgs a) {
                 u_hi = cur;
             }
             const double wn = Wd[cur + 1];
-            for (int j = jt; j < len; j += JPS) {
-                const int64_t pos = exporting ? (int64_t)v * len + j : (int64_t)j * K + v;
-                Real w = row[pos];
-                if (vplus >= 0) {  // jump at W[cur+1] into vplus: weight alpha_cur(v,j) A_{v,vplus}/A_v
-                    const Real L2 = ex2.log2((Real)(wn - Wd[j]));
-                    Real dsum = 0, hto = 0;
-#pragma unroll
-                    for (int s = 0; s < K; ++s) {
-                        const Real kE = ex2(P_KM1(s) * L2 - P_C2P(s));
-                        dsum += kE;
-                        hto = (s == vplus) ? kE : hto;
-                    }
-                    w *= dsum > (Real)0 ? hto * M::rcp(dsum) : (Real)0;
+            if (!exporting && (vplus < 0 || cur < i_final)) {
+                // scratch row holds g, [j][v]: first draw w = g (= alpha on the last row), jump draws w = g A_{v,vplus}.
+                // Unrolled so that the row loads of several entries are in flight before the first hazard.
+                const Real km1 = vplus >= 0 ? s_km1[vplus] : (Real)0, c2p = vplus >= 0 ? s_c2p[vplus] : (Real)0;
+#pragma unroll 4
+                for (int j = jt; j < len; j += JPS) {
+                    Real w = row[(int64_t)j * K + v];
+                    if (vplus >= 0) w *= ex2(km1 * ex2.log2((Real)(wn - Wd[j])) - c2p);
+                    wbuf[v * len + j] = w;
                 }
-                wbuf[v * len + j] = w;
+            } else {
+                for (int j = jt; j < len; j += JPS) {
+                    const int64_t pos = exporting ? (int64_t)v * len + j : (int64_t)j * K + v;
+                    Real w = row[pos];
+                    if (vplus >= 0) {  // jump at W[cur+1] into vplus: weight alpha_cur(v,j) A_{v,vplus}/A_v
+                        const Real L2 = ex2.log2((Real)(wn - Wd[j]));
+                        Real dsum = 0, hto = 0;
+#pragma unroll
+                        for (int s = 0; s < K; ++s) {
+                            const Real kE = ex2(P_KM1(s) * L2 - P_C2P(s));
+                            dsum += kE;
+                            hto = (s == vplus) ? kE : hto;
+                        }
+                        w *= dsum > (Real)0 ? hto * M::rcp(dsum) : (Real)0;
+                    }
+                    wbuf[v * len + j] = w;
+                }
             }
             __syncthreads();
             const int L = K * len;
