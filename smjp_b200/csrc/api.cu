@@ -1167,6 +1167,9 @@ int smjp_pf_host(smjp_ctx_t* c, int C, const int64_t* obs_offs, const double* ob
             while (cs < 16 && (int64_t)C * cs * 2 <= c->num_sms && N / (cs * 2) >= 2048) cs *= 2;
         }
         if (c->pf_cluster > 0) cs = c->pf_cluster;
+        if ((N + cs - 1) / cs > 32 * PF_MAXW)
+            return fail(SMJP_E_UNSUPPORTED, "particle filter: at most %d particles per CTA (N=%d over a cluster of %d)",
+                        32 * PF_MAXW, N, cs);
         const int threads = N / cs >= 4096 ? 1024 : 256;
         int n_clusters = C;
         if ((int64_t)n_clusters * cs > (int64_t)c->num_sms * 2) n_clusters = (c->num_sms * 2) / cs;

@@ -24,6 +24,7 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "ffbs.cuh"
 
 namespace smjp {
 
@@ -126,24 +127,57 @@ __device__ inline double igamci(double a, double q) {  // x with Q(a, x) = q
     return x;
 }
 
+// Arithmetic of one filter run: table-driven fp64 2^x / log2 (ffbs.cuh: the FP64 pipe is the scarce resource;
+// libdevice pow + log1p cost ~450 FP64-pipe instructions per draw, this form ~35), 1/k cached in shared memory.
+struct PfMath {
+    Exp2<double> ex2;
+    const double* shape;  // k (Weibull) or a (gamma)              [K*K] global
+    const double* c2;     // k log2(lambda)                        [K*K] global
+    const double* scale;  // lambda / theta                        [K*K] global
+    const double* rk;     // 1/k: shared-memory cache, or null -> divide
+};
+
+// tau ~ Weibull(k, lambda) given tau > hold:  tau = lambda ((hold/lambda)^k - log(1-u))^(1/k)
+// (distributions.py:296-304 in cancellation-free form); 1-u is exact for a 53-bit uniform.
+__device__ __forceinline__ double pf_cond_weibull(const PfMath& m, int t, double u, double log2_hold) {
+    constexpr double S = Exp2<double>::SCALE;
+    const double k = m.shape[t];
+    const double hk = log2_hold == -INFINITY ? 0.0 : m.ex2(S * (k * log2_hold - m.c2[t]));  // (hold/lambda)^k
+    const double e = hk - m.ex2.log2(1.0 - u) * 0.6931471805599453;
+    if (!(e > 0.0)) return 0.0;
+    const double rk = m.rk ? m.rk[t] : 1.0 / k;
+    return m.scale[t] * m.ex2(S * (rk * m.ex2.log2(e)));
+}
+
 // one propagation of a particle from clock t_cur towards t_obs; optionally records jumps
-__device__ __forceinline__ int pf_propagate(const PfArgs& a, uint32_t chain, uint32_t d, uint32_t slot, int& v,
-                                            double& l, double t_cur, double t_obs, int32_t* out_v, double* out_t,
-                                            int out_cap, int* out_n) {
+__device__ __forceinline__ int pf_propagate(const PfArgs& a, const PfMath& m, uint32_t chain, uint32_t d, uint32_t slot,
+                                            int& v, double& l, double t_cur, double t_obs, int32_t* out_v,
+                                            double* out_t, int out_cap, int* out_n) {
     const int K = a.K;
-    const double* shape = a.model;
-    const double* scale = a.model + 2 * K * K + K * a.Kobs;
     int it = 0;
     for (; it < a.max_iters; ++it) {
         double best = INFINITY;
         int arg = 0;
         const double hold = t_cur - l;
+        const double l2h = hold > 0.0 ? m.ex2.log2(hold) : -INFINITY;
+        Philox4 blk;
+        uint32_t blk_idx = 0xFFFFFFFFu;
         for (int s = 0; s < K; ++s) {
-            const double k = shape[v * K + s], lam = scale[v * K + s];
-            const double u = philox_u01(a.seed, TAG_PF_PROPAGATE, (uint64_t)(it * K + s), slot, d, chain);
-            const double tau = a.family == SMJP_HAZARD_GAMMA
-                                   ? lam * igamci(k, (1.0 - u) * igamc(k, hold / lam))
-                                   : lam * pow(pow(hold / lam, k) - log1p(-u), 1.0 / k);
+            // uniform r = it*K + s of stream (seed, TAG_PF_PROPAGATE, slot, d, chain): two per Philox block
+            const uint32_t r = (uint32_t)(it * K + s);
+            if ((r >> 1) != blk_idx) {
+                blk_idx = r >> 1;
+                blk = philox4x32_10(blk_idx, slot, d, chain, (uint32_t)a.seed, (uint32_t)(a.seed >> 32) ^ TAG_PF_PROPAGATE);
+            }
+            const double u = (r & 1) ? uniform53(blk.x[2], blk.x[3]) : uniform53(blk.x[0], blk.x[1]);
+            const int t = v * K + s;
+            double tau;
+            if (a.family == SMJP_HAZARD_GAMMA) {
+                const double k = m.shape[t], lam = m.scale[t];
+                tau = lam * igamci(k, (1.0 - u) * igamc(k, hold / lam));
+            } else {
+                tau = pf_cond_weibull(m, t, u, l2h);
+            }
             if (tau < best) { best = tau; arg = s; }
         }
         const double w_next = l + best;
@@ -161,17 +195,33 @@ __device__ __forceinline__ int pf_propagate(const PfArgs& a, uint32_t chain, uin
     return SMJP_ST_OVERFLOW;  // more than max_iters jumps inside one observation interval
 }
 
+constexpr int PF_MAXW = 2048;  // (tiles x warps) of one CTA's particle slice
+constexpr int PF_RK = 256;     // 1/k cache entries (K <= 16)
+
 // One thread-block CLUSTER of CS CTAs per filter run: the N particles are split over the CTAs of the
-// cluster, per-CTA weight totals are exchanged through distributed shared memory, and two cluster
-// barriers per observation order the shared CDF / particle arrays in global memory.  CS = 1 is the
-// single-CTA filter.
+// cluster; thread t of a CTA owns particles p_lo + t, p_lo + t + B, ... (coalesced).  Per observation:
+//   1. gather the state of the ancestor chosen by the previous resampling, propagate, weight; inclusive warp
+//      scans of the weights (warp-local sums to cdf[], warp totals to shared memory);
+//   2. block scan of the warp totals; CTA totals are exchanged through distributed shared memory (cluster
+//      barrier A), which gives every particle its global CDF value c_i;
+//   3. resampling.  Systematic: offspring p descends from the first i with c_i > (u + p)/N total, i.e. particle
+//      i owns the slots [S_{i-1}, S_i), S_i = #{p : target_p < c_i}: each particle computes its S_i (estimate +
+//      exact predicate fix-up), takes S_{i-1} from its neighbour and writes its own index into those slots --
+//      no search, no CDF round trip through memory.  Multinomial: c_i goes to cdf[], binary search per offspring.
+//   cluster barrier B, next observation.  The resampled STATE is never copied: step d+1 gathers through anc[d].
+// CS = 1 is the single-CTA filter.
 template <int B, int CS>
 __global__ void __launch_bounds__(B) pf_kernel(const PfArgs a) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     constexpr int NW = B / 32;
-    __shared__ double s_warp[NW + 1];
-    __shared__ double s_total;  // this CTA's weight total, read by the whole cluster
+    __shared__ double s_tot[PF_MAXW];   // warp totals, (tile, warp) order
+    __shared__ double s_off[PF_MAXW];   // their exclusive prefix within the CTA
+    __shared__ double s_rk[PF_RK];
+    __shared__ double s_tab[Exp2<double>::TAB];
+    __shared__ double2 s_ltab[Exp2<double>::LTAB];
+    __shared__ double s_total;          // this CTA's weight total, read by the whole cluster
+    __shared__ double s_last[2];        // warp offset and warp-local sum of this CTA's LAST particle, read by the next CTA
     __shared__ int s_flag;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int rank = CS > 1 ? (int)cluster.block_rank() : 0;
@@ -179,7 +229,23 @@ __global__ void __launch_bounds__(B) pf_kernel(const PfArgs a) {
     const int N = a.N, K = a.K;
     const int Np = (N + CS - 1) / CS;
     const int p_lo = min(rank * Np, N), p_hi = min(p_lo + Np, N);
+    const int tiles = (p_hi - p_lo + B - 1) / B, nwt = tiles * NW;
     const double* emis = a.model + 2 * K * K;
+    for (int t = tid; t < Exp2<double>::TAB; t += B) s_tab[t] = ::exp2((double)t / 256.0);
+    for (int t = tid; t < Exp2<double>::LTAB; t += B) {
+        const double rc = 1.0 / (1.0 + ((double)t + 0.5) / 128.0);
+        s_ltab[t] = make_double2(rc, -::log2(rc));
+    }
+    if (K * K <= PF_RK)
+        for (int t = tid; t < K * K; t += B) s_rk[t] = 1.0 / a.model[t];
+    PfMath m;
+    m.ex2.tab = s_tab;
+    m.ex2.ltab = s_ltab;
+    m.shape = a.model;
+    m.c2 = a.model + K * K;
+    m.scale = a.model + 2 * K * K + K * a.Kobs;
+    m.rk = K * K <= PF_RK ? s_rk : nullptr;
+    __syncthreads();
     for (int c = cluster_id; c < a.C; c += n_clusters) {
         const uint32_t chain = a.chain_base + (uint32_t)c;
         const int64_t o0 = a.obs_offs[c];
@@ -209,77 +275,135 @@ __global__ void __launch_bounds__(B) pf_kernel(const PfArgs a) {
         int cur = 0;
         double loglik = 0;
         bool dead = false;
+        const bool systematic = a.resampler == SMJP_RESAMPLE_SYSTEMATIC;
         for (int d = 0; d < D; ++d) {
             const double t_prev = d == 0 ? 0.0 : a.obs_t[o0 + d - 1];
             const double t_obs = a.obs_t[o0 + d];
             const int y = a.obs_y[o0 + d];
-            int32_t* v_in = pv + cur * N;
-            double* l_in = pl + cur * N;
+            const int32_t* v_in = pv + cur * N;
+            const double* l_in = pl + cur * N;
             int32_t* v_out = pv + (cur ^ 1) * N;
             double* l_out = pl + (cur ^ 1) * N;
-            // ---- propagate + weight: contiguous chunk per thread so that the scan is in particle order ----
-            const int q = (p_hi - p_lo + B - 1) / B;
-            const int beg = min(p_lo + tid * q, p_hi), end = min(beg + q, p_hi);
-            double loc = 0;
-            for (int p = beg; p < end; ++p) {
-                int v = v_in[p];
-                double l = l_in[p];
-                const int rc = pf_propagate(a, chain, (uint32_t)d, (uint32_t)p, v, l, t_prev, t_obs, nullptr, nullptr, 0, nullptr);
-                if (rc) atomicOr(&s_flag, rc);
-                v_in[p] = v;
-                l_in[p] = l;
-                const double w = emis[v * a.Kobs + y];
-                loc += w;
-                cdf[p] = loc;  // chunk-local inclusive sums; offsets added below
+            const int32_t* anc_prev = d > 0 ? anc + (int64_t)(d - 1) * N : nullptr;
+            int32_t* anc_d = anc + (int64_t)d * N;
+            // ---- 1. gather + propagate + weight, warp scans in particle order ----
+            for (int t = 0; t < tiles; ++t) {
+                const int p = p_lo + t * B + tid;
+                double w = 0.0;
+                if (p < p_hi) {
+                    int src = p;
+                    if (anc_prev) {
+                        src = anc_prev[p];
+                        // an unwritten slot can only come from CDF values that disagree in the last bit across a
+                        // warp boundary; its neighbours' ancestor is then correct to within that rounding
+                        if (src < 0) src = p > 0 && anc_prev[p - 1] >= 0 ? anc_prev[p - 1] : (p + 1 < N && anc_prev[p + 1] >= 0 ? anc_prev[p + 1] : p);
+                    }
+                    int v = v_in[src];
+                    double l = l_in[src];
+                    const int rc = pf_propagate(a, m, chain, (uint32_t)d, (uint32_t)p, v, l, t_prev, t_obs, nullptr, nullptr, 0, nullptr);
+                    if (rc) atomicOr(&s_flag, rc);
+                    v_out[p] = v;
+                    l_out[p] = l;
+                    w = emis[v * a.Kobs + y];
+                    if (systematic) anc_d[p] = -1;
+                }
+                const double incl = warp_inclusive_scan(w, lane);
+                if (p < p_hi) cdf[p] = incl;  // warp-local inclusive sum
+                if (p == p_hi - 1) s_last[1] = incl;
+                if (lane == 31) s_tot[t * NW + wid] = incl;
             }
-            double incl = warp_inclusive_scan(loc, lane);
-            if (lane == 31) s_warp[wid] = incl;
             __syncthreads();
-            double off = 0;
-            for (int w = 0; w < wid; ++w) off += s_warp[w];
-            double cta_total = 0;
-            for (int w = 0; w < NW; ++w) cta_total += s_warp[w];
-            if (tid == 0) s_total = cta_total;
-            double cta_excl = 0, total = cta_total;
-            if (CS > 1) {
-                cluster.sync();  // every CTA's s_total is written
-                total = 0;
-                for (int r = 0; r < CS; ++r) {
-                    const double tr = *cluster.map_shared_rank(&s_total, r);
-                    if (r < rank) cta_excl += tr;
-                    total += tr;
+            // ---- 2. exclusive scan of the (tile, warp) totals by warp 0, CTA totals over the cluster ----
+            if (wid == 0) {
+                double carry = 0;
+                for (int base = 0; base < nwt; base += 32) {
+                    const double x = base + lane < nwt ? s_tot[base + lane] : 0.0;
+                    const double inc = warp_inclusive_scan(x, lane);
+                    if (base + lane < nwt) s_off[base + lane] = carry + (inc - x);
+                    carry += __shfl_sync(0xffffffffu, inc, 31);
+                }
+                if (lane == 0) {
+                    s_total = nwt > 0 ? s_off[nwt - 1] + s_tot[nwt - 1] : 0.0;
+                    s_last[0] = nwt > 0 ? s_off[(p_hi - 1 - p_lo) / 32] : 0.0;
                 }
             }
-            const double excl = cta_excl + off + incl - loc;
-            for (int p = beg; p < end; ++p) cdf[p] += excl;
+            if (CS > 1) cluster.sync();  // A: every CTA's totals are published
+            else __syncthreads();
+            double cta_excl = 0, total = 0, prev_excl = 0;
+            if (CS > 1) {
+                for (int r = 0; r < CS; ++r) {
+                    const double tr = *cluster.map_shared_rank(&s_total, r);
+                    if (r < rank) { prev_excl = cta_excl; cta_excl += tr; }
+                    total += tr;
+                }
+            } else {
+                total = s_total;
+            }
             const double Zd = log(total) - log((double)N);
             loglik += Zd;
             if (rank == 0 && tid == 0 && a.logZ) a.logZ[o0 + d] = Zd;
-            if (CS > 1) cluster.sync();  // CDF and propagated particles of all CTAs are in global memory
-            else __syncthreads();
             if (!(total > 0.0)) {  // every particle has zero weight (uniform over the cluster)
                 dead = true;
                 break;
             }
-            // ---- resample: inverse CDF per offspring ----
-            const double u_sys = philox_u01(a.seed, TAG_PF_RESAMPLE, 0, 0u, (uint32_t)d, chain);
-            for (int p = p_lo + tid; p < p_hi; p += B) {
-                const double pos = a.resampler == SMJP_RESAMPLE_SYSTEMATIC
-                                       ? (u_sys + (double)p) / (double)N
-                                       : philox_u01(a.seed, TAG_PF_RESAMPLE, (uint64_t)p, 0u, (uint32_t)d, chain);
-                const double target = pos * total;
-                int lo = 0, hi = N;  // first index with cdf > target
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (cdf[mid] > target) hi = mid; else lo = mid + 1;
+            // ---- 3. resample ----
+            if (systematic) {
+                const double u_sys = philox_u01(a.seed, TAG_PF_RESAMPLE, 0, 0u, (uint32_t)d, chain);
+                const double n_over_total = (double)N / total;
+                const bool n_pow2 = (N & (N - 1)) == 0;  // then x / N == x * (1/N) bit for bit
+                const double inv_n = 1.0 / (double)N;
+                auto target = [&](int q) {
+                    const double x = u_sys + (double)q;
+                    return (n_pow2 ? x * inv_n : x / (double)N) * total;
+                };
+                // S(c) = #{p in [0,N) : ((u + p)/N) total < c}: estimate, then the oracle's own predicate
+                auto count_below = [&](double cv) {
+                    double e = ceil(cv * n_over_total - u_sys);
+                    int q = e < 0.0 ? 0 : (e > (double)N ? N : (int)e);
+                    while (q > 0 && !(target(q - 1) < cv)) --q;
+                    while (q < N && target(q) < cv) ++q;
+                    return q;
+                };
+                // CDF value of the last particle of the previous CTA, by that particle's own expression
+                double c_before = 0.0;
+                if (CS > 1 && rank > 0) {
+                    const double* pl_last = cluster.map_shared_rank(s_last, rank - 1);
+                    c_before = (prev_excl + pl_last[0]) + pl_last[1];
                 }
-                const int an = lo < N ? lo : N - 1;
-                anc[(int64_t)d * N + p] = an;
-                v_out[p] = v_in[an];
-                l_out[p] = l_in[an];
+                for (int t = 0; t < tiles; ++t) {
+                    const int p = p_lo + t * B + tid;
+                    const bool live = p < p_hi;
+                    const int idx = t * NW + wid;
+                    const double ci = live ? (cta_excl + s_off[idx]) + cdf[p] : 0.0;
+                    int s_hi = live ? count_below(ci) : 0;
+                    if (live && p == N - 1) s_hi = N;  // inverse-CDF searches that run off the end take the last particle
+                    int s_lo = __shfl_up_sync(0xffffffffu, s_hi, 1);
+                    if (lane == 0) s_lo = idx > 0 ? count_below((cta_excl + s_off[idx - 1]) + s_tot[idx - 1])
+                                                  : (rank > 0 ? count_below(c_before) : 0);
+                    if (live)
+                        for (int q = s_lo; q < s_hi; ++q) anc_d[q] = p;
+                }
+            } else {
+                for (int t = 0; t < tiles; ++t) {
+                    const int p = p_lo + t * B + tid;
+                    if (p < p_hi) cdf[p] = (cta_excl + s_off[t * NW + wid]) + cdf[p];
+                }
+                if (CS > 1) cluster.sync();  // the whole CDF is in global memory
+                else __syncthreads();
+                for (int p = p_lo + tid; p < p_hi; p += B) {
+                    const double pos = philox_u01(a.seed, TAG_PF_RESAMPLE, (uint64_t)p, 0u, (uint32_t)d, chain);
+                    const double target = pos * total;
+                    int lo = 0, hi = N;  // first index with cdf > target
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (cdf[mid] > target) hi = mid; else lo = mid + 1;
+                    }
+                    anc_d[p] = lo < N ? lo : N - 1;
+                }
             }
             cur ^= 1;
-            __syncthreads();
+            if (CS > 1) cluster.sync();  // B: ancestors of every slot are written; shared scratch is free again
+            else __syncthreads();
         }
         // combine the per-CTA flags on rank 0 and make the last resampling visible to it
         __shared__ int s_flag_pub;
@@ -327,13 +451,13 @@ __global__ void __launch_bounds__(B) pf_kernel(const PfArgs a) {
                 int nout = 1;
                 for (int d = 0; d < D && !(flag & SMJP_ST_OVERFLOW); ++d) {
                     const double t_prev = d == 0 ? 0.0 : a.obs_t[o0 + d - 1];
-                    const int rc = pf_propagate(a, chain, (uint32_t)d, (uint32_t)line[d], v, l, t_prev,
+                    const int rc = pf_propagate(a, m, chain, (uint32_t)d, (uint32_t)line[d], v, l, t_prev,
                                                 a.obs_t[o0 + d], ov, ot, cap - 1, &nout);
                     if (rc) flag |= rc;
                 }
                 if (a.extend && !(flag & SMJP_ST_OVERFLOW)) {
                     const double t_prev = D > 0 ? a.obs_t[o0 + D - 1] : 0.0;
-                    const int rc = pf_propagate(a, chain, (uint32_t)D, (uint32_t)(D > 0 ? line[D - 1] : 0), v, l, t_prev,
+                    const int rc = pf_propagate(a, m, chain, (uint32_t)D, (uint32_t)(D > 0 ? line[D - 1] : 0), v, l, t_prev,
                                                 a.t_end, ov, ot, cap - 1, &nout);
                     if (rc) flag |= rc;
                 }

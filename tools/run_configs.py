@@ -132,5 +132,7 @@ if __name__ == "__main__":
     for name in which:
         if name.startswith("cfg5:"):
             print(json.dumps(cfg5(threads=int(name[5:]))), flush=True)
+        elif name.startswith("cfg3:"):  # cfg3:C = number of filter runs in flight
+            print(json.dumps(cfg3(C=int(name[5:]))), flush=True)
         else:
             print(json.dumps(globals()[name]()), flush=True)
