@@ -135,52 +135,56 @@ struct PfMath {
     const double* c2;     // k log2(lambda)                        [K*K] global
     const double* scale;  // lambda / theta                        [K*K] global
     const double* rk;     // 1/k: shared-memory cache, or null -> divide
+    const double* l2lam;  // log2(lambda): shared-memory cache, or null -> c2 / k
 };
 
-// tau ~ Weibull(k, lambda) given tau > hold:  tau = lambda ((hold/lambda)^k - log(1-u))^(1/k)
-// (distributions.py:296-304 in cancellation-free form); 1-u is exact for a 53-bit uniform.
-__device__ __forceinline__ double pf_cond_weibull(const PfMath& m, int t, double u, double log2_hold) {
+// One round of competing risks for a particle in state v that has held for `hold`: K conditional holding-time
+// draws, the smallest wins.  Weibull: tau_s = lambda ((hold/lambda)^k - log(1-u))^(1/k) (distributions.py:296-304
+// in cancellation-free form; 1-u is exact for a 53-bit uniform) is compared in the log2 domain,
+// log2 tau_s = log2 lambda + log2(e_s)/k, so that only the winner is exponentiated.  Uniform r = it*K + s of
+// stream (seed, TAG_PF_PROPAGATE, slot, d, chain), two per Philox block.
+__device__ __forceinline__ double pf_round(const PfArgs& a, const PfMath& m, uint32_t chain, uint32_t d, uint32_t slot,
+                                           int it, int v, double hold, int& arg) {
     constexpr double S = Exp2<double>::SCALE;
-    const double k = m.shape[t];
-    const double hk = log2_hold == -INFINITY ? 0.0 : m.ex2(S * (k * log2_hold - m.c2[t]));  // (hold/lambda)^k
-    const double e = hk - m.ex2.log2(1.0 - u) * 0.6931471805599453;
-    if (!(e > 0.0)) return 0.0;
-    const double rk = m.rk ? m.rk[t] : 1.0 / k;
-    return m.scale[t] * m.ex2(S * (rk * m.ex2.log2(e)));
+    const int K = a.K;
+    const bool gamma = a.family == SMJP_HAZARD_GAMMA;
+    const double l2h = (!gamma && hold > 0.0) ? m.ex2.log2(hold) : -INFINITY;
+    double best = INFINITY;
+    arg = 0;
+    Philox4 blk;
+    uint32_t blk_idx = 0xFFFFFFFFu;
+    for (int s = 0; s < K; ++s) {
+        const uint32_t r = (uint32_t)(it * K + s);
+        if ((r >> 1) != blk_idx) {
+            blk_idx = r >> 1;
+            blk = philox4x32_10(blk_idx, slot, d, chain, (uint32_t)a.seed, (uint32_t)(a.seed >> 32) ^ TAG_PF_PROPAGATE);
+        }
+        const double u = (r & 1) ? uniform53(blk.x[2], blk.x[3]) : uniform53(blk.x[0], blk.x[1]);
+        const int t = v * K + s;
+        double key;  // gamma: tau itself; Weibull: log2 tau
+        if (gamma) {
+            const double k = m.shape[t], lam = m.scale[t];
+            key = lam * igamci(k, (1.0 - u) * igamc(k, hold / lam));
+        } else {
+            const double k = m.shape[t];
+            const double hk = l2h == -INFINITY ? 0.0 : m.ex2(S * (k * l2h - m.c2[t]));  // (hold/lambda)^k
+            const double e = hk - m.ex2.log2(1.0 - u) * 0.6931471805599453;
+            const double rk = m.rk ? m.rk[t] : 1.0 / k;
+            const double l2lam = m.l2lam ? m.l2lam[t] : m.c2[t] / k;
+            key = e > 0.0 ? l2lam + rk * m.ex2.log2(e) : -INFINITY;
+        }
+        if (key < best) { best = key; arg = s; }
+    }
+    return gamma ? best : (best == -INFINITY ? 0.0 : m.ex2(S * best));
 }
 
 // one propagation of a particle from clock t_cur towards t_obs; optionally records jumps
 __device__ __forceinline__ int pf_propagate(const PfArgs& a, const PfMath& m, uint32_t chain, uint32_t d, uint32_t slot,
                                             int& v, double& l, double t_cur, double t_obs, int32_t* out_v,
                                             double* out_t, int out_cap, int* out_n) {
-    const int K = a.K;
-    int it = 0;
-    for (; it < a.max_iters; ++it) {
-        double best = INFINITY;
-        int arg = 0;
-        const double hold = t_cur - l;
-        const double l2h = hold > 0.0 ? m.ex2.log2(hold) : -INFINITY;
-        Philox4 blk;
-        uint32_t blk_idx = 0xFFFFFFFFu;
-        for (int s = 0; s < K; ++s) {
-            // uniform r = it*K + s of stream (seed, TAG_PF_PROPAGATE, slot, d, chain): two per Philox block
-            const uint32_t r = (uint32_t)(it * K + s);
-            if ((r >> 1) != blk_idx) {
-                blk_idx = r >> 1;
-                blk = philox4x32_10(blk_idx, slot, d, chain, (uint32_t)a.seed, (uint32_t)(a.seed >> 32) ^ TAG_PF_PROPAGATE);
-            }
-            const double u = (r & 1) ? uniform53(blk.x[2], blk.x[3]) : uniform53(blk.x[0], blk.x[1]);
-            const int t = v * K + s;
-            double tau;
-            if (a.family == SMJP_HAZARD_GAMMA) {
-                const double k = m.shape[t], lam = m.scale[t];
-                tau = lam * igamci(k, (1.0 - u) * igamc(k, hold / lam));
-            } else {
-                tau = pf_cond_weibull(m, t, u, l2h);
-            }
-            if (tau < best) { best = tau; arg = s; }
-        }
-        const double w_next = l + best;
+    for (int it = 0; it < a.max_iters; ++it) {
+        int arg;
+        const double w_next = l + pf_round(a, m, chain, d, slot, it, v, t_cur - l, arg);
         if (w_next >= t_obs) return 0;
         t_cur = w_next;
         l = w_next;
@@ -218,6 +222,7 @@ __global__ void __launch_bounds__(B) pf_kernel(const PfArgs a) {
     __shared__ double s_tot[PF_MAXW];   // warp totals, (tile, warp) order
     __shared__ double s_off[PF_MAXW];   // their exclusive prefix within the CTA
     __shared__ double s_rk[PF_RK];
+    __shared__ double s_l2lam[PF_RK];
     __shared__ double s_tab[Exp2<double>::TAB];
     __shared__ double2 s_ltab[Exp2<double>::LTAB];
     __shared__ double s_total;          // this CTA's weight total, read by the whole cluster
@@ -237,7 +242,10 @@ __global__ void __launch_bounds__(B) pf_kernel(const PfArgs a) {
         s_ltab[t] = make_double2(rc, -::log2(rc));
     }
     if (K * K <= PF_RK)
-        for (int t = tid; t < K * K; t += B) s_rk[t] = 1.0 / a.model[t];
+        for (int t = tid; t < K * K; t += B) {
+            s_rk[t] = 1.0 / a.model[t];
+            s_l2lam[t] = a.model[K * K + t] / a.model[t];
+        }
     PfMath m;
     m.ex2.tab = s_tab;
     m.ex2.ltab = s_ltab;
@@ -245,6 +253,7 @@ __global__ void __launch_bounds__(B) pf_kernel(const PfArgs a) {
     m.c2 = a.model + K * K;
     m.scale = a.model + 2 * K * K + K * a.Kobs;
     m.rk = K * K <= PF_RK ? s_rk : nullptr;
+    m.l2lam = K * K <= PF_RK ? s_l2lam : nullptr;
     __syncthreads();
     for (int c = cluster_id; c < a.C; c += n_clusters) {
         const uint32_t chain = a.chain_base + (uint32_t)c;
@@ -286,27 +295,58 @@ __global__ void __launch_bounds__(B) pf_kernel(const PfArgs a) {
             double* l_out = pl + (cur ^ 1) * N;
             const int32_t* anc_prev = d > 0 ? anc + (int64_t)(d - 1) * N : nullptr;
             int32_t* anc_d = anc + (int64_t)d * N;
-            // ---- 1. gather + propagate + weight, warp scans in particle order ----
+            // ---- 1a. gather + propagate.  Particles need different numbers of competing-risk rounds, so the loop
+            // is flattened: every trip runs ONE round for each lane, and a lane whose particle has passed t_obs
+            // stores it and picks up its next one (p += B) instead of idling until the slowest lane of the warp
+            // is done (a warp-synchronous loop over particles was measured at 3.4 rounds per particle, the mean
+            // over particles being 1.4).
+            {
+                int p = p_lo + tid, it = 0, v = 0;
+                double l = 0.0, t_cur = t_prev;
+                bool have = false;
+                while (true) {
+                    if (!have && p < p_hi) {
+                        int src = p;
+                        if (anc_prev) {
+                            src = anc_prev[p];
+                            // an unwritten slot can only come from CDF values that disagree in the last bit across a
+                            // warp boundary; its neighbours' ancestor is then correct to within that rounding
+                            if (src < 0) src = p > 0 && anc_prev[p - 1] >= 0 ? anc_prev[p - 1] : (p + 1 < N && anc_prev[p + 1] >= 0 ? anc_prev[p + 1] : p);
+                        }
+                        v = v_in[src];
+                        l = l_in[src];
+                        t_cur = t_prev;
+                        it = 0;
+                        have = true;
+                    }
+                    if (!__any_sync(0xffffffffu, have)) break;
+                    if (have) {
+                        int arg;
+                        const double w_next = l + pf_round(a, m, chain, (uint32_t)d, (uint32_t)p, it, v, t_cur - l, arg);
+                        bool fin = w_next >= t_obs;
+                        if (!fin) {
+                            t_cur = w_next;
+                            l = w_next;
+                            v = arg;
+                            if (++it >= a.max_iters) {  // more than max_iters jumps inside one observation interval
+                                atomicOr(&s_flag, SMJP_ST_OVERFLOW);
+                                fin = true;
+                            }
+                        }
+                        if (fin) {
+                            v_out[p] = v;
+                            l_out[p] = l;
+                            if (systematic) anc_d[p] = -1;
+                            have = false;
+                            p += B;
+                        }
+                    }
+                }
+            }
+            // ---- 1b. weights, warp scans in particle order (each thread re-reads the states it just wrote) ----
             for (int t = 0; t < tiles; ++t) {
                 const int p = p_lo + t * B + tid;
-                double w = 0.0;
-                if (p < p_hi) {
-                    int src = p;
-                    if (anc_prev) {
-                        src = anc_prev[p];
-                        // an unwritten slot can only come from CDF values that disagree in the last bit across a
-                        // warp boundary; its neighbours' ancestor is then correct to within that rounding
-                        if (src < 0) src = p > 0 && anc_prev[p - 1] >= 0 ? anc_prev[p - 1] : (p + 1 < N && anc_prev[p + 1] >= 0 ? anc_prev[p + 1] : p);
-                    }
-                    int v = v_in[src];
-                    double l = l_in[src];
-                    const int rc = pf_propagate(a, m, chain, (uint32_t)d, (uint32_t)p, v, l, t_prev, t_obs, nullptr, nullptr, 0, nullptr);
-                    if (rc) atomicOr(&s_flag, rc);
-                    v_out[p] = v;
-                    l_out[p] = l;
-                    w = emis[v * a.Kobs + y];
-                    if (systematic) anc_d[p] = -1;
-                }
+                const double w = p < p_hi ? emis[v_out[p] * a.Kobs + y] : 0.0;
                 const double incl = warp_inclusive_scan(w, lane);
                 if (p < p_hi) cdf[p] = incl;  // warp-local inclusive sum
                 if (p == p_hi - 1) s_last[1] = incl;
