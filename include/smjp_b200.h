@@ -77,6 +77,7 @@ int64_t smjp_ctx_get_stat(smjp_ctx_t* ctx, const char* key);
  *        "hazard_family" (SMJP_HAZARD_*; gamma is honoured by smjp_pf_host only -- the FFBS / candidate /
  *        prior entry points return SMJP_E_UNSUPPORTED for it);
  *        "pf_cluster" (thread-block-cluster size of one particle-filter run: 0 = auto, 1, 2, 4, 8, 16);
+ *        "pf_threads" (threads per CTA of the particle filter: 0 = auto, 256, 512, 1024);
  *        "pf_extend" (0 = the particle-filter path is extended flat from the last observation to t_end
  *        as the reference does, pmcmc.py:307-309; 1 = the segment is simulated);
  *        "lpt_order" (0/1, default 1: the FFBS kernel starts the longest grids first);

@@ -109,7 +109,7 @@ struct smjp_ctx {
     int obs_product = 0;
     int pf_extend = 0;
     int hazard_family = SMJP_HAZARD_WEIBULL;
-    int pf_cluster = 0, last_pf_cluster = 0;
+    int pf_cluster = 0, last_pf_cluster = 0, pf_threads = 0;
     int item_k3 = 0;
     int last_grid = 0, last_threads = 0;
     int64_t ffbs_ncap_hint = 0;
@@ -243,6 +243,12 @@ int smjp_ctx_set_option(smjp_ctx_t* c, const char* key, int64_t value) {
     }
     if (!strcmp(key, "item_k3")) {
         c->item_k3 = value != 0;
+        return SMJP_OK;
+    }
+    if (!strcmp(key, "pf_threads")) {
+        if (value != 0 && value != 256 && value != 512 && value != 1024)
+            return fail(SMJP_E_INVALID, "pf_threads must be 0 (auto), 256, 512 or 1024");
+        c->pf_threads = (int)value;
         return SMJP_OK;
     }
     if (!strcmp(key, "pf_cluster")) {
@@ -1170,7 +1176,7 @@ int smjp_pf_host(smjp_ctx_t* c, int C, const int64_t* obs_offs, const double* ob
         if ((N + cs - 1) / cs > 32 * PF_MAXW)
             return fail(SMJP_E_UNSUPPORTED, "particle filter: at most %d particles per CTA (N=%d over a cluster of %d)",
                         32 * PF_MAXW, N, cs);
-        const int threads = N / cs >= 4096 ? 1024 : 256;
+        const int threads = c->pf_threads > 0 ? c->pf_threads : (N / cs >= 4096 ? 1024 : 256);
         int n_clusters = C;
         if ((int64_t)n_clusters * cs > (int64_t)c->num_sms * 2) n_clusters = (c->num_sms * 2) / cs;
         if (n_clusters < 1) n_clusters = 1;
@@ -1194,6 +1200,7 @@ int smjp_pf_host(smjp_ctx_t* c, int C, const int64_t* obs_offs, const double* ob
 #define PF_PICK(CSV)                                   \
     case CSV:                                          \
         if (threads == 1024) PF_LAUNCH(1024, CSV);     \
+        else if (threads == 512) PF_LAUNCH(512, CSV);  \
         else PF_LAUNCH(256, CSV);                      \
         break;
         switch (cs) {

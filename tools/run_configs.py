@@ -36,7 +36,7 @@ def cfg1():
             "state_steps_per_sec": ss / dt, "reference_measured_sweeps_per_sec": 1.04, "note": "latency-bound: 2 host calls per sweep"}
 
 
-def cfg3(N=65536, C=8):
+def cfg3(N=65536, C=8, cluster=0, threads=0):
     """pmcmc particle filter: 65536 particles per chain, 5-state sMJP, systematic resampling"""
     import torch
     from smjp_b200.engine import Engine, pf_host
@@ -46,6 +46,8 @@ def cfg3(N=65536, C=8):
     eng.set_model(rng.uniform(0.6, 3.0, (K, K)), np.ones((K, K)), 2.0, emission(K), 1.0, t_end)
     obs_t = np.arange(0.1, t_end, 0.1)
     y = rng.integers(0, K, len(obs_t))
+    eng.set_option("pf_cluster", cluster)
+    eng.set_option("pf_threads", threads)
     pf_host(eng, obs_t, y, np.ones(K) / K, N, seed=1, C=C)
     torch.cuda.synchronize()
     eng.set_option("time_kernels", 1)
@@ -53,8 +55,10 @@ def cfg3(N=65536, C=8):
     r = pf_host(eng, obs_t, y, np.ones(K) / K, N, seed=2, C=C)
     dt = time.perf_counter() - t0
     kms, _ = eng.kernel_time("pf")
+    cs = eng.lib.smjp_ctx_get_stat(eng.ctx, b"pf_cluster")
     eng.close()
     return {"config": "cfg3 particle filter N=%d, K=5 Weibull hazards, D=%d, %d filter runs, systematic" % (N, len(obs_t), C),
+            "cluster": cs, "threads": threads,
             "particle_steps_per_sec": N * len(obs_t) * C / dt, "seconds": dt, "kernel_ms": kms,
             "kernel_particle_steps_per_sec": N * len(obs_t) * C / (kms / 1e3), "loglik_spread": float(np.ptp(r["loglik"])),
             "algorithmic_GBps": 68.0 * N * len(obs_t) * C / dt / 1e9, "status_ok": bool(np.all(r["status"] == 0))}
@@ -132,7 +136,8 @@ if __name__ == "__main__":
     for name in which:
         if name.startswith("cfg5:"):
             print(json.dumps(cfg5(threads=int(name[5:]))), flush=True)
-        elif name.startswith("cfg3:"):  # cfg3:C = number of filter runs in flight
-            print(json.dumps(cfg3(C=int(name[5:]))), flush=True)
+        elif name.startswith("cfg3:"):  # cfg3:C[:cluster[:threads]] = filter runs in flight, launch geometry
+            f = [int(x) for x in name[5:].split(":")] + [0, 0]
+            print(json.dumps(cfg3(C=f[0], cluster=f[1], threads=f[2])), flush=True)
         else:
             print(json.dumps(globals()[name]()), flush=True)
