@@ -248,7 +248,9 @@ def poisson_inv(mu, u):
 def candidates(V, T, shape, scale, omega, seed, sweep, chain, mode="reference"):
     """sample_smjp_event_times (smjp_utils.py:194-210) + PoissonProcess.sample (:61-99).
 
-    Per sojourn q = (V[q], [T[q], T[q+1])) and target s: N ~ Poisson((Omega-1) * H_vs(tau))
+    Targets of one row with the SAME shape are merged (not the reference, which draws them one by one: the
+    superposition of their Poisson processes is the same process, drawn once with the first member's stream).
+    Per sojourn q = (V[q], [T[q], T[q+1])) and target (class) s: N ~ Poisson((Omega-1) * H_vs(tau))
     (weibull_mean with lambda_hat, :135-145), then N points.  mode='reference' draws them as the
     reference does -- unit-scale Weibull(k) density truncated to [0,tau] (distributions.py:295 via
     smjp_utils.py:80-84), realised by inverse CDF instead of rejection; mode='exact'
@@ -269,7 +271,13 @@ def candidates(V, T, shape, scale, omega, seed, sweep, chain, mode="reference"):
         pts = []
         for s in range(K):
             k = shape[v, s]
-            mu = (omega - 1.0) * (tau / scale[v, s]) ** k
+            cls = [u for u in range(K) if shape[v, u] == k]  # equal-shape targets superpose into one process
+            if cls[0] != s:
+                continue  # drawn with the class representative (its first member)
+            if len(cls) == 1:
+                mu = (omega - 1.0) * (tau / scale[v, s]) ** k
+            else:
+                mu = (omega - 1.0) * tau ** k * sum(scale[v, u] ** -k for u in cls)
             m = max(1, int(math.ceil(mu / POISSON_CHUNK)))
             a = q * K + s
             N = 0

@@ -307,12 +307,27 @@ int smjp_set_model(smjp_ctx_t* c, int K, int Kobs, const double* shape, const do
     c->omega = omega;
     c->power = likelihood_power;
     c->t_end = t_end;
-    // device layout: shape[K*K], c2[K*K] = k*log2(lambda), emis[K*Kobs], scale[K*K]
-    c->h_model.assign((size_t)3 * K * K + (size_t)K * Kobs, 0.0);
+    // device layout: shape[K*K], c2[K*K] = k*log2(lambda), emis[K*Kobs], scale[K*K], then for the candidate
+    // sampler crep[K*K] and csum[K*K]: targets of one row that share a shape form a class (thinned events of
+    // equal-shape Weibull hazards superpose into one Poisson process with the same position density);
+    // crep = first target of the class, csum = sum over the class of lambda^-k (at the representative)
+    c->h_model.assign((size_t)5 * K * K + (size_t)K * Kobs, 0.0);
     for (int t = 0; t < K * K; ++t) {
         c->h_model[t] = shape[t];
         c->h_model[K * K + t] = shape[t] * std::log2(scale[t]);
         c->h_model[2 * K * K + K * Kobs + t] = scale[t];
+    }
+    {
+        double* crep = c->h_model.data() + 3 * K * K + (size_t)K * Kobs;
+        double* csum = crep + K * K;
+        for (int v = 0; v < K; ++v)
+            for (int s = 0; s < K; ++s) {
+                int r = s;
+                for (int u = 0; u < s; ++u)
+                    if (shape[v * K + u] == shape[v * K + s]) { r = u; break; }
+                crep[v * K + s] = (double)r;
+                csum[v * K + r] += std::pow(scale[v * K + s], -shape[v * K + s]);
+            }
     }
     for (int t = 0; t < K * Kobs; ++t) c->h_model[2 * K * K + t] = emis[t];
     int rc = c->d_model.reserve(c->h_model.size() * sizeof(double));

@@ -54,10 +54,16 @@ __device__ __forceinline__ int sojourn_events(const CandArgs& a, int c, int q, i
     const int K = a.K;
     const double* shape = a.model;
     const double* scale = a.model + 2 * K * K + K * a.Kobs;
+    const double* crep = scale + K * K;  // class representative / class sum of lambda^-k (smjp_set_model)
+    const double* csum = crep + K * K;
     int total = 0;
     for (int s = 0; s < K; ++s) {
+        if ((int)crep[v * K + s] != s) continue;  // merged into an earlier target of the same shape
         const double k = shape[v * K + s];
-        const double mu = (a.omega - 1.0) * pow(tau / scale[v * K + s], k);
+        bool alone = true;
+        for (int u = s + 1; u < K; ++u) alone = alone && (int)crep[v * K + u] != s;
+        const double mu = alone ? (a.omega - 1.0) * pow(tau / scale[v * K + s], k)
+                                : (a.omega - 1.0) * pow(tau, k) * csum[v * K + s];
         int m = (int)ceil(mu / SMJP_POISSON_CHUNK);
         if (m < 1) m = 1;
         const uint32_t aa = (uint32_t)(q * K + s);

@@ -93,6 +93,32 @@ def test_candidates_large_mean_and_omega3(engine):
         assert len(Ws[c]) == len(ora) and np.allclose(Ws[c], ora, rtol=1e-12, atol=1e-14)
 
 
+@pytest.mark.parametrize("mode", ["reference", "exact"])
+def test_candidates_merge_equal_shape_targets(engine, mode):
+    """targets of a row that share a shape are drawn as ONE Poisson process (their superposition): the grids
+    equal the oracle's, and the number of thinned events has the mean the separate draws would have"""
+    from smjp_b200.engine import candidates_host
+    rng = np.random.default_rng(9)
+    K, t_end, omega = 4, 6.0, 2.5
+    shape = np.array([[1.0, 1.0, 1.0, 1.0], [2.0, 0.7, 2.0, 0.7], [1.3, 1.3, 0.9, 1.1], [0.8, 1.9, 1.5, 0.8]])
+    scale = rng.uniform(0.5, 2.0, (K, K))
+    engine.set_model(shape, scale, omega, O.emission_matrix(K), 1.0, t_end)
+    V, T = [], []
+    for c in range(24):
+        v, w = O.prior_path(shape, scale, np.ones(K) / K, t_end, seed=31, chain=c, honour_scale=True)
+        V.append(v); T.append(w)
+    Ws = candidates_host(engine, V, T, seed=17, sweep=2, mode=mode)
+    for c in range(24):
+        ora = O.candidates(V[c], T[c], shape, scale, omega, seed=17, sweep=2, chain=c, mode=mode)
+        assert len(Ws[c]) == len(ora) and np.allclose(Ws[c], ora, rtol=1e-12, atol=1e-14)
+    # one long sojourn in state 0 (all four targets merged), many chains: E[#events] = (Omega-1) tau sum 1/lambda
+    C = 4000
+    Ws = candidates_host(engine, [np.array([0, 0])] * C, [np.array([0.0, t_end])] * C, seed=18, sweep=0, mode=mode)
+    cnt = np.array([len(w) - 2 for w in Ws], dtype=np.float64)
+    mu = (omega - 1.0) * t_end * (1.0 / scale[0]).sum()
+    assert abs(cnt.mean() - mu) < 5 * np.sqrt(mu / C) and abs(cnt.var() - mu) < 0.15 * mu
+
+
 def test_sweep_host_matches_oracle_composition(engine):
     """sweep = candidates -> FFBS with Philox backward uniforms; compare every stage with the oracle."""
     from smjp_b200.engine import sweep_host
