@@ -338,6 +338,9 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32, 1) dense_smjp_kernel(const D
 #pragma unroll
                     for (int k = 0; k < SPL; ++k) nxt[k] = vbase + k < K ? mh[(int64_t)(i - 1) * K + vbase + k] : (Real)0;
                 }
+                // rows are read last-to-first, one per draw: only the newest are still in L2, so pull row i-8
+                // towards the SM now (the draw itself does not depend on it)
+                if (i >= 8 && vbase < K) asm volatile("prefetch.global.L1 [%0];" ::"l"(mh + (int64_t)(i - 8) * K + vbase));
                 Real w[SPL];
 #pragma unroll
                 for (int k = 0; k < SPL; ++k) w[k] = cur[k];
