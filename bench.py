@@ -253,7 +253,10 @@ def run_ours(args):
     eng.kernel_time()
     launches0 = eng.launch_count
     sampler = ClockSampler(local)
-    sampler.start()
+    # clocks are sampled INLINE, right after a sweep has been enqueued (its FFBS kernel is then running for
+    # the next ~20 ms): a sampling thread was measured to cost up to 5 ms per step, its NVML queries contending
+    # with the launch path of the timed loop; an NVML query occasionally takes 3-30 ms, hence only two of them
+    sample_at = {args.steps // 3, (2 * args.steps) // 3} if args.steps >= 3 else {0}  # two samples under load
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ss = gs = 0.0
     alg_bytes = 0.0
@@ -264,6 +267,11 @@ def run_ours(args):
     for i in range(args.steps):
         ch.sweep(seed=SEED, sweep=args.warmup + i, precision=prec)
         n_snap.append(ch.cur["offs"])  # device tensor of this sweep's grid windows; reduced after timing
+        if (i in sample_at) if sampler.nvml is not None else (i == args.steps // 2):
+            try:
+                sampler.sample()
+            except Exception:
+                pass
         if step_ev:
             step_ev[i].record()
     ev1.record()
@@ -271,8 +279,6 @@ def run_ours(args):
     ms = ev0.elapsed_time(ev1)
     if step_ev and rank == 0:
         print("per-step ms:", [round(ev0.elapsed_time(e), 2) for e in step_ev], file=sys.stderr)
-    sampler.stop_flag.set()
-    sampler.join()
     launches = eng.launch_count - launches0
     k_ms, k_cnt = eng.kernel_time()
     eng.set_option("time_kernels", 0)

@@ -67,27 +67,6 @@ inline DensePlan dense_plan(int K, int Kobs, size_t esz) {
     return p;
 }
 
-// SPL consecutive reals at a 16-byte-friendly shared address (p is SPL*sizeof(Real) aligned)
-template <typename Real, int SPL>
-__device__ __forceinline__ void lds_vec(const Real* p, Real (&o)[SPL]) {
-    if constexpr (sizeof(Real) == 4 && SPL == 2) {
-        const float2 t = *reinterpret_cast<const float2*>(p);
-        o[0] = t.x; o[1] = t.y;
-    } else if constexpr (sizeof(Real) == 4 && SPL == 4) {
-        const float4 t = *reinterpret_cast<const float4*>(p);
-        o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
-    } else if constexpr (sizeof(Real) == 8 && (SPL == 2 || SPL == 4)) {
-#pragma unroll
-        for (int k = 0; k < SPL; k += 2) {
-            const double2 t = *reinterpret_cast<const double2*>(p + k);
-            o[k] = t.x; o[k + 1] = t.y;
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < SPL; ++k) o[k] = p[k];
-    }
-}
-
 template <typename Real, int SPL>
 __global__ void __launch_bounds__(DENSE_WARPS * 32, 1) dense_smjp_kernel(const DenseArgs a, const int has_bt, const int has_em) {
     extern __shared__ __align__(16) unsigned char dsm[];

@@ -185,6 +185,27 @@ struct Exp2<float> {
     __device__ __forceinline__ float log2(float x) const { return Math<float>::log2(x); }
 };
 
+// N consecutive reals from shared memory; 128-bit (or 64-bit) loads when N allows (p must be N*sizeof(Real) aligned)
+template <typename Real, int SPL>
+__device__ __forceinline__ void lds_vec(const Real* p, Real (&o)[SPL]) {
+    if constexpr (sizeof(Real) == 4 && SPL == 2) {
+        const float2 t = *reinterpret_cast<const float2*>(p);
+        o[0] = t.x; o[1] = t.y;
+    } else if constexpr (sizeof(Real) == 4 && SPL == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+    } else if constexpr (sizeof(Real) == 8 && (SPL == 2 || SPL == 4)) {
+#pragma unroll
+        for (int k = 0; k < SPL; k += 2) {
+            const double2 t = *reinterpret_cast<const double2*>(p + k);
+            o[k] = t.x; o[k + 1] = t.y;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) o[k] = p[k];
+    }
+}
+
 // Warp reduction of N (a power of two <= 16) values at once.  Plain butterflies cost 5*N shuffles; here
 // the value index is folded into the lane index: at lane distance D each lane keeps one half of its
 // values and trades the other half, so the live count halves per level (N/2 + N/4 + ... shuffles), and
@@ -378,6 +399,7 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
             for (int v = 0; v < K; ++v) Jp[v] = 0;
             const int mi = i / B, ti = i - mi * B;  // slot and owner thread of the new state (v, W[i])
             Real* rowp = row_base + tid;  // row i-1: i entries per state
+            Real* rowg = row_base + (int64_t)K * i + tid;  // row i (scratch mode): i+1 entries per state
             Real* pa = st_a + tid;
             Real* ph = st_h + tid;
             const double* pw = Wd + tid;
@@ -410,7 +432,7 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
                     const Real g = of[v] * ex2.neg(-om_l2e * (hsum - hprev)) * base;
                     // scratch rows hold g = alpha / (Omega A_v) of row i itself (row i starts K*i past row i-1):
                     // the backward jump weight alpha A_{v,v+} / (Omega A_v) is then g A_{v,v+}, one hazard per entry
-                    if (!exporting) rowp[(int64_t)K * i + (int64_t)v * (i + 1)] = g;
+                    if (!exporting) rowg[v * (i + 1)] = g;
 #pragma unroll
                     for (int s = 0; s < K; ++s) Jp[s] += g * kE[s];
                     const Real an = g * (nonfinal ? omega_r * dsum : (Real)1);
@@ -430,6 +452,7 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
                 ph += K * B;
                 pw += B;
                 rowp += B;
+                rowg += B;
             }
             if (tid <= ti) pair(std::true_type(), tid == ti);
             // block reduction of (Z, J[0..K)) -- double-buffered scratch, one barrier per step
@@ -452,9 +475,11 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
             for (int v = 0; v < K; ++v) J[v] = 0;
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
-                Z += rb[w * (K + 1)];
+                Real part[K + 1];
+                lds_vec<Real, K + 1>(rb + w * (K + 1), part);  // one or two 128-bit loads when K + 1 == 4
+                Z += part[0];
 #pragma unroll
-                for (int v = 0; v < K; ++v) J[v] += rb[w * (K + 1) + 1 + v];
+                for (int v = 0; v < K; ++v) J[v] += part[1 + v];
             }
             if (!(Z > (Real)0) || !(Z < (Real)INFINITY)) {
                 degenerate = true;
@@ -589,7 +614,10 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
                 if (tid == 0) s_flag = 0;
             }
             const int idx = s_sel;
-            const int v = idx / len, j = idx - v * len;
+            int v = 0;  // idx / len without the integer division (v < K)
+#pragma unroll
+            for (int u = 1; u < K; ++u) v += idx >= u * len;
+            const int j = idx - v * len;
             if (a.aug_idx)
                 for (int t = j + tid; t <= cur; t += B) a.aug_idx[w0 + t] = v * n + j;
             if (tid == 0) {
