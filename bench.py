@@ -11,6 +11,7 @@ whole-job aggregate over all GPUs; chain-sweeps/s and grid-steps/s are reported 
 One JSON line on stdout (rank 0).
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -248,6 +249,10 @@ def run_ours(args):
 
     for sw in range(args.warmup):
         ch.sweep(seed=SEED, sweep=sw, precision=prec)
+    # the collector is kept out of the timed regions: a generation-2 pass of a process with torch loaded was
+    # seen to add 5-50 ms to a single step
+    gc.collect()
+    gc.disable()
     barrier()
     eng.set_option("time_kernels", 1)
     eng.kernel_time()
@@ -398,12 +403,17 @@ def run_ours(args):
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         snaps = []
         a0.record()
+        dbg = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)] if os.environ.get("SMJP_BENCH_DEBUG") else None
         for sw in range(args.steps):
             ch.sweep(seed=SEED + 11, sweep=3 + sw, precision="f32")
             snaps.append(ch.cur["offs"])
+            if dbg:
+                dbg[sw].record()
         a1.record()
         torch.cuda.synchronize()
         ms32 = a0.elapsed_time(a1)
+        if dbg:
+            print("f32 per-step ms:", [round(a0.elapsed_time(e), 2) for e in dbg], file=sys.stderr)
         k32, c32 = eng.kernel_time()
         eng.set_option("time_kernels", 0)
         ss32 = b32 = 0.0
@@ -421,6 +431,7 @@ def run_ours(args):
                                     "compute": compute_ceiling("f32", ss32 / K / max(c32, 1), k32 / max(c32, 1) / 1e3,
                                                                clk.get("sm_mhz"))},
                        "tolerance": "messages within 1e-4 of the reference (tests/test_ffbs_gpu.py)"}
+    gc.enable()
     if world == 1 and not args.no_cpu:
         ss_c, gs_c, wall_c = cpu_sample(16, 3, T_END, 1)  # ~10-20 s of CPU work
         line["cpu_baseline"] = {"value": ss_c / wall_c, "unit": UNIT, "cores": 1, "kind": "port",
