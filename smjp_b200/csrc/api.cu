@@ -10,6 +10,7 @@
 #include "candidates.cuh"
 #include "ffbs_launch.cuh"
 #include "dense_smjp.cuh"
+#include "ffbs_big.cuh"
 #include "hmm_dense.cuh"
 #include "params.cuh"
 #include "pf.cuh"
@@ -104,7 +105,7 @@ struct smjp_ctx {
     std::vector<double> h_model;
     DevBuf d_model;
     // workspaces
-    DevBuf d_queue, d_msg_scratch, d_obsf, d_order, d_dense_msg;
+    DevBuf d_queue, d_msg_scratch, d_obsf, d_order, d_dense_msg, d_big;
     bool lpt_order = true;
     int obs_product = 0;
     int pf_extend = 0;
@@ -181,6 +182,7 @@ void smjp_ctx_destroy(smjp_ctx_t* c) {
     c->d_obsf.release();
     c->d_order.release();
     c->d_dense_msg.release();
+    c->d_big.release();
     c->d_in.release();
     c->d_out.release();
     c->h_in.release();
@@ -352,15 +354,51 @@ cudaError_t ffbs_call(const FfbsArgs& a, FfbsLaunch& L, bool query) {
     return L.K <= 5 ? ffbs_dispatch_f32_lo(a, L, query) : ffbs_dispatch_f32_hi(a, L, query);
 }
 
+// run-time-K kernel (ffbs_big.cuh): 128 threads when the chain state fits next to the per-thread columns, else 64
+template <typename Real>
+cudaError_t ffbs_big_call(const FfbsArgs& a, FfbsLaunch& L, bool query) {
+    auto k128 = ffbs_big_kernel<Real, 128>;
+    auto k64 = ffbs_big_kernel<Real, 64>;
+    auto kern = L.threads == 128 ? k128 : k64;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    if (e != cudaSuccess) return e;
+    if (query) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&L.grid, kern, L.threads, L.smem);
+    if (L.threads == 128) k128<<<L.grid, 128, L.smem, L.stream>>>(a);
+    else k64<<<L.grid, 64, L.smem, L.stream>>>(a);
+    return cudaGetLastError();
+}
+
 template <typename Real>
 int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
     const int K = c->K;
-    if (K > 10) return fail(SMJP_E_UNSUPPORTED, "sMJP FFBS kernel is instantiated for K in [2,10]; K=%d", K);
-    const bool item_kernel = K >= 4 || (K == 3 && c->item_k3);
+    const bool big = K > 10;  // general shapes, run-time K
+    const bool item_kernel = !big && (K >= 4 || (K == 3 && c->item_k3));
+    a.K = K;
     a.use_item = item_kernel;  // thread per (v, j) for larger state spaces, thread per j for K <= 3
     int threads;
     size_t smem;
-    if (item_kernel) {
+    if (big) {
+        threads = 128;
+        smem = ffbs_big_smem_bytes<Real>(K, (int)n_max, threads);
+        if (smem > c->smem_optin) {
+            threads = 64;
+            smem = ffbs_big_smem_bytes<Real>(K, (int)n_max, threads);
+        }
+        // hazard parameters in the kernel's precision
+        const double S = sizeof(Real) == 8 ? 256.0 : 1.0;  // Exp2<Real>::SCALE
+        std::vector<Real> hp((size_t)3 * K * K);
+        for (int t = 0; t < K * K; ++t) {
+            const double k = c->h_model[t];
+            hp[t] = (Real)(1.0 / k);
+            hp[K * K + t] = (Real)((k - 1.0) * S);
+            hp[2 * K * K + t] = (Real)((c->h_model[K * K + t] - std::log2(k)) * S);
+        }
+        int rcb = c->d_big.reserve(hp.size() * sizeof(Real));
+        if (rcb) return rcb;
+        CUDA_TRY(cudaMemcpyAsync(c->d_big.p, hp.data(), hp.size() * sizeof(Real), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));  // hp is a stack-lifetime host buffer
+        a.big_params = c->d_big.p;
+    } else if (item_kernel) {
         threads = ffbs_item_threads(K, n_max);
         if (c->ffbs_threads == ffbs_item_base_threads(K) || c->ffbs_threads == 2 * ffbs_item_base_threads(K))
             threads = c->ffbs_threads;
@@ -392,7 +430,7 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
     L.smem = smem;
     L.grid = 0;
     L.stream = c->stream;
-    CUDA_TRY(ffbs_call<Real>(a, L, true));
+    CUDA_TRY(big ? ffbs_big_call<Real>(a, L, true) : ffbs_call<Real>(a, L, true));
     const int per_sm = L.grid;
     if (per_sm < 1) return fail(SMJP_E_UNSUPPORTED, "kernel cannot be resident (threads=%d smem=%zu)", threads, smem);
     int grid = c->num_sms * per_sm;
@@ -446,7 +484,7 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
         CUDA_TRY(cudaEventRecord(e0, c->stream));
     }
     L.grid = grid;
-    CUDA_TRY(ffbs_call<Real>(a, L, false));
+    CUDA_TRY(big ? ffbs_big_call<Real>(a, L, false) : ffbs_call<Real>(a, L, false));
     if (c->time_kernels) {
         CUDA_TRY(cudaEventRecord(e1, c->stream));
         c->ffbs_events.emplace_back(e0, e1);

@@ -58,6 +58,8 @@ struct FfbsArgs {
     unsigned int* queue;   // work counter, zeroed before launch
     const double* model;   // device: shape[K*K], c2[K*K] (= k*log2(lambda)), emis[K*Kobs], scale[K*K]
     int Kobs;
+    int K;                    // run-time K (ffbs_big.cuh only; the other kernels take it as a template parameter)
+    const void* big_params;   // ffbs_big.cuh: [3][K*K] reals = 1/k, (k-1) SCALE, (k log2 lambda - log2 k) SCALE
     int use_item;     // K == 3 only: run the item-parallel kernel instead of the thread-per-grid-point one
     int obs_product;  // 0: observations sharing a grid interval are SUMMED (reference); 1: multiplied
     double omega, power, t_end;

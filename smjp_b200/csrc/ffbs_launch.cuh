@@ -25,7 +25,7 @@ cudaError_t ffbs_do(const FfbsArgs& a, FfbsLaunch& L, bool query) {
 }
 
 // block sizes the kernel is instantiated for
-inline int ffbs_round_threads(int t) { return t <= 32 ? 32 : t <= 64 ? 64 : t <= 128 ? 128 : t <= 256 ? 256 : 512; }
+inline int ffbs_round_threads(int t) { return t <= 32 ? 32 : t <= 64 ? 64 : t <= 96 ? 96 : t <= 128 ? 128 : t <= 256 ? 256 : 512; }
 
 template <typename Real, int K>
 cudaError_t ffbs_pick(const FfbsArgs& a, FfbsLaunch& L, bool query) {
@@ -37,6 +37,7 @@ cudaError_t ffbs_pick(const FfbsArgs& a, FfbsLaunch& L, bool query) {
     switch (L.threads) {
         case 32: return ffbs_do<Real, K, 32, 8 * S>(a, L, query);
         case 64: return ffbs_do<Real, K, 64, 4 * S>(a, L, query);
+        case 96: return ffbs_do<Real, K, 96, sizeof(Real) == 8 ? 6 : 10>(a, L, query);
         case 128: return ffbs_do<Real, K, 128, (sizeof(Real) == 8 && K <= 3) ? 5 : 2 * S>(a, L, query);
         case 256: return ffbs_do<Real, K, 256, S>(a, L, query);
         case 512: return ffbs_do<Real, K, 512, (S + 1) / 2>(a, L, query);

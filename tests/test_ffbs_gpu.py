@@ -109,6 +109,67 @@ def test_fp64_matches_oracle_random(engine, K, n, D):
         assert np.array_equal(r["T"][c], ora["T"])
 
 
+@pytest.mark.parametrize("K,n,D,prec", [(11, 70, 30, "f64"), (16, 150, 60, "f64"), (33, 60, 25, "f64"),
+                                        (64, 40, 20, "f64"), (24, 90, 40, "f32"), (64, 100, 50, "f32")])
+def test_large_state_space_kernel_matches_oracle(engine, K, n, D, prec):
+    """K > 10 with general shapes runs on the run-time-K kernel (ffbs_big.cuh): exported messages, paths
+    with host uniforms, and the scratch (g-row) path with device Philox"""
+    from oracle import philox
+    from smjp_b200.engine import triangular_to_dense
+    rng = np.random.default_rng(1000 * K + n)
+    # fp32 has no room for a whole row below 1e-38 of the previous one (long intervals at large K): finer grid
+    t_end = n / (5.0 if prec == "f64" else 40.0)
+    shape, scale, W, obs_t, obs_y = random_problem(rng, K, t_end, n, D)
+    emis = O.emission_matrix(K)
+    engine.set_model(shape, scale, 2.0, emis, 1.0, t_end)
+    W2 = np.concatenate([[0.0], np.sort(rng.uniform(0, t_end, n // 2 - 1)), [t_end]])  # ragged batch
+    us = [rng.uniform(size=n), rng.uniform(size=len(W2) - 1)]
+    r = engine.ffbs_host([W, W2], obs_t, obs_y, uniforms=us, precision=prec, want_messages=True)
+    q = engine.ffbs_host([W, W2], obs_t, obs_y, uniforms=us, precision=prec, want_messages=False)
+    p = engine.ffbs_host([W, W2], obs_t, obs_y, seed=99, sweep=3, precision=prec)
+    assert np.all(r["status"] == 0) and np.all(q["status"] == 0) and np.all(p["status"] == 0)
+    for c, Wc in enumerate([W, W2]):
+        m = len(Wc) - 1
+        ora = O.ffbs(Wc, obs_t, obs_y, shape, scale, 2.0, emis, 1.0, t_end, us[c])
+        dense = triangular_to_dense(r["messages"][c], m, K)
+        # normalisation is deferred by one step, so an entry below ~1e-308 / Z_i of the row mass flushes to
+        # zero one step before it does in the reference (K = 16: Z_i reaches 1e-120): floor 1e-180
+        rel, ab = rel_err(dense, ora["alpha"].reshape(m, K * m), 1e-180 if prec == "f64" else 1e-30)
+        assert rel < (1e-9 if prec == "f64" else 2e-4), rel
+        assert np.allclose(r["logZ"][c], ora["logZ"], rtol=1e-10 if prec == "f64" else 1e-4, atol=1e-12 if prec == "f64" else 1e-4)
+        if prec == "f64":
+            for res in (r, q):  # exported (alpha rows) and scratch (g rows) backward passes agree with the oracle
+                assert np.array_equal(res["aug_idx"][c], ora["samples"])
+                assert np.array_equal(res["V"][c], ora["V"]) and np.array_equal(res["T"][c], ora["T"])
+            tis, jm = O.chain_metrics(ora["V"], ora["T"], K)
+            assert np.abs(q["time_in_state"][c] - tis).max() < 1e-12 and np.array_equal(q["jumps"][c], jm)
+            u = philox.u01(99, philox.TAG_BACKWARD, np.arange(m), 0, 3, c)
+            orap = O.ffbs(Wc, obs_t, obs_y, shape, scale, 2.0, emis, 1.0, t_end, u)
+            assert np.array_equal(p["V"][c], orap["V"]) and np.array_equal(p["T"][c], orap["T"])
+
+
+def test_large_state_space_sweeps_and_capacity_error(engine):
+    """Rao-Teh sweeps at K = 12 through DeviceChains; a grid whose state does not fit on chip is refused"""
+    from smjp_b200._lib import EngineError
+    from smjp_b200.chains import DeviceChains
+    rng = np.random.default_rng(5)
+    K, t_end = 12, 4.0
+    shape = rng.uniform(0.6, 3.0, (K, K)); scale = rng.uniform(2.0, 6.0, (K, K))
+    engine.set_model(shape, scale, 2.0, O.emission_matrix(K), 1.0, t_end)
+    ch = DeviceChains(engine, 64, np.arange(0.25, t_end, 0.25)).init_prior(np.ones(K) / K, seed=1, honour_scale=True)
+    ch.simulate_observations(seed=2)
+    for sw in range(3):
+        ch.sweep(seed=3, sweep=sw)
+    assert int((ch.status != 0).sum().item()) == 0
+    V, T = ch.paths_host()
+    assert all(t[0] == 0.0 and t[-1] == t_end and np.all(np.diff(t) > 0) for t in T)
+    K = 64
+    engine.set_model(np.full((K, K), 1.5), np.ones((K, K)), 2.0, O.emission_matrix(K), 1.0, 1.0)
+    W = np.linspace(0.0, 1.0, 2001)
+    with pytest.raises((EngineError, RuntimeError, ValueError)):
+        engine.ffbs_host([W], np.zeros(0), np.zeros(0, np.int32), uniforms=[np.full(2000, 0.5)])
+
+
 def test_ragged_batch_and_philox_backward(engine):
     """chains of different lengths in one launch; device Philox uniforms reproduce the oracle's."""
     from oracle import philox

@@ -98,6 +98,35 @@ def cfg4(C=1024, K=64, T=2000.0, sweeps=3):
     return {"config": "cfg4 dense K=%d exponential sMJP, %d chains, T=%g, Rao-Teh sweeps (candidates + dense FFBS)" % (K, C, T), **out}
 
 
+def cfg4b(C=1024, K=64, T=40.0, sweeps=2):
+    """K=64 sMJP with GENERAL Weibull shapes on a reduced horizon (the (v,l) path, run-time-K kernel)"""
+    import torch
+    from smjp_b200.chains import DeviceChains
+    from smjp_b200.engine import Engine
+    rng = np.random.default_rng(44)
+    eng = Engine(0)
+    eng.set_model(rng.uniform(0.6, 3.0, (K, K)), rng.uniform(0.7 * K, 1.3 * K, (K, K)), 2.0, emission(K), 1.0, T)
+    obs_t = np.arange(0.5, T, 1.0)
+    out = {}
+    for prec in ("f64", "f32"):
+        ch = DeviceChains(eng, C, obs_t).init_prior(np.ones(K) / K, seed=1, honour_scale=True, cap_per_chain=512)
+        ch.simulate_observations(seed=2)
+        ch.init_prior(np.ones(K) / K, seed=3, honour_scale=True, cap_per_chain=512)
+        for sw in range(2):
+            ch.sweep(seed=4, sweep=sw, precision=prec, mode="exact")
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for sw in range(sweeps):
+            ch.sweep(seed=4, sweep=2 + sw, precision=prec, mode="exact")
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        s, g = ch.state_steps_last_sweep()
+        out[prec] = {"ms_per_sweep": 1e3 * dt / sweeps, "mean_n": g / C, "state_steps_per_sec": s * sweeps / dt,
+                     "failed": int((ch.status != 0).sum().item())}
+    eng.close()
+    return {"config": "cfg4b K=%d general-shape sMJP on a reduced horizon T=%g, %d chains (ffbs_big kernel)" % (K, T, C), **out}
+
+
 def cfg5(C=16384, T=20.0, sweeps=4, threads=0):
     """10-state sMJP, many chains (one GPU's shard of the 65536-chain configuration)"""
     import torch
