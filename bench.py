@@ -390,7 +390,7 @@ def run_ours(args):
                      "compute": compute_ceiling(prec, ss_rank0 / K / max(k_cnt, 1), k_avg_s, clk.get("sm_mhz"))},
         "e2e": {"value": e_ss / e_wall, "unit": UNIT, "h2d_bytes_per_step": h2d // max(e2e_steps, 1),
                 "d2h_bytes_per_step": d2h // max(e2e_steps, 1), "steps": e2e_steps,
-                "api": "smjp_sweep_host (pinned host buffers in/out, H2D + D2H inside the timed call)"},
+                "api": "smjp_sweep_host (pinned host buffers in/out; H2D of paths + observations and D2H of the grid inside the timed call, new paths / metrics / status written by the kernels straight into the pinned output buffers)"},
     }
     if world == 1 and prec == "f64" and not args.no_alt:
         # the same workload in the engine's fp32 mode (north_star: messages within 1e-4), reported beside the

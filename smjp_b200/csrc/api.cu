@@ -116,6 +116,12 @@ struct smjp_ctx {
     int64_t ffbs_ncap_hint = 0;
     int64_t last_smem = 0;
     DevBuf d_in, d_out;  // staging for the host API
+    // host API overlap: a second stream carries the observation upload and the grid download of a sweep
+    // while the candidate kernels / the FFBS kernel run on the main stream
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_obs = nullptr, ev_fill = nullptr;
+    bool wait_obs = false;        // the next FFBS launch must wait for ev_obs
+    double* w_copy_dst = nullptr;  // pinned host destination of the grid, copied right after cand_fill
     PinBuf h_in, h_out;
     int ffbs_threads = 0;  // 0 = auto
     uint32_t chain_base = 0;
@@ -192,6 +198,14 @@ void smjp_ctx_destroy(smjp_ctx_t* c) {
     c->d_wlen.release();
     c->d_soff.release();
     c->h_stats.release();
+    if (c->ev_obs) cudaEventDestroy(c->ev_obs);
+    if (c->ev_fill) cudaEventDestroy(c->ev_fill);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (auto* evs : {&c->ffbs_events, &c->hmm_events, &c->pf_events})
+        for (auto& ev : *evs) {
+            cudaEventDestroy(ev.first);
+            cudaEventDestroy(ev.second);
+        }
     delete c;
 }
 
@@ -831,6 +845,15 @@ int smjp_sweep_dev(smjp_ctx_t* c, int C, const int64_t* p_offs, const int32_t* p
                     (long long)capacity);
     rc = smjp_candidates_fill_dev(c, C, p_offs, path_v, path_t, path_len, seed, sweep, mode, w_offs, soff, W);
     if (rc) return rc;
+    if (c->w_copy_dst) {  // host call: the grid goes home while the FFBS kernel runs
+        CUDA_TRY(cudaEventRecord(c->ev_fill, c->stream));
+        CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_fill, 0));
+        CUDA_TRY(cudaMemcpyAsync(c->w_copy_dst, W, (size_t)*total_w_host * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+    }
+    if (c->wait_obs) {  // host call: the observations were uploaded on the copy stream
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_obs, 0));
+        c->wait_obs = false;
+    }
     return smjp_ffbs_dev(c, C, w_offs, W, obs_offs, obs_t, obs_y, nullptr, seed, sweep, precision, nullptr,
                          nullptr, nullptr, nullptr, path_v_out, path_t_out, path_len_out, time_in_state, jumps,
                          status, *n_max_host, *total_w_host);
@@ -853,7 +876,7 @@ struct StagedPaths {
 
 int stage_paths(smjp_ctx* c, int C, const int64_t* p_offs, const int32_t* path_v, const double* path_t,
                 const int32_t* path_len, const int64_t* obs_offs, const double* obs_t, const int32_t* obs_y,
-                StagedPaths* out) {
+                StagedPaths* out, bool obs_on_copy_stream = false) {
     if (p_offs[0] != 0) return fail(SMJP_E_INVALID, "offsets must start at 0");
     const int64_t total_p = p_offs[C];
     for (int i = 0; i < C; ++i) {
@@ -879,9 +902,17 @@ int stage_paths(smjp_ctx* c, int C, const int64_t* p_offs, const int32_t* path_v
     CUDA_TRY(put(o_pt, path_t, total_p * 8));
     CUDA_TRY(put(o_pl, path_len, C * 4));
     if (obs_offs) {
-        CUDA_TRY(put(o_oo, obs_offs, (C + 1) * 8));
-        CUDA_TRY(put(o_ot, obs_t, total_o * 8));
-        CUDA_TRY(put(o_oy, obs_y, total_o * 4));
+        cudaStream_t os = obs_on_copy_stream ? c->copy_stream : c->stream;
+        auto puto = [&](size_t o, const void* src, size_t bytes) -> cudaError_t {
+            return bytes ? cudaMemcpyAsync(dd + o, src, bytes, cudaMemcpyHostToDevice, os) : cudaSuccess;
+        };
+        CUDA_TRY(puto(o_oo, obs_offs, (C + 1) * 8));
+        CUDA_TRY(puto(o_ot, obs_t, total_o * 8));
+        CUDA_TRY(puto(o_oy, obs_y, total_o * 4));
+        if (obs_on_copy_stream) {
+            CUDA_TRY(cudaEventRecord(c->ev_obs, c->copy_stream));
+            c->wait_obs = true;
+        }
     }
     char* d = (char*)c->d_in.p;
     out->p_offs = (const int64_t*)(d + o_po);
@@ -953,8 +984,31 @@ int smjp_sweep_host(smjp_ctx_t* c, int C, const int64_t* p_offs, const int32_t* 
     if (obs_offs[C] > 0 && (!obs_t || !obs_y)) return fail(SMJP_E_INVALID, "observations missing");
     CUDA_TRY(cudaSetDevice(c->device));
     const int K = c->K;
+    if (!c->copy_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_obs, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fill, cudaEventDisableTiming));
+    }
+    // Pinned (page-locked) caller buffers are addressable from the device: the kernels then write the new paths,
+    // the per-chain metrics and the status words STRAIGHT into the caller's memory (a few MB of scattered
+    // stores, overlapped with the sweep) instead of into a staging buffer that is copied back afterwards
+    // (capacity-sized: 26 MB for cfg2).  Pageable buffers keep the staged copy.
+    auto mapped = [&](void* hp) -> void* {
+        if (!hp) return nullptr;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, hp) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+    };
+    int32_t* m_pv = (int32_t*)mapped(path_v_out);
+    double* m_pt = (double*)mapped(path_t_out);
+    int32_t* m_pl = (int32_t*)mapped(path_len_out);
+    int32_t* m_st = (int32_t*)mapped(status);
+    double* m_tis = (double*)mapped(time_in_state);
+    int32_t* m_jm = (int32_t*)mapped(jumps);
+    const bool w_pinned = mapped(W) != nullptr;
+    const bool in_pinned = mapped((void*)obs_t) != nullptr || !obs_t;
     StagedPaths sp;
-    rc = stage_paths(c, C, p_offs, path_v, path_t, path_len, obs_offs, obs_t, obs_y, &sp);
+    rc = stage_paths(c, C, p_offs, path_v, path_t, path_len, obs_offs, obs_t, obs_y, &sp, in_pinned);
     if (rc) return rc;
     rc = c->d_soff.reserve((size_t)p_offs[C] * 4 + 16);
     if (rc) return rc;
@@ -963,28 +1017,39 @@ int smjp_sweep_host(smjp_ctx_t* c, int C, const int64_t* p_offs, const int32_t* 
     auto take = [&](size_t bytes) { size_t o = off; off += smjp::align_up(bytes, 16); return o; };
     const size_t o_wo = take((C + 1) * 8), o_pl = take(C * 4), o_st = take(C * 4);
     const size_t o_tis = take((size_t)C * K * 8), o_jm = take((size_t)C * K * 4);
-    const size_t o_W = take(capacity * 8), o_pv = take(capacity * 4), o_pt = take(capacity * 8);
+    const size_t o_W = take(capacity * 8);
+    const size_t o_pv = m_pv ? 0 : take(capacity * 4), o_pt = m_pt ? 0 : take(capacity * 8);
     rc = c->d_out.reserve(off);
     if (rc) return rc;
     char* d = (char*)c->d_out.p;
     int64_t n_max = 0;
+    c->w_copy_dst = w_pinned ? W : nullptr;
     rc = smjp_sweep_dev(c, C, sp.p_offs, sp.path_v, sp.path_t, sp.path_len, sp.obs_offs, sp.obs_t, sp.obs_y,
                         seed, sweep, mode, precision, capacity, (int64_t*)(d + o_wo), (int32_t*)c->d_soff.p,
-                        (double*)(d + o_W), (int32_t*)(d + o_pv), (double*)(d + o_pt), (int32_t*)(d + o_pl),
-                        (double*)(d + o_tis), (int32_t*)(d + o_jm), (int32_t*)(d + o_st), &n_max, total_w);
-    if (rc) return rc;
+                        (double*)(d + o_W), m_pv ? m_pv : (int32_t*)(d + o_pv), m_pt ? m_pt : (double*)(d + o_pt),
+                        m_pl ? m_pl : (int32_t*)(d + o_pl), time_in_state ? (m_tis ? m_tis : (double*)(d + o_tis)) : nullptr,
+                        jumps ? (m_jm ? m_jm : (int32_t*)(d + o_jm)) : nullptr, m_st ? m_st : (int32_t*)(d + o_st),
+                        &n_max, total_w);
+    c->w_copy_dst = nullptr;
+    c->wait_obs = false;
+    if (rc) {
+        cudaStreamSynchronize(c->copy_stream);
+        cudaStreamSynchronize(c->stream);
+        return rc;
+    }
     const int64_t tw = *total_w;
     auto get = [&](void* dst, size_t o, size_t bytes) -> cudaError_t {
         return (dst && bytes) ? cudaMemcpyAsync(dst, d + o, bytes, cudaMemcpyDeviceToHost, c->stream) : cudaSuccess;
     };
     CUDA_TRY(get(w_offs, o_wo, (C + 1) * 8));
-    CUDA_TRY(get(path_len_out, o_pl, C * 4));
-    CUDA_TRY(get(status, o_st, C * 4));
-    CUDA_TRY(get(time_in_state, o_tis, (size_t)C * K * 8));
-    CUDA_TRY(get(jumps, o_jm, (size_t)C * K * 4));
-    CUDA_TRY(get(W, o_W, tw * 8));
-    CUDA_TRY(get(path_v_out, o_pv, tw * 4));
-    CUDA_TRY(get(path_t_out, o_pt, tw * 8));
+    if (!m_pl) CUDA_TRY(get(path_len_out, o_pl, C * 4));
+    if (!m_st) CUDA_TRY(get(status, o_st, C * 4));
+    if (!m_tis) CUDA_TRY(get(time_in_state, o_tis, (size_t)C * K * 8));
+    if (!m_jm) CUDA_TRY(get(jumps, o_jm, (size_t)C * K * 4));
+    if (!w_pinned) CUDA_TRY(get(W, o_W, tw * 8));
+    if (!m_pv) CUDA_TRY(get(path_v_out, o_pv, tw * 4));
+    if (!m_pt) CUDA_TRY(get(path_t_out, o_pt, tw * 8));
+    CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return SMJP_OK;
 }

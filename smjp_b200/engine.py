@@ -353,7 +353,11 @@ class PackedSweep:
         return live * 12 + self.C * 12 + 8 + (self.C + 1) * 8 + len(self.obs_t) * 12
 
     def d2h_bytes(self):
-        return self.total_w * 20 + (self.C + 1) * 8 + self.C * 8 + self.C * self.K * 12
+        """bytes that reached the host in the last run(): the grid (copied while the FFBS kernel runs), the grid
+        offsets, and -- written by the kernels straight into these pinned buffers -- the live path entries,
+        path lengths, status words and per-state metrics"""
+        live = int(self.out_len[: self.C].sum())
+        return self.total_w * 8 + live * 12 + (self.C + 1) * 8 + self.C * 8 + self.C * self.K * 12
 
 
 def sweep_host(eng, V, T, obs_t, obs_y, seed, sweep=0, mode="reference", precision="f64"):
