@@ -78,3 +78,52 @@ def load_samples_in_pickle(fn):
     with open(fn, "rb") as f:
         d = pickle.load(f)
     return d["agg"], d["uuid_str"], d["omega"]
+
+
+# ------------------------------------------------------------------------------------------------
+# Columnar store for many chain-sweeps.  The reference pickles Python lists of
+# ragged arrays (mcmc_utils.py:436-451), which cannot hold a 65 536-chain run; here every ragged list
+# becomes one flat array plus int64 offsets inside a single .npz, and scalars / dense arrays are
+# stored as they are.  load_aggregate_columnar returns the same dict-of-lists the pickle held.
+# ------------------------------------------------------------------------------------------------
+def save_aggregate_columnar(fn, aggregate, omega=None, uuid_str=None):
+    """aggregate: dict whose values are lists of 1-D arrays (ragged: 'W', 'T', 'V', ...), lists of scalars
+    ('prob'), dense arrays (e.g. time_in_state [S,C,K]) or nested dicts of the same (e.g. 'prior')."""
+    cols = {}
+
+    def put(prefix, value):
+        if isinstance(value, dict):
+            cols[prefix + "@dict"] = np.array(sorted(value.keys()))
+            for k, v in value.items():
+                put(prefix + "/" + k, v)
+        elif isinstance(value, (list, tuple)) and len(value) and all(np.ndim(x) == 1 for x in value):
+            lens = np.array([len(x) for x in value], dtype=np.int64)
+            cols[prefix + "@offs"] = np.concatenate([[0], np.cumsum(lens)])
+            cols[prefix + "@flat"] = np.concatenate([np.asarray(x) for x in value]) if lens.sum() else np.zeros(0)
+        else:
+            cols[prefix + "@dense"] = np.asarray(value)
+
+    put("agg", aggregate)
+    if omega is not None:
+        cols["omega"] = np.float64(omega)
+    if uuid_str is not None:
+        cols["uuid_str"] = np.array(str(uuid_str))
+    np.savez_compressed(fn, **cols)
+    return fn if str(fn).endswith(".npz") else str(fn) + ".npz"
+
+
+def load_aggregate_columnar(fn):
+    """inverse of save_aggregate_columnar: returns (aggregate, uuid_str, omega) like load_samples_in_pickle"""
+    z = np.load(fn, allow_pickle=False)
+
+    def get(prefix):
+        if prefix + "@dict" in z:
+            return {str(k): get(prefix + "/" + str(k)) for k in z[prefix + "@dict"]}
+        if prefix + "@offs" in z:
+            offs, flat = z[prefix + "@offs"], z[prefix + "@flat"]
+            return [flat[offs[i]: offs[i + 1]] for i in range(len(offs) - 1)]
+        d = z[prefix + "@dense"]
+        return d.tolist() if d.ndim == 1 and d.dtype.kind == "f" and prefix.endswith("prob") else d
+
+    agg = get("agg")
+    return agg, (str(z["uuid_str"]) if "uuid_str" in z else None), (float(z["omega"]) if "omega" in z else None)

@@ -154,3 +154,22 @@ def test_raoteh_argument_checks():
     with pytest.raises(ValueError):
         inference_error_checking(["parameters"])
     inference_error_checking(["trajectory", "parameters"])
+
+
+def test_columnar_aggregate_round_trip(tmp_path):
+    """ragged lists, scalars, dense arrays and the nested 'prior' dict survive the columnar store"""
+    from smjp_b200.mcmc_utils import load_aggregate_columnar, save_aggregate_columnar
+    rng = np.random.default_rng(0)
+    agg = {"W": [rng.uniform(size=int(n)) for n in rng.integers(2, 40, 25)],
+           "V": [rng.integers(1, 4, int(n)).astype(np.float64) for n in rng.integers(2, 9, 25)],
+           "T": [np.sort(rng.uniform(size=int(n))) for n in rng.integers(2, 9, 25)],
+           "prob": [1.0] * 25,
+           "time_in_state": rng.uniform(size=(5, 7, 3)),
+           "prior": {"W": [np.arange(3.0), np.arange(5.0)], "V": [np.ones(2), np.ones(4)]}}
+    fn = save_aggregate_columnar(str(tmp_path / "run"), agg, omega=2.0, uuid_str="abc")
+    back, uid, omega = load_aggregate_columnar(fn)
+    assert uid == "abc" and omega == 2.0 and back["prob"] == agg["prob"]
+    for k in ("W", "V", "T"):
+        assert len(back[k]) == len(agg[k]) and all(np.array_equal(a, b) for a, b in zip(back[k], agg[k]))
+    assert np.array_equal(back["time_in_state"], agg["time_in_state"])
+    assert all(np.array_equal(a, b) for a, b in zip(back["prior"]["W"], agg["prior"]["W"]))
