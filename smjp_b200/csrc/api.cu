@@ -388,6 +388,17 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
     const bool big = K > 10;  // general shapes, run-time K
     const bool item_kernel = !big && (K >= 4 || (K == 3 && c->item_k3));
     a.K = K;
+    if (K <= 3) {  // hazard parameters of the thread-per-grid-point kernel travel as kernel arguments
+        for (int t = 0; t < K * K; ++t) {
+            const double k = c->h_model[t], c2p = c->h_model[K * K + t] - std::log2(k);
+            a.pc_d[0][t] = 1.0 / k;
+            a.pc_d[1][t] = (k - 1.0) * 256.0;  // Exp2<double>::SCALE
+            a.pc_d[2][t] = c2p * 256.0;
+            a.pc_f[0][t] = (float)(1.0 / k);
+            a.pc_f[1][t] = (float)(k - 1.0);
+            a.pc_f[2][t] = (float)c2p;
+        }
+    }
     a.use_item = item_kernel;  // thread per (v, j) for larger state spaces, thread per j for K <= 3
     int threads;
     size_t smem;

@@ -60,6 +60,10 @@ struct FfbsArgs {
     int Kobs;
     int K;                    // run-time K (ffbs_big.cuh only; the other kernels take it as a template parameter)
     const void* big_params;   // ffbs_big.cuh: [3][K*K] reals = 1/k, (k-1) SCALE, (k log2 lambda - log2 k) SCALE
+    // ffbs.cuh (K <= 3): the same three parameter sets as kernel arguments, in both precisions, so that the
+    // forward pass takes them as constant-bank operands instead of shared-memory loads ([3][9])
+    double pc_d[3][9];
+    float pc_f[3][9];
     int use_item;     // K == 3 only: run the item-parallel kernel instead of the thread-per-grid-point one
     int obs_product;  // 0: observations sharing a grid interval are SUMMED (reference); 1: multiplied
     double omega, power, t_end;
@@ -244,6 +248,10 @@ constexpr int log2_of(int x) { return x <= 1 ? 0 : x <= 2 ? 1 : x <= 4 ? 2 : x <
 template <typename Real> struct ScanAcc { typedef double type; };
 template <> struct ScanAcc<float> { typedef float type; };
 
+// hazard parameter set w (0: 1/k, 1: (k-1) SCALE, 2: (k log2 lambda - log2 k) SCALE), entry t -- a constant-bank
+// operand when t is a compile-time constant (the unrolled forward loops)
+#define PC(w, t) (sizeof(Real) == 8 ? (Real)a.pc_d[w][t] : (Real)a.pc_f[w][t])
+
 template <typename Real, int K, int B, int MINB>
 __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
     using M = Math<Real>;
@@ -426,8 +434,8 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
                     Real esum = 0, dsum = 0;
 #pragma unroll
                     for (int s = 0; s < K; ++s) {
-                        kE[s] = ex2(skm1[v * K + s] * L2 - sc2p[v * K + s]);  // A_vs(tau)
-                        esum += kE[s] * srk[v * K + s];
+                        kE[s] = ex2(PC(1, v * K + s) * L2 - PC(2, v * K + s));  // A_vs(tau)
+                        esum += kE[s] * PC(0, v * K + s);
                         dsum += kE[s];
                     }
                     const Real hsum = tau * esum;  // H_v(tau)
