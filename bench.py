@@ -16,7 +16,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -49,68 +48,81 @@ def algorithmic_bytes(n_per_chain, D, esz):
 
 
 # ------------------------------------------------------------------------------------------------
-class ClockSampler(threading.Thread):
-    """SM clocks / throttle reasons sampled DURING the timed region.  NVML in-process (a `nvidia-smi`
-    subprocess per sample holds the driver lock for ~0.2 s and was measured to stall the timed stream by
-    that much); nvidia-smi is only the fallback when pynvml is missing."""
+SAMPLER_SRC = r"""
+import json, sys, time, select
+idx = int(sys.argv[1])
+out = {"sm": [], "smmax": None, "mask": 0, "via": "nvml"}
+try:
+    import pynvml as n
+    n.nvmlInit()
+    h = n.nvmlDeviceGetHandleByIndex(idx)
+    out["smmax"] = float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM))
+    def reasons():
+        try:
+            return int(n.nvmlDeviceGetCurrentClocksEventReasons(h))
+        except Exception:
+            return int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+    n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM); reasons()      # first queries of each kind are slow
+    print("ready", flush=True)
+    sys.stdin.readline()                                         # "b": begin
+    while True:
+        out["sm"].append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+        out["mask"] |= reasons()
+        r, _, _ = select.select([sys.stdin], [], [], 0.02)
+        if r:
+            break
+except Exception as e:
+    out["error"] = repr(e)
+    print("ready", flush=True)
+print(json.dumps(out), flush=True)
+"""
+
+
+class ClockSampler:
+    """SM clocks / throttle reasons sampled DURING the timed region by a helper PROCESS with its own NVML
+    session (started and primed before the region, sampling every ~20 ms between begin() and end()).  NVML
+    queries take 5-50 ms now and then: issued from this process -- inline or from a thread -- they were
+    measured to stall the launch path of the timed loop by that much; a `nvidia-smi` subprocess per sample
+    costs ~0.2 s.  The helper does not touch this process."""
 
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index = index
-        self.stop_flag = threading.Event()
-        self.sm, self.smmax, self.reasons = [], [], set()
-        self.nvml = None
+        self.res = None
+        self.proc = None
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nvml = pynvml
-            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.smmax.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)))
-            self.sample()  # first queries of each kind are slow (they were seen to hold up the first timed launch)
-            self.sm.clear()
-            self.reasons.clear()
+            self.proc = subprocess.Popen([sys.executable, "-c", SAMPLER_SRC, str(index)], stdin=subprocess.PIPE,
+                                         stdout=subprocess.PIPE, text=True)
+            self.proc.stdout.readline()  # "ready"
         except Exception:
-            self.nvml = None
+            self.proc = None
 
-    def sample(self):
-        if self.nvml is not None:
-            n = self.nvml
-            self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+    def begin(self):
+        if self.proc:
             try:
-                mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
-            except Exception:
-                mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
-            for bit, name in self.REASONS.items():
-                if mask & bit:
-                    self.reasons.add(name)
-            return
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                             capture_output=True, text=True, timeout=5).stdout
-        f = [x.strip() for x in out.strip().split(",")]
-        self.sm.append(float(f[0]))
-        self.smmax.append(float(f[1]))
-        for nm, val in zip(names, f[2:6]):
-            if val.lower().startswith("active"):
-                self.reasons.add(nm)
-
-    def run(self):
-        while not self.stop_flag.is_set():
-            try:
-                self.sample()
+                self.proc.stdin.write("b\n")
+                self.proc.stdin.flush()
             except Exception:
                 pass
-            self.stop_flag.wait(0.05 if self.nvml is not None else 0.2)
+
+    def end(self):
+        if self.proc and self.res is None:
+            try:
+                self.proc.stdin.write("e\n")
+                self.proc.stdin.flush()
+                self.res = json.loads(self.proc.stdout.readline())
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.res = {"sm": [], "smmax": None, "mask": 0, "error": "sampler process failed"}
 
     def summary(self):
-        if not self.sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(np.max(self.smmax)) if self.smmax else None,
-                "reasons": sorted(self.reasons), "samples": len(self.sm), "via": "nvml" if self.nvml is not None else "nvidia-smi"}
+        self.end()
+        r = self.res or {"sm": [], "smmax": None, "mask": 0}
+        if not r["sm"]:
+            return {"sm_mhz": None, "sm_max_mhz": r.get("smmax"), "reasons": [], "samples": 0, "error": r.get("error")}
+        return {"sm_mhz": float(np.median(r["sm"])), "sm_max_mhz": r.get("smmax"),
+                "reasons": sorted(name for bit, name in self.REASONS.items() if r["mask"] & bit),
+                "samples": len(r["sm"]), "via": "nvml (helper process)"}
 
 
 def measured_peak():
@@ -258,29 +270,22 @@ def run_ours(args):
     eng.kernel_time()
     launches0 = eng.launch_count
     sampler = ClockSampler(local)
-    # clocks are sampled INLINE, right after a sweep has been enqueued (its FFBS kernel is then running for
-    # the next ~20 ms): a sampling thread was measured to cost up to 5 ms per step, its NVML queries contending
-    # with the launch path of the timed loop; an NVML query occasionally takes 3-30 ms, hence only two of them
-    sample_at = {args.steps // 3, (2 * args.steps) // 3} if args.steps >= 3 else {0}  # two samples under load
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ss = gs = 0.0
     alg_bytes = 0.0
     n_snap = []
     barrier()
     step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)] if os.environ.get("SMJP_BENCH_DEBUG") else None
+    sampler.begin()
     ev0.record()
     for i in range(args.steps):
         ch.sweep(seed=SEED, sweep=args.warmup + i, precision=prec)
         n_snap.append(ch.cur["offs"])  # device tensor of this sweep's grid windows; reduced after timing
-        if (i in sample_at) if sampler.nvml is not None else (i == args.steps // 2):
-            try:
-                sampler.sample()
-            except Exception:
-                pass
         if step_ev:
             step_ev[i].record()
     ev1.record()
     barrier()
+    sampler.end()
     ms = ev0.elapsed_time(ev1)
     if step_ev and rank == 0:
         print("per-step ms:", [round(ev0.elapsed_time(e), 2) for e in step_ev], file=sys.stderr)

@@ -685,4 +685,6 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
     }
 }
 
+#undef PC
+
 }  // namespace smjp
