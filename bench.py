@@ -280,7 +280,7 @@ def run_ours(args):
     ev0.record()
     for i in range(args.steps):
         ch.sweep(seed=SEED, sweep=args.warmup + i, precision=prec)
-        n_snap.append(ch.cur["offs"])  # device tensor of this sweep's grid windows; reduced after timing
+        n_snap.append(ch.cur["offs"].clone())  # this sweep's grid windows (the buffer is recycled two sweeps on)
         if step_ev:
             step_ev[i].record()
     ev1.record()
@@ -411,7 +411,7 @@ def run_ours(args):
         dbg = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)] if os.environ.get("SMJP_BENCH_DEBUG") else None
         for sw in range(args.steps):
             ch.sweep(seed=SEED + 11, sweep=3 + sw, precision="f32")
-            snaps.append(ch.cur["offs"])
+            snaps.append(ch.cur["offs"].clone())
             if dbg:
                 dbg[sw].record()
         a1.record()
@@ -428,6 +428,7 @@ def run_ours(args):
             b32 += algorithmic_bytes(n, D, 4)
         line["f32"] = {"value": ss32 / (ms32 / 1e3), "unit": UNIT, "ms_per_step": ms32 / args.steps,
                        "chain_sweeps_per_sec": C * args.steps / (ms32 / 1e3),
+                       "failed_chains": int((ch.status != 0).sum().item()),
                        "roofline": {"bound": "hbm", "achieved": (b32 / max(c32, 1)) / (k32 / max(c32, 1) / 1e3) / 1e9,
                                     "peak": peak, "unit": "GB/s",
                                     "frac": (b32 / max(c32, 1)) / (k32 / max(c32, 1) / 1e3) / 1e9 / peak,

@@ -78,6 +78,8 @@ int64_t smjp_ctx_get_stat(smjp_ctx_t* ctx, const char* key);
  *        prior entry points return SMJP_E_UNSUPPORTED for it);
  *        "pf_cluster" (thread-block-cluster size of one particle-filter run: 0 = auto, 1, 2, 4, 8, 16);
  *        "pf_threads" (threads per CTA of the particle filter: 0 = auto, 256, 512, 1024);
+ *        "f32_rescue" (default 1: chains whose fp32 FFBS pass loses its row sum -- a grid step over which every
+ *        live state changes by more than 38 orders of magnitude -- are redone by the fp64 kernel);
  *        "pf_extend" (0 = the particle-filter path is extended flat from the last observation to t_end
  *        as the reference does, pmcmc.py:307-309; 1 = the segment is simulated);
  *        "lpt_order" (0/1, default 1: the FFBS kernel starts the longest grids first);

@@ -105,7 +105,8 @@ struct smjp_ctx {
     std::vector<double> h_model;
     DevBuf d_model;
     // workspaces
-    DevBuf d_queue, d_msg_scratch, d_obsf, d_order, d_dense_msg, d_big;
+    DevBuf d_queue, d_msg_scratch, d_obsf, d_order, d_dense_msg, d_big, d_failed;
+    int f32_rescue = 1;  // chains that fail in fp32 are redone by the fp64 kernel
     bool lpt_order = true;
     int obs_product = 0;
     int pf_extend = 0;
@@ -189,6 +190,7 @@ void smjp_ctx_destroy(smjp_ctx_t* c) {
     c->d_order.release();
     c->d_dense_msg.release();
     c->d_big.release();
+    c->d_failed.release();
     c->d_in.release();
     c->d_out.release();
     c->h_in.release();
@@ -259,6 +261,10 @@ int smjp_ctx_set_option(smjp_ctx_t* c, const char* key, int64_t value) {
     }
     if (!strcmp(key, "item_k3")) {
         c->item_k3 = value != 0;
+        return SMJP_OK;
+    }
+    if (!strcmp(key, "f32_rescue")) {
+        c->f32_rescue = value ? 1 : 0;
         return SMJP_OK;
     }
     if (!strcmp(key, "pf_threads")) {
@@ -445,6 +451,25 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
         threads = ffbs_round_threads(threads);
         smem = ffbs_smem_bytes<Real>(K, (int)n_max, threads);
     }
+    // fp64 rescue of chains that fail in fp32 (scratch mode, K <= 10): geometry of the fp64 launch
+    constexpr int RESCUE_GRID = 32;
+    bool rescue = sizeof(Real) == 4 && c->f32_rescue && !a.messages && !big;
+    int rescue_threads = 0;
+    size_t rescue_smem = 0;
+    if (rescue) {
+        if (item_kernel) {
+            rescue_threads = threads;
+            rescue_smem = ffbs_item_smem_bytes<double>(K, (int)n_max, rescue_threads);
+            if (rescue_smem > c->smem_optin && rescue_threads == ffbs_item_base_threads(K)) {
+                rescue_threads *= 2;
+                rescue_smem = ffbs_item_smem_bytes<double>(K, (int)n_max, rescue_threads);
+            }
+        } else {
+            rescue_threads = threads;
+            rescue_smem = ffbs_smem_bytes<double>(K, (int)n_max, rescue_threads);
+        }
+        if (rescue_smem > c->smem_optin) rescue = false;
+    }
     if (smem > c->smem_optin)
         return fail(SMJP_E_UNSUPPORTED,
                     "grid with %lld intervals x K=%d needs %zu B of shared memory (> %zu): "
@@ -471,6 +496,7 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
         c->ffbs_ncap_hint = hint;
         const int64_t stride = (int64_t)K * hint * (hint + 1) / 2;
         size_t bytes = (size_t)stride * sizeof(Real) * (size_t)grid;
+        if (rescue && bytes < (size_t)stride * 8 * RESCUE_GRID) bytes = (size_t)stride * 8 * RESCUE_GRID;
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
         size_t budget = free_b + c->d_msg_scratch.cap;
@@ -487,12 +513,16 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
         a.msg_scratch = c->d_msg_scratch.p;
         a.msg_scratch_stride = stride;
     }
-    rc = c->d_obsf.reserve((size_t)grid * n_max * K * sizeof(Real));
+    {
+        size_t ob = (size_t)grid * n_max * K * sizeof(Real);
+        if (rescue && ob < (size_t)RESCUE_GRID * n_max * K * 8) ob = (size_t)RESCUE_GRID * n_max * K * 8;
+        rc = c->d_obsf.reserve(ob);
+    }
     if (rc) return rc;
     a.obsf_scratch = c->d_obsf.p;
     rc = c->d_queue.reserve(256);
     if (rc) return rc;
-    CUDA_TRY(cudaMemsetAsync(c->d_queue.p, 0, sizeof(unsigned int), c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->d_queue.p, 0, 2 * sizeof(unsigned int), c->stream));
     a.queue = (unsigned int*)c->d_queue.p;
     if (a.C > grid && c->lpt_order) {  // more chains than resident CTAs: start the long grids first
         rc = c->d_order.reserve((size_t)a.C * sizeof(int32_t));
@@ -510,6 +540,30 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
     }
     L.grid = grid;
     CUDA_TRY(big ? ffbs_big_call<Real>(a, L, false) : ffbs_call<Real>(a, L, false));
+    if (rescue) {
+        // fp32 has ~38 orders of magnitude per grid step: a step over which every live state loses more than
+        // that (or gains it) leaves a chain without a row sum.  Those chains -- rare, none on most sweeps --
+        // are listed on the device and redone by the fp64 kernel on a few CTAs, same scratch, same stream.
+        rc = c->d_failed.reserve((size_t)a.C * sizeof(int32_t) + 16);
+        if (rc) return rc;
+        int32_t* cnt = (int32_t*)c->d_failed.p;
+        int32_t* list = cnt + 4;
+        collect_failed_kernel<<<1, 1024, 0, c->stream>>>(a.C, a.status, list, cnt);
+        CUDA_TRY(cudaGetLastError());
+        FfbsArgs r = a;
+        r.order = list;
+        r.C_dev = cnt;
+        r.queue = (unsigned int*)c->d_queue.p + 1;
+        FfbsLaunch R;
+        R.K = K;
+        R.threads = rescue_threads;
+        R.smem = rescue_smem;
+        R.stream = c->stream;
+        R.grid = RESCUE_GRID < a.C ? RESCUE_GRID : a.C;
+        r.nslot = item_kernel ? ffbs_item_nslot(K, (int)n_max, rescue_threads) : ffbs_nslot((int)n_max, rescue_threads);
+        CUDA_TRY(ffbs_call<double>(r, R, false));
+        c->launches += 2;
+    }
     if (c->time_kernels) {
         CUDA_TRY(cudaEventRecord(e1, c->stream));
         c->ffbs_events.emplace_back(e0, e1);

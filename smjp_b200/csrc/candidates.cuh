@@ -345,4 +345,15 @@ __global__ void chain_order_kernel(int C, const int64_t* w_offs, int n_max, int3
     }
 }
 
+// chains whose fp32 pass ended without a path (row sum under/overflow in single precision): list for the fp64 rescue
+__global__ void collect_failed_kernel(int C, const int32_t* status, int32_t* list, int32_t* count) {
+    __shared__ int s_n;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+        if (status[c] & SMJP_ST_DEGENERATE) list[atomicAdd(&s_n, 1)] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) *count = s_n;
+}
+
 }  // namespace smjp

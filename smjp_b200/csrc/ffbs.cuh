@@ -55,6 +55,7 @@ struct FfbsArgs {
     int32_t* jumps;
     int32_t* status;
     const int32_t* order;  // optional chain processing order (longest first)
+    const int32_t* C_dev;  // optional: number of entries of `order` to process, read on the device
     unsigned int* queue;   // work counter, zeroed before launch
     const double* model;   // device: shape[K*K], c2[K*K] (= k*log2(lambda)), emis[K*Kobs], scale[K*K]
     int Kobs;
@@ -283,6 +284,7 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
 
     __shared__ int s_chain;
     __shared__ int s_sel;
+    __shared__ int s_found;
     __shared__ int s_flag;
     __shared__ double s_tab[Exp2<Real>::TAB ? Exp2<Real>::TAB : 1];
     __shared__ double2 s_ltab[Exp2<Real>::LTAB ? Exp2<Real>::LTAB : 1];
@@ -314,7 +316,8 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
         __syncthreads();
         if (tid == 0) {
             unsigned int q = atomicAdd(a.queue, 1u);
-            s_chain = (q < (unsigned)a.C) ? (a.order ? a.order[q] : (int)q) : -1;
+            const unsigned limit = a.C_dev ? (unsigned)*a.C_dev : (unsigned)a.C;  // device-side count: fp64 rescue list
+            s_chain = (q < limit) ? (a.order ? a.order[q] : (int)q) : -1;
             s_flag = 0;
         }
         __syncthreads();
@@ -583,7 +586,7 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
             for (int t = beg; t < end; ++t) loc += (Acc)wbuf[t];
             Acc incl = warp_inclusive_scan(loc, lane);
             if (lane == 31) scan_s[wid + 1] = incl;
-            if (tid == 0) scan_s[0] = 0;
+            if (tid == 0) { scan_s[0] = 0; s_found = 0; }
             __syncthreads();
             Acc off = 0;
             for (int w = 1; w <= wid; ++w) off += scan_s[w];
@@ -600,7 +603,7 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
             const double u = a.uniforms ? a.uniforms[w0 + cur] : ubuf[u_hi - cur];
             const Acc target = (Acc)u * total;
             // owner: excl <= target < incl (the intervals partition [0,total) exactly)
-            const bool has = incl > excl;
+            const bool has = end > beg && incl > excl;  // empty chunks never own a draw (see below)
             if (has && target >= excl && target < incl) {
                 Acc acc = excl;
                 int sel = -1, lastpos = beg;
@@ -611,10 +614,16 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
                     if (acc > target) { sel = t; break; }
                 }
                 s_sel = sel >= 0 ? sel : lastpos;
+                s_found = 1;
             }
-            if (target >= total && has) atomicMax(&s_flag, tid + 1);  // rare: u*total rounded up
             __syncthreads();
-            if (target >= total) {  // block-uniform condition
+            // No owner: u*total rounded up to the total, or the target fell between the inclusive value of the
+            // last thread that holds weights and the warp total (a shuffle scan over zero-padded lanes is not
+            // monotone to the last bit -- in fp32 that happens about once per 1e7 draws).  The last thread with
+            // mass then takes its last positive entry, as the reference's inverse CDF does at u -> 1.
+            if (!s_found) {  // block-uniform
+                if (has) atomicMax(&s_flag, tid + 1);
+                __syncthreads();
                 if (tid + 1 == s_flag) {
                     int lastpos = beg;
                     for (int t = beg; t < end; ++t) if ((Acc)wbuf[t] > (Acc)0) lastpos = t;

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(B) ffbs_big_kernel(const FfbsArgs a) {
     Real* Zp_s = red_s + K + 1;  // [B]
     int* soj = (int*)st_h;
 
-    __shared__ int s_chain, s_sel, s_flag;
+    __shared__ int s_chain, s_sel, s_flag, s_found;
     __shared__ double s_tab[Exp2<Real>::TAB ? Exp2<Real>::TAB : 1];
     __shared__ double2 s_ltab[Exp2<Real>::LTAB ? Exp2<Real>::LTAB : 1];
     for (int t = tid; t < Exp2<Real>::TAB; t += B) s_tab[t] = ::exp2((double)t / 256.0);
@@ -88,7 +88,8 @@ __global__ void __launch_bounds__(B) ffbs_big_kernel(const FfbsArgs a) {
         __syncthreads();
         if (tid == 0) {
             unsigned int q = atomicAdd(a.queue, 1u);
-            s_chain = (q < (unsigned)a.C) ? (a.order ? a.order[q] : (int)q) : -1;
+            const unsigned limit = a.C_dev ? (unsigned)*a.C_dev : (unsigned)a.C;  // device-side count: fp64 rescue list
+            s_chain = (q < limit) ? (a.order ? a.order[q] : (int)q) : -1;
             s_flag = 0;
         }
         __syncthreads();
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(B) ffbs_big_kernel(const FfbsArgs a) {
             for (int t = beg; t < end; ++t) loc += (Acc)wbuf[t];
             Acc incl = warp_inclusive_scan(loc, lane);
             if (lane == 31) scan_s[wid + 1] = incl;
-            if (tid == 0) scan_s[0] = 0;
+            if (tid == 0) { scan_s[0] = 0; s_found = 0; }
             __syncthreads();
             Acc off = 0;
             for (int w = 1; w <= wid; ++w) off += scan_s[w];
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(B) ffbs_big_kernel(const FfbsArgs a) {
             }
             const double u = a.uniforms ? a.uniforms[w0 + cur] : ubuf[u_hi - cur];
             const Acc target = (Acc)u * total;
-            const bool has = incl > excl;
+            const bool has = end > beg && incl > excl;  // empty chunks never own a draw (see below)
             if (has && target >= excl && target < incl) {
                 Acc acc = excl;
                 int sel = -1, lastpos = beg;
@@ -297,10 +298,16 @@ __global__ void __launch_bounds__(B) ffbs_big_kernel(const FfbsArgs a) {
                     if (acc > target) { sel = t; break; }
                 }
                 s_sel = sel >= 0 ? sel : lastpos;
+                s_found = 1;
             }
-            if (target >= total && has) atomicMax(&s_flag, tid + 1);  // rare: u*total rounded up
             __syncthreads();
-            if (target >= total) {  // block-uniform condition
+            // No owner: u*total rounded up to the total, or the target fell between the inclusive value of the
+            // last thread that holds weights and the warp total (a shuffle scan over zero-padded lanes is not
+            // monotone to the last bit -- in fp32 that happens about once per 1e7 draws).  The last thread with
+            // mass then takes its last positive entry, as the reference's inverse CDF does at u -> 1.
+            if (!s_found) {  // block-uniform
+                if (has) atomicMax(&s_flag, tid + 1);
+                __syncthreads();
                 if (tid + 1 == s_flag) {
                     int lastpos = beg;
                     for (int t = beg; t < end; ++t) if ((Acc)wbuf[t] > (Acc)0) lastpos = t;

@@ -260,3 +260,21 @@ def test_packed_sweep_equals_list_api(engine):
         assert np.array_equal(ps.jumps[: C * K].reshape(C, K), r["jumps"])
         ps.swap()
         V, T = r["V"], r["T"]
+
+
+def test_fp32_sweeps_leave_no_failed_chain(engine):
+    """1.2e7 fp32 backward draws (4096 chains x 24 sweeps): none may lose its path.  Regression for a draw whose
+    target fell between the inclusive scan value of the last thread holding weights and the warp total (a
+    shuffle scan over zero-padded lanes is not monotone to the last bit): an empty chunk then 'owned' the draw
+    and returned an index one past the row, which repeated a grid point in the path and killed the chain on
+    the next sweep.  Every path must stay strictly increasing in time."""
+    from smjp_b200.chains import DeviceChains
+    K, T, C = 3, 100.0, 4096
+    engine.set_model(SHAPE3, np.ones((K, K)), 2.0, O.emission_matrix(K), 1.0, T)
+    ch = DeviceChains(engine, C, np.arange(0.1, T, 0.1)).init_prior(np.ones(K) / K, seed=1).simulate_observations(seed=2)
+    ch.init_prior(np.ones(K) / K, seed=3)
+    for sw in range(24):
+        ch.sweep(seed=4, sweep=sw, precision="f32")
+    assert int((ch.status != 0).sum().item()) == 0
+    V, Tt = ch.paths_host()
+    assert all(np.all(np.diff(t) > 0) for t in Tt)
