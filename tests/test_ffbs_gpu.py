@@ -235,3 +235,31 @@ def test_product_observation_likelihood_matches_oracle(engine):
     engine.set_model(shape, scale, 2.0, emis, 0.7, t_end)  # back to the reference behaviour
     r2 = engine.ffbs_host([W], [obs_t], [obs_y], uniforms=[u], want_messages=True)
     assert np.abs(r2["messages"][0] - r["messages"][0]).max() > 1e-3  # the two targets really differ
+
+
+def test_fp32_chain_that_underflows_is_redone_in_fp64(engine):
+    """a grid interval over which every state's survival factor is below fp32's range (exp(-200)) leaves the
+    fp32 pass without a row sum; by default such chains are redone by the fp64 kernel in the same call"""
+    rng = np.random.default_rng(21)
+    K, t_end = 3, 4.0
+    shape = np.full((K, K), 2.5); scale = np.full((K, K), 0.25)
+    emis = O.emission_matrix(K)
+    engine.set_model(shape, scale, 2.0, emis, 1.0, t_end)
+    fine = np.sort(rng.uniform(1.0, t_end, 60))
+    W_bad = np.concatenate([[0.0], fine, [t_end]])          # first interval [0, ~1]: H_v grows by ~100
+    W_ok = np.concatenate([[0.0], np.sort(rng.uniform(0, t_end, 400)), [t_end]])  # ~0.01 apart: fine in fp32
+    obs_t = np.arange(0.5, t_end, 0.5); obs_y = rng.integers(0, K, len(obs_t))
+    us = [rng.uniform(size=len(W_bad) - 1), rng.uniform(size=len(W_ok) - 1)]
+    ref64 = engine.ffbs_host([W_bad, W_ok], obs_t, obs_y, uniforms=us, precision="f64")
+    assert np.all(ref64["status"] == 0)
+    try:
+        engine.set_option("f32_rescue", 0)
+        raw = engine.ffbs_host([W_bad, W_ok], obs_t, obs_y, uniforms=us, precision="f32")
+        assert raw["status"][0] == 2 and raw["status"][1] == 0  # SMJP_ST_DEGENERATE
+    finally:
+        engine.set_option("f32_rescue", 1)
+    r = engine.ffbs_host([W_bad, W_ok], obs_t, obs_y, uniforms=us, precision="f32")
+    assert np.all(r["status"] == 0)
+    assert np.array_equal(r["V"][0], ref64["V"][0]) and np.array_equal(r["T"][0], ref64["T"][0])  # the fp64 result
+    assert np.array_equal(r["time_in_state"][0], ref64["time_in_state"][0])
+    assert len(r["V"][1]) >= 2 and r["T"][1][0] == 0.0
