@@ -70,7 +70,9 @@ void smjp_ctx_destroy(smjp_ctx_t* ctx);
 int smjp_ctx_sync(smjp_ctx_t* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t smjp_ctx_launch_count(smjp_ctx_t* ctx);
-/* launch geometry of the last FFBS kernel: "ffbs_grid", "ffbs_threads", "ffbs_smem"; "num_sms"; "pf_cluster" */
+/* launch geometry of the last FFBS kernel: "ffbs_grid", "ffbs_threads", "ffbs_smem"; "num_sms"; "pf_cluster";
+ * "ffbs_live_pairs": grid pairs (i, j) inside the live window that the K <= 3 FFBS kernel processed since the
+ * last query (synchronises; the nominal count is n(n+1)/2 per chain) */
 int64_t smjp_ctx_get_stat(smjp_ctx_t* ctx, const char* key);
 /* knobs: "ffbs_threads" (0 = auto, else threads per CTA of the FFBS kernel);
  *        "time_kernels" (0/1, see smjp_ctx_kernel_time);

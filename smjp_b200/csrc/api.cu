@@ -105,7 +105,7 @@ struct smjp_ctx {
     std::vector<double> h_model;
     DevBuf d_model;
     // workspaces
-    DevBuf d_queue, d_msg_scratch, d_obsf, d_order, d_dense_msg, d_big, d_failed;
+    DevBuf d_queue, d_msg_scratch, d_obsf, d_order, d_dense_msg, d_big, d_failed, d_live;
     int f32_rescue = 1;  // chains that fail in fp32 are redone by the fp64 kernel
     bool lpt_order = true;
     int obs_product = 0;
@@ -191,6 +191,7 @@ void smjp_ctx_destroy(smjp_ctx_t* c) {
     c->d_dense_msg.release();
     c->d_big.release();
     c->d_failed.release();
+    c->d_live.release();
     c->d_in.release();
     c->d_out.release();
     c->h_in.release();
@@ -226,6 +227,15 @@ int64_t smjp_ctx_get_stat(smjp_ctx_t* c, const char* key) {
     if (!strcmp(key, "ffbs_smem")) return c->last_smem;
     if (!strcmp(key, "num_sms")) return c->num_sms;
     if (!strcmp(key, "pf_cluster")) return c->last_pf_cluster;
+    if (!strcmp(key, "ffbs_live_pairs")) {  // grid pairs processed by the FFBS kernels since the last query
+        if (!c->d_live.p) return 0;
+        unsigned long long v = 0;
+        cudaSetDevice(c->device);
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
+        if (cudaMemcpy(&v, c->d_live.p, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        cudaMemsetAsync(c->d_live.p, 0, 8, c->stream);
+        return (int64_t)v;
+    }
     return -1;
 }
 
@@ -442,7 +452,9 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
         threads = c->ffbs_threads;
         if (threads == 0) {
             // a full row should give every thread a few grid points; small grids use small CTAs
-            threads = 128;
+            // fp32: the live window (~100 grid points on cfg2) keeps two warps busy, and two warps reduce and
+            // synchronise faster than four (4.6 vs 5.2 ms on cfg2); fp64's window is ~250 points: four warps
+            threads = sizeof(Real) == 4 ? 64 : 128;
             if (n_max > 1024) threads = 256;
             if (n_max > 3072) threads = 512;
             if (n_max <= 96) threads = 64;
@@ -487,6 +499,7 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
     if (grid > a.C) grid = a.C;
     a.ncap = (int)n_max;
     a.nslot = item_kernel ? ffbs_item_nslot(K, (int)n_max, threads) : ffbs_nslot((int)n_max, threads);
+    if (!item_kernel && !big) a.lay = ffbs_layout<Real>(K, (int)n_max, threads);
     int rc;
     if (!a.messages) {
         // grid lengths drift from sweep to sweep: size the per-CTA scratch for a rounded-up, never
@@ -522,6 +535,12 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
     a.obsf_scratch = c->d_obsf.p;
     rc = c->d_queue.reserve(256);
     if (rc) return rc;
+    if (!c->d_live.p) {
+        rc = c->d_live.reserve(8);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemsetAsync(c->d_live.p, 0, 8, c->stream));
+    }
+    a.live_pairs = (unsigned long long*)c->d_live.p;
     CUDA_TRY(cudaMemsetAsync(c->d_queue.p, 0, 2 * sizeof(unsigned int), c->stream));
     a.queue = (unsigned int*)c->d_queue.p;
     if (a.C > grid && c->lpt_order) {  // more chains than resident CTAs: start the long grids first
@@ -561,6 +580,7 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
         R.stream = c->stream;
         R.grid = RESCUE_GRID < a.C ? RESCUE_GRID : a.C;
         r.nslot = item_kernel ? ffbs_item_nslot(K, (int)n_max, rescue_threads) : ffbs_nslot((int)n_max, rescue_threads);
+        if (!item_kernel) r.lay = ffbs_layout<double>(K, (int)n_max, rescue_threads);
         CUDA_TRY(ffbs_call<double>(r, R, false));
         c->launches += 2;
     }

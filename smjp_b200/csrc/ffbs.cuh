@@ -30,6 +30,11 @@
 
 namespace smjp {
 
+// shared-memory byte offsets of ffbs_kernel (see ffbs_layout)
+struct FfbsLayout {
+    int wd, ubuf, scan, sta, sth, red, par, jlo, total;
+};
+
 struct FfbsArgs {
     int C;
     const int64_t* w_offs;
@@ -56,6 +61,8 @@ struct FfbsArgs {
     int32_t* status;
     const int32_t* order;  // optional chain processing order (longest first)
     const int32_t* C_dev;  // optional: number of entries of `order` to process, read on the device
+    unsigned long long* live_pairs;  // optional device counter: grid pairs (i, j) actually processed (live window)
+    FfbsLayout lay;                  // shared-memory byte offsets of ffbs_kernel (ffbs_layout)
     unsigned int* queue;   // work counter, zeroed before launch
     const double* model;   // device: shape[K*K], c2[K*K] (= k*log2(lambda)), emis[K*Kobs], scale[K*K]
     int Kobs;
@@ -72,24 +79,33 @@ struct FfbsArgs {
     int nslot;  // grid slots per thread: ceil((ncap + 1) / blockDim.x)
 };
 
-__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) & ~(a - 1); }  // a: power of two
 
 // grid slots per thread: ceil((ncap + 1) / threads)
 __host__ __device__ inline int ffbs_nslot(int ncap, int threads) { return (ncap + threads) / threads; }
 
-// dynamic shared memory bytes for (Real, K, ncap, threads)
+// dynamic shared memory layout of ffbs_kernel for (Real, K, ncap, threads): byte offsets, computed on the host
+// and passed as kernel arguments (constant-bank operands; carving the pointers in the kernel cost ~40
+// rematerialised instructions per grid pair at 64 registers)
+template <typename Real>
+__host__ __device__ inline FfbsLayout ffbs_layout(int K, int ncap, int threads) {
+    const size_t state = (size_t)ffbs_nslot(ncap, threads) * K * threads;
+    FfbsLayout L;
+    size_t b = 0;
+    L.wd = (int)b;   b += align_up((size_t)(ncap + 1) * sizeof(double), 16);                  // Wd
+    L.ubuf = (int)b; b += align_up((size_t)threads * sizeof(double), 16);                     // buffered backward uniforms
+    L.scan = (int)b; b += align_up((size_t)(threads / 32 + 1) * sizeof(double), 16);          // scan scratch
+    L.sta = (int)b;  b += align_up(state * sizeof(Real), 16);                                 // st_a / wbuf
+    L.sth = (int)b;  b += align_up(state * sizeof(Real), 16);                                 // st_h / sojourn list
+    L.red = (int)b;  b += align_up((size_t)2 * (threads / 32) * (K + 1) * sizeof(Real), 16);  // reduction scratch
+    L.par = (int)b;  b += align_up((size_t)(4 * K * K) * sizeof(Real), 16);                   // model
+    L.jlo = (int)b;  b += align_up((size_t)(ncap + 1) * sizeof(int), 16);                     // live-window start of every row
+    L.total = (int)b;
+    return L;
+}
 template <typename Real>
 __host__ __device__ inline size_t ffbs_smem_bytes(int K, int ncap, int threads) {
-    const size_t state = (size_t)ffbs_nslot(ncap, threads) * K * threads;
-    size_t b = 0;
-    b += align_up((size_t)(ncap + 1) * sizeof(double), 16);                  // Wd
-    b += align_up((size_t)threads * sizeof(double), 16);                     // buffered backward uniforms
-    b += align_up((size_t)(threads / 32 + 1) * sizeof(double), 16);          // scan scratch
-    b += align_up(state * sizeof(Real), 16);                                 // st_a / wbuf
-    b += align_up(state * sizeof(Real), 16);                                 // st_h / sojourn list
-    b += align_up((size_t)2 * (threads / 32) * (K + 1) * sizeof(Real), 16);  // reduction scratch
-    b += align_up((size_t)(4 * K * K) * sizeof(Real), 16);                   // model
-    return b;
+    return (size_t)ffbs_layout<Real>(K, ncap, threads).total;
 }
 
 // item-parallel kernel (ffbs_item.cuh): a slot holds threads/K grid points for all K states
@@ -263,28 +279,23 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
     const int ncap = a.ncap, Kobs = a.Kobs;
     const size_t state = (size_t)a.nslot * K * B;
 
-    unsigned char* sp = smem_raw;
-    double* Wd = (double*)sp;
-    sp += align_up((size_t)(ncap + 1) * sizeof(double), 16);
-    double* ubuf = (double*)sp;  // backward uniforms of steps (u_hi - B, u_hi]
-    sp += align_up((size_t)B * sizeof(double), 16);
-    Acc* scan_s = (Acc*)sp;  // [NW + 1] warp totals
-    sp += align_up((size_t)(NW + 1) * sizeof(double), 16);
-    Real* st_a = (Real*)sp;  // forward: unnormalised message [slot][v][B]; backward: weights [K][len]
-    sp += align_up(state * sizeof(Real), 16);
-    Real* st_h = (Real*)sp;  // forward: H_v(tau) [slot][v][B]; backward: sojourn list (int pairs)
-    sp += align_up(state * sizeof(Real), 16);
-    Real* red = (Real*)sp;
-    sp += align_up((size_t)2 * NW * (K + 1) * sizeof(Real), 16);
-    Real* srk = (Real*)sp;       // 1 / k_vs
+    double* Wd = (double*)(smem_raw + a.lay.wd);
+    double* ubuf = (double*)(smem_raw + a.lay.ubuf);  // backward uniforms of steps (u_hi - B, u_hi]
+    Acc* scan_s = (Acc*)(smem_raw + a.lay.scan);      // [NW + 1] warp totals
+    Real* st_a = (Real*)(smem_raw + a.lay.sta);  // forward: unnormalised message [slot][v][B]; backward: weights [K][len]
+    Real* st_h = (Real*)(smem_raw + a.lay.sth);  // forward: H_v(tau) [slot][v][B]; backward: sojourn list (int pairs)
+    Real* red = (Real*)(smem_raw + a.lay.red);
+    Real* srk = (Real*)(smem_raw + a.lay.par);   // 1 / k_vs
     Real* skm1 = srk + K * K;    // (k_vs - 1) * SCALE
     Real* sc2p = skm1 + K * K;   // (k_vs log2(lambda_vs) - log2(k_vs)) * SCALE: 2^(((k-1) L - c2p)/SCALE) = k E = A_vs
     Real* sk = sc2p + K * K;     // k_vs
+    int* jlo_arr = (int*)(smem_raw + a.lay.jlo);  // [ncap + 1] first live grid point of every row (scratch mode)
     int* soj = (int*)st_h;       // [2][ncap+1]: state, grid index of each sojourn (backward pass)
 
     __shared__ int s_chain;
     __shared__ int s_sel;
     __shared__ int s_found;
+    __shared__ int s_jmin[2 * NW];  // per-warp smallest live grid point of the oldest slot, double-buffered
     __shared__ int s_flag;
     __shared__ double s_tab[Exp2<Real>::TAB ? Exp2<Real>::TAB : 1];
     __shared__ double2 s_ltab[Exp2<Real>::LTAB ? Exp2<Real>::LTAB : 1];
@@ -399,9 +410,18 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
         while (i_final > 0 && np_isclose(a.t_end, Wd[i_final])) --i_final;
         Real* row_base = msg;  // start of row i-1 (row r holds K*(r+1) values)
         const Real* obsf_next = obsf + K;
+        // Live window.  A state (v, W[j]) loses at least the thinning factor 1 - 1/Omega per grid step, so old
+        // grid points underflow to EXACT zeros -- on cfg2 56 % of the fp64 and 85 % of the fp32 message entries
+        // -- and a zero stays zero.  j_lo is the first grid point with a non-zero entry: pairs, row stores and
+        // row loads below it are skipped, which changes no result bit.  Exported messages keep j_lo = 0.
+        int j_lo = 0;
+        unsigned long long live = 0;
         for (int i = 0; i < n; ++i) {
             const double wn = Wd[i + 1];
             const bool nonfinal = i < i_final;
+            const int m_lo = j_lo / B, t_lo = j_lo - m_lo * B;  // slot / thread of the first live grid point
+            if (tid == 0) jlo_arr[i] = j_lo;
+            live += (unsigned long long)(i - j_lo + 1);
             Real ofn[K];  // next step's observation factors, fetched under this step's arithmetic
 #pragma unroll
             for (int v = 0; v < K; ++v) ofn[v] = (i + 1 < n) ? obsf_next[v] : (Real)1;
@@ -411,11 +431,11 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
 #pragma unroll
             for (int v = 0; v < K; ++v) Jp[v] = 0;
             const int mi = i / B, ti = i - mi * B;  // slot and owner thread of the new state (v, W[i])
-            Real* rowp = row_base + tid;  // row i-1: i entries per state
-            Real* rowg = row_base + (int64_t)K * i + tid;  // row i (scratch mode): i+1 entries per state
-            Real* pa = st_a + tid;
-            Real* ph = st_h + tid;
-            const double* pw = Wd + tid;
+            Real* rowp = row_base + tid;  // row i-1: i entries per state (exported messages: m_lo == 0)
+            Real* rowg = row_base + (int64_t)K * i + m_lo * B + tid;  // row i (scratch mode): i+1 entries per state
+            Real* pa = st_a + (size_t)m_lo * K * B + tid;
+            Real* ph = st_h + (size_t)m_lo * K * B + tid;
+            const double* pw = Wd + m_lo * B + tid;
             // one grid point (i, j): all K*K hazards, emission, thinned update, jump contributions
             auto pair = [&](auto partial_tag, bool diag) {
                 constexpr bool PARTIAL = decltype(partial_tag)::value;
@@ -458,8 +478,18 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
 #define SMJP_PAIR_UNROLL 1
 #endif
             constexpr int PAIR_UNROLL = SMJP_PAIR_UNROLL;
+            int m = m_lo;
+            if (m < mi) {  // oldest live slot: threads below the window start own a dead grid point
+                if (tid >= t_lo) pair(std::false_type(), false);
+                pa += K * B;
+                ph += K * B;
+                pw += B;
+                rowp += B;
+                rowg += B;
+                ++m;
+            }
 #pragma unroll PAIR_UNROLL
-            for (int m = 0; m < mi; ++m) {  // full slots: every thread owns a live j < i
+            for (; m < mi; ++m) {  // full slots: every thread owns a live j < i
                 pair(std::false_type(), false);
                 pa += K * B;
                 ph += K * B;
@@ -467,7 +497,20 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
                 rowp += B;
                 rowg += B;
             }
-            if (tid <= ti) pair(std::true_type(), tid == ti);
+            if (tid <= ti && (mi > m_lo || tid >= t_lo)) pair(std::true_type(), tid == ti);
+            if (!exporting) {  // smallest grid point of the oldest slot that still carries mass
+                int mylive = 0x7fffffff;
+                const int j0 = m_lo * B + tid;
+                if (j0 >= j_lo && j0 <= i) {
+                    const Real* q = st_a + (size_t)m_lo * K * B + tid;
+                    bool alive = false;
+#pragma unroll
+                    for (int v = 0; v < K; ++v) alive = alive || q[v * B] != (Real)0;
+                    if (alive) mylive = j0;
+                }
+                mylive = __reduce_min_sync(0xffffffffu, mylive);
+                if (lane == 0) s_jmin[(i & 1) * NW + wid] = mylive;
+            }
             // block reduction of (Z, J[0..K)) -- double-buffered scratch, one barrier per step
             Real* rb = red + (i & 1) * NW * (K + 1);
             {
@@ -506,7 +549,14 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
             }
             if (a.logZ && tid == 0) a.logZ[w0 + i] = log((double)Z);
             if (i > 0) row_base += (int64_t)K * i;  // row i-1 done: advance to row i
+            if (!exporting) {
+                int jl = 0x7fffffff;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) jl = min(jl, s_jmin[(i & 1) * NW + w]);
+                j_lo = max(j_lo, min(jl, min((m_lo + 1) * B, i + 1)));
+            }
         }
+        if (a.live_pairs && tid == 0) atomicAdd(a.live_pairs, live);
         if (degenerate) {
             if (tid == 0) {
                 a.status[c] = SMJP_ST_DEGENERATE;
@@ -530,14 +580,20 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
         while (true) {
             const int len = cur + 1;
             const Real* row = msg + (int64_t)K * cur * (cur + 1) / 2;
+            const int lo = exporting ? 0 : jlo_arr[cur];  // live window of this row: entries below lo are exact zeros
+            const int wl = len - lo;
             {   // The next draw reads row j*-1 where W[j*] starts the sojourn found now; sojourns are a few grid
-                // steps long, so rows cur-1 .. cur-3 (contiguous, just below this row) cover ~7/8 of the cases:
-                // pull them into L2 now, one draw ahead of the HBM round trip that would otherwise be exposed.
-                const int r0 = cur > 3 ? cur - 3 : 0;
-                const char* p0 = (const char*)(msg + (int64_t)K * r0 * (r0 + 1) / 2);
-                const char* p1 = (const char*)row;
-                for (const char* p = p0 + (size_t)tid * 128; p < p1; p += (size_t)B * 128)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+                // steps long, so rows cur-1 .. cur-3 (just below this row) cover ~7/8 of the cases: pull their
+                // live parts into L2 now, one draw ahead of the HBM round trip that would otherwise be exposed.
+                // One 128-byte line per thread: thread t takes line t / (3K) of segment t % (3K) = (row, state).
+                const int seg = tid % (3 * K), line = tid / (3 * K);
+                const int r = cur - 1 - seg / K, v = seg - (seg / K) * K;
+                if (r >= 0) {
+                    const int rlo = exporting ? 0 : jlo_arr[r];
+                    const char* p = (const char*)(msg + (int64_t)K * r * (r + 1) / 2 + (int64_t)v * (r + 1) + rlo) + line * 128;
+                    if (p < (const char*)(msg + (int64_t)K * r * (r + 1) / 2 + (int64_t)(v + 1) * (r + 1)))
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+                }
             }
             if (!a.uniforms && (u_hi < 0 || cur <= u_hi - B)) {  // refill B uniforms: steps cur, cur-1, ...
                 if (cur - tid >= 0)
@@ -545,23 +601,27 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
                                            a.chain_base + (uint32_t)c);
                 u_hi = cur;
             }
+            // weights over the live window, state-major: wbuf[v * wl + (j - lo)]
             if (vplus < 0) {  // a_{n-1} ~ alpha_{n-1}  (fast_hmm.py:124-125)
-                for (int t = tid; t < K * len; t += B) wbuf[t] = row[t];
+                for (int j = lo + tid; j < len; j += B) {
+#pragma unroll
+                    for (int v = 0; v < K; ++v) wbuf[v * wl + (j - lo)] = row[(int64_t)v * len + j];
+                }
             } else if (!exporting && cur < i_final) {  // scratch row holds g: w = g_cur(v,j) A_{v,vplus}(tau)
                 const double wn = Wd[cur + 1];
 #pragma unroll 2
-                for (int j = tid; j < len; j += B) {
+                for (int j = lo + tid; j < len; j += B) {
                     Real rv[K];
 #pragma unroll
                     for (int v = 0; v < K; ++v) rv[v] = row[(int64_t)v * len + j];
                     const Real L2 = ex2.log2((Real)(wn - Wd[j]));
 #pragma unroll
                     for (int v = 0; v < K; ++v)
-                        wbuf[v * len + j] = rv[v] * ex2(skm1[v * K + vplus] * L2 - sc2p[v * K + vplus]);
+                        wbuf[v * wl + (j - lo)] = rv[v] * ex2(skm1[v * K + vplus] * L2 - sc2p[v * K + vplus]);
                 }
             } else {  // jump at W[cur+1] into vplus: w = alpha_cur(v,j) A_{v,vplus}/A_v  (fast_hmm.py:153-171)
                 const double wn = Wd[cur + 1];
-                for (int j = tid; j < len; j += B) {
+                for (int j = lo + tid; j < len; j += B) {
                     const Real L2 = ex2.log2((Real)(wn - Wd[j]));
 #pragma unroll
                     for (int v = 0; v < K; ++v) {
@@ -573,13 +633,13 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
                             hto = (s == vplus) ? kE : hto;
                         }
                         const Real r = dsum > (Real)0 ? hto * M::rcp(dsum) : (Real)0;
-                        wbuf[v * len + j] = row[(int64_t)v * len + j] * r;
+                        wbuf[v * wl + (j - lo)] = row[(int64_t)v * len + j] * r;
                     }
                 }
             }
             __syncthreads();
             // inclusive scan over the flat weight vector, contiguous chunk per thread
-            const int L = K * len;
+            const int L = K * wl;
             const int q = (L + B - 1) / B;
             const int beg = min(tid * q, L), end = min(beg + q, L);
             Acc loc = 0;
@@ -633,10 +693,10 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
                 if (tid == 0) s_flag = 0;
             }
             const int idx = s_sel;
-            int v = 0;  // idx / len without the integer division (v < K)
+            int v = 0;  // idx / wl without the integer division (v < K)
 #pragma unroll
-            for (int u = 1; u < K; ++u) v += idx >= u * len;
-            const int j = idx - v * len;
+            for (int u = 1; u < K; ++u) v += idx >= u * wl;
+            const int j = lo + idx - v * wl;
             if (a.aug_idx)
                 for (int t = j + tid; t <= cur; t += B) a.aug_idx[w0 + t] = v * n + j;
             if (tid == 0) {
