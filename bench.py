@@ -247,6 +247,7 @@ def run_ours(args):
     eng.set_model(SHAPE, np.ones((K, K)), OMEGA, emis, 1.0, T_END)
     eng.set_option("ffbs_threads", args.threads)
     eng.set_option("item_k3", args.item_k3)
+    eng.set_option("window_log2", args.window_log2)
     obs_t = np.arange(OBS_DT, T_END, OBS_DT)
     D = len(obs_t)
     # ground-truth path -> observations; independent prior draw as the initial state
@@ -462,6 +463,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (kernel experiments)")
     ap.add_argument("--threads", type=int, default=0, help="threads per CTA of the FFBS kernel (0 = auto)")
     ap.add_argument("--item-k3", type=int, default=0, help="experiment: item-parallel kernel for K=3")
+    ap.add_argument("--window-log2", type=int, default=0, dest="window_log2",
+                    help="0: exact live window (default); -L: prune states below 2^-L of the row sum")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

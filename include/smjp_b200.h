@@ -80,6 +80,10 @@ int64_t smjp_ctx_get_stat(smjp_ctx_t* ctx, const char* key);
  *        prior entry points return SMJP_E_UNSUPPORTED for it);
  *        "pf_cluster" (thread-block-cluster size of one particle-filter run: 0 = auto, 1, 2, 4, 8, 16);
  *        "pf_threads" (threads per CTA of the particle filter: 0 = auto, 256, 512, 1024);
+ *        "window_log2" (K <= 3 FFBS kernel, scratch mode.  0, the default: EXACT live window -- only grid points
+ *        whose states have underflowed to exact zeros are skipped, results unchanged to the last bit.  -L: states
+ *        below 2^-L of their row's sum leave the window too (live-window pruning, an approximation; -70 is far
+ *        below fp64 rounding of the row sums));
  *        "f32_rescue" (default 1: chains whose fp32 FFBS pass loses its row sum -- a grid step over which every
  *        live state changes by more than 38 orders of magnitude -- are redone by the fp64 kernel);
  *        "pf_extend" (0 = the particle-filter path is extended flat from the last observation to t_end

@@ -107,6 +107,7 @@ struct smjp_ctx {
     // workspaces
     DevBuf d_queue, d_msg_scratch, d_obsf, d_order, d_dense_msg, d_big, d_failed, d_live;
     int f32_rescue = 1;  // chains that fail in fp32 are redone by the fp64 kernel
+    int window_log2 = 0;  // 0: exact live window; -L: states below 2^-L of their row's sum leave the window
     bool lpt_order = true;
     int obs_product = 0;
     int pf_extend = 0;
@@ -271,6 +272,11 @@ int smjp_ctx_set_option(smjp_ctx_t* c, const char* key, int64_t value) {
     }
     if (!strcmp(key, "item_k3")) {
         c->item_k3 = value != 0;
+        return SMJP_OK;
+    }
+    if (!strcmp(key, "window_log2")) {
+        if (value > 0 || value < -1000) return fail(SMJP_E_INVALID, "window_log2 must be 0 (exact) or in [-1000,-1]");
+        c->window_log2 = (int)value;
         return SMJP_OK;
     }
     if (!strcmp(key, "f32_rescue")) {
@@ -500,6 +506,7 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
     a.ncap = (int)n_max;
     a.nslot = item_kernel ? ffbs_item_nslot(K, (int)n_max, threads) : ffbs_nslot((int)n_max, threads);
     if (!item_kernel && !big) a.lay = ffbs_layout<Real>(K, (int)n_max, threads);
+    a.window_eps = c->window_log2 < 0 ? std::ldexp(1.0, c->window_log2) : 0.0;
     int rc;
     if (!a.messages) {
         // grid lengths drift from sweep to sweep: size the per-CTA scratch for a rounded-up, never

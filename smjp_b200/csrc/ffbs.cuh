@@ -63,6 +63,7 @@ struct FfbsArgs {
     const int32_t* C_dev;  // optional: number of entries of `order` to process, read on the device
     unsigned long long* live_pairs;  // optional device counter: grid pairs (i, j) actually processed (live window)
     FfbsLayout lay;                  // shared-memory byte offsets of ffbs_kernel (ffbs_layout)
+    double window_eps;               // 0: exact live window (only exact zeros are dropped); else relative threshold
     unsigned int* queue;   // work counter, zeroed before launch
     const double* model;   // device: shape[K*K], c2[K*K] (= k*log2(lambda)), emis[K*Kobs], scale[K*K]
     int Kobs;
@@ -416,12 +417,30 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
         // row loads below it are skipped, which changes no result bit.  Exported messages keep j_lo = 0.
         int j_lo = 0;
         unsigned long long live = 0;
+        const Real weps = (Real)a.window_eps;
         for (int i = 0; i < n; ++i) {
             const double wn = Wd[i + 1];
             const bool nonfinal = i < i_final;
             const int m_lo = j_lo / B, t_lo = j_lo - m_lo * B;  // slot / thread of the first live grid point
             if (tid == 0) jlo_arr[i] = j_lo;
             live += (unsigned long long)(i - j_lo + 1);
+            const bool judge = !exporting && (i & 3) == 0;  // the window start is re-examined every fourth step
+            if (judge) {
+                // smallest grid point of the oldest slot that still carries mass after step i-1: above zero
+                // (exact mode), or above window_eps times that row's sum (pruned mode, SURVEY.md 7 hard part 2)
+                int mylive = 0x7fffffff;
+                const int j0 = m_lo * B + tid;
+                if (j0 >= j_lo && j0 < i) {
+                    const Real thr = weps > (Real)0 ? weps / invZ_prev : (Real)0;  // eps * Z_{i-1}
+                    const Real* q = st_a + (size_t)m_lo * K * B + tid;
+                    bool alive = false;
+#pragma unroll
+                    for (int v = 0; v < K; ++v) alive = alive || q[v * B] > thr;
+                    if (alive) mylive = j0;
+                }
+                mylive = __reduce_min_sync(0xffffffffu, mylive);
+                if (lane == 0) s_jmin[(i & 1) * NW + wid] = mylive;
+            }
             Real ofn[K];  // next step's observation factors, fetched under this step's arithmetic
 #pragma unroll
             for (int v = 0; v < K; ++v) ofn[v] = (i + 1 < n) ? obsf_next[v] : (Real)1;
@@ -498,19 +517,6 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
                 rowg += B;
             }
             if (tid <= ti && (mi > m_lo || tid >= t_lo)) pair(std::true_type(), tid == ti);
-            if (!exporting) {  // smallest grid point of the oldest slot that still carries mass
-                int mylive = 0x7fffffff;
-                const int j0 = m_lo * B + tid;
-                if (j0 >= j_lo && j0 <= i) {
-                    const Real* q = st_a + (size_t)m_lo * K * B + tid;
-                    bool alive = false;
-#pragma unroll
-                    for (int v = 0; v < K; ++v) alive = alive || q[v * B] != (Real)0;
-                    if (alive) mylive = j0;
-                }
-                mylive = __reduce_min_sync(0xffffffffu, mylive);
-                if (lane == 0) s_jmin[(i & 1) * NW + wid] = mylive;
-            }
             // block reduction of (Z, J[0..K)) -- double-buffered scratch, one barrier per step
             Real* rb = red + (i & 1) * NW * (K + 1);
             {
@@ -549,11 +555,11 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
             }
             if (a.logZ && tid == 0) a.logZ[w0 + i] = log((double)Z);
             if (i > 0) row_base += (int64_t)K * i;  // row i-1 done: advance to row i
-            if (!exporting) {
+            if (judge) {
                 int jl = 0x7fffffff;
 #pragma unroll
                 for (int w = 0; w < NW; ++w) jl = min(jl, s_jmin[(i & 1) * NW + w]);
-                j_lo = max(j_lo, min(jl, min((m_lo + 1) * B, i + 1)));
+                j_lo = max(j_lo, min(jl, min((m_lo + 1) * B, i)));  // the states of step i itself are not judged yet
             }
         }
         if (a.live_pairs && tid == 0) atomicAdd(a.live_pairs, live);
