@@ -269,6 +269,7 @@ def run_ours(args):
     barrier()
     eng.set_option("time_kernels", 1)
     eng.kernel_time()
+    eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_live_pairs")  # reset the live-window counter
     launches0 = eng.launch_count
     sampler = ClockSampler(local)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -292,6 +293,7 @@ def run_ours(args):
         print("per-step ms:", [round(ev0.elapsed_time(e), 2) for e in step_ev], file=sys.stderr)
     launches = eng.launch_count - launches0
     k_ms, k_cnt = eng.kernel_time()
+    live_pairs = float(eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_live_pairs"))
     eng.set_option("time_kernels", 0)
     for offs in n_snap:
         n = (offs[1:] - offs[:-1] - 1).cpu().numpy()
@@ -393,6 +395,12 @@ def run_ours(args):
                      "threads": eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_threads"),
                      "smem": eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_smem"), "kernel_share_of_step": k_ms / ms,
                      "algorithmic_bytes_per_launch": alg_bytes / max(k_cnt, 1),
+                     # the kernel skips grid points whose states have underflowed to EXACT zeros (results unchanged
+                     # to the last bit): `achieved` counts the nominal K n(n+1)/2 states of SURVEY 8(d), the two keys
+                     # below say how many of them were actually touched and what that means in bytes per second
+                     "live_fraction": live_pairs / max(ss_rank0 / K, 1.0),
+                     "achieved_live": achieved * live_pairs / max(ss_rank0 / K, 1.0),
+                     "window": "exact (zeros only)" if args.window_log2 == 0 else "pruned below 2^%d of the row sum" % args.window_log2,
                      "compute": compute_ceiling(prec, ss_rank0 / K / max(k_cnt, 1), k_avg_s, clk.get("sm_mhz"))},
         "e2e": {"value": e_ss / e_wall, "unit": UNIT, "h2d_bytes_per_step": h2d // max(e2e_steps, 1),
                 "d2h_bytes_per_step": d2h // max(e2e_steps, 1), "steps": e2e_steps,
@@ -438,6 +446,39 @@ def run_ours(args):
                                     "compute": compute_ceiling("f32", ss32 / K / max(c32, 1), k32 / max(c32, 1) / 1e3,
                                                                clk.get("sm_mhz"))},
                        "tolerance": "messages within 1e-4 of the reference (tests/test_ffbs_gpu.py)"}
+    if world == 1 and prec == "f64" and not args.no_alt and args.window_log2 == 0:
+        # the same fp64 workload with live-window PRUNING (SURVEY.md 7 hard part 2): states below 2^-70 of their
+        # row's sum leave the window.  An approximation (far below fp64 rounding of the row sums), hence reported
+        # beside the exact headline, never as it.
+        eng.set_option("window_log2", -70)
+        for sw in range(3):
+            ch.sweep(seed=SEED + 13, sweep=sw, precision="f64")
+        torch.cuda.synchronize()
+        eng.set_option("time_kernels", 1)
+        eng.kernel_time()
+        eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_live_pairs")
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        snaps = []
+        p0.record()
+        for sw in range(args.steps):
+            ch.sweep(seed=SEED + 13, sweep=3 + sw, precision="f64")
+            snaps.append(ch.cur["offs"].clone())
+        p1.record()
+        torch.cuda.synchronize()
+        msp = p0.elapsed_time(p1)
+        kp, cp = eng.kernel_time()
+        lp = float(eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_live_pairs"))
+        eng.set_option("time_kernels", 0)
+        eng.set_option("window_log2", 0)
+        ssp = 0.0
+        for offs in snaps:
+            n = (offs[1:] - offs[:-1] - 1).cpu().numpy()
+            ssp += float(np.sum(K * n.astype(np.float64) * (n + 1) / 2))
+        line["pruned"] = {"window": "states below 2^-70 of the row sum are dropped", "dtype": "f64",
+                          "nominal_state_steps_per_sec": ssp / (msp / 1e3), "retained_state_steps_per_sec": K * lp / (msp / 1e3),
+                          "live_fraction": K * lp / max(ssp, 1.0), "unit": UNIT, "ms_per_step": msp / args.steps,
+                          "chain_sweeps_per_sec": C * args.steps / (msp / 1e3), "kernel_ms_avg": kp / max(cp, 1),
+                          "failed_chains": int((ch.status != 0).sum().item())}
     gc.enable()
     if world == 1 and not args.no_cpu:
         ss_c, gs_c, wall_c = cpu_sample(16, 3, T_END, 1)  # ~10-20 s of CPU work

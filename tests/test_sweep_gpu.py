@@ -278,3 +278,33 @@ def test_fp32_sweeps_leave_no_failed_chain(engine):
     assert int((ch.status != 0).sum().item()) == 0
     V, Tt = ch.paths_host()
     assert all(np.all(np.diff(t) > 0) for t in Tt)
+
+
+def test_live_window_exact_and_pruned_modes(engine):
+    """The exact live window skips only grid points whose states are exact zeros (same paths as the oracle, tested
+    throughout this suite); here: the counter of processed pairs is below the nominal n(n+1)/2, and the opt-in
+    pruned mode (states below 2^-70 of the row sum dropped) processes fewer still and returns the same paths."""
+    from smjp_b200.chains import DeviceChains
+    K, T, C = 3, 60.0, 256
+    engine.set_model(SHAPE3, np.ones((K, K)), 2.0, O.emission_matrix(K), 1.0, T)
+    obs_t = np.arange(0.1, T, 0.1)
+    out = {}
+    for wl in (0, -70):
+        engine.set_option("window_log2", wl)
+        try:
+            ch = DeviceChains(engine, C, obs_t).init_prior(np.ones(K) / K, seed=1).simulate_observations(seed=2)
+            ch.init_prior(np.ones(K) / K, seed=3)
+            for sw in range(3):
+                ch.sweep(seed=4, sweep=sw)
+            engine.lib.smjp_ctx_get_stat(engine.ctx, b"ffbs_live_pairs")
+            ch.sweep(seed=4, sweep=3)
+            live = engine.lib.smjp_ctx_get_stat(engine.ctx, b"ffbs_live_pairs")
+            nominal = ch.state_steps_last_sweep()[0] / K
+            assert int((ch.status != 0).sum().item()) == 0
+            out[wl] = (live / nominal, ch.paths_host())
+        finally:
+            engine.set_option("window_log2", 0)
+    assert 0.2 < out[0][0] <= 1.0 and out[-70][0] < out[0][0]
+    (Ve, Te), (Vp, Tp) = out[0][1], out[-70][1]
+    same = sum(np.array_equal(a, b) and np.array_equal(s, t) for a, b, s, t in zip(Ve, Vp, Te, Tp))
+    assert same == C  # dropped mass is below the rounding of the row sums: no draw moves
