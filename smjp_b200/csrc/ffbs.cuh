@@ -126,6 +126,7 @@ __host__ __device__ inline size_t ffbs_item_smem_bytes(int K, int ncap, int thre
     b += align_up(state * sizeof(Real), 16);
     b += align_up((size_t)2 * (threads / 32) * (K + 1) * sizeof(Real), 16);
     b += align_up((size_t)(4 * K * K) * sizeof(Real), 16);
+    b += align_up((size_t)(ncap + 1) * sizeof(int), 16);  // live-window start of every row
     return b;
 }
 

@@ -44,11 +44,14 @@ __global__ void __launch_bounds__(B, MINB) ffbs_item_kernel(const FfbsArgs a) {
     Real* srk = (Real*)sp;
     Real* skm1 = srk + K * K;
     Real* sc2p = skm1 + K * K;
+    sp += align_up((size_t)(4 * K * K) * sizeof(Real), 16);
+    int* jlo_arr = (int*)sp;  // [ncap + 1] first live grid point of every row (scratch mode), see ffbs.cuh
     int* soj = (int*)st_h;
 
     __shared__ int s_chain;
     __shared__ int s_sel;
     __shared__ int s_found;
+    __shared__ int s_jmin[2 * NW];
     __shared__ int s_flag;
     __shared__ double s_tab[Exp2<Real>::TAB ? Exp2<Real>::TAB : 1];
     __shared__ double2 s_ltab[Exp2<Real>::LTAB ? Exp2<Real>::LTAB : 1];
@@ -172,18 +175,36 @@ __global__ void __launch_bounds__(B, MINB) ffbs_item_kernel(const FfbsArgs a) {
         int i_final = n;
         while (i_final > 0 && np_isclose(a.t_end, Wd[i_final])) --i_final;
         Real* row_base = msg;  // start of row i-1
+        // exact live window (ffbs.cuh): grid points below j_lo hold exact zeros for every state and are skipped
+        int j_lo = 0;
+        unsigned long long live = 0;
+        const Real weps = (Real)a.window_eps;
         for (int i = 0; i < n; ++i) {
             const double wn = Wd[i + 1];
             const bool nonfinal = i < i_final;
+            const int m_lo = j_lo / JPS, t_lo = j_lo - m_lo * JPS;
+            if (tid == 0) jlo_arr[i] = j_lo;
+            live += (unsigned long long)(i - j_lo + 1);
+            const bool judge = !exporting && (i & 3) == 0;
+            if (judge) {  // smallest grid point of the oldest slot with a state above zero (or above eps * Z_{i-1})
+                int mylive = 0x7fffffff;
+                const int j0 = m_lo * JPS + jt;
+                if (j0 >= j_lo && j0 < i) {
+                    const Real thr = weps > (Real)0 ? weps / invZ_prev : (Real)0;
+                    if (st_a[(size_t)m_lo * B + tid] > thr) mylive = j0;
+                }
+                mylive = __reduce_min_sync(0xffffffffu, mylive);
+                if (lane == 0) s_jmin[(i & 1) * NW + wid] = mylive;
+            }
             const Real ofn_v = (i + 1 < n) ? obsf[(i + 1) * K + v] : (Real)1;
             Real Zp = 0;
             Real Jp[K];
 #pragma unroll
             for (int u = 0; u < K; ++u) Jp[u] = 0;
             const int mi = i / JPS, ji = i - mi * JPS;  // slot of the new states (., W[i]); their jt
-            Real* pa = st_a + tid;
-            Real* ph = st_h + tid;
-            const double* pw = Wd + jt;
+            Real* pa = st_a + (size_t)m_lo * B + tid;
+            Real* ph = st_h + (size_t)m_lo * B + tid;
+            const double* pw = Wd + m_lo * JPS + jt;
             // one augmented state (v, j): K hazards of row v, emission, thinned update, jump contributions
             auto item = [&](auto partial_tag, bool diag, int j) {
                 constexpr bool PARTIAL = decltype(partial_tag)::value;
@@ -217,15 +238,24 @@ __global__ void __launch_bounds__(B, MINB) ffbs_item_kernel(const FfbsArgs a) {
                 *ph = hsum;
                 Zp += an;
             };
-            int j = jt;
-            for (int m = 0; m < mi; ++m) {  // full slots: j < i for every thread
+            int j = m_lo * JPS + jt;
+            int m = m_lo;
+            if (m < mi) {  // oldest live slot: grid points below the window start are dead
+                if (jt >= t_lo) item(std::false_type(), false, j);
+                pa += B;
+                ph += B;
+                pw += JPS;
+                j += JPS;
+                ++m;
+            }
+            for (; m < mi; ++m) {  // full slots: j < i for every thread
                 item(std::false_type(), false, j);
                 pa += B;
                 ph += B;
                 pw += JPS;
                 j += JPS;
             }
-            if (jt <= ji) item(std::true_type(), jt == ji, j);
+            if (jt <= ji && (mi > m_lo || jt >= t_lo)) item(std::true_type(), jt == ji, j);
             // block reduction of (Z, J[0..K))
             Real* rb = red + (i & 1) * NW * (K + 1);
             {
@@ -257,7 +287,14 @@ __global__ void __launch_bounds__(B, MINB) ffbs_item_kernel(const FfbsArgs a) {
             of_v = ofn_v;
             if (a.logZ && tid == 0) a.logZ[w0 + i] = log((double)Z);
             if (i > 0) row_base += (int64_t)K * i;
+            if (judge) {
+                int jl = 0x7fffffff;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) jl = min(jl, s_jmin[(i & 1) * NW + w]);
+                j_lo = max(j_lo, min(jl, min((m_lo + 1) * JPS, i)));
+            }
         }
+        if (a.live_pairs && tid == 0) atomicAdd(a.live_pairs, live);
         if (degenerate) {
             if (tid == 0) {
                 a.status[c] = SMJP_ST_DEGENERATE;
@@ -278,14 +315,18 @@ __global__ void __launch_bounds__(B, MINB) ffbs_item_kernel(const FfbsArgs a) {
         while (true) {
             const int len = cur + 1;
             const Real* row = msg + (int64_t)K * cur * (cur + 1) / 2;
+            const int lo = exporting ? 0 : jlo_arr[cur];  // live window of this row (entries below lo are exact zeros)
+            const int wl = len - lo;
             {   // The next draw reads row j*-1 where W[j*] starts the sojourn found now; sojourns are a few grid
-                // steps long, so rows cur-1 .. cur-3 (contiguous, just below this row) cover ~7/8 of the cases:
-                // pull them into L2 now, one draw ahead of the HBM round trip that would otherwise be exposed.
-                const int r0 = cur > 3 ? cur - 3 : 0;
-                const char* p0 = (const char*)(msg + (int64_t)K * r0 * (r0 + 1) / 2);
-                const char* p1 = (const char*)row;
-                for (const char* p = p0 + (size_t)tid * 128; p < p1; p += (size_t)B * 128)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+                // steps long, so rows cur-1 .. cur-3 cover ~7/8 of the cases: pull their live parts (one contiguous
+                // [j][v] segment per scratch row) into L2 now, one draw ahead of the HBM round trip.
+                const int r = cur - 1 - tid % 3, line = tid / 3;
+                if (r >= 0) {
+                    const int rlo = exporting ? 0 : jlo_arr[r];
+                    const Real* rb0 = msg + (int64_t)K * r * (r + 1) / 2;
+                    const char* p = (const char*)(rb0 + (int64_t)K * rlo) + (size_t)line * 128;
+                    if (p < (const char*)(rb0 + (int64_t)K * (r + 1))) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+                }
             }
             if (!a.uniforms && (u_hi < 0 || cur <= u_hi - B)) {
                 if (cur - tid >= 0)
@@ -294,18 +335,19 @@ __global__ void __launch_bounds__(B, MINB) ffbs_item_kernel(const FfbsArgs a) {
                 u_hi = cur;
             }
             const double wn = Wd[cur + 1];
+            // weights over the live window, state-major: wbuf[v * wl + (j - lo)]
             if (!exporting && (vplus < 0 || cur < i_final)) {
                 // scratch row holds g, [j][v]: first draw w = g (= alpha on the last row), jump draws w = g A_{v,vplus}.
                 // Unrolled so that the row loads of several entries are in flight before the first hazard.
                 const Real km1 = vplus >= 0 ? s_km1[vplus] : (Real)0, c2p = vplus >= 0 ? s_c2p[vplus] : (Real)0;
 #pragma unroll 4
-                for (int j = jt; j < len; j += JPS) {
+                for (int j = lo + jt; j < len; j += JPS) {
                     Real w = row[(int64_t)j * K + v];
                     if (vplus >= 0) w *= ex2(km1 * ex2.log2((Real)(wn - Wd[j])) - c2p);
-                    wbuf[v * len + j] = w;
+                    wbuf[v * wl + (j - lo)] = w;
                 }
             } else {
-                for (int j = jt; j < len; j += JPS) {
+                for (int j = lo + jt; j < len; j += JPS) {
                     const int64_t pos = exporting ? (int64_t)v * len + j : (int64_t)j * K + v;
                     Real w = row[pos];
                     if (vplus >= 0) {  // jump at W[cur+1] into vplus: weight alpha_cur(v,j) A_{v,vplus}/A_v
@@ -319,11 +361,11 @@ __global__ void __launch_bounds__(B, MINB) ffbs_item_kernel(const FfbsArgs a) {
                         }
                         w *= dsum > (Real)0 ? hto * M::rcp(dsum) : (Real)0;
                     }
-                    wbuf[v * len + j] = w;
+                    wbuf[v * wl + (j - lo)] = w;
                 }
             }
             __syncthreads();
-            const int L = K * len;
+            const int L = K * wl;
             const int q = (L + B - 1) / B;
             const int beg = min(tid * q, L), end = min(beg + q, L);
             Acc loc = 0;
@@ -376,7 +418,7 @@ __global__ void __launch_bounds__(B, MINB) ffbs_item_kernel(const FfbsArgs a) {
                 if (tid == 0) s_flag = 0;
             }
             const int idx = s_sel;
-            const int vs = idx / len, js = idx - vs * len;
+            const int vs = idx / wl, js = lo + idx - vs * wl;
             if (a.aug_idx)
                 for (int t = js + tid; t <= cur; t += B) a.aug_idx[w0 + t] = vs * n + js;
             if (tid == 0) {
