@@ -248,6 +248,8 @@ def run_ours(args):
     eng.set_option("ffbs_threads", args.threads)
     eng.set_option("item_k3", args.item_k3)
     eng.set_option("window_log2", args.window_log2)
+    eng.set_option("ffbs_warp", args.warp)
+    eng.set_option("ffbs_ring", args.ring)
     obs_t = np.arange(OBS_DT, T_END, OBS_DT)
     D = len(obs_t)
     # ground-truth path -> observations; independent prior draw as the initial state
@@ -504,6 +506,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (kernel experiments)")
     ap.add_argument("--threads", type=int, default=0, help="threads per CTA of the FFBS kernel (0 = auto)")
     ap.add_argument("--item-k3", type=int, default=0, help="experiment: item-parallel kernel for K=3")
+    ap.add_argument("--warp", type=int, default=-1, help="warp-per-chain ring kernel (ffbs_warp.cuh): -1 auto, 0 off, 1 on")
+    ap.add_argument("--ring", type=int, default=0, help="ring slots of 32 grid points for --warp (0 = auto)")
     ap.add_argument("--window-log2", type=int, default=0, dest="window_log2",
                     help="0: exact live window (default); -L: prune states below 2^-L of the row sum")
     args = ap.parse_args()

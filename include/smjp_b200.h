@@ -84,6 +84,9 @@ int64_t smjp_ctx_get_stat(smjp_ctx_t* ctx, const char* key);
  *        whose states have underflowed to exact zeros are skipped, results unchanged to the last bit.  -L: states
  *        below 2^-L of their row's sum leave the window too (live-window pruning, an approximation; -70 is far
  *        below fp64 rounding of the row sums));
+ *        "ffbs_warp" (-1 auto (default), 0, 1: run K <= 3 scratch-mode FFBS with one warp per chain and the live
+ *        window in a shared-memory ring of "ffbs_ring" slots of 32 grid points (0 = auto); chains whose window
+ *        outgrows the ring are redone by the full-size kernel, so results never depend on the ring);
  *        "f32_rescue" (default 1: chains whose fp32 FFBS pass loses its row sum -- a grid step over which every
  *        live state changes by more than 38 orders of magnitude -- are redone by the fp64 kernel);
  *        "pf_extend" (0 = the particle-filter path is extended flat from the last observation to t_end

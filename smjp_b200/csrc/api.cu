@@ -11,6 +11,7 @@
 #include "ffbs_launch.cuh"
 #include "dense_smjp.cuh"
 #include "ffbs_big.cuh"
+#include "ffbs_warp.cuh"
 #include "hmm_dense.cuh"
 #include "params.cuh"
 #include "pf.cuh"
@@ -108,6 +109,11 @@ struct smjp_ctx {
     DevBuf d_queue, d_msg_scratch, d_obsf, d_order, d_dense_msg, d_big, d_failed, d_live;
     int f32_rescue = 1;  // chains that fail in fp32 are redone by the fp64 kernel
     int window_log2 = 0;  // 0: exact live window; -L: states below 2^-L of their row's sum leave the window
+    int ffbs_warp = -1;   // one warp per chain, live window in a shared-memory ring (K <= 3, scratch mode): -1 auto, 0 off, 1 on
+    int ring_boost[2] = {0, 0};      // extra ring slots learnt from rescue counts, per precision (f64, f32)
+    int warp_off[2] = {0, 0};        // the ring kernel kept overflowing for this precision: block kernel from now on
+    int last_warp_prec = -1, last_warp_C = 0;  // the previous launch used the ring kernel: its rescue count is pending
+    int ffbs_ring = 0;    // ring slots of 32 grid points (0 = auto)
     bool lpt_order = true;
     int obs_product = 0;
     int pf_extend = 0;
@@ -274,6 +280,17 @@ int smjp_ctx_set_option(smjp_ctx_t* c, const char* key, int64_t value) {
         c->item_k3 = value != 0;
         return SMJP_OK;
     }
+    if (!strcmp(key, "ffbs_warp")) {
+        if (value < -1 || value > 1) return fail(SMJP_E_INVALID, "ffbs_warp must be -1 (auto), 0 or 1");
+        c->ffbs_warp = (int)value;
+        c->warp_off[0] = c->warp_off[1] = 0;
+        return SMJP_OK;
+    }
+    if (!strcmp(key, "ffbs_ring")) {
+        if (value < 0 || value > 64) return fail(SMJP_E_INVALID, "ffbs_ring must be in [0,64]");
+        c->ffbs_ring = (int)value;
+        return SMJP_OK;
+    }
     if (!strcmp(key, "window_log2")) {
         if (value > 0 || value < -1000) return fail(SMJP_E_INVALID, "window_log2 must be 0 (exact) or in [-1000,-1]");
         c->window_log2 = (int)value;
@@ -404,6 +421,20 @@ cudaError_t ffbs_big_call(const FfbsArgs& a, FfbsLaunch& L, bool query) {
     return cudaGetLastError();
 }
 
+// warp-per-chain ring kernel (ffbs_warp.cuh), K = 2, 3
+template <typename Real>
+cudaError_t ffbs_warp_call(const FfbsArgs& a, FfbsLaunch& L, bool query) {
+    auto k2 = ffbs_warp_kernel<Real, 2>;
+    auto k3 = ffbs_warp_kernel<Real, 3>;
+    auto kern = L.K == 2 ? k2 : k3;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    if (e != cudaSuccess) return e;
+    if (query) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&L.grid, kern, FFBS_WARPS * 32, L.smem);
+    if (L.K == 2) k2<<<L.grid, FFBS_WARPS * 32, L.smem, L.stream>>>(a);
+    else k3<<<L.grid, FFBS_WARPS * 32, L.smem, L.stream>>>(a);
+    return cudaGetLastError();
+}
+
 template <typename Real>
 int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
     const int K = c->K;
@@ -469,9 +500,37 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
         threads = ffbs_round_threads(threads);
         smem = ffbs_smem_bytes<Real>(K, (int)n_max, threads);
     }
-    // fp64 rescue of chains that fail in fp32 (scratch mode, K <= 10): geometry of the fp64 launch
+    // warp-per-chain ring kernel (option ffbs_warp): K <= 3, scratch mode
+    const int pidx = sizeof(Real) == 4 ? 1 : 0;
+    if (c->last_warp_prec >= 0) {
+        // the previous ring-kernel launch: how many of its chains outgrew the ring and went to the rescue pass?
+        // (a few are harmless; many mean this workload's windows are wider than the ring: widen it, or give up)
+        int32_t resc = 0;
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        if (c->d_failed.p) CUDA_TRY(cudaMemcpy(&resc, c->d_failed.p, 4, cudaMemcpyDeviceToHost));
+        if (resc * 50 > c->last_warp_C) {
+            c->ring_boost[c->last_warp_prec] += 2;
+            if (c->ring_boost[c->last_warp_prec] > 8) c->warp_off[c->last_warp_prec] = 1;
+        }
+        c->last_warp_prec = -1;
+    }
+    // auto: fp32 (window ~100-150 grid points on cfg2) and pruned windows; the exact fp64 window (~250-300 points)
+    // needs a ring that leaves 12 warps per SM and gains 5 % only: block kernel
+    const bool want_warp = c->ffbs_warp == 1 || (c->ffbs_warp == -1 && (sizeof(Real) == 4 || c->window_log2 < 0));
+    bool use_warp = want_warp && !c->warp_off[pidx] && K <= 3 && !item_kernel && !a.messages && n_max <= 65535 && c->f32_rescue;
+    int ring = 0;
+    size_t warp_smem = 0;
+    if (use_warp) {
+        ring = c->ffbs_ring > 0 ? c->ffbs_ring : (c->window_log2 < 0 ? 4 : (sizeof(Real) == 4 ? 6 : 10)) + c->ring_boost[pidx];
+        const int full = (int)(n_max / 32) + 1;  // slots that hold a whole grid: the ring never needs more
+        if (ring > full) ring = full;
+        warp_smem = ffbs_warp_smem_bytes<Real>(K, ring, (int)n_max);
+        if (warp_smem > c->smem_optin) use_warp = false;
+    }
+    // rescue pass: chains that fail in fp32, or whose live window outgrows the ring, are redone by the full-size
+    // fp64 kernel (scratch mode, K <= 10): geometry of that launch
     constexpr int RESCUE_GRID = 32;
-    bool rescue = sizeof(Real) == 4 && c->f32_rescue && !a.messages && !big;
+    bool rescue = (sizeof(Real) == 4 || use_warp) && c->f32_rescue && !a.messages && !big;
     int rescue_threads = 0;
     size_t rescue_smem = 0;
     if (rescue) {
@@ -494,17 +553,18 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
                     "chain state does not fit on chip", (long long)n_max, K, smem, c->smem_optin);
     FfbsLaunch L;
     L.K = K;
-    L.threads = threads;
-    L.smem = smem;
+    L.threads = use_warp ? FFBS_WARPS * 32 : threads;
+    L.smem = use_warp ? warp_smem : smem;
     L.grid = 0;
     L.stream = c->stream;
-    CUDA_TRY(big ? ffbs_big_call<Real>(a, L, true) : ffbs_call<Real>(a, L, true));
+    CUDA_TRY(use_warp ? ffbs_warp_call<Real>(a, L, true) : big ? ffbs_big_call<Real>(a, L, true) : ffbs_call<Real>(a, L, true));
     const int per_sm = L.grid;
-    if (per_sm < 1) return fail(SMJP_E_UNSUPPORTED, "kernel cannot be resident (threads=%d smem=%zu)", threads, smem);
+    if (per_sm < 1) return fail(SMJP_E_UNSUPPORTED, "kernel cannot be resident (threads=%d smem=%zu)", L.threads, L.smem);
     int grid = c->num_sms * per_sm;
-    if (grid > a.C) grid = a.C;
+    const int regions_per_cta = use_warp ? FFBS_WARPS : 1;  // scratch regions: one per chain in flight
+    if (grid > (a.C + regions_per_cta - 1) / regions_per_cta) grid = (a.C + regions_per_cta - 1) / regions_per_cta;
     a.ncap = (int)n_max;
-    a.nslot = item_kernel ? ffbs_item_nslot(K, (int)n_max, threads) : ffbs_nslot((int)n_max, threads);
+    a.nslot = use_warp ? ring : item_kernel ? ffbs_item_nslot(K, (int)n_max, threads) : ffbs_nslot((int)n_max, threads);
     if (!item_kernel && !big) a.lay = ffbs_layout<Real>(K, (int)n_max, threads);
     a.window_eps = c->window_log2 < 0 ? std::ldexp(1.0, c->window_log2) : 0.0;
     int rc;
@@ -515,18 +575,18 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
         if (hint < c->ffbs_ncap_hint) hint = c->ffbs_ncap_hint;
         c->ffbs_ncap_hint = hint;
         const int64_t stride = (int64_t)K * hint * (hint + 1) / 2;
-        size_t bytes = (size_t)stride * sizeof(Real) * (size_t)grid;
+        size_t bytes = (size_t)stride * sizeof(Real) * (size_t)grid * regions_per_cta;
         if (rescue && bytes < (size_t)stride * 8 * RESCUE_GRID) bytes = (size_t)stride * 8 * RESCUE_GRID;
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
         size_t budget = free_b + c->d_msg_scratch.cap;
         budget -= budget / 10;
         if (bytes > budget) {  // fewer resident CTAs rather than failing
-            int g2 = (int)(budget / ((size_t)stride * sizeof(Real)));
+            int g2 = (int)(budget / ((size_t)stride * sizeof(Real) * regions_per_cta));
             if (g2 < 1)
                 return fail(SMJP_E_NOMEM, "message scratch for one chain (%zu B) does not fit", (size_t)stride * sizeof(Real));
             grid = g2;
-            bytes = (size_t)stride * sizeof(Real) * (size_t)grid;
+            bytes = (size_t)stride * sizeof(Real) * (size_t)grid * regions_per_cta;
         }
         rc = c->d_msg_scratch.reserve(bytes);
         if (rc) return rc;
@@ -534,7 +594,17 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
         a.msg_scratch_stride = stride;
     }
     {
-        size_t ob = (size_t)grid * n_max * K * sizeof(Real);
+        // per chain in flight: K observation factors per interval; the warp kernel reuses its region for the
+        // sojourn records (12 bytes per grid point)
+        int64_t per = (int64_t)n_max * K;
+        if (use_warp) {
+            per = (int64_t)(n_max + 2) * K;
+            const int64_t rec = (12 * (n_max + 2) + (int64_t)sizeof(Real) - 1) / (int64_t)sizeof(Real);
+            if (per < rec) per = rec;
+            per = (per + 3) / 4 * 4;  // keeps every region 16-byte aligned
+            a.obsf_stride = per;
+        }
+        size_t ob = (size_t)grid * regions_per_cta * per * sizeof(Real);
         if (rescue && ob < (size_t)RESCUE_GRID * n_max * K * 8) ob = (size_t)RESCUE_GRID * n_max * K * 8;
         rc = c->d_obsf.reserve(ob);
     }
@@ -565,7 +635,7 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
         CUDA_TRY(cudaEventRecord(e0, c->stream));
     }
     L.grid = grid;
-    CUDA_TRY(big ? ffbs_big_call<Real>(a, L, false) : ffbs_call<Real>(a, L, false));
+    CUDA_TRY(use_warp ? ffbs_warp_call<Real>(a, L, false) : big ? ffbs_big_call<Real>(a, L, false) : ffbs_call<Real>(a, L, false));
     if (rescue) {
         // fp32 has ~38 orders of magnitude per grid step: a step over which every live state loses more than
         // that (or gains it) leaves a chain without a row sum.  Those chains -- rare, none on most sweeps --
@@ -590,6 +660,10 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
         if (!item_kernel) r.lay = ffbs_layout<double>(K, (int)n_max, rescue_threads);
         CUDA_TRY(ffbs_call<double>(r, R, false));
         c->launches += 2;
+        if (use_warp) {
+            c->last_warp_prec = pidx;
+            c->last_warp_C = a.C;
+        }
     }
     if (c->time_kernels) {
         CUDA_TRY(cudaEventRecord(e1, c->stream));
@@ -597,8 +671,8 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
     }
     c->launches += 1;
     c->last_grid = grid;
-    c->last_threads = threads;
-    c->last_smem = (int64_t)smem;
+    c->last_threads = L.threads;
+    c->last_smem = (int64_t)L.smem;
     return SMJP_OK;
 }
 

@@ -51,6 +51,7 @@ struct FfbsArgs {
     void* msg_scratch;  // per-CTA message scratch when not exporting
     int64_t msg_scratch_stride;
     void* obsf_scratch;  // per-CTA observation factors [ncap][K]
+    int64_t obsf_stride; // ffbs_warp.cuh: elements per warp region of obsf_scratch
     double* logZ;
     int32_t* aug_idx;
     int32_t* path_v;

@@ -64,6 +64,11 @@ class Engine:
             raise _lib.EngineError(self.lib.smjp_last_error().decode())
         self.K = None
         self.Kobs = None
+        # experiment switches for whole-suite runs: SMJP_FFBS_WARP=1 (warp-per-chain ring kernel), SMJP_FFBS_RING=R
+        import os
+        for env, key in (("SMJP_FFBS_WARP", "ffbs_warp"), ("SMJP_FFBS_RING", "ffbs_ring")):
+            if os.environ.get(env):
+                self.set_option(key, int(os.environ[env]))
 
     def close(self):
         if getattr(self, "ctx", None):
