@@ -177,12 +177,13 @@ __global__ void __launch_bounds__(FFBS_WARPS * 32) ffbs_warp_kernel(const FfbsAr
             Real Jp[K];
 #pragma unroll
             for (int v = 0; v < K; ++v) Jp[v] = 0;
-            for (int m = j_lo >> 5; m <= mi; ++m) {
+            int rs = (j_lo >> 5) % R;  // ring slot of the oldest live slot, advanced without a division per slot
+            for (int m = j_lo >> 5; m <= mi; ++m, rs = rs + 1 == R ? 0 : rs + 1) {
                 const int j = (m << 5) + lane;
                 if (j < j_lo || j > i) continue;
                 const bool diag = j == i;
-                Real* pa = st_a + (size_t)(m % R) * K * 32 + lane;
-                Real* ph = st_h + (size_t)(m % R) * K * 32 + lane;
+                Real* pa = st_a + rs * (K * 32) + lane;
+                Real* ph = st_h + rs * (K * 32) + lane;
                 const Real tau = (Real)(wn - Wg[j]);
                 const Real L2 = ex2.log2(tau);
 #pragma unroll
