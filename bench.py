@@ -444,7 +444,7 @@ def run_ours(args):
                                     "peak": peak, "unit": "GB/s",
                                     "frac": (b32 / max(c32, 1)) / (k32 / max(c32, 1) / 1e3) / 1e9 / peak,
                                     "traffic": ((traffic or {}).get("f32") or {}).get("dram_bytes_per_launch"),
-                                    "kernel": "ffbs_kernel<float,3>", "kernel_ms_avg": k32 / max(c32, 1),
+                                    "kernel": "ffbs_warp_kernel<float,3> (auto) / ffbs_kernel<float,3>", "kernel_ms_avg": k32 / max(c32, 1),
                                     "compute": compute_ceiling("f32", ss32 / K / max(c32, 1), k32 / max(c32, 1) / 1e3,
                                                                clk.get("sm_mhz"))},
                        "tolerance": "messages within 1e-4 of the reference (tests/test_ffbs_gpu.py)"}
