@@ -422,17 +422,25 @@ cudaError_t ffbs_big_call(const FfbsArgs& a, FfbsLaunch& L, bool query) {
 }
 
 // warp-per-chain ring kernel (ffbs_warp.cuh), K = 2, 3
-template <typename Real>
-cudaError_t ffbs_warp_call(const FfbsArgs& a, FfbsLaunch& L, bool query) {
-    auto k2 = ffbs_warp_kernel<Real, 2>;
-    auto k3 = ffbs_warp_kernel<Real, 3>;
-    auto kern = L.K == 2 ? k2 : k3;
+template <typename Real, int K>
+cudaError_t ffbs_warp_do(const FfbsArgs& a, FfbsLaunch& L, bool query) {
+    auto kern = ffbs_warp_kernel<Real, K>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
     if (e != cudaSuccess) return e;
     if (query) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&L.grid, kern, FFBS_WARPS * 32, L.smem);
-    if (L.K == 2) k2<<<L.grid, FFBS_WARPS * 32, L.smem, L.stream>>>(a);
-    else k3<<<L.grid, FFBS_WARPS * 32, L.smem, L.stream>>>(a);
+    kern<<<L.grid, FFBS_WARPS * 32, L.smem, L.stream>>>(a);
     return cudaGetLastError();
+}
+// K >= 4 was tried in fp32 (K = 10: 228 registers, 128 with spills; 28-32 ms per cfg5 sweep against 15.5 ms for
+// the item-parallel kernel): the ring kernel stays with K <= 3
+constexpr int ffbs_warp_max_k(size_t) { return 3; }
+template <typename Real>
+cudaError_t ffbs_warp_call(const FfbsArgs& a, FfbsLaunch& L, bool query) {
+    switch (L.K) {
+        case 2: return ffbs_warp_do<Real, 2>(a, L, query);
+        case 3: return ffbs_warp_do<Real, 3>(a, L, query);
+    }
+    return cudaErrorInvalidValue;
 }
 
 template <typename Real>
@@ -517,11 +525,12 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
     // auto: fp32 (window ~100-150 grid points on cfg2) and pruned windows; the exact fp64 window (~250-300 points)
     // needs a ring that leaves 12 warps per SM and gains 5 % only: block kernel
     const bool want_warp = c->ffbs_warp == 1 || (c->ffbs_warp == -1 && (sizeof(Real) == 4 || c->window_log2 < 0));
-    bool use_warp = want_warp && !c->warp_off[pidx] && K <= 3 && !item_kernel && !a.messages && n_max <= 65535 && c->f32_rescue;
+    bool use_warp = want_warp && !c->warp_off[pidx] && K <= ffbs_warp_max_k(sizeof(Real)) && !(K == 3 && c->item_k3) &&
+                    !a.messages && n_max <= 65535 && c->f32_rescue;
     int ring = 0;
     size_t warp_smem = 0;
     if (use_warp) {
-        ring = c->ffbs_ring > 0 ? c->ffbs_ring : (c->window_log2 < 0 ? 4 : (sizeof(Real) == 4 ? 6 : 10)) + c->ring_boost[pidx];
+        ring = c->ffbs_ring > 0 ? c->ffbs_ring : (c->window_log2 < 0 || K > 3 ? 4 : (sizeof(Real) == 4 ? 6 : 10)) + c->ring_boost[pidx];
         const int full = (int)(n_max / 32) + 1;  // slots that hold a whole grid: the ring never needs more
         if (ring > full) ring = full;
         warp_smem = ffbs_warp_smem_bytes<Real>(K, ring, (int)n_max);

@@ -1,4 +1,4 @@
-// FFBS, one WARP per chain, live window in a shared-memory ring (K <= 3, scratch mode).
+// FFBS, one WARP per chain, live window in a shared-memory ring (K <= 3, scratch mode; the code is generic in K).
 //
 // Same arithmetic, outputs and reference lines as ffbs.cuh.  What the exact live window of ffbs.cuh makes
 // possible: on cfg2 only ~250 (fp64) / ~100 (fp32) grid points per row carry non-zero states, so the chain
@@ -16,7 +16,9 @@
 
 namespace smjp {
 
-#define PC(w, t) (sizeof(Real) == 8 ? (Real)a.pc_d[w][t] : (Real)a.pc_f[w][t])  // as in ffbs.cuh
+#define PC(w, t) (sizeof(Real) == 8 ? (Real)a.pc_d[w][t] : (Real)a.pc_f[w][t])  // as in ffbs.cuh (K <= 3)
+// hazard parameter set w, entry t: kernel-argument constants for K <= 3, shared memory beyond
+#define PW(w, t) (K <= 3 ? PC(w, (K <= 3 ? (t) : 0)) : s_par[(w) * K * K + (t)])
 
 constexpr int FFBS_WARPS = 4;  // chains in flight per CTA (independent warps)
 
@@ -28,7 +30,7 @@ __host__ __device__ inline size_t ffbs_warp_smem_bytes(int K, int ring, int ncap
 }
 
 template <typename Real, int K>
-__global__ void __launch_bounds__(FFBS_WARPS * 32) ffbs_warp_kernel(const FfbsArgs a) {
+__global__ void __launch_bounds__(FFBS_WARPS * 32, (K > 3 ? 4 : 1)) ffbs_warp_kernel(const FfbsArgs a) {
     using M = Math<Real>;
     using Acc = typename ScanAcc<Real>::type;
     constexpr unsigned FULL = 0xffffffffu;
@@ -51,8 +53,15 @@ __global__ void __launch_bounds__(FFBS_WARPS * 32) ffbs_warp_kernel(const FfbsAr
         s_ltab[t] = make_double2(rc, -::log2(rc));
     }
     for (int t = threadIdx.x; t < K * K; t += blockDim.x) {
-        s_par[K * K + t] = PC(1, t);
-        s_par[2 * K * K + t] = PC(2, t);
+        const double k = a.model[t];
+        s_par[t] = (Real)(1.0 / k);
+        s_par[K * K + t] = (Real)((k - 1.0) * (double)Exp2<Real>::SCALE);
+        s_par[2 * K * K + t] = (Real)((a.model[K * K + t] - ::log2(k)) * (double)Exp2<Real>::SCALE);
+        if (K <= 3) {  // the same values the constant-bank copies hold (host-rounded)
+            s_par[t] = PC(0, (K <= 3 ? t : 0));
+            s_par[K * K + t] = PC(1, (K <= 3 ? t : 0));
+            s_par[2 * K * K + t] = PC(2, (K <= 3 ? t : 0));
+        }
     }
     __syncthreads();
     const Real* skm1 = s_par + K * K;
@@ -195,8 +204,8 @@ __global__ void __launch_bounds__(FFBS_WARPS * 32) ffbs_warp_kernel(const FfbsAr
                     Real esum = 0, dsum = 0;
 #pragma unroll
                     for (int s = 0; s < K; ++s) {
-                        kE[s] = ex2(PC(1, v * K + s) * L2 - PC(2, v * K + s));  // A_vs(tau)
-                        esum += kE[s] * PC(0, v * K + s);
+                        kE[s] = ex2(PW(1, v * K + s) * L2 - PW(2, v * K + s));  // A_vs(tau)
+                        esum += kE[s] * PW(0, v * K + s);
                         dsum += kE[s];
                     }
                     const Real hsum = tau * esum;  // H_v(tau)
@@ -261,13 +270,13 @@ __global__ void __launch_bounds__(FFBS_WARPS * 32) ffbs_warp_kernel(const FfbsAr
             const int len = cur + 1;
             const Real* row = msg + (int64_t)K * cur * (cur + 1) / 2;
             const int lo = jlo_arr[cur], wl = len - lo;
-            {   // next rows' live parts into L2 (ffbs.cuh): one 128-byte line per lane and (row, state) segment
-#pragma unroll
-                for (int seg = 0; seg < 3 * K; ++seg) {
+            {   // next rows' live parts into L2 (ffbs.cuh): (row, state) segments, up to four 128-byte lines each
+                for (int t = lane; t < 3 * K * 4; t += 32) {
+                    const int seg = t % (3 * K), line = t / (3 * K);
                     const int r = cur - 1 - seg / K, v = seg % K;
                     if (r >= 0) {
                         const int rlo = jlo_arr[r];
-                        const char* p = (const char*)(msg + (int64_t)K * r * (r + 1) / 2 + (int64_t)v * (r + 1) + rlo) + lane * 128;
+                        const char* p = (const char*)(msg + (int64_t)K * r * (r + 1) / 2 + (int64_t)v * (r + 1) + rlo) + line * 128;
                         if (p < (const char*)(msg + (int64_t)K * r * (r + 1) / 2 + (int64_t)(v + 1) * (r + 1)))
                             asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
                     }
@@ -422,6 +431,7 @@ __global__ void __launch_bounds__(FFBS_WARPS * 32) ffbs_warp_kernel(const FfbsAr
     }
 }
 
+#undef PW
 #undef PC
 
 }  // namespace smjp
