@@ -25,7 +25,10 @@ def cfg1():
     import experiments
     from smjp_b200.raoteh import raoteh
     m = experiments.build_experiment_2_model()
-    n = 300
+    raoteh(["trajectory"], 20, 300, m["state_space"], m["time_final"], m["emission"], m["data"], m["pi_0"],
+           m["hazard_A"], m["hazard_B"], m["poisson_process_A_hat"], m["poisson_process_B"], "cfg1", m["omega"],
+           m["obs_times"], None, False, seed=0, save=False)  # context creation, module load: not part of a sweep
+    n = 2000
     t0 = time.perf_counter()
     agg, _, _ = raoteh(["trajectory"], n, 300, m["state_space"], m["time_final"], m["emission"], m["data"], m["pi_0"],
                        m["hazard_A"], m["hazard_B"], m["poisson_process_A_hat"], m["poisson_process_B"], "cfg1", m["omega"],
