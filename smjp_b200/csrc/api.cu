@@ -234,6 +234,16 @@ int64_t smjp_ctx_get_stat(smjp_ctx_t* c, const char* key) {
     if (!strcmp(key, "ffbs_smem")) return c->last_smem;
     if (!strcmp(key, "num_sms")) return c->num_sms;
     if (!strcmp(key, "pf_cluster")) return c->last_pf_cluster;
+    if (!strcmp(key, "ffbs_ring_boost_f32")) return c->ring_boost[1] + 100 * c->warp_off[1];
+    if (!strcmp(key, "ffbs_ring_boost_f64")) return c->ring_boost[0] + 100 * c->warp_off[0];
+    if (!strcmp(key, "ffbs_rescued")) {  // chains the last launch handed to the rescue pass (synchronises)
+        if (!c->d_failed.p) return 0;
+        int32_t v = 0;
+        cudaSetDevice(c->device);
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
+        if (cudaMemcpy(&v, c->d_failed.p, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        return v;
+    }
     if (!strcmp(key, "ffbs_live_pairs")) {  // grid pairs processed by the FFBS kernels since the last query
         if (!c->d_live.p) return 0;
         unsigned long long v = 0;

@@ -499,26 +499,19 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
 #define SMJP_PAIR_UNROLL 1
 #endif
             constexpr int PAIR_UNROLL = SMJP_PAIR_UNROLL;
-            int m = m_lo;
-            if (m < mi) {  // oldest live slot: threads below the window start own a dead grid point
-                if (tid >= t_lo) pair(std::false_type(), false);
-                pa += K * B;
-                ph += K * B;
-                pw += B;
-                rowp += B;
-                rowg += B;
-                ++m;
-            }
-#pragma unroll PAIR_UNROLL
-            for (; m < mi; ++m) {  // full slots: every thread owns a live j < i
-                pair(std::false_type(), false);
+            // ONE copy of the pair code serves every slot (the kernel is 90 KB of SASS; a second, diag-free copy
+            // for the full slots cost more in instruction fetch than its two selects per state save): the
+            // oldest slot masks the threads below the window start, the newest those above the new grid point
+#pragma unroll 1
+            for (int m = m_lo; m <= mi; ++m) {
+                const bool active = (m > m_lo || tid >= t_lo) && (m < mi || tid <= ti);
+                if (active) pair(std::true_type(), m == mi && tid == ti);
                 pa += K * B;
                 ph += K * B;
                 pw += B;
                 rowp += B;
                 rowg += B;
             }
-            if (tid <= ti && (mi > m_lo || tid >= t_lo)) pair(std::true_type(), tid == ti);
             // block reduction of (Z, J[0..K)) -- double-buffered scratch, one barrier per step
             Real* rb = red + (i & 1) * NW * (K + 1);
             {

@@ -30,7 +30,9 @@ __host__ __device__ inline size_t ffbs_warp_smem_bytes(int K, int ring, int ncap
 }
 
 template <typename Real, int K>
-__global__ void __launch_bounds__(FFBS_WARPS * 32, (K > 3 ? 4 : 1)) ffbs_warp_kernel(const FfbsArgs a) {
+// resident CTAs the register budget is tuned for: 7 in fp32 (72 registers), 4 in fp64 (<= 128); an explicit 1 lets
+// the compiler take 107 / 161 registers and costs 17 % (measured)
+__global__ void __launch_bounds__(FFBS_WARPS * 32, (sizeof(Real) == 4 && K <= 3 ? 7 : 4)) ffbs_warp_kernel(const FfbsArgs a) {
     using M = Math<Real>;
     using Acc = typename ScanAcc<Real>::type;
     constexpr unsigned FULL = 0xffffffffu;
@@ -270,13 +272,13 @@ __global__ void __launch_bounds__(FFBS_WARPS * 32, (K > 3 ? 4 : 1)) ffbs_warp_ke
             const int len = cur + 1;
             const Real* row = msg + (int64_t)K * cur * (cur + 1) / 2;
             const int lo = jlo_arr[cur], wl = len - lo;
-            {   // next rows' live parts into L2 (ffbs.cuh): (row, state) segments, up to four 128-byte lines each
-                for (int t = lane; t < 3 * K * 4; t += 32) {
-                    const int seg = t % (3 * K), line = t / (3 * K);
+            {   // next rows' live parts into L2 (ffbs.cuh): one 128-byte line per lane and (row, state) segment
+#pragma unroll
+                for (int seg = 0; seg < 3 * K; ++seg) {
                     const int r = cur - 1 - seg / K, v = seg % K;
                     if (r >= 0) {
                         const int rlo = jlo_arr[r];
-                        const char* p = (const char*)(msg + (int64_t)K * r * (r + 1) / 2 + (int64_t)v * (r + 1) + rlo) + line * 128;
+                        const char* p = (const char*)(msg + (int64_t)K * r * (r + 1) / 2 + (int64_t)v * (r + 1) + rlo) + lane * 128;
                         if (p < (const char*)(msg + (int64_t)K * r * (r + 1) / 2 + (int64_t)(v + 1) * (r + 1)))
                             asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
                     }
