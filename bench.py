@@ -68,7 +68,7 @@ try:
     while True:
         out["sm"].append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
         out["mask"] |= reasons()
-        r, _, _ = select.select([sys.stdin], [], [], 0.02)
+        r, _, _ = select.select([sys.stdin], [], [], 0.08)
         if r:
             break
 except Exception as e:
@@ -80,7 +80,8 @@ print(json.dumps(out), flush=True)
 
 class ClockSampler:
     """SM clocks / throttle reasons sampled DURING the timed region by a helper PROCESS with its own NVML
-    session (started and primed before the region, sampling every ~20 ms between begin() and end()).  NVML
+    session (started and primed before the region, sampling every ~80 ms between begin() and end(): every NVML
+    query holds a driver lock for a few ms, whichever process issues it, so there are few of them).  NVML
     queries take 5-50 ms now and then: issued from this process -- inline or from a thread -- they were
     measured to stall the launch path of the timed loop by that much; a `nvidia-smi` subprocess per sample
     costs ~0.2 s.  The helper does not touch this process."""
