@@ -561,7 +561,8 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
                 rescue_smem = ffbs_item_smem_bytes<double>(K, (int)n_max, rescue_threads);
             }
         } else {
-            rescue_threads = threads;
+            // the rescued chains run alone at the end of the launch: give each the CTA size that is fastest per chain
+            rescue_threads = (threads < 128 && n_max > 96) ? 128 : threads;
             rescue_smem = ffbs_smem_bytes<double>(K, (int)n_max, rescue_threads);
         }
         if (rescue_smem > c->smem_optin) rescue = false;
