@@ -20,8 +20,14 @@
 // J_{i+1}(s) is g k_vs E_vs.  The K*K powers computed for (i, j) serve e_i(v,j) AND J_{i+1}: B_i is
 // generated in-kernel and never stored.  State carried per live (v,j): the unnormalised message and
 // H_v(tau) -- both in shared memory, indexed so that consecutive threads hit consecutive banks.
-// Normalisation is deferred by one step (row i-1 is scaled and streamed to HBM while row i is being
-// computed), so each grid step costs exactly one __syncthreads().
+// Normalisation is deferred by one step (the next step multiplies by 1/Z_i), so each grid step costs exactly
+// one __syncthreads().  Message rows: exported on request as the reference's normalised alpha (scaled and
+// streamed one step late); otherwise per-CTA scratch rows hold g = alpha / (Omega A_v), which is what the
+// backward pass needs (one hazard per entry instead of K).  Exact live window: grid points whose states have
+// underflowed to exact zeros are skipped in the forward pass, the row stores and the backward row scans
+// (see "Live window" in the kernel); window_eps > 0 turns that into threshold pruning (opt-in).
+// Siblings: ffbs_item.cuh (4 <= K <= 10, thread per state), ffbs_big.cuh (K <= 64, run-time K),
+// ffbs_warp.cuh (K <= 3, one warp per chain, window in a shared-memory ring).
 #pragma once
 #include "../../include/smjp_b200.h"
 #include <type_traits>
