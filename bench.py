@@ -51,6 +51,7 @@ def algorithmic_bytes(n_per_chain, D, esz):
 SAMPLER_SRC = r"""
 import json, sys, time, select
 idx = int(sys.argv[1])
+period = float(sys.argv[2])
 out = {"sm": [], "smmax": None, "mask": 0, "via": "nvml"}
 try:
     import pynvml as n
@@ -68,7 +69,7 @@ try:
     while True:
         out["sm"].append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
         out["mask"] |= reasons()
-        r, _, _ = select.select([sys.stdin], [], [], 0.08)
+        r, _, _ = select.select([sys.stdin], [], [], period)
         if r:
             break
 except Exception as e:
@@ -92,7 +93,7 @@ class ClockSampler:
         self.res = None
         self.proc = None
         try:
-            self.proc = subprocess.Popen([sys.executable, "-c", SAMPLER_SRC, str(index)], stdin=subprocess.PIPE,
+            self.proc = subprocess.Popen([sys.executable, "-c", SAMPLER_SRC, str(index), os.environ.get("SMJP_BENCH_SAMPLER_S", "0.08")], stdin=subprocess.PIPE,
                                          stdout=subprocess.PIPE, text=True)
             self.proc.stdout.readline()  # "ready"
         except Exception:
@@ -251,6 +252,7 @@ def run_ours(args):
     eng.set_option("window_log2", args.window_log2)
     eng.set_option("ffbs_warp", args.warp)
     eng.set_option("ffbs_ring", args.ring)
+    eng.set_option("speculate", 0 if args.no_speculate else 1)
     obs_t = np.arange(OBS_DT, T_END, OBS_DT)
     D = len(obs_t)
     # ground-truth path -> observations; independent prior draw as the initial state
@@ -274,6 +276,7 @@ def run_ours(args):
     eng.kernel_time()
     eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_live_pairs")  # reset the live-window counter
     launches0 = eng.launch_count
+    spec0 = [eng.lib.smjp_ctx_get_stat(eng.ctx, k) for k in (b"spec_launches", b"spec_misses")]
     sampler = ClockSampler(local)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ss = gs = 0.0
@@ -295,6 +298,7 @@ def run_ours(args):
     if step_ev and rank == 0:
         print("per-step ms:", [round(ev0.elapsed_time(e), 2) for e in step_ev], file=sys.stderr)
     launches = eng.launch_count - launches0
+    spec = [eng.lib.smjp_ctx_get_stat(eng.ctx, k) - v0 for k, v0 in zip((b"spec_launches", b"spec_misses"), spec0)]
     k_ms, k_cnt = eng.kernel_time()
     live_pairs = float(eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_live_pairs"))
     eng.set_option("time_kernels", 0)
@@ -406,6 +410,9 @@ def run_ours(args):
                      "achieved_live": achieved * live_pairs / max(ss_rank0 / K, 1.0),
                      "window": "exact (zeros only)" if args.window_log2 == 0 else "pruned below 2^%d of the row sum" % args.window_log2,
                      "compute": compute_ceiling(prec, ss_rank0 / K / max(k_cnt, 1), k_avg_s, clk.get("sm_mhz"))},
+        # sweeps whose kernels were enqueued for the grid size predicted from the previous sweep, before their own
+        # counts reached the host, and how many of those had to be launched again (rank 0)
+        "speculative_launches": {"launches": spec[0], "repeated": spec[1]},
         "e2e": {"value": e_ss / e_wall, "unit": UNIT, "h2d_bytes_per_step": h2d // max(e2e_steps, 1),
                 "d2h_bytes_per_step": d2h // max(e2e_steps, 1), "steps": e2e_steps,
                 "api": "smjp_sweep_host (pinned host buffers in/out; H2D of paths + observations and D2H of the grid inside the timed call, new paths / metrics / status written by the kernels straight into the pinned output buffers)"},
@@ -509,6 +516,8 @@ def main():
     ap.add_argument("--threads", type=int, default=0, help="threads per CTA of the FFBS kernel (0 = auto)")
     ap.add_argument("--item-k3", type=int, default=0, help="experiment: item-parallel kernel for K=3")
     ap.add_argument("--warp", type=int, default=-1, help="warp-per-chain ring kernel (ffbs_warp.cuh): -1 auto, 0 off, 1 on")
+    ap.add_argument("--no-speculate", action="store_true", dest="no_speculate",
+                    help="wait for every sweep's grid sizes on the host before launching its FFBS kernel")
     ap.add_argument("--ring", type=int, default=0, help="ring slots of 32 grid points for --warp (0 = auto)")
     ap.add_argument("--window-log2", type=int, default=0, dest="window_log2",
                     help="0: exact live window (default); -L: prune states below 2^-L of the row sum")

@@ -72,7 +72,8 @@ int smjp_ctx_sync(smjp_ctx_t* ctx);
 int64_t smjp_ctx_launch_count(smjp_ctx_t* ctx);
 /* launch geometry of the last FFBS kernel: "ffbs_grid", "ffbs_threads", "ffbs_smem"; "num_sms"; "pf_cluster";
  * "ffbs_live_pairs": grid pairs (i, j) inside the live window that the K <= 3 FFBS kernel processed since the
- * last query (synchronises; the nominal count is n(n+1)/2 per chain) */
+ * last query (synchronises; the nominal count is n(n+1)/2 per chain); "spec_launches" / "spec_misses": speculative
+ * sweep launches and how many of them had to be repeated (option "speculate") */
 int64_t smjp_ctx_get_stat(smjp_ctx_t* ctx, const char* key);
 /* knobs: "ffbs_threads" (0 = auto, else threads per CTA of the FFBS kernel);
  *        "time_kernels" (0/1, see smjp_ctx_kernel_time);
@@ -89,6 +90,11 @@ int64_t smjp_ctx_get_stat(smjp_ctx_t* ctx, const char* key);
  *        outgrows the ring are redone by the full-size kernel, so results never depend on the ring);
  *        "f32_rescue" (default 1: chains whose fp32 FFBS pass loses its row sum -- a grid step over which every
  *        live state changes by more than 38 orders of magnitude -- are redone by the fp64 kernel);
+ *        "speculate" (default 1: smjp_sweep_dev enqueues a sweep's fill and FFBS kernels for the grid size predicted
+ *        from the previous sweep BEFORE this sweep's counts reach the host; the kernels check the real counts on
+ *        the device and return at once if the prediction was too small, in which case the sweep is launched again
+ *        with the real size.  Results never depend on it; stats "spec_launches" / "spec_misses" count both; 2 = test setting
+ *        that under-predicts on purpose so that most launches are repeated);
  *        "pf_extend" (0 = the particle-filter path is extended flat from the last observation to t_end
  *        as the reference does, pmcmc.py:307-309; 1 = the segment is simulated);
  *        "lpt_order" (0/1, default 1: the FFBS kernel starts the longest grids first);

@@ -112,7 +112,6 @@ struct smjp_ctx {
     int ffbs_warp = -1;   // one warp per chain, live window in a shared-memory ring (K <= 3, scratch mode): -1 auto, 0 off, 1 on
     int ring_boost[2] = {0, 0};      // extra ring slots learnt from rescue counts, per precision (f64, f32)
     int warp_off[2] = {0, 0};        // the ring kernel kept overflowing for this precision: block kernel from now on
-    int last_warp_prec = -1, last_warp_C = 0;  // the previous launch used the ring kernel: its rescue count is pending
     int ffbs_ring = 0;    // ring slots of 32 grid points (0 = auto)
     bool lpt_order = true;
     int obs_product = 0;
@@ -135,6 +134,20 @@ struct smjp_ctx {
     uint32_t chain_base = 0;
     DevBuf d_stats, d_pi0, d_wlen, d_soff;
     PinBuf h_stats;
+    // speculative sweeps (smjp_sweep_dev): the FFBS kernel of a sweep is enqueued for a predicted grid size before
+    // this sweep's counts have reached the host, so that the host is never between the GPU and its next kernel
+    int speculate = 1;
+    int64_t pred_nmax = 0;          // geometry the next sweep is launched for (0: no prediction yet)
+    int pred_C = 0, pred_prec = -1;
+    cudaEvent_t ev_stats = nullptr;  // {n_max, total} of the current sweep are in h_stats
+    const int64_t* guard = nullptr;  // while a speculative sweep is being enqueued: device {n_max, total} + limits
+    int64_t guard_nmax = 0, guard_total = 0;
+    int64_t spec_launches = 0, spec_misses = 0;
+    // rescue counts of ring-kernel launches come home asynchronously, two launches in flight
+    PinBuf h_resc;
+    cudaEvent_t ev_resc[2] = {nullptr, nullptr};
+    int resc_prec[2] = {-1, -1}, resc_C[2] = {0, 0};
+    int resc_idx = 0;
     // optional per-kernel timing (CUDA events on the launching stream)
     bool time_kernels = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ffbs_events, hmm_events, pf_events;
@@ -210,6 +223,10 @@ void smjp_ctx_destroy(smjp_ctx_t* c) {
     c->h_stats.release();
     if (c->ev_obs) cudaEventDestroy(c->ev_obs);
     if (c->ev_fill) cudaEventDestroy(c->ev_fill);
+    if (c->ev_stats) cudaEventDestroy(c->ev_stats);
+    for (int i = 0; i < 2; ++i)
+        if (c->ev_resc[i]) cudaEventDestroy(c->ev_resc[i]);
+    c->h_resc.release();
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (auto* evs : {&c->ffbs_events, &c->hmm_events, &c->pf_events})
         for (auto& ev : *evs) {
@@ -236,6 +253,8 @@ int64_t smjp_ctx_get_stat(smjp_ctx_t* c, const char* key) {
     if (!strcmp(key, "pf_cluster")) return c->last_pf_cluster;
     if (!strcmp(key, "ffbs_ring_boost_f32")) return c->ring_boost[1] + 100 * c->warp_off[1];
     if (!strcmp(key, "ffbs_ring_boost_f64")) return c->ring_boost[0] + 100 * c->warp_off[0];
+    if (!strcmp(key, "spec_launches")) return c->spec_launches;
+    if (!strcmp(key, "spec_misses")) return c->spec_misses;
     if (!strcmp(key, "ffbs_rescued")) {  // chains the last launch handed to the rescue pass (synchronises)
         if (!c->d_failed.p) return 0;
         int32_t v = 0;
@@ -306,6 +325,11 @@ int smjp_ctx_set_option(smjp_ctx_t* c, const char* key, int64_t value) {
         c->window_log2 = (int)value;
         return SMJP_OK;
     }
+    if (!strcmp(key, "speculate")) {  // 2 (tests): predict 3/4 of the previous size, so that most launches are repeated
+        c->speculate = value == 2 ? 2 : (value ? 1 : 0);
+        c->pred_nmax = 0;
+        return SMJP_OK;
+    }
     if (!strcmp(key, "f32_rescue")) {
         c->f32_rescue = value ? 1 : 0;
         return SMJP_OK;
@@ -362,11 +386,20 @@ int smjp_set_model(smjp_ctx_t* c, int K, int Kobs, const double* shape, const do
     for (int t = 0; t < K * K; ++t)
         if (!(shape[t] > 0.0) || !(scale[t] > 0.0) || !std::isfinite(shape[t]) || !std::isfinite(scale[t]))
             return fail(SMJP_E_INVALID, "shape/scale entry %d is not positive finite", t);
+    // the fp64 kernels evaluate 2^x with a 32-bit integer part of 256 x (Exp2<double>), so |x| must stay below
+    // 2^23 for every positive double tau (|log2 tau| <= 1075): x = (k-1) log2 tau - (k log2 lambda - log2 k)
+    // for a hazard, k log2(tau/lambda) and log2 lambda + log2(e)/k in the particle filter's holding times
+    for (int t = 0; t < K * K; ++t) {
+        const double k = shape[t], l2 = std::fabs(std::log2(scale[t]));
+        if ((k + 1.0) * 1075.0 + k * l2 + std::fabs(std::log2(k)) >= 8388608.0 || 1075.0 / k + l2 >= 8388608.0)
+            return fail(SMJP_E_INVALID, "shape/scale entry %d: exponents leave the +-2^23 range of the device arithmetic", t);
+    }
     for (int t = 0; t < K * Kobs; ++t)
         if (!(emis[t] >= 0.0) || !std::isfinite(emis[t]))
             return fail(SMJP_E_INVALID, "emission entry %d is negative or not finite", t);
     CUDA_TRY(cudaSetDevice(c->device));
     if (K != c->K) c->ffbs_ncap_hint = 0;
+    c->pred_nmax = 0;  // grid sizes follow the model: no speculative launch for the next sweep
     c->K = K;
     c->Kobs = Kobs;
     c->omega = omega;
@@ -520,17 +553,21 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
     }
     // warp-per-chain ring kernel (option ffbs_warp): K <= 3, scratch mode
     const int pidx = sizeof(Real) == 4 ? 1 : 0;
-    if (c->last_warp_prec >= 0) {
-        // the previous ring-kernel launch: how many of its chains outgrew the ring and went to the rescue pass?
-        // (a few are harmless; many mean this workload's windows are wider than the ring: widen it, or give up)
-        int32_t resc = 0;
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
-        if (c->d_failed.p) CUDA_TRY(cudaMemcpy(&resc, c->d_failed.p, 4, cudaMemcpyDeviceToHost));
-        if (resc * 50 > c->last_warp_C) {
-            c->ring_boost[c->last_warp_prec] += 2;
-            if (c->ring_boost[c->last_warp_prec] > 8) c->warp_off[c->last_warp_prec] = 1;
+    {
+        // an earlier ring-kernel launch: how many of its chains outgrew the ring and went to the rescue pass?
+        // (a few are harmless; many mean this workload's windows are wider than the ring: widen it, or give up).
+        // The count of launch i travels home behind it and is read when launch i+2 is prepared.
+        const int slot = c->resc_idx & 1;
+        if (c->resc_prec[slot] >= 0) {
+            CUDA_TRY(cudaEventSynchronize(c->ev_resc[slot]));
+            const int32_t resc = ((const int32_t*)c->h_resc.p)[slot];
+            const int pp = c->resc_prec[slot];
+            if ((int64_t)resc * 50 > c->resc_C[slot]) {
+                c->ring_boost[pp] += 2;
+                if (c->ring_boost[pp] > 8) c->warp_off[pp] = 1;
+            }
+            c->resc_prec[slot] = -1;
         }
-        c->last_warp_prec = -1;
     }
     // auto: fp32 (window ~100-150 grid points on cfg2) and pruned windows; the exact fp64 window (~250-300 points)
     // needs a ring that leaves 12 warps per SM and gains 5 % only: block kernel
@@ -597,16 +634,18 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
         const int64_t stride = (int64_t)K * hint * (hint + 1) / 2;
         size_t bytes = (size_t)stride * sizeof(Real) * (size_t)grid * regions_per_cta;
         if (rescue && bytes < (size_t)stride * 8 * RESCUE_GRID) bytes = (size_t)stride * 8 * RESCUE_GRID;
-        size_t free_b = 0, total_b = 0;
-        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-        size_t budget = free_b + c->d_msg_scratch.cap;
-        budget -= budget / 10;
-        if (bytes > budget) {  // fewer resident CTAs rather than failing
-            int g2 = (int)(budget / ((size_t)stride * sizeof(Real) * regions_per_cta));
-            if (g2 < 1)
-                return fail(SMJP_E_NOMEM, "message scratch for one chain (%zu B) does not fit", (size_t)stride * sizeof(Real));
-            grid = g2;
-            bytes = (size_t)stride * sizeof(Real) * (size_t)grid * regions_per_cta;
+        if (bytes > c->d_msg_scratch.cap) {  // (steady state: no growth, and no trip into the driver for the query)
+            size_t free_b = 0, total_b = 0;
+            CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+            size_t budget = free_b + c->d_msg_scratch.cap;
+            budget -= budget / 10;
+            if (bytes > budget) {  // fewer resident CTAs rather than failing
+                int g2 = (int)(budget / ((size_t)stride * sizeof(Real) * regions_per_cta));
+                if (g2 < 1)
+                    return fail(SMJP_E_NOMEM, "message scratch for one chain (%zu B) does not fit", (size_t)stride * sizeof(Real));
+                grid = g2;
+                bytes = (size_t)stride * sizeof(Real) * (size_t)grid * regions_per_cta;
+            }
         }
         rc = c->d_msg_scratch.reserve(bytes);
         if (rc) return rc;
@@ -681,8 +720,14 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
         CUDA_TRY(ffbs_call<double>(r, R, false));
         c->launches += 2;
         if (use_warp) {
-            c->last_warp_prec = pidx;
-            c->last_warp_C = a.C;
+            const int slot = c->resc_idx & 1;
+            rc = c->h_resc.reserve(2 * sizeof(int32_t));
+            if (rc) return rc;
+            if (!c->ev_resc[slot]) CUDA_TRY(cudaEventCreateWithFlags(&c->ev_resc[slot], cudaEventDisableTiming));
+            CUDA_TRY(cudaMemcpyAsync((int32_t*)c->h_resc.p + slot, cnt, 4, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaEventRecord(c->ev_resc[slot], c->stream));
+            c->resc_prec[slot] = pidx;
+            c->resc_C[slot] = a.C;
         }
     }
     if (c->time_kernels) {
@@ -690,6 +735,7 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
         c->ffbs_events.emplace_back(e0, e1);
     }
     c->launches += 1;
+    ++c->resc_idx;
     c->last_grid = grid;
     c->last_threads = L.threads;
     c->last_smem = (int64_t)L.smem;
@@ -750,6 +796,9 @@ int smjp_ffbs_dev(smjp_ctx_t* c, int C, const int64_t* w_offs, const double* W,
     a.omega = c->omega;
     a.power = c->power;
     a.t_end = c->t_end;
+    a.guard = c->guard;
+    a.guard_nmax = c->guard_nmax;
+    a.guard_total = c->guard_total;
     return precision == SMJP_F64 ? ffbs_dev_impl<double>(c, a, n_max) : ffbs_dev_impl<float>(c, a, n_max);
 }
 
@@ -879,6 +928,8 @@ CandArgs make_cand_args(smjp_ctx* c, int C, const int64_t* p_offs, const int32_t
     a.seed = seed;
     a.sweep = sweep;
     a.chain_base = c->chain_base;
+    a.guard = c->guard;
+    a.guard_total = c->guard_total;
     return a;
 }
 
@@ -959,16 +1010,19 @@ int smjp_simulate_obs_dev(smjp_ctx_t* c, int C, const int64_t* p_offs, const int
     return SMJP_OK;
 }
 
-int smjp_candidates_count_dev(smjp_ctx_t* c, int C, const int64_t* p_offs, const int32_t* path_v,
-                              const double* path_t, const int32_t* path_len, uint64_t seed,
-                              uint32_t sweep, int64_t* w_offs, int32_t* soff, int64_t* n_max_host,
-                              int64_t* total_w_host) {
+}  // extern "C"
+
+namespace {
+// count pass of the candidate sampler: per-chain grid lengths, their prefix sums (w_offs) and {n_max, total} on
+// their way to c->h_stats; c->ev_stats is recorded behind the copy
+int cand_count_enqueue(smjp_ctx* c, int C, const int64_t* p_offs, const int32_t* path_v, const double* path_t,
+                       const int32_t* path_len, uint64_t seed, uint32_t sweep, int64_t* w_offs, int32_t* soff) {
     int rc = model_ready(c);
     if (rc) return rc;
     rc = weibull_only(c, "the candidate sampler");
     if (rc) return rc;
     if (C <= 0) return fail(SMJP_E_INVALID, "C <= 0");
-    if (!p_offs || !path_v || !path_t || !path_len || !w_offs || !soff || !n_max_host || !total_w_host)
+    if (!p_offs || !path_v || !path_t || !path_len || !w_offs || !soff)
         return fail(SMJP_E_INVALID, "null required pointer");
     CUDA_TRY(cudaSetDevice(c->device));
     rc = c->d_wlen.reserve((size_t)C * sizeof(int64_t));
@@ -977,6 +1031,7 @@ int smjp_candidates_count_dev(smjp_ctx_t* c, int C, const int64_t* p_offs, const
     if (rc) return rc;
     rc = c->h_stats.reserve(2 * sizeof(int64_t));
     if (rc) return rc;
+    if (!c->ev_stats) CUDA_TRY(cudaEventCreateWithFlags(&c->ev_stats, cudaEventDisableTiming));
     CandArgs a = make_cand_args(c, C, p_offs, path_v, path_t, path_len, seed, sweep);
     a.soff = soff;
     a.w_len = (int64_t*)c->d_wlen.p;
@@ -987,7 +1042,31 @@ int smjp_candidates_count_dev(smjp_ctx_t* c, int C, const int64_t* p_offs, const
     CUDA_TRY(cudaGetLastError());
     c->launches += 2;
     CUDA_TRY(cudaMemcpyAsync(c->h_stats.p, c->d_stats.p, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev_stats, c->stream));
+    return SMJP_OK;
+}
+
+// geometry the NEXT sweep is launched for, from this sweep's longest grid: a few per cent of head room (the
+// maximum over thousands of chains moves by ~2 % between sweeps), but not across a 128-point slot boundary of
+// the block kernel when the boundary itself leaves room -- a slot more costs a resident CTA per SM
+int64_t predict_nmax(int64_t n_max) {
+    int64_t pred = n_max + (n_max / 24 > 16 ? n_max / 24 : 16);
+    const int64_t edge = (n_max / 128 + 1) * 128 - 1;
+    if (pred > edge && edge >= n_max + 8) pred = edge;
+    return pred;
+}
+}  // namespace
+
+extern "C" {
+
+int smjp_candidates_count_dev(smjp_ctx_t* c, int C, const int64_t* p_offs, const int32_t* path_v,
+                              const double* path_t, const int32_t* path_len, uint64_t seed,
+                              uint32_t sweep, int64_t* w_offs, int32_t* soff, int64_t* n_max_host,
+                              int64_t* total_w_host) {
+    if (!n_max_host || !total_w_host) return fail(SMJP_E_INVALID, "null required pointer");
+    int rc = cand_count_enqueue(c, C, p_offs, path_v, path_t, path_len, seed, sweep, w_offs, soff);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventSynchronize(c->ev_stats));
     *n_max_host = ((int64_t*)c->h_stats.p)[0];
     *total_w_host = ((int64_t*)c->h_stats.p)[1];
     return SMJP_OK;
@@ -1023,12 +1102,65 @@ int smjp_sweep_dev(smjp_ctx_t* c, int C, const int64_t* p_offs, const int32_t* p
                    int32_t* path_v_out, double* path_t_out, int32_t* path_len_out,
                    double* time_in_state, int32_t* jumps, int32_t* status, int64_t* n_max_host,
                    int64_t* total_w_host) {
-    int rc = smjp_candidates_count_dev(c, C, p_offs, path_v, path_t, path_len, seed, sweep, w_offs, soff,
-                                       n_max_host, total_w_host);
+    if (!c) return fail(SMJP_E_INVALID, "null context");
+    if (!n_max_host || !total_w_host) return fail(SMJP_E_INVALID, "null required pointer");
+    int rc = cand_count_enqueue(c, C, p_offs, path_v, path_t, path_len, seed, sweep, w_offs, soff);
     if (rc) return rc;
-    if (*total_w_host > capacity)
+    // Speculative launch.  The FFBS geometry (shared memory, scratch, grid) needs this sweep's longest grid, which
+    // is known on the device only.  Waiting for it leaves the GPU idle while the host prepares the launch, and
+    // exposes every host hiccup.  Instead the fill and FFBS kernels are enqueued NOW for the size predicted from
+    // the previous sweep, guarded on the device by the real counts; the host then collects the counts while the
+    // kernels run, and only a sweep that outgrew the prediction (its kernels returned at once) is launched again.
+    const bool spec = c->speculate && c->pred_nmax > 0 && c->pred_C == C && c->pred_prec == precision;
+    const int64_t pred = c->pred_nmax;
+    int spec_rc = SMJP_OK;
+    size_t events_before = c->ffbs_events.size();
+    if (spec) {
+        ++c->spec_launches;
+        c->guard = (const int64_t*)c->d_stats.p;
+        c->guard_nmax = pred;
+        c->guard_total = capacity;
+        spec_rc = smjp_candidates_fill_dev(c, C, p_offs, path_v, path_t, path_len, seed, sweep, mode, w_offs, soff, W);
+        if (!spec_rc) {
+            if (c->w_copy_dst) cudaEventRecord(c->ev_fill, c->stream);  // host call: the grid is copied once its size is known
+            if (c->wait_obs) {
+                cudaStreamWaitEvent(c->stream, c->ev_obs, 0);
+                c->wait_obs = false;
+            }
+            spec_rc = smjp_ffbs_dev(c, C, w_offs, W, obs_offs, obs_t, obs_y, nullptr, seed, sweep, precision, nullptr,
+                                    nullptr, nullptr, nullptr, path_v_out, path_t_out, path_len_out, time_in_state,
+                                    jumps, status, pred, capacity);
+        }
+        c->guard = nullptr;
+        c->guard_nmax = c->guard_total = 0;
+    }
+    CUDA_TRY(cudaEventSynchronize(c->ev_stats));
+    *n_max_host = ((int64_t*)c->h_stats.p)[0];
+    *total_w_host = ((int64_t*)c->h_stats.p)[1];
+    if (*total_w_host > capacity) {
+        c->pred_nmax = 0;
         return fail(SMJP_E_NOMEM, "sweep needs %lld grid points, buffers hold %lld", (long long)*total_w_host,
                     (long long)capacity);
+    }
+    c->pred_nmax = c->speculate == 2 ? (*n_max_host * 3 / 4 > 1 ? *n_max_host * 3 / 4 : 1) : predict_nmax(*n_max_host);
+    c->pred_C = C;
+    c->pred_prec = precision;
+    if (spec) {
+        if (!spec_rc && *n_max_host <= pred) {
+            if (c->w_copy_dst) {  // host call: the grid goes home while the FFBS kernel runs
+                CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_fill, 0));
+                CUDA_TRY(cudaMemcpyAsync(c->w_copy_dst, W, (size_t)*total_w_host * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+            }
+            return SMJP_OK;
+        }
+        // the guarded kernels returned without touching anything (or were never launched): launch for the real size
+        ++c->spec_misses;
+        while (c->ffbs_events.size() > events_before) {  // the empty launch is not a kernel time
+            cudaEventDestroy(c->ffbs_events.back().first);
+            cudaEventDestroy(c->ffbs_events.back().second);
+            c->ffbs_events.pop_back();
+        }
+    }
     rc = smjp_candidates_fill_dev(c, C, p_offs, path_v, path_t, path_len, seed, sweep, mode, w_offs, soff, W);
     if (rc) return rc;
     if (c->w_copy_dst) {  // host call: the grid goes home while the FFBS kernel runs

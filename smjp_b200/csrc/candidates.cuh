@@ -46,6 +46,10 @@ struct CandArgs {
     int64_t* w_len;   // per chain grid length (count pass) / w_offs (fill pass)
     const int64_t* w_offs;
     double* W;
+    // speculative fill (smjp_sweep_dev): guard -> {n_max, total} of this sweep on the device; a grid that would
+    // not fit the caller's W (guard_total points) is not written
+    const int64_t* guard;
+    int64_t guard_total;
 };
 
 // number of thinned events of sojourn q of chain c (all targets), optionally emitting them
@@ -161,6 +165,7 @@ __global__ void chain_scan_kernel(int C, const int64_t* len, int64_t* offs, int6
 
 // thread per sojourn: W[base] = T[q]; W[base+1 ..] = sorted thinned events
 __global__ void cand_fill_kernel(const CandArgs a) {
+    if (a.guard && a.guard[1] > a.guard_total) return;
     const int tid = threadIdx.x, B = blockDim.x;
     for (int c = blockIdx.x; c < a.C; c += gridDim.x) {
         const int64_t p0 = a.p_offs[c], w0 = a.w_offs[c];

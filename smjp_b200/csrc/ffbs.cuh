@@ -83,6 +83,11 @@ struct FfbsArgs {
     int use_item;     // K == 3 only: run the item-parallel kernel instead of the thread-per-grid-point one
     int obs_product;  // 0: observations sharing a grid interval are SUMMED (reference); 1: multiplied
     double omega, power, t_end;
+    // speculative launch (smjp_sweep_dev): the kernel was sized for guard_nmax intervals and guard_total grid points
+    // before this sweep's counts reached the host; guard -> {n_max, total} on the device, and a launch whose
+    // geometry turns out too small returns at once (the host relaunches it with the real numbers)
+    const int64_t* guard;
+    int64_t guard_nmax, guard_total;
     int ncap;   // max grid intervals any chain of this launch has (smem carve-up)
     int nslot;  // grid slots per thread: ceil((ncap + 1) / blockDim.x)
 };
@@ -169,25 +174,31 @@ struct Exp2<double> {
     static constexpr int TAB = 256;
     static constexpr int LTAB = 128;
     // Arguments arrive PRE-SCALED by SCALE = 256 (the callers fold it into their constants): xs = 256 x.
-    // 2^x for |xs| < 2^31: n = round(xs) and r = xs - n go through the conversion unit (F2I/I2F, XU pipe) so
-    // that range reduction costs one FP64-pipe instruction; the power of two is added to the exponent field
+    // 2^x for |xs| < 2^31: n = round(xs) and r = xs - n come from the add-a-magic-constant trick (three DADD:
+    // the FP64 pipe has headroom, the F2I/I2F conversions it replaces are long-latency XU instructions -- 1.4 %
+    // of the cfg2 sweep); the power of two is added to the exponent field
     // of the TABLE value before the last fma, so the result needs no repacking; the exponent is clamped to
     // the normal range with two integer min/max (results saturate at 2^-1022 / 2^1023 instead of 0 / inf).
     static constexpr double SCALE = 256.0;
-    __device__ __forceinline__ double operator()(double xs) const {
-        const int n = __double2int_rn(xs);
-        const double r = xs - (double)n;
+    static constexpr double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: the low word of xs + MAGIC is round(xs)
+    template <bool CLAMP>
+    __device__ __forceinline__ double core(double xs) const {
+        const double t = xs + MAGIC;
+        const int n = __double2loint(t);
+        const double r = xs - (t - MAGIC);
         double q = fma(r, c_exp2s[3], c_exp2s[2]);
         q = fma(r, q, c_exp2s[1]);
         q = fma(r, q, c_exp2s[0]);
         const double tv = tab[n & 255];
-        const int e = max(min(n >> 8, 1023), -1022);
+        const int e = CLAMP ? max(min(n >> 8, 1023), -1022) : (n >> 8);
         const double ts = __hiloint2double(__double2hiint(tv) + (e << 20), __double2loint(tv));
         return fma(ts, r * q, ts);
     }
-    // any xs <= 0 including -inf (survival factors): exact 0 below 2^-1022
+    __device__ __forceinline__ double operator()(double xs) const { return core<true>(xs); }
+    // any xs <= 0 including -inf (survival factors): exact 0 below 2^-1022.  No clamp is needed: whatever
+    // the core makes of an argument below the normal range (a wrapped exponent, NaN) is replaced by the select
     __device__ __forceinline__ double neg(double xs) const {
-        const double y = (*this)(fmax(xs, -2048.0 * SCALE));
+        const double y = core<false>(xs);
         return xs < -1022.0 * SCALE ? 0.0 : y;
     }
     __device__ __forceinline__ double log2(double x) const {
@@ -284,6 +295,7 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
     using Acc = typename ScanAcc<Real>::type;
     constexpr int NW = B / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (a.guard && (a.guard[0] > a.guard_nmax || a.guard[1] > a.guard_total)) return;  // mis-speculated geometry
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int ncap = a.ncap, Kobs = a.Kobs;
     const size_t state = (size_t)a.nslot * K * B;

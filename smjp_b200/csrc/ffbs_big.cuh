@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(B) ffbs_big_kernel(const FfbsArgs a) {
     using Acc = typename ScanAcc<Real>::type;
     constexpr int NW = B / 32, BP = B + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (a.guard && (a.guard[0] > a.guard_nmax || a.guard[1] > a.guard_total)) return;  // mis-speculated geometry
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int K = a.K, ncap = a.ncap, Kobs = a.Kobs;
     const size_t state = (size_t)a.nslot * K * B;

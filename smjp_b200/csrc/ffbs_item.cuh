@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(B, MINB) ffbs_item_kernel(const FfbsArgs a) {
     constexpr int NW = B / 32;
     constexpr int JPS = B / K;  // grid points per slot
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (a.guard && (a.guard[0] > a.guard_nmax || a.guard[1] > a.guard_total)) return;  // mis-speculated geometry
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int v = tid % K, jt = tid / K;
     const int ncap = a.ncap, Kobs = a.Kobs;

@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(FFBS_WARPS * 32, (sizeof(Real) == 4 && K <= 3 
     using Acc = typename ScanAcc<Real>::type;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (a.guard && (a.guard[0] > a.guard_nmax || a.guard[1] > a.guard_total)) return;  // mis-speculated geometry
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int ncap = a.ncap, Kobs = a.Kobs, R = a.nslot;  // nslot = ring slots here
     const size_t ring_b = align_up((size_t)R * K * 32 * sizeof(Real), 16);

@@ -204,6 +204,30 @@ def test_non_increasing_grid_is_reported(engine):
         raise_for_status(r["status"])
 
 
+def test_parameter_range_of_the_device_exponent_arithmetic(engine):
+    """shapes whose hazard exponents would leave the integer range of the fp64 2^x are refused up front;
+    wide but valid shapes (k = 0.05 .. 40) over a grid with 1e-9 gaps still match the oracle"""
+    from smjp_b200._lib import EngineError
+    K = 3
+    for bad in (1.0e4, 1.0e-5):
+        shape = np.full((K, K), 1.5); shape[1, 2] = bad
+        with pytest.raises((EngineError, ValueError)):
+            engine.set_model(shape, np.ones((K, K)), 2.0, O.emission_matrix(K), 1.0, 2.0)
+    rng = np.random.default_rng(3)
+    shape = np.array([[0.05, 1.0, 40.0], [3.0, 0.3, 12.0], [25.0, 0.7, 1.9]])
+    scale = rng.uniform(0.8, 2.5, (K, K)); emis = O.emission_matrix(K); t_end = 3.0
+    engine.set_model(shape, scale, 2.0, emis, 1.0, t_end)
+    inner = np.sort(rng.uniform(0.0, t_end, 40))
+    W = np.concatenate([[0.0], inner, inner[::5] + 1e-9, [t_end]]); W.sort()
+    ot = np.sort(rng.uniform(0, t_end, 12)); oy = rng.integers(0, K, 12)
+    u = rng.uniform(size=len(W) - 1)
+    r = engine.ffbs_host([W], ot, oy, uniforms=[u], precision="f64", want_messages=True)
+    ora = O.ffbs(W, ot, oy, shape, scale, 2.0, emis, 1.0, t_end, u)
+    assert r["status"][0] == 0
+    assert np.allclose(r["logZ"][0], ora["logZ"], rtol=1e-9, atol=1e-11)
+    assert np.array_equal(r["V"][0], ora["V"]) and np.array_equal(r["T"][0], ora["T"])
+
+
 def test_fp32_path_mismatches_only_near_cdf_boundaries(engine):
     """fp32 messages differ by ~1e-5, so a sampled index may differ from the fp64 one only when the
     uniform lands within that tolerance of a CDF boundary."""

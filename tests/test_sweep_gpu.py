@@ -235,8 +235,19 @@ def test_sharded_chains_equal_unsharded_bit_for_bit(engine):
     assert np.array_equal(np.concatenate([a[2], b[2]]), full[2]) and np.array_equal(np.concatenate([a[3], b[3]]), full[3])
 
 
-def test_packed_sweep_equals_list_api(engine):
-    """PackedSweep (pinned, no per-chain Python work: the e2e path of bench.py) == sweep_host on lists"""
+@pytest.mark.parametrize("speculate", [1, 2, 0])
+def test_packed_sweep_equals_list_api(engine, speculate):
+    """PackedSweep (pinned, no per-chain Python work: the e2e path of bench.py) == sweep_host on lists; with the
+    normal speculative launches, with forced mis-predictions (2) and with synchronous launches (0)"""
+    from smjp_b200.engine import PackedSweep, sweep_host, ragged_offsets
+    engine.set_option("speculate", speculate)
+    try:
+        _packed_sweep_case(engine)
+    finally:
+        engine.set_option("speculate", 1)
+
+
+def _packed_sweep_case(engine):
     from smjp_b200.engine import PackedSweep, sweep_host, ragged_offsets
     K, t_end = 3, 8.0
     emis = O.emission_matrix(K)
@@ -249,7 +260,7 @@ def test_packed_sweep_equals_list_api(engine):
         V.append(v); T.append(w); Y.append(O.simulate_observations(v, w, obs_t, emis, seed=2, chain=c))
     ps = PackedSweep(engine, C, ragged_offsets([len(obs_t)] * C), np.tile(obs_t, C), np.concatenate(Y), 64)  # tiny: forces regrowth
     ps.set_paths(V, T)
-    for sw in range(3):
+    for sw in range(6):
         r = sweep_host(engine, V, T, [obs_t] * C, Y, seed=5, sweep=sw)
         ps.run(5, sw)
         for c in range(C):
@@ -308,3 +319,41 @@ def test_live_window_exact_and_pruned_modes(engine):
     (Ve, Te), (Vp, Tp) = out[0][1], out[-70][1]
     same = sum(np.array_equal(a, b) and np.array_equal(s, t) for a, b, s, t in zip(Ve, Vp, Te, Tp))
     assert same == C  # dropped mass is below the rounding of the row sums: no draw moves
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_speculative_sweep_launches_change_no_result(engine, precision):
+    """smjp_sweep_dev enqueues a sweep's kernels for the grid size predicted from the previous sweep and repeats the
+    launch when the prediction was too small (option "speculate").  1: the normal prediction (a few per cent of head
+    room); 2: a test setting that predicts 3/4 of the previous size, so that nearly every launch returns at once and
+    is repeated; 0: the synchronous sequence.  All three give the same grids and paths."""
+    from smjp_b200.chains import DeviceChains
+    K, T, C, S = 3, 40.0, 6, 24
+    engine.set_model(SHAPE3, np.ones((K, K)), 2.0, O.emission_matrix(K), 1.0, T)
+    obs_t = np.arange(0.1, T, 0.1)
+    out = {}
+    for spec in (1, 2, 0):
+        engine.set_option("speculate", spec)
+        try:
+            l0 = engine.lib.smjp_ctx_get_stat(engine.ctx, b"spec_launches")
+            m0 = engine.lib.smjp_ctx_get_stat(engine.ctx, b"spec_misses")
+            ch = DeviceChains(engine, C, obs_t).init_prior(np.ones(K) / K, seed=1).simulate_observations(seed=2)
+            ch.init_prior(np.ones(K) / K, seed=3)
+            hist = []
+            for sw in range(S):
+                ch.sweep(seed=4, sweep=sw, precision=precision)
+                hist.append((ch.n_max, ch.total_w))
+            assert int((ch.status != 0).sum().item()) == 0
+            out[spec] = (ch.paths_host(), hist, engine.lib.smjp_ctx_get_stat(engine.ctx, b"spec_launches") - l0,
+                         engine.lib.smjp_ctx_get_stat(engine.ctx, b"spec_misses") - m0)
+        finally:
+            engine.set_option("speculate", 1)
+    (V0, T0), h0, l_off, m_off = out[0]
+    assert l_off == 0 and m_off == 0
+    for spec in (1, 2):
+        (V1, T1), h1, launches, misses = out[spec]
+        assert h1 == h0
+        assert all(np.array_equal(a, b) and np.array_equal(s, t) for a, b, s, t in zip(V1, V0, T1, T0))
+        assert launches == S - 1 and 0 <= misses <= launches
+        if spec == 2:
+            assert misses >= launches // 2, (launches, misses)
