@@ -164,6 +164,11 @@ class DeviceChains:
         return {k: (v[0] if pooled else v) for k, v in out.items()}
 
     # ------------------------------------------------------------------------------------------
+    def record(self, history):
+        """append this sweep's per-chain metrics to a summaries.SummaryHistory (stays on the device)"""
+        history.append(self.time_in_state, self.jumps)
+        return self
+
     def paths_host(self):
         """current trajectories as host lists (V state indices, T times)"""
         p = self.cur

@@ -193,3 +193,51 @@ def test_bench_reference_arm_prints_the_contract_line():
         assert k in d, k
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
+def test_batched_summaries_match_numpy_and_scipy():
+    """smjp_b200.summaries: batched autocorrelation / ESS / KS / moments == the per-series host
+    computations of the drop-in functions (utils.compute_autocorrelation, scipy.stats.ks_2samp, numpy)."""
+    import scipy.special
+    import scipy.stats as sss
+    import torch
+    from smjp_b200 import summaries as S
+    from smjp_b200.utils import compute_autocorrelation
+    rng = np.random.default_rng(0)
+    n, C, K = 400, 3, 2
+    phi = np.array([0.0, 0.5, 0.9, 0.3]).reshape(1, 1, 4)
+    x = np.zeros((n, C, 2 * K))
+    e = rng.normal(size=x.shape)
+    for t in range(1, n):
+        x[t] = phi * x[t - 1] + e[t]
+    xt = torch.from_numpy(x)
+    ac = S.autocorrelation(xt).numpy()
+    for c in range(C):
+        for k in range(2 * K):
+            assert np.allclose(ac[:, c, k], compute_autocorrelation(x[:, c, k]), atol=1e-10)
+    assert np.all(S.autocorrelation(torch.ones(16, 2, dtype=torch.float64)).numpy() == 0.0)  # constant series
+    ess = S.effective_sample_size(torch.from_numpy(x[:, :, :])).numpy()
+    # AR(1): ESS/n -> (1 - phi)/(1 + phi); a 400-step series estimates it within a factor ~2
+    want = n * (1 - phi.ravel()) / (1 + phi.ravel())
+    assert np.all(ess.mean(axis=0) > 0.4 * want) and np.all(ess.mean(axis=0) < 2.5 * want)
+    assert ess[:, 2].mean() < ess[:, 1].mean() < ess[:, 0].mean()
+    # KS: continuous columns and columns with ties (jump counts are small integers)
+    a = np.c_[rng.normal(size=(300, 2)), rng.poisson(3.0, size=(300, 2)).astype(float)]
+    b = np.c_[rng.normal(0.3, 1.0, size=(170, 2)), rng.poisson(3.5, size=(170, 2)).astype(float)]
+    d, p = S.ks_two_sample(torch.from_numpy(a), torch.from_numpy(b))
+    en = np.sqrt(300 * 170 / 470.0)
+    for k in range(4):
+        r = sss.ks_2samp(a[:, k], b[:, k])
+        assert abs(float(d[k]) - r.statistic) < 1e-12
+        assert abs(float(p[k]) - scipy.special.kolmogorov(en * r.statistic)) < 1e-9
+        assert abs(float(p[k]) - r.pvalue) < 0.05
+    # history, thinning, moments
+    h = S.SummaryHistory(C, K, 8, "cpu")
+    for t in range(n):
+        h.append(torch.from_numpy(x[t, :, :K]), torch.from_numpy(np.round(x[t, :, K:]).astype(np.int32)))
+    assert h.n == n and h.buf.shape[0] >= n
+    tm, jm = h.moments(skip=3, burn=10)
+    flat = np.c_[x[10::3, :, :K].reshape(-1, K), np.round(x[10::3, :, K:]).reshape(-1, K)]
+    assert np.allclose(tm["mean"].numpy(), flat[:, :K].mean(axis=0)) and np.allclose(jm["var"].numpy(), flat[:, K:].var(axis=0))
+    assert np.allclose(tm["median"].numpy(), np.median(flat[:, :K], axis=0))
+    assert np.allclose(jm["median"].numpy(), np.median(flat[:, K:], axis=0))

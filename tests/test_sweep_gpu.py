@@ -357,3 +357,47 @@ def test_speculative_sweep_launches_change_no_result(engine, precision):
         assert launches == S - 1 and 0 <= misses <= launches
         if spec == 2:
             assert misses >= launches // 2, (launches, misses)
+
+
+def test_device_summaries_of_posterior_and_prior_chains(engine):
+    """the metric history of posterior chains (and of prior draws) stays on the device and is
+    reduced there; the batched KS of smjp_b200.summaries equals the reference's host rule
+    (mcmc_utils.compute_ks_twosample_time_jump) on the same samples, and ESS / moments are sane."""
+    import torch
+    from smjp_b200 import mcmc_utils, summaries
+    from smjp_b200.chains import DeviceChains
+    K, t_end = 3, 2.0
+    engine.set_model(SHAPE3, np.ones((K, K)), 2.0, O.emission_matrix(K), 1.0, t_end)
+    obs_t = np.arange(0.1, 2.0, 0.1)
+    y = np.array([1, 1, 1, 1, 1, 1, 2, 2, 2, 1, 1, 1, 1, 3, 3, 2, 1, 1, 3]) - 1   # experiments.py:217
+    C, S = 64, 60
+    post = summaries.SummaryHistory(C, K, 16, "cuda:0")
+    prior = summaries.SummaryHistory(C, K, 16, "cuda:0")
+    ch = DeviceChains(engine, C, obs_t).init_prior(np.ones(K) / K, seed=5).set_observations(y)
+    pr = DeviceChains(engine, C, obs_t)
+    states = [1, 2, 3]
+    for sw in range(S):
+        ch.sweep(seed=6, sweep=sw)
+        ch.record(post)
+        pr.init_prior(np.ones(K) / K, seed=100 + sw)
+        V, T = pr.paths_host()
+        tt, jj = mcmc_utils.compute_evaluation_chain_metrics({"V": [v + 1 for v in V], "T": T}, states)
+        prior.append(torch.tensor(np.array([tt[s] for s in states]).T, device="cuda:0"),
+                     torch.tensor(np.array([jj[s] for s in states]).T, device="cuda:0", dtype=torch.int32))
+    assert post.n == S and post.buf.is_cuda
+    skip = 7
+    r = summaries.ks_time_jump(post, prior, skip=skip)
+    a = post.samples(skip).reshape(-1, 2 * K).cpu().numpy()
+    b = prior.samples(skip).reshape(-1, 2 * K).cpu().numpy()
+    host = mcmc_utils.compute_ks_twosample_time_jump({s: a[:, k] for k, s in enumerate(states)}, {s: b[:, k] for k, s in enumerate(states)},
+                                                    {s: a[:, K + k] for k, s in enumerate(states)}, {s: b[:, K + k] for k, s in enumerate(states)},
+                                                    states, skip=1, verbose=False)
+    assert abs(r["ub"] - host["ub"]) < 1e-15
+    assert np.allclose(r["times_ks"][:, 0].cpu().numpy(), host["times_ks"][:, 0], atol=1e-12)
+    assert np.allclose(r["jumps_ks"][:, 0].cpu().numpy(), host["jumps_ks"][:, 0], atol=1e-12)
+    assert np.array_equal(r["reject_times"].cpu().numpy(), host["reject_times"])
+    assert bool(r["reject_times"].any())  # 19 observations do move the posterior away from the prior
+    ess = post.ess().cpu().numpy()
+    assert ess.shape == (C, 2 * K) and np.all(ess > 1.0) and np.all(ess <= S * 4)
+    tm, jm = post.moments(burn=10)
+    assert abs(float(tm["mean"].sum()) - t_end) < 1e-9  # the times in the K states add up to the horizon
