@@ -287,3 +287,29 @@ def test_fp32_chain_that_underflows_is_redone_in_fp64(engine):
     assert np.array_equal(r["V"][0], ref64["V"][0]) and np.array_equal(r["T"][0], ref64["T"][0])  # the fp64 result
     assert np.array_equal(r["time_in_state"][0], ref64["time_in_state"][0])
     assert len(r["V"][1]) >= 2 and r["T"][1][0] == 0.0
+
+
+def test_empty_batch_and_observations_on_grid_points(engine):
+    """C = 0 is a no-op through the C ABI; an observation whose time equals a grid point belongs to BOTH
+    neighbouring intervals, as in the reference (closed interval test, smjp_utils.py:45)."""
+    import ctypes
+    K, t_end = 3, 4.0
+    rng = np.random.default_rng(11)
+    shape = rng.uniform(0.6, 3.0, (K, K)); scale = np.ones((K, K)); emis = O.emission_matrix(K)
+    engine.set_model(shape, scale, 2.0, emis, 1.0, t_end)
+    rc = engine.lib.smjp_ffbs_host(engine.ctx, 0, None, None, None, None, None, None, ctypes.c_uint64(0), 0, 0, None, None,
+                                   None, None, None, None, None, None, None, None)
+    assert rc == 0
+    W = np.array([0.0, 0.5, 1.0, 1.75, 2.5, 3.0, t_end])
+    ot = np.array([0.5, 1.0, 1.2, 2.5, 2.5, 4.0])      # four on grid points (one of them twice), one at t_end
+    oy = np.array([0, 1, 2, 1, 0, 2])
+    u = rng.uniform(size=len(W) - 1)
+    r = engine.ffbs_host([W], ot, oy, uniforms=[u], precision="f64", want_messages=True)
+    ora = O.ffbs(W, ot, oy, shape, scale, 2.0, emis, 1.0, t_end, u)
+    assert r["status"][0] == 0
+    assert np.allclose(r["logZ"][0], ora["logZ"], rtol=1e-10, atol=1e-12)
+    assert np.array_equal(r["aug_idx"][0], ora["samples"])
+    assert np.array_equal(r["V"][0], ora["V"]) and np.array_equal(r["T"][0], ora["T"])
+    # the shared observation really is counted twice: dropping it from either side changes logZ of both intervals
+    r2 = engine.ffbs_host([W], ot[1:], oy[1:], uniforms=[u], precision="f64")
+    assert abs(r2["logZ"][0][0] - r["logZ"][0][0]) > 1e-6 and abs(r2["logZ"][0][1] - r["logZ"][0][1]) > 1e-6
