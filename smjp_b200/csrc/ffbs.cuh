@@ -167,9 +167,15 @@ __constant__ double c_exp2s[4] = {6.931471805599453e-01 / 256.0, 2.4022650695910
 __constant__ double c_log2[6] = {1.442695040888963e+00, -7.213475204444817e-01, 4.808983469629878e-01,
                                  -3.606737602222409e-01, 2.885390081777927e-01, -2.404491734814939e-01};  // (-1)^(i+1)/(i ln2)
 
+// entry i of the 2^(i/256) table in the form Exp2<double>::core wants it: (i << 12) subtracted from the high word
+__device__ __forceinline__ double exp2_table_entry(int i) {
+    const double v = ::exp2((double)i / 256.0);
+    return __hiloint2double(__double2hiint(v) - (int)((unsigned)i << 12), __double2loint(v));
+}
+
 template <>
 struct Exp2<double> {
-    const double* tab;    // [256] 2^(i/256)
+    const double* tab;    // [256] 2^(i/256), high words offset (exp2_table_entry)
     const double2* ltab;  // [128] {1/c_i, -log2(1/c_i)}, c_i = 1 + (i + 1/2)/128
     static constexpr int TAB = 256;
     static constexpr int LTAB = 128;
@@ -177,7 +183,7 @@ struct Exp2<double> {
     // 2^x for |xs| < 2^31: n = round(xs) and r = xs - n come from the add-a-magic-constant trick (three DADD:
     // the FP64 pipe has headroom, the F2I/I2F conversions it replaces are long-latency XU instructions -- 1.4 %
     // of the cfg2 sweep); the power of two is added to the exponent field
-    // of the TABLE value before the last fma, so the result needs no repacking; the exponent is clamped to
+    // of the TABLE value before the last fma, so the result needs no repacking; n is clamped to
     // the normal range with two integer min/max (results saturate at 2^-1022 / 2^1023 instead of 0 / inf).
     static constexpr double SCALE = 256.0;
     static constexpr double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: the low word of xs + MAGIC is round(xs)
@@ -189,9 +195,12 @@ struct Exp2<double> {
         double q = fma(r, c_exp2s[3], c_exp2s[2]);
         q = fma(r, q, c_exp2s[1]);
         q = fma(r, q, c_exp2s[0]);
-        const double tv = tab[n & 255];
-        const int e = CLAMP ? max(min(n >> 8, 1023), -1022) : (n >> 8);
-        const double ts = __hiloint2double(__double2hiint(tv) + (e << 20), __double2loint(tv));
+        // 2^(n/256) = 2^(n >> 8) * tab[n & 255]: the table stores each entry with (i << 12) taken off its high word
+        // (exp2_table_entry), so that adding n << 12 -- the exponent in bits 20.., the index back in bits 12..19 --
+        // gives the scaled value with one shift-add and no separate n >> 8
+        const int nc = CLAMP ? max(min(n, 1023 * 256 + 255), -1022 * 256) : n;
+        const double tv = tab[nc & 255];
+        const double ts = __hiloint2double(__double2hiint(tv) + (int)((unsigned)nc << 12), __double2loint(tv));
         return fma(ts, r * q, ts);
     }
     __device__ __forceinline__ double operator()(double xs) const { return core<true>(xs); }
@@ -328,7 +337,7 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
         skm1[t] = (Real)((k - 1.0) * (double)Exp2<Real>::SCALE);  // exponent arguments carry Exp2's scale
         sc2p[t] = (Real)((a.model[K * K + t] - ::log2(k)) * (double)Exp2<Real>::SCALE);
     }
-    for (int t = tid; t < Exp2<Real>::TAB; t += B) s_tab[t] = ::exp2((double)t / 256.0);
+    for (int t = tid; t < Exp2<Real>::TAB; t += B) s_tab[t] = exp2_table_entry(t);
     for (int t = tid; t < Exp2<Real>::LTAB; t += B) {
         const double rc = 1.0 / (1.0 + ((double)t + 0.5) / 128.0);
         s_ltab[t] = make_double2(rc, -::log2(rc));

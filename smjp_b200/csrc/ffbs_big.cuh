@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(B) ffbs_big_kernel(const FfbsArgs a) {
     __shared__ int s_chain, s_sel, s_flag, s_found;
     __shared__ double s_tab[Exp2<Real>::TAB ? Exp2<Real>::TAB : 1];
     __shared__ double2 s_ltab[Exp2<Real>::LTAB ? Exp2<Real>::LTAB : 1];
-    for (int t = tid; t < Exp2<Real>::TAB; t += B) s_tab[t] = ::exp2((double)t / 256.0);
+    for (int t = tid; t < Exp2<Real>::TAB; t += B) s_tab[t] = exp2_table_entry(t);
     for (int t = tid; t < Exp2<Real>::LTAB; t += B) {
         const double rc = 1.0 / (1.0 + ((double)t + 0.5) / 128.0);
         s_ltab[t] = make_double2(rc, -::log2(rc));

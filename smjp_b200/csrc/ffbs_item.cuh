@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(B, MINB) ffbs_item_kernel(const FfbsArgs a) {
         skm1[t] = (Real)((k - 1.0) * (double)Exp2<Real>::SCALE);
         sc2p[t] = (Real)((a.model[K * K + t] - ::log2(k)) * (double)Exp2<Real>::SCALE);
     }
-    for (int t = tid; t < Exp2<Real>::TAB; t += B) s_tab[t] = ::exp2((double)t / 256.0);
+    for (int t = tid; t < Exp2<Real>::TAB; t += B) s_tab[t] = exp2_table_entry(t);
     for (int t = tid; t < Exp2<Real>::LTAB; t += B) {
         const double rc = 1.0 / (1.0 + ((double)t + 0.5) / 128.0);
         s_ltab[t] = make_double2(rc, -::log2(rc));

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(FFBS_WARPS * 32, (sizeof(Real) == 4 && K <= 3 
     __shared__ double s_tab[Exp2<Real>::TAB ? Exp2<Real>::TAB : 1];
     __shared__ double2 s_ltab[Exp2<Real>::LTAB ? Exp2<Real>::LTAB : 1];
     __shared__ Real s_par[3 * K * K];  // (k-1) SCALE, c2p SCALE for the backward's run-time target index
-    for (int t = threadIdx.x; t < Exp2<Real>::TAB; t += blockDim.x) s_tab[t] = ::exp2((double)t / 256.0);
+    for (int t = threadIdx.x; t < Exp2<Real>::TAB; t += blockDim.x) s_tab[t] = exp2_table_entry(t);
     for (int t = threadIdx.x; t < Exp2<Real>::LTAB; t += blockDim.x) {
         const double rc = 1.0 / (1.0 + ((double)t + 0.5) / 128.0);
         s_ltab[t] = make_double2(rc, -::log2(rc));

@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(B) pf_kernel(const PfArgs a) {
     const int p_lo = min(rank * Np, N), p_hi = min(p_lo + Np, N);
     const int tiles = (p_hi - p_lo + B - 1) / B, nwt = tiles * NW;
     const double* emis = a.model + 2 * K * K;
-    for (int t = tid; t < Exp2<double>::TAB; t += B) s_tab[t] = ::exp2((double)t / 256.0);
+    for (int t = tid; t < Exp2<double>::TAB; t += B) s_tab[t] = exp2_table_entry(t);
     for (int t = tid; t < Exp2<double>::LTAB; t += B) {
         const double rc = 1.0 / (1.0 + ((double)t + 0.5) / 128.0);
         s_ltab[t] = make_double2(rc, -::log2(rc));
