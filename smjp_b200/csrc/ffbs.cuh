@@ -522,10 +522,6 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
                     Zp += an;
                 }
             };
-#ifndef SMJP_PAIR_UNROLL
-#define SMJP_PAIR_UNROLL 1
-#endif
-            constexpr int PAIR_UNROLL = SMJP_PAIR_UNROLL;
             // ONE copy of the pair code serves every slot (the kernel is 90 KB of SASS; a second, diag-free copy
             // for the full slots cost more in instruction fetch than its two selects per state save): the
             // oldest slot masks the threads below the window start, the newest those above the new grid point
