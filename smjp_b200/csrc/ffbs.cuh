@@ -323,8 +323,8 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
     int* soj = (int*)st_h;       // [2][ncap+1]: state, grid index of each sojourn (backward pass)
 
     __shared__ int s_chain;
-    __shared__ int s_sel;
-    __shared__ int s_found;
+    __shared__ int s_sel, s_selv;
+    __shared__ int s_found[2];  // an owner claimed the draw; double-buffered by draw parity (reset one draw ahead)
     __shared__ int s_jmin[2 * NW];  // per-warp smallest live grid point of the oldest slot, double-buffered
     __shared__ int s_flag;
     __shared__ double s_tab[Exp2<Real>::TAB ? Exp2<Real>::TAB : 1];
@@ -596,10 +596,10 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
                 for (int v = 0; v < K; ++v) row_last[(int64_t)v * n + j] = p[v * B] * invZ_prev;
             }
         }
+        if (tid == 0) s_found[0] = s_found[1] = 0;
         __syncthreads();
 
         // =========================== backward ===========================
-        Real* wbuf = st_a;  // [K][len] contiguous: the reference's state-major order a = v*len + j
         int cur = n - 1, vplus = -1, cnt = 0, u_hi = -1;
         while (true) {
             const int len = cur + 1;
@@ -625,102 +625,151 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
                                            a.chain_base + (uint32_t)c);
                 u_hi = cur;
             }
-            // weights over the live window, state-major: wbuf[v * wl + (j - lo)]
-            if (vplus < 0) {  // a_{n-1} ~ alpha_{n-1}  (fast_hmm.py:124-125)
-                for (int j = lo + tid; j < len; j += B) {
+            // Categorical draw over the flat vector w[v * wl + (j - lo)] (state-major, the reference's order) without
+            // materialising it: every thread owns a contiguous run of grid points, computes the K weights of each on
+            // the fly (one log2 per grid point, shared by the states), and the prefix sums are K per-state scans --
+            // one barrier for the warp totals, one for the verdict; the owner recomputes its few weights to find the
+            // entry.  (An earlier version wrote the weights to shared memory and scanned thread-chunks of the flat
+            // vector: a third barrier and a store/load round trip per entry, 8 % of the kernel's stall samples.)
+            const int mode = vplus < 0 ? 0 : ((!exporting && cur < i_final) ? 1 : 2);
+            const double wnb = Wd[cur + 1];
+            // weights of grid point j for all states (mode 0: a_{n-1} ~ alpha_{n-1}, fast_hmm.py:124-125; mode 1: the
+            // scratch row holds g, w = g_cur(v,j) A_{v,vplus}(tau); mode 2: w = alpha_cur(v,j) A_{v,vplus}/A_v,
+            // fast_hmm.py:153-171)
+            auto weights = [&](int j, Real (&w)[K]) {
+                Real rv[K];
 #pragma unroll
-                    for (int v = 0; v < K; ++v) wbuf[v * wl + (j - lo)] = row[(int64_t)v * len + j];
+                for (int v = 0; v < K; ++v) rv[v] = row[(int64_t)v * len + j];
+                if (mode == 0) {
+#pragma unroll
+                    for (int v = 0; v < K; ++v) w[v] = rv[v];
+                    return;
                 }
-            } else if (!exporting && cur < i_final) {  // scratch row holds g: w = g_cur(v,j) A_{v,vplus}(tau)
-                const double wn = Wd[cur + 1];
-#pragma unroll 2
-                for (int j = lo + tid; j < len; j += B) {
-                    Real rv[K];
+                const Real L2 = ex2.log2((Real)(wnb - Wd[j]));
+                if (mode == 1) {
 #pragma unroll
-                    for (int v = 0; v < K; ++v) rv[v] = row[(int64_t)v * len + j];
-                    const Real L2 = ex2.log2((Real)(wn - Wd[j]));
-#pragma unroll
-                    for (int v = 0; v < K; ++v)
-                        wbuf[v * wl + (j - lo)] = rv[v] * ex2(skm1[v * K + vplus] * L2 - sc2p[v * K + vplus]);
+                    for (int v = 0; v < K; ++v) w[v] = rv[v] * ex2(skm1[v * K + vplus] * L2 - sc2p[v * K + vplus]);
+                    return;
                 }
-            } else {  // jump at W[cur+1] into vplus: w = alpha_cur(v,j) A_{v,vplus}/A_v  (fast_hmm.py:153-171)
-                const double wn = Wd[cur + 1];
-                for (int j = lo + tid; j < len; j += B) {
-                    const Real L2 = ex2.log2((Real)(wn - Wd[j]));
 #pragma unroll
-                    for (int v = 0; v < K; ++v) {
-                        Real dsum = 0, hto = 0;
+                for (int v = 0; v < K; ++v) {
+                    Real dsum = 0, hto = 0;
 #pragma unroll
-                        for (int s = 0; s < K; ++s) {
-                            const Real kE = ex2(skm1[v * K + s] * L2 - sc2p[v * K + s]);
-                            dsum += kE;
-                            hto = (s == vplus) ? kE : hto;
-                        }
-                        const Real r = dsum > (Real)0 ? hto * M::rcp(dsum) : (Real)0;
-                        wbuf[v * wl + (j - lo)] = row[(int64_t)v * len + j] * r;
+                    for (int s2 = 0; s2 < K; ++s2) {
+                        const Real kE = ex2(skm1[v * K + s2] * L2 - sc2p[v * K + s2]);
+                        dsum += kE;
+                        hto = (s2 == vplus) ? kE : hto;
                     }
+                    const Real r = dsum > (Real)0 ? hto * M::rcp(dsum) : (Real)0;
+                    w[v] = rv[v] * r;
                 }
+            };
+            const int q = (wl + B - 1) / B;
+            const int jb = min(lo + tid * q, len), je = min(jb + q, len);  // this thread's grid points
+            Acc loc[K];
+#pragma unroll
+            for (int v = 0; v < K; ++v) loc[v] = 0;
+            for (int j = jb; j < je; ++j) {
+                Real w[K];
+                weights(j, w);
+#pragma unroll
+                for (int v = 0; v < K; ++v) loc[v] += (Acc)w[v];
+            }
+            Acc incl[K];
+#pragma unroll
+            for (int v = 0; v < K; ++v) incl[v] = warp_inclusive_scan(loc[v], lane);
+            Acc* wsum = (Acc*)red;  // [NW][K] warp totals per state (the forward pass's reduction scratch is free now)
+            if (lane == 31) {
+#pragma unroll
+                for (int v = 0; v < K; ++v) wsum[wid * K + v] = incl[v];
             }
             __syncthreads();
-            // inclusive scan over the flat weight vector, contiguous chunk per thread
-            const int L = K * wl;
-            const int q = (L + B - 1) / B;
-            const int beg = min(tid * q, L), end = min(beg + q, L);
-            Acc loc = 0;
-            for (int t = beg; t < end; ++t) loc += (Acc)wbuf[t];
-            Acc incl = warp_inclusive_scan(loc, lane);
-            if (lane == 31) scan_s[wid + 1] = incl;
-            if (tid == 0) { scan_s[0] = 0; s_found = 0; }
-            __syncthreads();
-            Acc off = 0;
-            for (int w = 1; w <= wid; ++w) off += scan_s[w];
-            incl += off;
-            Acc excl = __shfl_up_sync(0xffffffffu, incl, 1);
-            if (lane == 0) excl = off;
-            Acc total = 0;
+            if (tid == 0) s_found[(cnt + 1) & 1] = 0;  // the next draw's flag: nobody touches it during this draw
+            // state totals and the state the target falls into
+            Acc cum[K + 1];
+            cum[0] = 0;
 #pragma unroll
-            for (int w = 1; w <= NW; ++w) total += scan_s[w];
+            for (int v = 0; v < K; ++v) {
+                Acc tv = 0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) tv += wsum[w * K + v];
+                cum[v + 1] = cum[v] + tv;
+            }
+            const Acc total = cum[K];
             if (!(total > (Acc)0) || !(total < (Acc)INFINITY)) {
                 degenerate = true;
                 break;
             }
             const double u = a.uniforms ? a.uniforms[w0 + cur] : ubuf[u_hi - cur];
             const Acc target = (Acc)u * total;
-            // owner: excl <= target < incl (the intervals partition [0,total) exactly)
-            const bool has = end > beg && incl > excl;  // empty chunks never own a draw (see below)
-            if (has && target >= excl && target < incl) {
-                Acc acc = excl;
-                int sel = -1, lastpos = beg;
-                for (int t = beg; t < end; ++t) {
-                    const Acc wv = (Acc)wbuf[t];
-                    if (wv > (Acc)0) lastpos = t;
-                    acc += wv;
-                    if (acc > target) { sel = t; break; }
+            int vs = -1;  // first state whose cumulative total exceeds the target (none: u * total rounded up to total)
+#pragma unroll
+            for (int v = K - 1; v >= 0; --v) vs = (target < cum[v + 1]) ? v : vs;
+            if (vs >= 0) {
+                Acc my_loc = 0, my_incl = 0, off = 0;
+#pragma unroll
+                for (int v = 0; v < K; ++v) {
+                    if (v == vs) {
+                        my_loc = loc[v];
+                        my_incl = incl[v];
+                        off = cum[v];
+                    }
                 }
-                s_sel = sel >= 0 ? sel : lastpos;
-                s_found = 1;
+                for (int w = 0; w < wid; ++w) off += wsum[w * K + vs];
+                my_incl += off;
+                Acc excl = __shfl_up_sync(0xffffffffu, my_incl, 1);
+                if (lane == 0) excl = off;
+                // owner: excl <= target < incl (the intervals partition [cum[vs], cum[vs+1]) exactly); runs without
+                // mass never own a draw (a shuffle scan over zero-padded lanes is not monotone to the last bit)
+                const bool has = je > jb && my_incl > excl && my_loc > (Acc)0;
+                if (has && target >= excl && target < my_incl) {
+                    Acc acc = excl;
+                    int sel = -1, lastpos = jb;
+                    for (int j = jb; j < je; ++j) {
+                        Real w[K];
+                        weights(j, w);
+                        Acc wv = 0;
+#pragma unroll
+                        for (int v = 0; v < K; ++v) wv = (v == vs) ? (Acc)w[v] : wv;
+                        if (wv > (Acc)0) lastpos = j;
+                        acc += wv;
+                        if (acc > target) { sel = j; break; }
+                    }
+                    s_sel = sel >= 0 ? sel : lastpos;
+                    s_selv = vs;
+                    s_found[cnt & 1] = 1;
+                }
             }
             __syncthreads();
-            // No owner: u*total rounded up to the total, or the target fell between the inclusive value of the
-            // last thread that holds weights and the warp total (a shuffle scan over zero-padded lanes is not
-            // monotone to the last bit -- in fp32 that happens about once per 1e7 draws).  The last thread with
-            // mass then takes its last positive entry, as the reference's inverse CDF does at u -> 1.
-            if (!s_found) {  // block-uniform
-                if (has) atomicMax(&s_flag, tid + 1);
+            // No owner: u*total rounded up to the total, or the target fell between the inclusive value of the last
+            // thread that holds weights and the warp total (in fp32 that happens about once per 1e7 draws).  The last
+            // entry with mass in the flat order -- largest state, then largest grid point -- takes the draw, as the
+            // reference's inverse CDF does at u -> 1.
+            if (!s_found[cnt & 1]) {  // block-uniform
+                int key = 0;
+#pragma unroll
+                for (int v = 0; v < K; ++v) key = (je > jb && loc[v] > (Acc)0) ? v * B + tid + 1 : key;
+                if (key) atomicMax(&s_flag, key);
                 __syncthreads();
-                if (tid + 1 == s_flag) {
-                    int lastpos = beg;
-                    for (int t = beg; t < end; ++t) if ((Acc)wbuf[t] > (Acc)0) lastpos = t;
+                if (key && key == s_flag) {
+                    const int vf = (key - 1) / B;
+                    int lastpos = jb;
+                    for (int j = jb; j < je; ++j) {
+                        Real w[K];
+                        weights(j, w);
+                        Acc wv = 0;
+#pragma unroll
+                        for (int v = 0; v < K; ++v) wv = (v == vf) ? (Acc)w[v] : wv;
+                        if (wv > (Acc)0) lastpos = j;
+                    }
                     s_sel = lastpos;
+                    s_selv = vf;
                 }
                 __syncthreads();
                 if (tid == 0) s_flag = 0;
             }
-            const int idx = s_sel;
-            int v = 0;  // idx / wl without the integer division (v < K)
-#pragma unroll
-            for (int u = 1; u < K; ++u) v += idx >= u * wl;
-            const int j = lo + idx - v * wl;
+            const int j = s_sel;
+            const int v = s_selv;
             if (a.aug_idx)
                 for (int t = j + tid; t <= cur; t += B) a.aug_idx[w0 + t] = v * n + j;
             if (tid == 0) {
