@@ -600,6 +600,7 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
         __syncthreads();
 
         // =========================== backward ===========================
+        Real* wbuf = st_a;  // [K][wl] weights of the current draw, each entry written and read by its own thread only
         int cur = n - 1, vplus = -1, cnt = 0, u_hi = -1;
         while (true) {
             const int len = cur + 1;
@@ -628,8 +629,8 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
             // Categorical draw over the flat vector w[v * wl + (j - lo)] (state-major, the reference's order) without
             // materialising it: every thread owns a contiguous run of grid points, computes the K weights of each on
             // the fly (one log2 per grid point, shared by the states), and the prefix sums are K per-state scans --
-            // one barrier for the warp totals, one for the verdict; the owner recomputes its few weights to find the
-            // entry.  (An earlier version wrote the weights to shared memory and scanned thread-chunks of the flat
+            // one barrier for the warp totals, one for the verdict; the owner walks its own few weights (parked in
+            // shared memory by itself: no other thread reads them) to find the entry.  (An earlier version wrote the weights to shared memory and scanned thread-chunks of the flat
             // vector: a third barrier and a store/load round trip per entry, 8 % of the kernel's stall samples.)
             const int mode = vplus < 0 ? 0 : ((!exporting && cur < i_final) ? 1 : 2);
             const double wnb = Wd[cur + 1];
@@ -673,7 +674,10 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
                 Real w[K];
                 weights(j, w);
 #pragma unroll
-                for (int v = 0; v < K; ++v) loc[v] += (Acc)w[v];
+                for (int v = 0; v < K; ++v) {
+                    loc[v] += (Acc)w[v];
+                    wbuf[v * wl + (j - lo)] = w[v];  // kept for this thread's own walk, should it own the draw
+                }
             }
             Acc incl[K];
 #pragma unroll
@@ -726,11 +730,7 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
                     Acc acc = excl;
                     int sel = -1, lastpos = jb;
                     for (int j = jb; j < je; ++j) {
-                        Real w[K];
-                        weights(j, w);
-                        Acc wv = 0;
-#pragma unroll
-                        for (int v = 0; v < K; ++v) wv = (v == vs) ? (Acc)w[v] : wv;
+                        const Acc wv = (Acc)wbuf[vs * wl + (j - lo)];
                         if (wv > (Acc)0) lastpos = j;
                         acc += wv;
                         if (acc > target) { sel = j; break; }
@@ -754,14 +754,8 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
                 if (key && key == s_flag) {
                     const int vf = (key - 1) / B;
                     int lastpos = jb;
-                    for (int j = jb; j < je; ++j) {
-                        Real w[K];
-                        weights(j, w);
-                        Acc wv = 0;
-#pragma unroll
-                        for (int v = 0; v < K; ++v) wv = (v == vf) ? (Acc)w[v] : wv;
-                        if (wv > (Acc)0) lastpos = j;
-                    }
+                    for (int j = jb; j < je; ++j)
+                        if ((Acc)wbuf[vf * wl + (j - lo)] > (Acc)0) lastpos = j;
                     s_sel = lastpos;
                     s_selv = vf;
                 }
