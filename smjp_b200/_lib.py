@@ -72,7 +72,7 @@ class EngineError(RuntimeError):
 
 def build(verbose=False):
     """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    r = subprocess.run(["make", "-C", CSRC], capture_output=True, text=True)
+    r = subprocess.run(["make", "-j8", "-C", CSRC], capture_output=True, text=True)
     if verbose or r.returncode:
         print(r.stdout[-4000:])
         print(r.stderr[-4000:])
