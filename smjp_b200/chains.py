@@ -122,13 +122,15 @@ class DeviceChains:
             if self.soff is None or self.soff.numel() < cur["cap"]:
                 self.soff = t.zeros(cur["cap"], dtype=t.int32, device=self.dev)
             nx = self.nxt
+            # the new paths and the grid share one bound: a recycled path buffer may be larger than W
+            cap_call = min(int(nx["cap"]), int(self.W.numel()))
             rc = (self.eng.lib.smjp_sweep_dense_dev if dense else self.eng.lib.smjp_sweep_dev)(
                 self.eng.ctx, self.C, _ptr(cur["offs"]), _ptr(cur["v"]), _ptr(cur["t"]), _ptr(cur["len"]),
                 _ptr(self.obs_offs), _ptr(self.obs_t), _ptr(self.obs_y), int(seed) & 0xFFFFFFFFFFFFFFFF, int(sweep),
-                CAND_MODES[mode], PRECISIONS[precision], int(nx["cap"]), _ptr(nx["offs"]), _ptr(self.soff),
+                CAND_MODES[mode], PRECISIONS[precision], cap_call, _ptr(nx["offs"]), _ptr(self.soff),
                 _ptr(self.W), _ptr(nx["v"]), _ptr(nx["t"]), _ptr(nx["len"]), _ptr(self.time_in_state),
                 _ptr(self.jumps), _ptr(self.status), ctypes.byref(n_max), ctypes.byref(total))
-            if rc == -3 and total.value > nx["cap"]:  # buffers too small for this sweep's grids: regrow, redo
+            if rc == -3 and total.value > cap_call:  # buffers too small for this sweep's grids: regrow, redo
                 self.cap = int(total.value * 1.5) + 1024
                 self.nxt = None
                 self.W = None

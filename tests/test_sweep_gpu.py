@@ -401,3 +401,28 @@ def test_device_summaries_of_posterior_and_prior_chains(engine):
     assert ess.shape == (C, 2 * K) and np.all(ess > 1.0) and np.all(ess <= S * 4)
     tm, jm = post.moments(burn=10)
     assert abs(float(tm["mean"].sum()) - t_end) < 1e-9  # the times in the K states add up to the horizon
+
+
+def test_device_chains_regrow_when_the_grid_outgrows_its_buffer(engine):
+    """Short prior paths (few entries per chain) leave DeviceChains with a small grid buffer next to a larger,
+    recycled path buffer; a model whose sweeps produce long grids must trigger the regrow-and-redo path instead of
+    writing past the grid buffer.  Same paths as chains that start with generous buffers."""
+    from smjp_b200.chains import DeviceChains
+    K, t_end, C = 3, 30.0, 200
+    shape = np.full((K, K), 1.0); scale = np.full((K, K), 40.0)   # rare jumps: prior paths of ~2 entries
+    engine.set_model(shape, scale, 25.0, O.emission_matrix(K), 1.0, t_end)   # large Omega: many candidates per sojourn
+    obs_t = np.arange(0.5, t_end, 0.5)
+    out = []
+    for generous in (False, True):
+        ch = DeviceChains(engine, C, obs_t).init_prior(np.ones(K) / K, seed=1).simulate_observations(seed=2)
+        if generous:
+            ch.cap = 1 << 20
+        for sw in range(4):
+            ch.sweep(seed=3, sweep=sw)
+        assert int((ch.status != 0).sum().item()) == 0
+        assert ch.W.numel() >= ch.total_w
+        out.append((ch.paths_host(), ch.total_w))
+    (Va, Ta), ta = out[0]
+    (Vb, Tb), tb = out[1]
+    assert ta == tb and ta > 9 * 3 * C  # the grids really are longer than three times the live path entries
+    assert all(np.array_equal(a, b) and np.array_equal(s, t) for a, b, s, t in zip(Va, Vb, Ta, Tb))
