@@ -205,7 +205,8 @@ int smjp_candidates_host(smjp_ctx_t* ctx, int C, const int64_t* p_offs, const in
  * DEVICE buffers.  The new grids/paths use windows w_offs (written here); W, path_v_out and
  * path_t_out must have room for `capacity` elements, else SMJP_E_NOMEM is returned with the required
  * size in *total_w_host (nothing else written).  Backward uniforms come from the Philox stream
- * (seed, sweep, chain).  Synchronises once (sizes), then enqueues the FFBS kernel asynchronously.
+ * (seed, sweep, chain).  Returns when the two sizes are on the host; the FFBS kernel is then still running (or,
+ * with option "speculate", already enqueued before the sizes arrived): outputs are valid in stream order.
  */
 int smjp_sweep_dev(smjp_ctx_t* ctx, int C, const int64_t* p_offs, const int32_t* path_v,
                    const double* path_t, const int32_t* path_len, const int64_t* obs_offs,
