@@ -39,12 +39,36 @@ def workload_name(chains):
     return "cfg2: %d chains/GPU, K=3 Weibull sMJP (experiments.py:172-174), T=100, Omega=2, D=999 obs" % chains
 
 
-def algorithmic_bytes(n_per_chain, D, esz):
+def algorithmic_bytes(n_per_chain, D, esz, k=K):
     """per chain-sweep 2*sizeof(real) per live state-step (message written once by the
     forward pass, read once by the backward pass) + 40 B per grid step (W, uniform, index, logZ, path)
-    + 12 B per observation."""
+    + 12 B per observation.  NOMINAL count: every state (v, W[j]), j <= i, of every row i."""
     n = n_per_chain.astype(np.float64)
-    return float(np.sum(2 * esz * K * n * (n + 1) / 2 + 40 * n + 12 * D))
+    return float(np.sum(2 * esz * k * n * (n + 1) / 2 + 40 * n + 12 * D))
+
+
+def retained_bytes(live_pairs, n_per_chain, D, esz, k=K):
+    """SURVEY.md 8(d) with a live window: "the count is the states actually retained" -- the same formula with the
+    K * (grid pairs the kernels processed) in place of K n(n+1)/2 (device counter ffbs_live_pairs)."""
+    n = n_per_chain.astype(np.float64)
+    return float(2 * esz * k * live_pairs + np.sum(40 * n + 12 * D))
+
+
+def roofline_block(kernel, retained, nominal, launches, kernel_ms, peak, peak_src, live_fraction, traffic, **extra):
+    """`achieved` / `frac`: RETAINED algorithmic bytes per launch / the kernel's average launch duration (CUDA events
+    on the launching stream) / measured HBM peak.  The nominal K n(n+1)/2 figure (what an engine without the live
+    window would have to move) is kept beside it under `nominal_*`; it is not a bandwidth."""
+    launches = max(launches, 1)
+    k_s = kernel_ms / launches / 1e3
+    ach = retained / launches / k_s / 1e9
+    nom = nominal / launches / k_s / 1e9
+    r = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+         "peak_source": peak_src, "kernel": kernel, "kernel_ms_avg": kernel_ms / launches,
+         "algorithmic_bytes_per_launch": retained / launches, "live_fraction": live_fraction,
+         "nominal_bytes_per_launch": nominal / launches, "nominal_achieved": nom, "nominal_frac": nom / peak,
+         "traffic_over_algorithmic": (traffic / (retained / launches)) if traffic else None}
+    r.update(extra)
+    return r
 
 
 # ------------------------------------------------------------------------------------------------
@@ -280,7 +304,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ss = gs = 0.0
-    alg_bytes = 0.0
+    alg_bytes = tail_bytes = 0.0
     n_snap = []
     barrier()
     step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)] if os.environ.get("SMJP_BENCH_DEBUG") else None
@@ -307,6 +331,7 @@ def run_ours(args):
         ss += float(np.sum(K * n.astype(np.float64) * (n + 1) / 2))
         gs += float(n.sum())
         alg_bytes += algorithmic_bytes(n, D, esz)
+        tail_bytes += float(np.sum(40.0 * n + 12 * D))
     status_bad = int((ch.status != 0).sum().item())
 
     # ---- end to end through the host-buffer C-ABI call (smjp_sweep_host) ----
@@ -365,7 +390,8 @@ def run_ours(args):
     value = ss / secs
     peak, peak_src = measured_peak()
     k_avg_s = (k_ms / max(k_cnt, 1)) / 1e3  # rank 0's FFBS kernel, average launch
-    achieved = (alg_bytes / max(k_cnt, 1)) / k_avg_s / 1e9
+    live_frac = live_pairs / max(ss_rank0 / K, 1.0)
+    ret_bytes = 2 * esz * K * live_pairs + tail_bytes
     traffic = ncu_traffic()
 
     def compute_ceiling(precision, pairs_per_launch, kernel_s, sm_mhz):
@@ -396,20 +422,15 @@ def run_ours(args):
         "chain_sweeps_per_sec": C * world * args.steps / secs, "grid_steps_per_sec": gs / secs,
         "gpu_launches": int(launches), "failed_chains": status_bad,
         "clocks": clk,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ((traffic or {}).get(prec) or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
-                     "kernel": "ffbs_kernel<%s,3>" % ("double" if prec == "f64" else "float"),
-                     "kernel_ms_avg": k_ms / max(k_cnt, 1), "grid": eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_grid"),
-                     "threads": eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_threads"),
-                     "smem": eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_smem"), "kernel_share_of_step": k_ms / ms,
-                     "algorithmic_bytes_per_launch": alg_bytes / max(k_cnt, 1),
-                     # the kernel skips grid points whose states have underflowed to EXACT zeros (results unchanged
-                     # to the last bit): `achieved` counts the nominal K n(n+1)/2 states of SURVEY 8(d), the two keys
-                     # below say how many of them were actually touched and what that means in bytes per second
-                     "live_fraction": live_pairs / max(ss_rank0 / K, 1.0),
-                     "achieved_live": achieved * live_pairs / max(ss_rank0 / K, 1.0),
-                     "window": "exact (zeros only)" if args.window_log2 == 0 else "pruned below 2^%d of the row sum" % args.window_log2,
-                     "compute": compute_ceiling(prec, ss_rank0 / K / max(k_cnt, 1), k_avg_s, clk.get("sm_mhz"))},
+        "roofline": roofline_block(
+            "ffbs_kernel<%s,3>" % ("double" if prec == "f64" else "float"), ret_bytes, alg_bytes, k_cnt, k_ms, peak, peak_src,
+            live_frac, ((traffic or {}).get(prec) or {}).get("dram_bytes_per_launch"),
+            grid=eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_grid"), threads=eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_threads"),
+            smem=eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_smem"), kernel_share_of_step=k_ms / ms,
+            # the kernel skips grid points whose states have underflowed to EXACT zeros (results unchanged to the
+            # last bit): `achieved`/`frac` count the states actually retained, `nominal_*` all K n(n+1)/2
+            window="exact (zeros only)" if args.window_log2 == 0 else "pruned below 2^%d of the row sum" % args.window_log2,
+            compute=compute_ceiling(prec, ss_rank0 / K / max(k_cnt, 1), k_avg_s, clk.get("sm_mhz"))),
         # sweeps whose kernels were enqueued for the grid size predicted from the previous sweep, before their own
         # counts reached the host, and how many of those had to be launched again (rank 0)
         "speculative_launches": {"launches": spec[0], "repeated": spec[1]},
@@ -425,6 +446,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         eng.set_option("time_kernels", 1)
         eng.kernel_time()
+        eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_live_pairs")
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         snaps = []
         a0.record()
@@ -440,22 +462,22 @@ def run_ours(args):
         if dbg:
             print("f32 per-step ms:", [round(a0.elapsed_time(e), 2) for e in dbg], file=sys.stderr)
         k32, c32 = eng.kernel_time()
+        lp32 = float(eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_live_pairs"))
         eng.set_option("time_kernels", 0)
-        ss32 = b32 = 0.0
+        ss32 = b32 = r32 = 0.0
         for offs in snaps:
             n = (offs[1:] - offs[:-1] - 1).cpu().numpy()
             ss32 += float(np.sum(K * n.astype(np.float64) * (n + 1) / 2))
             b32 += algorithmic_bytes(n, D, 4)
+            r32 += float(np.sum(40.0 * n + 12 * D))
+        r32 += 2 * 4 * K * lp32
         line["f32"] = {"value": ss32 / (ms32 / 1e3), "unit": UNIT, "ms_per_step": ms32 / args.steps,
                        "chain_sweeps_per_sec": C * args.steps / (ms32 / 1e3),
                        "failed_chains": int((ch.status != 0).sum().item()),
-                       "roofline": {"bound": "hbm", "achieved": (b32 / max(c32, 1)) / (k32 / max(c32, 1) / 1e3) / 1e9,
-                                    "peak": peak, "unit": "GB/s",
-                                    "frac": (b32 / max(c32, 1)) / (k32 / max(c32, 1) / 1e3) / 1e9 / peak,
-                                    "traffic": ((traffic or {}).get("f32") or {}).get("dram_bytes_per_launch"),
-                                    "kernel": "ffbs_warp_kernel<float,3> (auto) / ffbs_kernel<float,3>", "kernel_ms_avg": k32 / max(c32, 1),
-                                    "compute": compute_ceiling("f32", ss32 / K / max(c32, 1), k32 / max(c32, 1) / 1e3,
-                                                               clk.get("sm_mhz"))},
+                       "roofline": roofline_block(
+                           "ffbs_warp_kernel<float,3> (auto) / ffbs_kernel<float,3>", r32, b32, c32, k32, peak, peak_src,
+                           K * lp32 / max(ss32, 1.0), ((traffic or {}).get("f32") or {}).get("dram_bytes_per_launch"),
+                           compute=compute_ceiling("f32", ss32 / K / max(c32, 1), k32 / max(c32, 1) / 1e3, clk.get("sm_mhz"))),
                        "tolerance": "messages within 1e-4 of the reference (tests/test_ffbs_gpu.py)"}
     if world == 1 and prec == "f64" and not args.no_alt and args.window_log2 == 0:
         # the same fp64 workload with live-window PRUNING (SURVEY.md 7 hard part 2): states below 2^-70 of their

@@ -604,6 +604,9 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
         }
         if (rescue_smem > c->smem_optin) rescue = false;
     }
+    // the ring kernel hands chains whose window outgrows the ring to the rescue pass: without one (the full-size fp64
+    // kernel does not fit) it must not run -- the block kernel of this precision handles every chain itself
+    if (use_warp && !rescue) use_warp = false;
     if (smem > c->smem_optin)
         return fail(SMJP_E_UNSUPPORTED,
                     "grid with %lld intervals x K=%d needs %zu B of shared memory (> %zu): "
@@ -827,6 +830,8 @@ int smjp_ffbs_host(smjp_ctx_t* c, int C, const int64_t* w_offs, const double* W,
         if (len - 1 > n_max) n_max = len - 1;
     }
     if (total_o > 0 && (!obs_t || !obs_y)) return fail(SMJP_E_INVALID, "observations missing");
+    for (int64_t d = 0; d < total_o; ++d)  // the kernels index emis[v * Kobs + y] unchecked
+        if (obs_y[d] < 0 || obs_y[d] >= c->Kobs) return fail(SMJP_E_INVALID, "observation symbol outside [0,Kobs)");
     const size_t esz = precision == SMJP_F64 ? 8 : 4;
     const int64_t total_msg = messages ? msg_offs[C] : 0;
 

@@ -514,8 +514,13 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
                     // scratch rows hold g = alpha / (Omega A_v) of row i itself (row i starts K*i past row i-1):
                     // the backward jump weight alpha A_{v,v+} / (Omega A_v) is then g A_{v,v+}, one hazard per entry
                     if (!exporting) rowg[v * (i + 1)] = g;
+                    Real gj = g;
+                    // a final row (right end = t_end, smjp_utils.py:544-547) holds alpha = g WITHOUT the Omega A_v factor, so the
+                    // 1/(Omega A_v) of the jump term (smjp_utils.py:409-412) does not cancel there (matters when a grid point lies
+                    // within isclose() of t_end: two or more final rows)
+                    if (!nonfinal) gj = dsum > (Real)0 ? g * M::rcp(omega_r * dsum) : (Real)0;
 #pragma unroll
-                    for (int s = 0; s < K; ++s) Jp[s] += g * kE[s];
+                    for (int s = 0; s < K; ++s) Jp[s] += gj * kE[s];
                     const Real an = g * (nonfinal ? omega_r * dsum : (Real)1);
                     pa[v * B] = an;
                     ph[v * B] = hsum;

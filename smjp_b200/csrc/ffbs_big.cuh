@@ -188,7 +188,12 @@ __global__ void __launch_bounds__(B) ffbs_big_kernel(const FfbsArgs a) {
                     const Real hsum = tau * esum;  // H_v(tau)
                     const Real g = of_s[v] * ex2.neg(-om_l2e * (hsum - hprev)) * base;
                     if (!exporting) row_base[(int64_t)K * i + (int64_t)v * (i + 1) + j] = g;  // row i
-                    for (int s = 0; s < K; ++s) Jp_s[s * BP + tid] += g * kE_s[s * BP + tid];
+                    Real gj = g;
+                    // a final row (right end = t_end, smjp_utils.py:544-547) holds alpha = g WITHOUT the Omega A_v factor, so the
+                    // 1/(Omega A_v) of the jump term (smjp_utils.py:409-412) does not cancel there (matters when a grid point lies
+                    // within isclose() of t_end: two or more final rows)
+                    if (!nonfinal) gj = dsum > (Real)0 ? g * M::rcp(omega_r * dsum) : (Real)0;
+                    for (int s = 0; s < K; ++s) Jp_s[s * BP + tid] += gj * kE_s[s * BP + tid];
                     const Real an = g * (nonfinal ? omega_r * dsum : (Real)1);
                     pa[v * B] = an;
                     ph[v * B] = hsum;

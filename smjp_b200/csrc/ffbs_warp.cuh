@@ -214,8 +214,13 @@ __global__ void __launch_bounds__(FFBS_WARPS * 32, (sizeof(Real) == 4 && K <= 3 
                     const Real hsum = tau * esum;  // H_v(tau)
                     const Real g = of[v] * ex2.neg(-om_l2e * (hsum - hprev)) * base;
                     row_i[v * (i + 1) + j] = g;  // scratch rows hold g (ffbs.cuh, Backward)
+                    Real gj = g;
+                    // a final row (right end = t_end, smjp_utils.py:544-547) holds alpha = g WITHOUT the Omega A_v factor, so the
+                    // 1/(Omega A_v) of the jump term (smjp_utils.py:409-412) does not cancel there (matters when a grid point lies
+                    // within isclose() of t_end: two or more final rows)
+                    if (!nonfinal) gj = dsum > (Real)0 ? g * M::rcp(omega_r * dsum) : (Real)0;
 #pragma unroll
-                    for (int s = 0; s < K; ++s) Jp[s] += g * kE[s];
+                    for (int s = 0; s < K; ++s) Jp[s] += gj * kE[s];
                     const Real an = g * (nonfinal ? omega_r * dsum : (Real)1);
                     pa[v * 32] = an;
                     ph[v * 32] = hsum;
