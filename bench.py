@@ -276,6 +276,10 @@ def run_ours(args):
     eng.set_option("window_log2", args.window_log2)
     eng.set_option("ffbs_warp", args.warp)
     eng.set_option("ffbs_ring", args.ring)
+    eng.set_option("ffbs_fast", args.fast)
+    eng.set_option("fast_ring", args.fast_ring)
+    eng.set_option("fast_ways", args.fast_ways)
+    eng.set_option("fast_cpb", args.fast_cpb)
     eng.set_option("speculate", 0 if args.no_speculate else 1)
     obs_t = np.arange(OBS_DT, T_END, OBS_DT)
     D = len(obs_t)
@@ -421,9 +425,12 @@ def run_ours(args):
                    "mean_grid_intervals": gs / (C * world * args.steps), "candidates": "reference (Q5)"},
         "chain_sweeps_per_sec": C * world * args.steps / secs, "grid_steps_per_sec": gs / secs,
         "gpu_launches": int(launches), "failed_chains": status_bad,
+        "rescue": {"chains_redone_last_launch": int(eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_rescued")),
+                   "ring_boost": int(eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_fast_boost_f64"))},
         "clocks": clk,
         "roofline": roofline_block(
-            "ffbs_kernel<%s,3>" % ("double" if prec == "f64" else "float"), ret_bytes, alg_bytes, k_cnt, k_ms, peak, peak_src,
+            "%s<%s,3>" % ({0: "ffbs_kernel", 3: "ffbs_warp_kernel", 4: "ffbs_fast_kernel"}.get(eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_kernel"), "ffbs_item_kernel"),
+                          "double" if prec == "f64" else "float"), ret_bytes, alg_bytes, k_cnt, k_ms, peak, peak_src,
             live_frac, ((traffic or {}).get(prec) or {}).get("dram_bytes_per_launch"),
             grid=eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_grid"), threads=eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_threads"),
             smem=eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_smem"), kernel_share_of_step=k_ms / ms,
@@ -540,6 +547,10 @@ def main():
     ap.add_argument("--warp", type=int, default=-1, help="warp-per-chain ring kernel (ffbs_warp.cuh): -1 auto, 0 off, 1 on")
     ap.add_argument("--no-speculate", action="store_true", dest="no_speculate",
                     help="wait for every sweep's grid sizes on the host before launching its FFBS kernel")
+    ap.add_argument("--fast", type=int, default=-1, help="ffbs_fast.cuh (deferred normalisation, split barriers): -1 auto, 0 off, 1 on")
+    ap.add_argument("--fast-cpb", type=int, default=0, dest="fast_cpb", help="fast kernel: chains per CTA, one warp each (0 auto)")
+    ap.add_argument("--fast-ways", type=int, default=0, dest="fast_ways", help="fast kernel: grid pairs in flight per thread (0 auto, 1, 2, 4)")
+    ap.add_argument("--fast-ring", type=int, default=0, dest="fast_ring", help="its ring slots (0 = auto)")
     ap.add_argument("--ring", type=int, default=0, help="ring slots of 32 grid points for --warp (0 = auto)")
     ap.add_argument("--window-log2", type=int, default=0, dest="window_log2",
                     help="0: exact live window (default); -L: prune states below 2^-L of the row sum")

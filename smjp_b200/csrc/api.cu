@@ -113,13 +113,19 @@ struct smjp_ctx {
     int ring_boost[2] = {0, 0};      // extra ring slots learnt from rescue counts, per precision (f64, f32)
     int warp_off[2] = {0, 0};        // the ring kernel kept overflowing for this precision: block kernel from now on
     int ffbs_ring = 0;    // ring slots of 32 grid points (0 = auto)
+    int ffbs_fast = -1;   // ffbs_fast.cuh (K <= 3, scratch mode): -1 auto (exact fp64), 0 off, 1 on (both precisions)
+    int fast_ring = 0;    // its ring slots of `threads` grid points (0 = auto: ~384 grid points)
+    int fast_ways = 0;    // grid pairs in flight per thread (0 = auto; 1, 2, 4)
+    int fast_cpb = 0;     // chains per CTA, one warp each (0 = auto; 1..11) -- 32-thread groups only
+    int fast_boost[2] = {0, 0};  // extra ring slots learnt from rescue counts, per precision
+    int fast_off[2] = {0, 0};    // kept overflowing: ffbs.cuh from now on
     bool lpt_order = true;
     int obs_product = 0;
     int pf_extend = 0;
     int hazard_family = SMJP_HAZARD_WEIBULL;
     int pf_cluster = 0, last_pf_cluster = 0, pf_threads = 0;
     int item_k3 = 0;
-    int last_grid = 0, last_threads = 0;
+    int last_grid = 0, last_threads = 0, last_kernel = 0;
     int64_t ffbs_ncap_hint = 0;
     int64_t last_smem = 0;
     DevBuf d_in, d_out;  // staging for the host API
@@ -146,7 +152,7 @@ struct smjp_ctx {
     // rescue counts of ring-kernel launches come home asynchronously, two launches in flight
     PinBuf h_resc;
     cudaEvent_t ev_resc[2] = {nullptr, nullptr};
-    int resc_prec[2] = {-1, -1}, resc_C[2] = {0, 0};
+    int resc_prec[2] = {-1, -1}, resc_C[2] = {0, 0}, resc_fast[2] = {0, 0};
     int resc_idx = 0;
     // optional per-kernel timing (CUDA events on the launching stream)
     bool time_kernels = false;
@@ -253,6 +259,9 @@ int64_t smjp_ctx_get_stat(smjp_ctx_t* c, const char* key) {
     if (!strcmp(key, "pf_cluster")) return c->last_pf_cluster;
     if (!strcmp(key, "ffbs_ring_boost_f32")) return c->ring_boost[1] + 100 * c->warp_off[1];
     if (!strcmp(key, "ffbs_ring_boost_f64")) return c->ring_boost[0] + 100 * c->warp_off[0];
+    if (!strcmp(key, "ffbs_fast_boost_f32")) return c->fast_boost[1] + 100 * c->fast_off[1];
+    if (!strcmp(key, "ffbs_fast_boost_f64")) return c->fast_boost[0] + 100 * c->fast_off[0];
+    if (!strcmp(key, "ffbs_kernel")) return c->last_kernel;  // 0 ffbs.cuh, 1 ffbs_item, 2 ffbs_big, 3 ffbs_warp, 4 ffbs_fast
     if (!strcmp(key, "spec_launches")) return c->spec_launches;
     if (!strcmp(key, "spec_misses")) return c->spec_misses;
     if (!strcmp(key, "ffbs_rescued")) {  // chains the last launch handed to the rescue pass (synchronises)
@@ -318,6 +327,27 @@ int smjp_ctx_set_option(smjp_ctx_t* c, const char* key, int64_t value) {
     if (!strcmp(key, "ffbs_ring")) {
         if (value < 0 || value > 64) return fail(SMJP_E_INVALID, "ffbs_ring must be in [0,64]");
         c->ffbs_ring = (int)value;
+        return SMJP_OK;
+    }
+    if (!strcmp(key, "ffbs_fast")) {
+        if (value < -1 || value > 1) return fail(SMJP_E_INVALID, "ffbs_fast must be -1 (auto), 0 or 1");
+        c->ffbs_fast = (int)value;
+        c->fast_off[0] = c->fast_off[1] = 0;
+        return SMJP_OK;
+    }
+    if (!strcmp(key, "fast_ways")) {
+        if (value < 0 || value > 4) return fail(SMJP_E_INVALID, "fast_ways must be 0 (auto), 1, 2, 3 or 4");
+        c->fast_ways = (int)value;
+        return SMJP_OK;
+    }
+    if (!strcmp(key, "fast_cpb")) {
+        if (value < 0 || value > 11) return fail(SMJP_E_INVALID, "fast_cpb must be in [0,11]");
+        c->fast_cpb = (int)value;
+        return SMJP_OK;
+    }
+    if (!strcmp(key, "fast_ring")) {
+        if (value < 0 || value > 64) return fail(SMJP_E_INVALID, "fast_ring must be in [0,64]");
+        c->fast_ring = (int)value;
         return SMJP_OK;
     }
     if (!strcmp(key, "window_log2")) {
@@ -563,8 +593,13 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
             const int32_t resc = ((const int32_t*)c->h_resc.p)[slot];
             const int pp = c->resc_prec[slot];
             if ((int64_t)resc * 50 > c->resc_C[slot]) {
-                c->ring_boost[pp] += 2;
-                if (c->ring_boost[pp] > 8) c->warp_off[pp] = 1;
+                if (c->resc_fast[slot]) {
+                    c->fast_boost[pp] += 1;
+                    if (c->fast_boost[pp] > 4) c->fast_off[pp] = 1;
+                } else {
+                    c->ring_boost[pp] += 2;
+                    if (c->ring_boost[pp] > 8) c->warp_off[pp] = 1;
+                }
             }
             c->resc_prec[slot] = -1;
         }
@@ -583,10 +618,35 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
         warp_smem = ffbs_warp_smem_bytes<Real>(K, ring, (int)n_max);
         if (warp_smem > c->smem_optin) use_warp = false;
     }
+    // ffbs_fast.cuh (K <= 3, scratch mode): deferred normalisation, split barriers, state ring.  Auto: the exact fp64
+    // window (fp32 and pruned windows are narrower and run best one warp per chain, above)
+    const bool want_fast = c->ffbs_fast == 1 || (c->ffbs_fast == -1 && sizeof(Real) == 8 && c->window_log2 == 0);
+    bool use_fast = want_fast && !use_warp && !c->fast_off[pidx] && !big && !item_kernel && K <= 3 && !a.messages &&
+                    c->f32_rescue;
+    int fast_threads = 0, fast_ns = 0, fast_cpb = 1, fast_ways = 1;
+    size_t fast_smem = 0;
+    if (use_fast) {
+        // default geometry: ONE WARP PER CHAIN, two grid pairs in flight per lane, several chains per CTA (they share
+        // the 2^x / log2 tables) -- measured on cfg2: 128 threads per chain 14.1 ms, 64: 11.8, 32: 11.3 (7 chains per
+        // SM, shared memory bound), 32 with the grid and the row starts moved to L2 and 5 chains per CTA: see DESIGN
+        fast_threads = c->ffbs_threads ? ffbs_fast_round_threads(c->ffbs_threads) : 32;
+        fast_ways = c->fast_ways ? c->fast_ways : (fast_threads <= 64 ? 2 : 1);
+        fast_cpb = fast_threads == 32 ? (c->fast_cpb ? c->fast_cpb : 1) : 1;
+        if (!ffbs_fast_has_variant(fast_threads, fast_ways, fast_cpb)) {
+            fast_ways = fast_threads <= 64 ? 2 : 1;
+            fast_cpb = 1;
+        }
+        const int full = ffbs_nslot((int)n_max, fast_threads);
+        // ring: the exact fp64 window of cfg2 is <= ~250 grid points; + RS steps between judgements + one slot of slack
+        fast_ns = c->fast_ring > 0 ? c->fast_ring : (288 + fast_threads - 1) / fast_threads + 1 + c->fast_boost[pidx];
+        if (fast_ns > full) fast_ns = full;
+        fast_smem = (size_t)ffbs_fast_layout<Real>(K, fast_ns, (int)n_max, fast_threads).total * fast_cpb;
+        if (fast_smem > c->smem_optin) use_fast = false;
+    }
     // rescue pass: chains that fail in fp32, or whose live window outgrows the ring, are redone by the full-size
     // fp64 kernel (scratch mode, K <= 10): geometry of that launch
     constexpr int RESCUE_GRID = 32;
-    bool rescue = (sizeof(Real) == 4 || use_warp) && c->f32_rescue && !a.messages && !big;
+    bool rescue = (sizeof(Real) == 4 || use_warp || use_fast) && c->f32_rescue && !a.messages && !big;
     int rescue_threads = 0;
     size_t rescue_smem = 0;
     if (rescue) {
@@ -607,13 +667,21 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
     // the ring kernel hands chains whose window outgrows the ring to the rescue pass: without one (the full-size fp64
     // kernel does not fit) it must not run -- the block kernel of this precision handles every chain itself
     if (use_warp && !rescue) use_warp = false;
+    if (use_fast && !rescue) use_fast = false;
+    if (use_fast) {
+        threads = fast_threads;
+        smem = fast_smem;
+    }
+    a.use_fast = use_fast;
+    a.fast_ways = fast_ways;
+    a.fast_cpb = fast_cpb;
     if (smem > c->smem_optin)
         return fail(SMJP_E_UNSUPPORTED,
                     "grid with %lld intervals x K=%d needs %zu B of shared memory (> %zu): "
                     "chain state does not fit on chip", (long long)n_max, K, smem, c->smem_optin);
     FfbsLaunch L;
     L.K = K;
-    L.threads = use_warp ? FFBS_WARPS * 32 : threads;
+    L.threads = use_warp ? FFBS_WARPS * 32 : threads;  // (fast kernel: threads per CHAIN; the CTA has threads * fast_cpb)
     L.smem = use_warp ? warp_smem : smem;
     L.grid = 0;
     L.stream = c->stream;
@@ -621,11 +689,11 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
     const int per_sm = L.grid;
     if (per_sm < 1) return fail(SMJP_E_UNSUPPORTED, "kernel cannot be resident (threads=%d smem=%zu)", L.threads, L.smem);
     int grid = c->num_sms * per_sm;
-    const int regions_per_cta = use_warp ? FFBS_WARPS : 1;  // scratch regions: one per chain in flight
+    const int regions_per_cta = use_warp ? FFBS_WARPS : use_fast ? fast_cpb : 1;  // scratch regions: one per chain in flight
     if (grid > (a.C + regions_per_cta - 1) / regions_per_cta) grid = (a.C + regions_per_cta - 1) / regions_per_cta;
     a.ncap = (int)n_max;
-    a.nslot = use_warp ? ring : item_kernel ? ffbs_item_nslot(K, (int)n_max, threads) : ffbs_nslot((int)n_max, threads);
-    if (!item_kernel && !big) a.lay = ffbs_layout<Real>(K, (int)n_max, threads);
+    a.nslot = use_warp ? ring : use_fast ? fast_ns : item_kernel ? ffbs_item_nslot(K, (int)n_max, threads) : ffbs_nslot((int)n_max, threads);
+    if (!item_kernel && !big) a.lay = use_fast ? ffbs_fast_layout<Real>(K, fast_ns, (int)n_max, threads) : ffbs_layout<Real>(K, (int)n_max, threads);
     a.window_eps = c->window_log2 < 0 ? std::ldexp(1.0, c->window_log2) : 0.0;
     int rc;
     if (!a.messages) {
@@ -664,6 +732,10 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
             const int64_t rec = (12 * (n_max + 2) + (int64_t)sizeof(Real) - 1) / (int64_t)sizeof(Real);
             if (per < rec) per = rec;
             per = (per + 3) / 4 * 4;  // keeps every region 16-byte aligned
+            a.obsf_stride = per;
+        } else if (use_fast) {  // + the window start of every row (ints), see ffbs_fast.cuh
+            per += ((int64_t)(n_max + 2) * 4 + (int64_t)sizeof(Real) - 1) / (int64_t)sizeof(Real);
+            per = (per + 3) / 4 * 4;
             a.obsf_stride = per;
         }
         size_t ob = (size_t)grid * regions_per_cta * per * sizeof(Real);
@@ -709,6 +781,7 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
         collect_failed_kernel<<<1, 1024, 0, c->stream>>>(a.C, a.status, list, cnt);
         CUDA_TRY(cudaGetLastError());
         FfbsArgs r = a;
+        r.use_fast = 0;
         r.order = list;
         r.C_dev = cnt;
         r.queue = (unsigned int*)c->d_queue.p + 1;
@@ -722,8 +795,9 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
         if (!item_kernel) r.lay = ffbs_layout<double>(K, (int)n_max, rescue_threads);
         CUDA_TRY(ffbs_call<double>(r, R, false));
         c->launches += 2;
-        if (use_warp) {
+        if (use_warp || use_fast) {
             const int slot = c->resc_idx & 1;
+            c->resc_fast[slot] = use_fast ? 1 : 0;
             rc = c->h_resc.reserve(2 * sizeof(int32_t));
             if (rc) return rc;
             if (!c->ev_resc[slot]) CUDA_TRY(cudaEventCreateWithFlags(&c->ev_resc[slot], cudaEventDisableTiming));
@@ -741,6 +815,7 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
     ++c->resc_idx;
     c->last_grid = grid;
     c->last_threads = L.threads;
+    c->last_kernel = use_warp ? 3 : use_fast ? 4 : big ? 2 : item_kernel ? 1 : 0;
     c->last_smem = (int64_t)L.smem;
     return SMJP_OK;
 }

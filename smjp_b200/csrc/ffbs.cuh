@@ -81,6 +81,9 @@ struct FfbsArgs {
     double pc_d[3][9];
     float pc_f[3][9];
     int use_item;     // K == 3 only: run the item-parallel kernel instead of the thread-per-grid-point one
+    int use_fast;     // K <= 3, scratch mode: ffbs_fast.cuh (nslot = ring slots, lay = ffbs_fast_layout)
+    int fast_ways;    // its grid pairs in flight per thread (1, 2 or 4)
+    int fast_cpb;     // its chains per CTA (one warp each when > 1)
     int obs_product;  // 0: observations sharing a grid interval are SUMMED (reference); 1: multiplied
     double omega, power, t_end;
     // speculative launch (smjp_sweep_dev): the kernel was sized for guard_nmax intervals and guard_total grid points

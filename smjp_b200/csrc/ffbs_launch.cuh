@@ -3,6 +3,11 @@
 #pragma once
 #include "ffbs.cuh"
 #include "ffbs_item.cuh"
+#include "ffbs_fast.cuh"
+
+#ifndef FFBS_FAST_MINB_F64_128
+#define FFBS_FAST_MINB_F64_128 5  // resident CTAs per SM the fp64 128-thread fast kernel is compiled for (96 registers)
+#endif
 
 namespace smjp {
 
@@ -45,6 +50,50 @@ cudaError_t ffbs_pick(const FfbsArgs& a, FfbsLaunch& L, bool query) {
     return cudaErrorInvalidValue;
 }
 
+// ---- K <= 3, scratch mode: ffbs_fast.cuh (deferred normalisation, split barriers, state ring, WAYS pairs in flight) ----
+template <typename Real, int K, int B, int MINB, int WAYS, int CPB = 1>
+cudaError_t ffbs_fast_do(const FfbsArgs& a, FfbsLaunch& L, bool query) {
+    auto kern = ffbs_fast_kernel<Real, K, B, MINB, WAYS, CPB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    if (e != cudaSuccess) return e;
+    // the driver's default carve-out can stop short of what the registers allow: ask for all of it
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    if (query) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&L.grid, kern, B * CPB, L.smem);
+    kern<<<L.grid, B * CPB, L.smem, L.stream>>>(a);
+    return cudaGetLastError();
+}
+
+// (threads per chain, ways, chains per CTA) the kernel is instantiated for
+inline bool ffbs_fast_has_variant(int threads, int ways, int cpb) {
+    if (threads == 32) return (ways == 2 && (cpb == 1 || cpb == 2 || cpb == 5 || cpb == 9)) || (cpb == 1 && (ways == 1 || ways == 3 || ways == 4));
+    if (threads == 64) return cpb == 1 && (ways == 1 || ways == 2);
+    return cpb == 1 && ways == 1 && (threads == 96 || threads == 128 || threads == 256);
+}
+template <typename Real, int K>
+cudaError_t ffbs_fast_pick(const FfbsArgs& a, FfbsLaunch& L, bool query) {
+    constexpr bool D = sizeof(Real) == 8;
+    const int w = a.fast_ways, cpb = a.fast_cpb;
+    switch (L.threads) {
+        case 32:
+            if (w == 2 && cpb == 9) return ffbs_fast_do<Real, K, 32, 1, 2, 9>(a, L, query);   // 9 chains/SM, <= 224 registers
+            if (w == 2 && cpb == 5) return ffbs_fast_do<Real, K, 32, 2, 2, 5>(a, L, query);   // 10 chains/SM, <= 200
+            if (w == 2 && cpb == 2) return ffbs_fast_do<Real, K, 32, 5, 2, 2>(a, L, query);   // 10 chains/SM, <= 200
+            if (w == 4) return ffbs_fast_do<Real, K, 32, 7, 4>(a, L, query);
+            if (w == 3) return ffbs_fast_do<Real, K, 32, 8, 3>(a, L, query);
+            if (w == 2) return ffbs_fast_do<Real, K, 32, 8, 2>(a, L, query);                  // 8 chains/SM, <= 256
+            return ffbs_fast_do<Real, K, 32, D ? 16 : 32, 1>(a, L, query);
+        case 64:
+            if (w == 2) return ffbs_fast_do<Real, K, 64, 7, 2>(a, L, query);
+            return ffbs_fast_do<Real, K, 64, D ? 10 : 16, 1>(a, L, query);
+        case 96: return ffbs_fast_do<Real, K, 96, D ? 7 : 10, 1>(a, L, query);
+        case 128: return ffbs_fast_do<Real, K, 128, D ? 5 : 8, 1>(a, L, query);
+        case 256: return ffbs_fast_do<Real, K, 256, D ? 2 : 4, 1>(a, L, query);
+    }
+    return cudaErrorInvalidValue;
+}
+inline int ffbs_fast_round_threads(int t) { return t <= 32 ? 32 : t <= 64 ? 64 : t <= 96 ? 96 : t <= 128 ? 128 : 256; }
+
 // ---- K >= 4: item-parallel kernel, block size a multiple of K (two sizes per K) ----
 constexpr int ffbs_item_base_threads(int K) {
     return K == 3 ? 96 : K == 4 ? 128 : K == 5 ? 160 : K == 6 ? 192 : K == 7 ? 224 : K == 8 ? 128 : K == 9 ? 288 : 160;
@@ -79,8 +128,9 @@ cudaError_t ffbs_item_pick(const FfbsArgs& a, FfbsLaunch& L, bool query) {
 template <typename Real>
 cudaError_t ffbs_dispatch_lo(const FfbsArgs& a, FfbsLaunch& L, bool query) {
     switch (L.K) {
-        case 2: return ffbs_pick<Real, 2>(a, L, query);
-        case 3: return a.use_item ? ffbs_item_pick<Real, 3>(a, L, query) : ffbs_pick<Real, 3>(a, L, query);
+        case 2: return a.use_fast ? ffbs_fast_pick<Real, 2>(a, L, query) : ffbs_pick<Real, 2>(a, L, query);
+        case 3: return a.use_item ? ffbs_item_pick<Real, 3>(a, L, query)
+                       : a.use_fast ? ffbs_fast_pick<Real, 3>(a, L, query) : ffbs_pick<Real, 3>(a, L, query);
         case 4: return ffbs_item_pick<Real, 4>(a, L, query);
         case 5: return ffbs_item_pick<Real, 5>(a, L, query);
     }

@@ -66,7 +66,7 @@ class Engine:
         self.Kobs = None
         # experiment switches for whole-suite runs: SMJP_FFBS_WARP=1 (warp-per-chain ring kernel), SMJP_FFBS_RING=R
         import os
-        for env, key in (("SMJP_FFBS_WARP", "ffbs_warp"), ("SMJP_FFBS_RING", "ffbs_ring")):
+        for env, key in (("SMJP_FFBS_WARP", "ffbs_warp"), ("SMJP_FFBS_RING", "ffbs_ring"), ("SMJP_FFBS_FAST", "ffbs_fast")):
             if os.environ.get(env):
                 self.set_option(key, int(os.environ[env]))
 

@@ -105,50 +105,97 @@ def cfg2_case():
     return dict(C=C, K=K, t_end=t_end, scale=scale, emis=emis, obs_t=obs_t, Ws=Ws, Ys=Ys, oras=oras)
 
 
-@pytest.mark.parametrize("threads,warp", [(128, 0), (0, 0), (64, 0), (256, 0), (0, 1)])
-def test_cfg2_scratch_mode_fp64_equals_oracle(engine, cfg2_case, threads, warp):
-    """the instantiation the headline times (ffbs_threads = 128 -> ffbs_kernel<double,3,128,MINB>, scratch rows, open
-    live window), the other CTA sizes, and the fp64 warp-per-chain ring kernel: bit-equal paths, logZ to 1e-10"""
-    g = cfg2_case
-    engine.set_model(SHAPE3, g["scale"], 2.0, g["emis"], 1.0, g["t_end"])
+KERNEL_NAMES = {0: "ffbs_kernel", 1: "ffbs_item_kernel", 2: "ffbs_big_kernel", 3: "ffbs_warp_kernel", 4: "ffbs_fast_kernel"}
+
+
+def set_kernel(engine, threads=0, warp=-1, fast=-1):
     engine.set_option("ffbs_threads", threads)
     engine.set_option("ffbs_warp", warp)
+    engine.set_option("ffbs_fast", fast)
+
+
+def kernel_used(engine):
+    return KERNEL_NAMES[int(engine.lib.smjp_ctx_get_stat(engine.ctx, b"ffbs_kernel"))]
+
+
+@pytest.mark.parametrize("threads,warp,fast,kernel", [
+    (0, -1, -1, "ffbs_fast_kernel"),       # what a sweep launches by default: ffbs_fast_kernel<double,3,32,2,2,5> (warp per chain)
+    (128, 0, 1, "ffbs_fast_kernel"), (64, 0, 1, "ffbs_fast_kernel"), (256, 0, 1, "ffbs_fast_kernel"), (32, 0, 1, "ffbs_fast_kernel"),
+    (128, 0, 0, "ffbs_kernel"), (64, 0, 0, "ffbs_kernel"), (256, 0, 0, "ffbs_kernel"),   # the round-1 kernel (now: export / rescue)
+    (0, 1, 0, "ffbs_warp_kernel")])
+def test_cfg2_scratch_mode_fp64_equals_oracle(engine, cfg2_case, threads, warp, fast, kernel):
+    """the instantiation the headline times (default options -> ffbs_fast_kernel<double,3,128,5>, scratch rows, open
+    live window in a state ring), its other CTA sizes, the round-1 block kernel and the fp64 warp-per-chain ring
+    kernel: bit-equal paths, logZ to 1e-10"""
+    g = cfg2_case
+    engine.set_model(SHAPE3, g["scale"], 2.0, g["emis"], 1.0, g["t_end"])
+    set_kernel(engine, threads, warp, fast)
     try:
         live_pairs(engine)
         r = engine.ffbs_host(g["Ws"], [g["obs_t"]] * g["C"], g["Ys"], seed=SEED_BACK, sweep=7, precision="f64")
         live = live_pairs(engine)
-        if threads:
-            assert warp or engine.lib.smjp_ctx_get_stat(engine.ctx, b"ffbs_threads") == threads
+        assert kernel_used(engine) == kernel
+        # threads per chain: the fast kernel's default is one warp per chain (several chains per CTA)
+        assert engine.lib.smjp_ctx_get_stat(engine.ctx, b"ffbs_threads") == (threads if threads and warp != 1 else 32 if kernel == "ffbs_fast_kernel" else 128)
+        rescued = int(engine.lib.smjp_ctx_get_stat(engine.ctx, b"ffbs_rescued")) if kernel != "ffbs_kernel" else 0
     finally:
-        engine.set_option("ffbs_threads", 0)
-        engine.set_option("ffbs_warp", -1)
+        set_kernel(engine)
+    assert rescued == 0   # no chain was handed to the rescue pass: the kernel under test produced these results
     assert_exact_parity(r, g["oras"], g["K"])
     nominal = sum(n * (n + 1) // 2 for n in r["n"])
     exact = sum(exact_live_pairs(o["alpha"])[0] for o in g["oras"])
     widest = max(exact_live_pairs(o["alpha"])[1] for o in g["oras"])
     assert min(r["n"]) > 400 and widest < min(r["n"]) // 2      # BASELINE scale, and the window does open
     # the kernel drops only exact zeros and looks every few steps: never fewer pairs than the oracle's zero pattern
-    # allows, and well below the nominal triangle
-    assert exact <= live < 0.75 * nominal, (exact, live, nominal)
+    # allows (deferred normalisation moves an underflow by a step or two at most: 1 % slack), and well below the
+    # nominal triangle
+    assert 0.99 * exact <= live < 0.75 * nominal, (exact, live, nominal)
     assert live < 1.1 * exact, (exact, live)
 
 
-@pytest.mark.parametrize("warp", [1, 0])
-def test_cfg2_scratch_mode_fp32_against_oracle(engine, cfg2_case, warp):
+def test_fast_kernel_ring_overflow_and_range_go_to_the_rescue_pass(engine, cfg2_case):
+    """results never depend on the ring size: with one ring slot (128 grid points, the cfg2 window needs ~250) every
+    chain overflows and is redone by the rescue pass (ffbs.cuh) -- same paths; a grid with a 1e-300 gap leaves the
+    range of the unclamped fp64 arithmetic and takes the same route"""
+    g = cfg2_case
+    engine.set_model(SHAPE3, g["scale"], 2.0, g["emis"], 1.0, g["t_end"])
+    engine.set_option("fast_ring", 1)
+    try:
+        r = engine.ffbs_host(g["Ws"], [g["obs_t"]] * g["C"], g["Ys"], seed=SEED_BACK, sweep=7, precision="f64")
+        assert kernel_used(engine) == "ffbs_fast_kernel"
+        assert int(engine.lib.smjp_ctx_get_stat(engine.ctx, b"ffbs_rescued")) == g["C"]
+    finally:
+        engine.set_option("fast_ring", 0)
+    assert_exact_parity(r, g["oras"], g["K"])
+    W = np.sort(np.concatenate([g["Ws"][0], [g["Ws"][0][5] * (1 + 1e-15)]]))                 # a gap of ~1e-15: in range
+    Wt = np.concatenate([[0.0, 1.0e-300], g["Ws"][1][1:]])                                   # and one of 1e-300
+    us = [np.random.default_rng(1).uniform(size=len(x) - 1) for x in (W, Wt)]
+    r = engine.ffbs_host([W, Wt], [g["obs_t"]] * 2, g["Ys"][:2], uniforms=us, precision="f64")
+    assert int(engine.lib.smjp_ctx_get_stat(engine.ctx, b"ffbs_rescued")) == 1
+    for c, (Wc, Y) in enumerate(zip((W, Wt), g["Ys"][:2])):
+        ora = O.ffbs(Wc, g["obs_t"], Y, SHAPE3, g["scale"], 2.0, g["emis"], 1.0, g["t_end"], us[c])
+        assert r["status"][c] == 0
+        assert np.array_equal(r["V"][c], ora["V"]) and np.array_equal(r["T"][c], ora["T"])
+        assert np.abs(r["logZ"][c] - ora["logZ"]).max() < 1e-9
+
+
+@pytest.mark.parametrize("warp,fast", [(1, 0), (0, 0), (0, 1)])
+def test_cfg2_scratch_mode_fp32_against_oracle(engine, cfg2_case, warp, fast):
     """ffbs_warp_kernel<float,3> (warp = 1: what bench.py's f32 block times) and the fp32 block kernel in scratch
     mode: logZ within 1e-4; a path may differ from the fp64 oracle's only where the uniform of the first differing
     draw sits within fp32 rounding of a CDF boundary -- counted and bounded"""
     g = cfg2_case
     K = g["K"]
     engine.set_model(SHAPE3, g["scale"], 2.0, g["emis"], 1.0, g["t_end"])
-    engine.set_option("ffbs_warp", warp)
+    set_kernel(engine, 0, warp, fast)
     try:
         live_pairs(engine)
         r = engine.ffbs_host(g["Ws"], [g["obs_t"]] * g["C"], g["Ys"], seed=SEED_BACK, sweep=7, precision="f32")
         live = live_pairs(engine)
         rescued = int(engine.lib.smjp_ctx_get_stat(engine.ctx, b"ffbs_rescued"))
+        assert kernel_used(engine) == ("ffbs_warp_kernel" if warp else "ffbs_fast_kernel" if fast else "ffbs_kernel")
     finally:
-        engine.set_option("ffbs_warp", -1)
+        set_kernel(engine)
     assert np.all(r["status"] == 0)
     assert rescued == 0   # every chain was done by the fp32 kernel itself, not by the fp64 rescue pass
     nominal = sum(n * (n + 1) // 2 for n in r["n"])
@@ -222,9 +269,10 @@ def test_cfg2_sweep_device_loop_equals_oracle_composition(engine):
             V[c], T[c] = Vd[c], Td[c]
 
 
-@pytest.mark.parametrize("K,precision,warp", [(3, "f64", 0), (3, "f64", 1), (2, "f64", 0), (5, "f64", 0), (10, "f64", 0),
-                                              (12, "f64", 0), (3, "f32", 1), (3, "f32", 0), (10, "f32", 0)])
-def test_grid_points_within_isclose_of_t_end(engine, K, precision, warp):
+@pytest.mark.parametrize("K,precision,warp,fast", [(3, "f64", 0, 1), (3, "f64", 0, 0), (3, "f64", 1, 0), (2, "f64", 0, 1), (2, "f64", 0, 0),
+                                                   (5, "f64", 0, 0), (10, "f64", 0, 0), (12, "f64", 0, 0), (3, "f32", 1, 0),
+                                                   (3, "f32", 0, 0), (3, "f32", 0, 1), (10, "f32", 0, 0)])
+def test_grid_points_within_isclose_of_t_end(engine, K, precision, warp, fast):
     """A candidate within numpy.isclose() of t_end (|w - T| <= 1e-8 + 1e-5 T; 0.5 % of the cfg2 chain-sweeps) gives two
     or more rows without the B_v factor in the emission (smjp_utils.py:544-547) while the transition keeps
     A_vv'/B_v (:409-412): every kernel, scratch and export mode, against the oracle (itself pinned on the reference's
@@ -240,12 +288,12 @@ def test_grid_points_within_isclose_of_t_end(engine, K, precision, warp):
           np.concatenate([[0.0], inner[::3], [t_end]])]                                   # the usual single one
     obs_t = np.arange(0.1, t_end, 0.1); obs_y = rng.integers(0, K, len(obs_t))
     us = [rng.uniform(size=len(W) - 1) for W in Ws]
-    engine.set_option("ffbs_warp", warp)
+    set_kernel(engine, 0, warp, fast)
     try:
         q = engine.ffbs_host(Ws, obs_t, obs_y, uniforms=us, precision=precision)                       # scratch mode
         r = engine.ffbs_host(Ws, obs_t, obs_y, uniforms=us, precision=precision, want_messages=True)   # export mode
     finally:
-        engine.set_option("ffbs_warp", -1)
+        set_kernel(engine)
     tol = 1e-10 if precision == "f64" else 2e-4
     for c, W in enumerate(Ws):
         m = len(W) - 1
