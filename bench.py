@@ -248,6 +248,80 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+K10_CHAINS = 16384   # one GPU's shard of BASELINE configs[4] at 4 GPUs; north_star: ">= 4096 concurrent chains of a 10-state sMJP"
+K10_T = 20.0
+K10_K = 10
+
+
+def k10_model():
+    rng = np.random.default_rng(5)  # shapes ~ U(0.6, 3) (seed 5), scale 1, T = 20
+    shape = rng.uniform(0.6, 3.0, (K10_K, K10_K))
+    emis = np.ones((K10_K, K10_K)) + 9 * np.eye(K10_K)
+    return shape, emis / emis.sum(axis=1, keepdims=True)
+
+
+def k10_block(local, steps, peak, peak_src, chains=K10_CHAINS, chain_base=0, precisions=("f64", "f32"), opts=None):
+    """The north_star target workload on one GPU: `chains` chains of the 10-state Weibull sMJP of cfg5 (T = 20,
+    n ~ 206), device-resident Rao-Teh sweeps; per precision the sweep time, state-steps/s and the roofline of the FFBS
+    kernel on RETAINED bytes."""
+    import torch
+    from smjp_b200.chains import DeviceChains
+    from smjp_b200.engine import Engine
+    shape, emis = k10_model()
+    eng = Engine(local)
+    eng.set_model(shape, np.ones((K10_K, K10_K)), OMEGA, emis, 1.0, K10_T)
+    for k, v in (opts or {}).items():
+        eng.set_option(k, v)
+    obs_t = np.arange(OBS_DT, K10_T, OBS_DT)
+    D = len(obs_t)
+    out = {"workload": "cfg5 shard: %d chains, K=10 Weibull sMJP, shapes~U(0.6,3) seed 5, T=20, D=%d obs" % (chains, D)}
+    names = {1: "ffbs_item_kernel", 5: "ffbs_fastk_kernel"}
+    for prec in precisions:
+        esz = 8 if prec == "f64" else 4
+        ch = DeviceChains(eng, chains, obs_t, chain_base=chain_base)
+        ch.init_prior(np.ones(K10_K) / K10_K, seed=SEED + 21).simulate_observations(seed=SEED + 22)
+        ch.init_prior(np.ones(K10_K) / K10_K, seed=SEED + 23)
+        for sw in range(3):
+            ch.sweep(seed=SEED + 24, sweep=sw, precision=prec)
+        torch.cuda.synchronize()
+        eng.set_option("time_kernels", 1)
+        eng.kernel_time()
+        eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_live_pairs")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        snaps = []
+        e0.record()
+        for sw in range(steps):
+            ch.sweep(seed=SEED + 24, sweep=3 + sw, precision=prec)
+            snaps.append(ch.cur["offs"].clone())
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        k_ms, k_cnt = eng.kernel_time()
+        lp = float(eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_live_pairs"))
+        eng.set_option("time_kernels", 0)
+        ss = nominal = tail = gs = 0.0
+        for offs in snaps:
+            n = (offs[1:] - offs[:-1] - 1).cpu().numpy()
+            ss += float(np.sum(K10_K * n.astype(np.float64) * (n + 1) / 2))
+            gs += float(n.sum())
+            nominal += algorithmic_bytes(n, D, esz, K10_K)
+            tail += float(np.sum(40.0 * n + 12 * D))
+        kid = int(eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_kernel"))
+        out[prec] = {"value": ss / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+                     "chain_sweeps_per_sec": chains * steps / (ms / 1e3), "mean_grid_intervals": gs / (chains * steps),
+                     "failed_chains": int((ch.status != 0).sum().item()),
+                     "chains_redone_by_rescue_pass_last_launch": int(eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_rescued")),
+                     "roofline": roofline_block("%s<%s,10>" % (names.get(kid, "kernel %d" % kid), "double" if prec == "f64" else "float"),
+                                                2 * esz * K10_K * lp + tail, nominal, k_cnt, k_ms, peak, peak_src,
+                                                K10_K * lp / max(ss, 1.0), None, kernel_share_of_step=k_ms / ms,
+                                                grid=int(eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_grid")),
+                                                smem=int(eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_smem")))}
+        del ch
+    eng.close()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -519,6 +593,9 @@ def run_ours(args):
                           "live_fraction": K * lp / max(ssp, 1.0), "unit": UNIT, "ms_per_step": msp / args.steps,
                           "chain_sweeps_per_sec": C * args.steps / (msp / 1e3), "kernel_ms_avg": kp / max(cp, 1),
                           "failed_chains": int((ch.status != 0).sum().item())}
+    if world == 1 and not args.no_alt:
+        # north_star's stated target: >= 4096 concurrent chains of a 10-state sMJP (BASELINE configs[4]'s chains)
+        line["k10"] = k10_block(local, max(3, min(args.steps, 6)), peak, peak_src)
     gc.enable()
     if world == 1 and not args.no_cpu:
         ss_c, gs_c, wall_c = cpu_sample(16, 3, T_END, 1)  # ~10-20 s of CPU work

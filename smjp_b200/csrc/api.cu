@@ -261,7 +261,7 @@ int64_t smjp_ctx_get_stat(smjp_ctx_t* c, const char* key) {
     if (!strcmp(key, "ffbs_ring_boost_f64")) return c->ring_boost[0] + 100 * c->warp_off[0];
     if (!strcmp(key, "ffbs_fast_boost_f32")) return c->fast_boost[1] + 100 * c->fast_off[1];
     if (!strcmp(key, "ffbs_fast_boost_f64")) return c->fast_boost[0] + 100 * c->fast_off[0];
-    if (!strcmp(key, "ffbs_kernel")) return c->last_kernel;  // 0 ffbs.cuh, 1 ffbs_item, 2 ffbs_big, 3 ffbs_warp, 4 ffbs_fast
+    if (!strcmp(key, "ffbs_kernel")) return c->last_kernel;  // 0 ffbs.cuh, 1 ffbs_item, 2 ffbs_big, 3 ffbs_warp, 4 ffbs_fast, 5 ffbs_fastk
     if (!strcmp(key, "spec_launches")) return c->spec_launches;
     if (!strcmp(key, "spec_misses")) return c->spec_misses;
     if (!strcmp(key, "ffbs_rescued")) {  // chains the last launch handed to the rescue pass (synchronises)
@@ -430,6 +430,10 @@ int smjp_set_model(smjp_ctx_t* c, int K, int Kobs, const double* shape, const do
     CUDA_TRY(cudaSetDevice(c->device));
     if (K != c->K) c->ffbs_ncap_hint = 0;
     c->pred_nmax = 0;  // grid sizes follow the model: no speculative launch for the next sweep
+    for (int p = 0; p < 2; ++p) {  // ring sizes learnt from rescue counts belong to the previous model's windows
+        c->ring_boost[p] = c->warp_off[p] = 0;
+        c->fast_boost[p] = c->fast_off[p] = 0;
+    }
     c->K = K;
     c->Kobs = Kobs;
     c->omega = omega;
@@ -621,26 +625,42 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
     // ffbs_fast.cuh (K <= 3, scratch mode): deferred normalisation, split barriers, state ring.  Auto: the exact fp64
     // window (fp32 and pruned windows are narrower and run best one warp per chain, above)
     const bool want_fast = c->ffbs_fast == 1 || (c->ffbs_fast == -1 && sizeof(Real) == 8 && c->window_log2 == 0);
-    bool use_fast = want_fast && !use_warp && !c->fast_off[pidx] && !big && !item_kernel && K <= 3 && !a.messages &&
-                    c->f32_rescue;
+    // ffbs_fastk.cuh is the same design for 4 <= K <= 10 (lane = (grid point, source state)), both precisions
+    const bool want_fastk = c->ffbs_fast == 1 || (c->ffbs_fast == -1 && c->window_log2 == 0);
+    const bool fastk = item_kernel && K >= 4 && K <= 10;
+    bool use_fast = (fastk ? want_fastk : want_fast && !item_kernel && K <= 3) && !use_warp && !c->fast_off[pidx] && !big &&
+                    !a.messages && c->f32_rescue;
     int fast_threads = 0, fast_ns = 0, fast_cpb = 1, fast_ways = 1;
     size_t fast_smem = 0;
     if (use_fast) {
         // default geometry: ONE WARP PER CHAIN, two grid pairs in flight per lane, several chains per CTA (they share
         // the 2^x / log2 tables) -- measured on cfg2: 128 threads per chain 14.1 ms, 64: 11.8, 32: 11.3 (7 chains per
         // SM, shared memory bound), 32 with the grid and the row starts moved to L2 and 5 chains per CTA: see DESIGN
-        fast_threads = c->ffbs_threads ? ffbs_fast_round_threads(c->ffbs_threads) : 32;
+        fast_threads = fastk ? 32 : c->ffbs_threads ? ffbs_fast_round_threads(c->ffbs_threads) : 32;
         fast_ways = c->fast_ways ? c->fast_ways : (fast_threads <= 64 ? 2 : 1);
         fast_cpb = fast_threads == 32 ? (c->fast_cpb ? c->fast_cpb : 1) : 1;
         if (!ffbs_fast_has_variant(fast_threads, fast_ways, fast_cpb)) {
             fast_ways = fast_threads <= 64 ? 2 : 1;
             fast_cpb = 1;
         }
-        const int full = ffbs_nslot((int)n_max, fast_threads);
-        // ring: the exact fp64 window of cfg2 is <= ~250 grid points; + RS steps between judgements + one slot of slack
-        fast_ns = c->fast_ring > 0 ? c->fast_ring : (288 + fast_threads - 1) / fast_threads + 1 + c->fast_boost[pidx];
-        if (fast_ns > full) fast_ns = full;
-        fast_smem = (size_t)ffbs_fast_layout<Real>(K, fast_ns, (int)n_max, fast_threads).total * fast_cpb;
+        if (fastk) {
+            // ring of slots of JPS = 32 / K grid points: the exact window of a 10-state chain at T = 20 is <= ~90 grid
+            // points in fp64 (~40 in fp32); + RS steps between judgements + slack; learnt upwards from rescue counts
+            const int jps = 32 / K;
+            const int pts = (sizeof(Real) == 8 ? 104 : 96) + 16 * c->fast_boost[pidx];
+            const int full = (int)(n_max / jps) + 1;
+            fast_cpb = 1;
+            fast_ways = c->fast_ways == 1 ? 1 : 2;
+            fast_ns = c->fast_ring > 0 ? c->fast_ring : (pts + jps - 1) / jps;
+            if (fast_ns > full) fast_ns = full;
+            fast_smem = (size_t)ffbs_fastk_layout<Real>(K, fast_ns, (int)n_max).total;
+        } else {
+            const int full = ffbs_nslot((int)n_max, fast_threads);
+            // ring: the exact fp64 window of cfg2 is <= ~250 grid points; + RS steps between judgements + one slot of slack
+            fast_ns = c->fast_ring > 0 ? c->fast_ring : (288 + fast_threads - 1) / fast_threads + 1 + c->fast_boost[pidx];
+            if (fast_ns > full) fast_ns = full;
+            fast_smem = (size_t)ffbs_fast_layout<Real>(K, fast_ns, (int)n_max, fast_threads).total * fast_cpb;
+        }
         if (fast_smem > c->smem_optin) use_fast = false;
     }
     // rescue pass: chains that fail in fp32, or whose live window outgrows the ring, are redone by the full-size
@@ -693,7 +713,8 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
     if (grid > (a.C + regions_per_cta - 1) / regions_per_cta) grid = (a.C + regions_per_cta - 1) / regions_per_cta;
     a.ncap = (int)n_max;
     a.nslot = use_warp ? ring : use_fast ? fast_ns : item_kernel ? ffbs_item_nslot(K, (int)n_max, threads) : ffbs_nslot((int)n_max, threads);
-    if (!item_kernel && !big) a.lay = use_fast ? ffbs_fast_layout<Real>(K, fast_ns, (int)n_max, threads) : ffbs_layout<Real>(K, (int)n_max, threads);
+    if (use_fast && fastk) a.lay = ffbs_fastk_layout<Real>(K, fast_ns, (int)n_max);
+    else if (!item_kernel && !big) a.lay = use_fast ? ffbs_fast_layout<Real>(K, fast_ns, (int)n_max, threads) : ffbs_layout<Real>(K, (int)n_max, threads);
     a.window_eps = c->window_log2 < 0 ? std::ldexp(1.0, c->window_log2) : 0.0;
     int rc;
     if (!a.messages) {
@@ -815,7 +836,7 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
     ++c->resc_idx;
     c->last_grid = grid;
     c->last_threads = L.threads;
-    c->last_kernel = use_warp ? 3 : use_fast ? 4 : big ? 2 : item_kernel ? 1 : 0;
+    c->last_kernel = use_warp ? 3 : use_fast ? (fastk ? 5 : 4) : big ? 2 : item_kernel ? 1 : 0;
     c->last_smem = (int64_t)L.smem;
     return SMJP_OK;
 }

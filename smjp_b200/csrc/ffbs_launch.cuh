@@ -4,6 +4,7 @@
 #include "ffbs.cuh"
 #include "ffbs_item.cuh"
 #include "ffbs_fast.cuh"
+#include "ffbs_fastk.cuh"
 
 #ifndef FFBS_FAST_MINB_F64_128
 #define FFBS_FAST_MINB_F64_128 5  // resident CTAs per SM the fp64 128-thread fast kernel is compiled for (96 registers)
@@ -94,6 +95,25 @@ cudaError_t ffbs_fast_pick(const FfbsArgs& a, FfbsLaunch& L, bool query) {
 }
 inline int ffbs_fast_round_threads(int t) { return t <= 32 ? 32 : t <= 64 ? 64 : t <= 96 ? 96 : t <= 128 ? 128 : 256; }
 
+// ---- 4 <= K <= 10, scratch mode: ffbs_fastk.cuh (one warp per chain, lane = (grid point, source state)) ----
+template <typename Real, int K, int WAYS>
+cudaError_t ffbs_fastk_do(const FfbsArgs& a, FfbsLaunch& L, bool query) {
+    constexpr int MINB = sizeof(Real) == 8 ? 8 : 16;  // <= 255 / <= 128 registers
+    auto kern = ffbs_fastk_kernel<Real, K, WAYS, MINB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    if (query) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&L.grid, kern, 32, L.smem);
+    kern<<<L.grid, 32, L.smem, L.stream>>>(a);
+    return cudaGetLastError();
+}
+template <typename Real, int K>
+cudaError_t ffbs_fastk_pick(const FfbsArgs& a, FfbsLaunch& L, bool query) {
+    if (a.fast_ways == 1) return ffbs_fastk_do<Real, K, 1>(a, L, query);
+    return ffbs_fastk_do<Real, K, 2>(a, L, query);
+}
+
 // ---- K >= 4: item-parallel kernel, block size a multiple of K (two sizes per K) ----
 constexpr int ffbs_item_base_threads(int K) {
     return K == 3 ? 96 : K == 4 ? 128 : K == 5 ? 160 : K == 6 ? 192 : K == 7 ? 224 : K == 8 ? 128 : K == 9 ? 288 : 160;
@@ -131,8 +151,8 @@ cudaError_t ffbs_dispatch_lo(const FfbsArgs& a, FfbsLaunch& L, bool query) {
         case 2: return a.use_fast ? ffbs_fast_pick<Real, 2>(a, L, query) : ffbs_pick<Real, 2>(a, L, query);
         case 3: return a.use_item ? ffbs_item_pick<Real, 3>(a, L, query)
                        : a.use_fast ? ffbs_fast_pick<Real, 3>(a, L, query) : ffbs_pick<Real, 3>(a, L, query);
-        case 4: return ffbs_item_pick<Real, 4>(a, L, query);
-        case 5: return ffbs_item_pick<Real, 5>(a, L, query);
+        case 4: return a.use_fast ? ffbs_fastk_pick<Real, 4>(a, L, query) : ffbs_item_pick<Real, 4>(a, L, query);
+        case 5: return a.use_fast ? ffbs_fastk_pick<Real, 5>(a, L, query) : ffbs_item_pick<Real, 5>(a, L, query);
     }
     return cudaErrorInvalidValue;
 }
@@ -140,11 +160,11 @@ cudaError_t ffbs_dispatch_lo(const FfbsArgs& a, FfbsLaunch& L, bool query) {
 template <typename Real>
 cudaError_t ffbs_dispatch_hi(const FfbsArgs& a, FfbsLaunch& L, bool query) {
     switch (L.K) {
-        case 6: return ffbs_item_pick<Real, 6>(a, L, query);
-        case 7: return ffbs_item_pick<Real, 7>(a, L, query);
-        case 8: return ffbs_item_pick<Real, 8>(a, L, query);
-        case 9: return ffbs_item_pick<Real, 9>(a, L, query);
-        case 10: return ffbs_item_pick<Real, 10>(a, L, query);
+        case 6: return a.use_fast ? ffbs_fastk_pick<Real, 6>(a, L, query) : ffbs_item_pick<Real, 6>(a, L, query);
+        case 7: return a.use_fast ? ffbs_fastk_pick<Real, 7>(a, L, query) : ffbs_item_pick<Real, 7>(a, L, query);
+        case 8: return a.use_fast ? ffbs_fastk_pick<Real, 8>(a, L, query) : ffbs_item_pick<Real, 8>(a, L, query);
+        case 9: return a.use_fast ? ffbs_fastk_pick<Real, 9>(a, L, query) : ffbs_item_pick<Real, 9>(a, L, query);
+        case 10: return a.use_fast ? ffbs_fastk_pick<Real, 10>(a, L, query) : ffbs_item_pick<Real, 10>(a, L, query);
     }
     return cudaErrorInvalidValue;
 }

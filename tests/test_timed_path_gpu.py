@@ -105,7 +105,8 @@ def cfg2_case():
     return dict(C=C, K=K, t_end=t_end, scale=scale, emis=emis, obs_t=obs_t, Ws=Ws, Ys=Ys, oras=oras)
 
 
-KERNEL_NAMES = {0: "ffbs_kernel", 1: "ffbs_item_kernel", 2: "ffbs_big_kernel", 3: "ffbs_warp_kernel", 4: "ffbs_fast_kernel"}
+KERNEL_NAMES = {0: "ffbs_kernel", 1: "ffbs_item_kernel", 2: "ffbs_big_kernel", 3: "ffbs_warp_kernel", 4: "ffbs_fast_kernel",
+                5: "ffbs_fastk_kernel"}
 
 
 def set_kernel(engine, threads=0, warp=-1, fast=-1):
@@ -212,23 +213,36 @@ def test_cfg2_scratch_mode_fp32_against_oracle(engine, cfg2_case, warp, fast):
     assert differ <= 1, differ
 
 
-def test_cfg5_scale_item_kernel_scratch_mode_equals_oracle(engine):
-    """K = 10, T = 20 (cfg5's chain shape, n ~ 200): ffbs_item_kernel<double,10,...> in scratch mode with an open live
-    window, bit-equal paths; fp32 within tolerance"""
+@pytest.mark.parametrize("fast,ways,kernel", [(-1, 0, "ffbs_fastk_kernel"), (1, 1, "ffbs_fastk_kernel"), (0, 0, "ffbs_item_kernel")])
+def test_cfg5_scale_k10_scratch_mode_equals_oracle(engine, fast, ways, kernel):
+    """K = 10, T = 20 (cfg5's chain shape, n ~ 200) in scratch mode with an open live window: ffbs_fastk_kernel<double,10>
+    (what a sweep launches by default; one and two slots in flight) and ffbs_item_kernel<double,10,...> (export / rescue
+    kernel): bit-equal paths, logZ to 1e-10; fp32 within tolerance"""
     C, K, t_end = 6, 10, 20.0
     shape = np.random.default_rng(5).uniform(0.6, 3.0, (K, K))
     scale, emis, obs_t, Ws, Ys = make_chains(C, K, shape, t_end, 500)
     oras = oracle_runs(Ws, Ys, obs_t, shape, scale, emis, t_end, sweep=2)
     engine.set_model(shape, scale, 2.0, emis, 1.0, t_end)
-    live_pairs(engine)
-    r = engine.ffbs_host(Ws, [obs_t] * C, Ys, seed=SEED_BACK, sweep=2, precision="f64")
-    live = live_pairs(engine)
+    set_kernel(engine, 0, -1, fast)
+    engine.set_option("fast_ways", ways)
+    try:
+        live_pairs(engine)
+        r = engine.ffbs_host(Ws, [obs_t] * C, Ys, seed=SEED_BACK, sweep=2, precision="f64")
+        live = live_pairs(engine)
+        assert kernel_used(engine) == kernel
+        rescued = int(engine.lib.smjp_ctx_get_stat(engine.ctx, b"ffbs_rescued")) if fast else 0
+        r32 = engine.ffbs_host(Ws, [obs_t] * C, Ys, seed=SEED_BACK, sweep=2, precision="f32")
+        assert kernel_used(engine) == kernel
+        rescued32 = int(engine.lib.smjp_ctx_get_stat(engine.ctx, b"ffbs_rescued"))
+    finally:
+        set_kernel(engine)
+        engine.set_option("fast_ways", 0)
+    assert rescued == 0 and rescued32 == 0
     assert_exact_parity(r, oras, K)
     nominal = sum(n * (n + 1) // 2 for n in r["n"])
     exact = sum(exact_live_pairs(o["alpha"])[0] for o in oras)
     assert min(r["n"]) > 120
-    assert exact <= live < 0.85 * nominal, (exact, live, nominal)
-    r32 = engine.ffbs_host(Ws, [obs_t] * C, Ys, seed=SEED_BACK, sweep=2, precision="f32")
+    assert 0.99 * exact <= live < 0.85 * nominal, (exact, live, nominal)
     assert np.all(r32["status"] == 0)
     differ = 0
     for c, ora in enumerate(oras):
@@ -238,6 +252,29 @@ def test_cfg5_scale_item_kernel_scratch_mode_equals_oracle(engine):
             i = int(np.nonzero(r32["aug_idx"][c] != ora["samples"])[0][-1])
             assert boundary_distance(ora, Ws[c], shape, scale, K, i) < 1e-4, (c, i)
     assert differ <= 1, differ
+
+
+@pytest.mark.parametrize("K", [4, 5, 6, 7, 8, 9, 10])
+def test_fastk_every_K_against_oracle(engine, K):
+    """ffbs_fastk_kernel for every K it is instantiated for (JPS = 32 / K grid points per warp slot: 8, 6, 5, 4, 4, 3,
+    3), ragged batch, non-unit scales, Omega = 3, a ring too small for one of the chains (rescue pass)"""
+    rng = np.random.default_rng(70 + K)
+    t_end, omega = 12.0, 3.0
+    shape = rng.uniform(0.6, 3.0, (K, K)); scale = rng.uniform(2.0, 4.0, (K, K)); emis = O.emission_matrix(K)
+    engine.set_model(shape, scale, omega, emis, 0.8, t_end)
+    Ws = [np.concatenate([[0.0], np.sort(rng.uniform(0, t_end, m)), [t_end]]) for m in (150, 6, 3, 77, 230)]
+    obs_t = np.arange(0.25, t_end, 0.25); obs_y = rng.integers(0, K, len(obs_t))
+    us = [rng.uniform(size=len(W) - 1) for W in Ws]
+    r = engine.ffbs_host(Ws, obs_t, obs_y, uniforms=us, precision="f64")
+    assert kernel_used(engine) == "ffbs_fastk_kernel"
+    for c, W in enumerate(Ws):
+        ora = O.ffbs(W, obs_t, obs_y, shape, scale, omega, emis, 0.8, t_end, us[c])
+        assert r["status"][c] == 0
+        assert np.array_equal(r["aug_idx"][c], ora["samples"]), c
+        assert np.array_equal(r["V"][c], ora["V"]) and np.array_equal(r["T"][c], ora["T"])
+        assert np.abs(r["logZ"][c] - ora["logZ"]).max() < 1e-10
+        tis, jm = O.chain_metrics(ora["V"], ora["T"], K)
+        assert np.array_equal(r["jumps"][c], jm) and np.abs(r["time_in_state"][c] - tis).max() < 1e-12
 
 
 def test_cfg2_sweep_device_loop_equals_oracle_composition(engine):
@@ -270,8 +307,8 @@ def test_cfg2_sweep_device_loop_equals_oracle_composition(engine):
 
 
 @pytest.mark.parametrize("K,precision,warp,fast", [(3, "f64", 0, 1), (3, "f64", 0, 0), (3, "f64", 1, 0), (2, "f64", 0, 1), (2, "f64", 0, 0),
-                                                   (5, "f64", 0, 0), (10, "f64", 0, 0), (12, "f64", 0, 0), (3, "f32", 1, 0),
-                                                   (3, "f32", 0, 0), (3, "f32", 0, 1), (10, "f32", 0, 0)])
+                                                   (5, "f64", 0, 0), (5, "f64", 0, 1), (10, "f64", 0, 0), (10, "f64", 0, 1), (12, "f64", 0, 0),
+                                                   (3, "f32", 1, 0), (3, "f32", 0, 0), (3, "f32", 0, 1), (10, "f32", 0, 0), (10, "f32", 0, 1)])
 def test_grid_points_within_isclose_of_t_end(engine, K, precision, warp, fast):
     """A candidate within numpy.isclose() of t_end (|w - T| <= 1e-8 + 1e-5 T; 0.5 % of the cfg2 chain-sweeps) gives two
     or more rows without the B_v factor in the emission (smjp_utils.py:544-547) while the transition keeps
