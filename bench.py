@@ -321,6 +321,79 @@ def k10_block(local, steps, peak, peak_src, chains=K10_CHAINS, chain_base=0, pre
     return out
 
 
+CFG5_CHAINS = 65536  # BASELINE configs[4]: 65536 chains, 10-state sMJP, SPLIT over the GPUs of the run
+
+
+def cfg5_block(rank, world, local, dev, steps, barrier, overlap=False):
+    """BASELINE configs[4] as stated: 65536 chains of the 10-state sMJP (k10_model, T = 20) split over the N ranks of
+    this run (contiguous ranges, Philox streams keyed by the GLOBAL chain index), Rao-Teh sweeps with the NCCL
+    all-gather of the posterior jump-count / holding-time summaries ([65536, 2K] doubles, mcmc_utils.py:40-56) once per
+    sweep INSIDE the timed loop, on a side stream under the next sweep.  STRONG scaling: the total work is fixed.
+    Rank 0 returns the block; `summaries_sha1` of the gathered summaries after the last sweep is the same at every N
+    (sharded == unsharded, bit for bit)."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    from smjp_b200.chains import DeviceChains
+    from smjp_b200.distributed import SummaryGather, shard_range
+    from smjp_b200.engine import Engine
+    shape, emis = k10_model()
+    lo, hi = shard_range(CFG5_CHAINS, rank, world)
+    C = hi - lo
+    obs_t = np.arange(OBS_DT, K10_T, OBS_DT)
+    out = {"workload": "cfg5: %d chains total, K=10 Weibull sMJP, T=20, D=%d obs, split over %d GPU(s)" % (CFG5_CHAINS, len(obs_t), world),
+           "scaling": "strong", "n_gpus": world, "chains_per_gpu": C, "unit": UNIT}
+    eng = Engine(local)
+    eng.set_model(shape, np.ones((K10_K, K10_K)), OMEGA, emis, 1.0, K10_T)
+    for prec in ("f64", "f32"):
+        ch = DeviceChains(eng, C, obs_t, chain_base=lo)
+        ch.init_prior(np.ones(K10_K) / K10_K, seed=SEED + 31).simulate_observations(seed=SEED + 32)
+        ch.init_prior(np.ones(K10_K) / K10_K, seed=SEED + 33)
+        gather = SummaryGather(CFG5_CHAINS, K10_K, rank, world, dev, overlap=overlap)
+        for sw in range(3):
+            ch.sweep(seed=SEED + 34, sweep=sw, precision=prec)
+            gather.launch(ch.time_in_state, ch.jumps)
+        gather.result()
+        gather.timing.clear()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        snaps = []
+        e0.record()
+        for sw in range(steps):
+            ch.sweep(seed=SEED + 34, sweep=3 + sw, precision=prec)
+            gather.launch(ch.time_in_state, ch.jumps)
+            snaps.append(ch.cur["offs"].clone())
+        tis, jm = gather.result()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        ss = gs = 0.0
+        for offs in snaps:
+            n = (offs[1:] - offs[:-1] - 1).to(torch.float64)
+            ss += float((K10_K * n * (n + 1) / 2).sum().item())
+            gs += float(n.sum().item())
+        st = torch.tensor([ms, ss, gs, float((ch.status != 0).sum().item())], dtype=torch.float64, device=dev)
+        if world > 1:
+            mx = st.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = st.clone()
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            ms, ss, gs, bad = float(mx[0]), float(sm[1]), float(sm[2]), int(sm[3])
+        else:
+            bad = int(st[3])
+        h = hashlib.sha1(tis.cpu().numpy().tobytes() + jm.cpu().numpy().tobytes()).hexdigest()
+        out[prec] = {"value": ss / (ms / 1e3), "ms_per_step": ms / steps, "steps": steps,
+                     "chain_sweeps_per_sec": CFG5_CHAINS * steps / (ms / 1e3), "mean_grid_intervals": gs / (CFG5_CHAINS * steps),
+                     "failed_chains": bad,
+                     "collective": {"op": "all_gather_into_tensor [65536, 20] f64" if world > 1 else "none (1 GPU: staging copy only)",
+                                    "backend": "nccl" if world > 1 else None, "per_sweep": True, "inside_timed_region": True,
+                                    "bytes_per_gather": gather.bytes_per_gather, "gather_ms_avg": gather.gather_ms()},
+                     "summaries_sha1": h}
+        del ch, gather
+    eng.close()
+    return out if rank == 0 else None
+
+
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -380,6 +453,10 @@ def run_ours(args):
     launches0 = eng.launch_count
     spec0 = [eng.lib.smjp_ctx_get_stat(eng.ctx, k) for k in (b"spec_launches", b"spec_misses")]
     sampler = ClockSampler(local)
+    from smjp_b200.distributed import SummaryGather
+    # posterior summaries of ALL chains on every rank, every sweep, inside the timed region: one NCCL all-gather of
+    # [C, 2K] doubles per sweep on a side stream, overlapped with the next sweep (mcmc_utils.py:40-56 per chain)
+    gather = SummaryGather(C * world, K, rank, world, dev, overlap=bool(args.gather_overlap))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ss = gs = 0.0
     alg_bytes = tail_bytes = 0.0
@@ -390,13 +467,16 @@ def run_ours(args):
     ev0.record()
     for i in range(args.steps):
         ch.sweep(seed=SEED, sweep=args.warmup + i, precision=prec)
+        gather.launch(ch.time_in_state, ch.jumps)
         n_snap.append(ch.cur["offs"].clone())  # this sweep's grid windows (the buffer is recycled two sweeps on)
         if step_ev:
             step_ev[i].record()
+    all_tis, all_jumps = gather.result()  # waits for the last gather: inside the timed region
     ev1.record()
     barrier()
     sampler.end()
     ms = ev0.elapsed_time(ev1)
+    gather_ms = gather.gather_ms()
     if step_ev and rank == 0:
         print("per-step ms:", [round(ev0.elapsed_time(e), 2) for e in step_ev], file=sys.stderr)
     launches = eng.launch_count - launches0
@@ -440,6 +520,8 @@ def run_ours(args):
         e_wall = max(time.perf_counter() - t0, 1e-9)
         assert int(np.count_nonzero(ps.status[:C])) == 0
 
+    cfg5 = None if args.no_cfg5 else cfg5_block(rank, world, local, dev, max(3, min(args.steps, 5)), barrier, bool(args.gather_overlap))
+
     # ---- reduce over ranks: time = max, work = sum ----
     ss_rank0 = ss  # this rank's own state-steps (the kernel figures below are rank 0's)
     stats = torch.tensor([ms, ss, gs, alg_bytes, float(launches), k_ms, float(k_cnt), e_wall, e_ss, float(status_bad),
@@ -449,10 +531,6 @@ def run_ours(args):
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        # gather posterior summaries the way a multi-GPU run reports them (NCCL all_gather of [C,2K])
-        summ = torch.cat([ch.time_in_state, ch.jumps.to(torch.float64)], dim=1)
-        out = [torch.empty_like(summ) for _ in range(world)]
-        dist.all_gather(out, summ)
         ms, e_wall = float(mx[0]), float(mx[7])
         ss, gs, alg_total, launches, e_ss = float(sm[1]), float(sm[2]), float(sm[3]), float(sm[4]), float(sm[8])
         status_bad = int(sm[9])
@@ -515,6 +593,14 @@ def run_ours(args):
         # sweeps whose kernels were enqueued for the grid size predicted from the previous sweep, before their own
         # counts reached the host, and how many of those had to be launched again (rank 0)
         "speculative_launches": {"launches": spec[0], "repeated": spec[1]},
+        # the collective of the data path: posterior summaries of every chain gathered on every rank once per sweep,
+        # inside the timed region, overlapped with the next sweep on a side stream
+        "collective": {"op": "all_gather_into_tensor [chains_total, 2K] f64 (time in state, jump counts)" if world > 1 else "none (1 GPU: staging copy only)",
+                       "backend": "nccl" if world > 1 else None, "per_sweep": True, "inside_timed_region": True,
+                       "overlapped_with_next_sweep": bool(args.gather_overlap),
+                       "bytes_per_gather": gather.bytes_per_gather, "gather_ms_avg": gather_ms,
+                       "rows_gathered": int(all_tis.shape[0]), "time_in_state_checksum": float(all_tis.sum().item())},
+        "cfg5": cfg5,
         "e2e": {"value": e_ss / e_wall, "unit": UNIT, "h2d_bytes_per_step": h2d // max(e2e_steps, 1),
                 "d2h_bytes_per_step": d2h // max(e2e_steps, 1), "steps": e2e_steps,
                 "api": "smjp_sweep_host (pinned host buffers in/out; H2D of paths + observations and D2H of the grid inside the timed call, new paths / metrics / status written by the kernels straight into the pinned output buffers)"},
@@ -619,6 +705,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-alt", action="store_true", help="skip the secondary fp32 measurement")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (kernel experiments)")
+    ap.add_argument("--gather-overlap", type=int, default=1, dest="gather_overlap",
+                    help="1: the per-sweep NCCL gather runs on a side stream under the next sweep; 0: ordered between sweeps")
+    ap.add_argument("--no-cfg5", action="store_true", dest="no_cfg5", help="skip the cfg5 strong-scaling block")
     ap.add_argument("--threads", type=int, default=0, help="threads per CTA of the FFBS kernel (0 = auto)")
     ap.add_argument("--item-k3", type=int, default=0, help="experiment: item-parallel kernel for K=3")
     ap.add_argument("--warp", type=int, default=-1, help="warp-per-chain ring kernel (ffbs_warp.cuh): -1 auto, 0 off, 1 on")

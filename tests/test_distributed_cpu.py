@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from smjp_b200.distributed import gather_lognorm, gather_summaries, shard_by_work, shard_range
+from smjp_b200.distributed import SummaryGather, gather_lognorm, gather_summaries, shard_by_work, shard_range
 
 
 def test_shard_ranges_partition_the_chains():
@@ -41,6 +41,12 @@ def _worker(rank, world, port, total, K, q):
     t, j = gather_summaries(full_t[lo:hi].clone(), full_j[lo:hi].clone())
     l = gather_lognorm(full_l[lo:hi].clone())
     ok = bool(torch.equal(t, full_t) and torch.equal(j, full_j) and torch.equal(l, full_l))
+    # the overlapped gather bench.py keeps inside its timed loop (synchronous on CPU tensors)
+    sg = SummaryGather(total, K, rank, world, "cpu")
+    for rep in range(2):
+        sg.launch(full_t[lo:hi] + rep, full_j[lo:hi] + rep)
+    t2, j2 = sg.result()
+    ok = ok and bool(torch.equal(t2, full_t + 1) and torch.equal(j2, full_j + 1)) and sg.launched == 2
     q.put((rank, ok, tuple(t.shape)))
     dist.barrier()
     dist.destroy_process_group()
