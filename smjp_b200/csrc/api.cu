@@ -10,6 +10,7 @@
 #include "candidates.cuh"
 #include "ffbs_launch.cuh"
 #include "dense_smjp.cuh"
+#include "dense_tc.cuh"
 #include "ffbs_big.cuh"
 #include "ffbs_warp.cuh"
 #include "hmm_dense.cuh"
@@ -116,6 +117,10 @@ struct smjp_ctx {
     int ffbs_fast = -1;   // ffbs_fast.cuh (K <= 3, scratch mode): -1 auto (exact fp64), 0 off, 1 on (both precisions)
     int fast_ring = 0;    // its ring slots of `threads` grid points (0 = auto: ~384 grid points)
     int fast_ways = 0;    // grid pairs in flight per thread (0 = auto; 1, 2, 4)
+    int dense_tc = -1;    // tensor-core forward of the dense K-state path (dense_tc.cuh): -1 auto (fp32, 32 <= K <= 64, >= 32768 chains), 0, 1
+    DevBuf d_tile;
+    int last_dense_tc = 0;
+    int64_t dense_nmax_hint = 0;
     int fast_cpb = 0;     // chains per CTA, one warp each (0 = auto; 1..11) -- 32-thread groups only
     int fast_boost[2] = {0, 0};  // extra ring slots learnt from rescue counts, per precision
     int fast_off[2] = {0, 0};    // kept overflowing: ffbs.cuh from now on
@@ -218,6 +223,7 @@ void smjp_ctx_destroy(smjp_ctx_t* c) {
     c->d_big.release();
     c->d_failed.release();
     c->d_live.release();
+    c->d_tile.release();
     c->d_in.release();
     c->d_out.release();
     c->h_in.release();
@@ -261,6 +267,7 @@ int64_t smjp_ctx_get_stat(smjp_ctx_t* c, const char* key) {
     if (!strcmp(key, "ffbs_ring_boost_f64")) return c->ring_boost[0] + 100 * c->warp_off[0];
     if (!strcmp(key, "ffbs_fast_boost_f32")) return c->fast_boost[1] + 100 * c->fast_off[1];
     if (!strcmp(key, "ffbs_fast_boost_f64")) return c->fast_boost[0] + 100 * c->fast_off[0];
+    if (!strcmp(key, "dense_tc")) return c->last_dense_tc;
     if (!strcmp(key, "ffbs_kernel")) return c->last_kernel;  // 0 ffbs.cuh, 1 ffbs_item, 2 ffbs_big, 3 ffbs_warp, 4 ffbs_fast, 5 ffbs_fastk
     if (!strcmp(key, "spec_launches")) return c->spec_launches;
     if (!strcmp(key, "spec_misses")) return c->spec_misses;
@@ -338,6 +345,11 @@ int smjp_ctx_set_option(smjp_ctx_t* c, const char* key, int64_t value) {
     if (!strcmp(key, "fast_ways")) {
         if (value < 0 || value > 4) return fail(SMJP_E_INVALID, "fast_ways must be 0 (auto), 1, 2, 3 or 4");
         c->fast_ways = (int)value;
+        return SMJP_OK;
+    }
+    if (!strcmp(key, "dense_tc")) {
+        if (value < -1 || value > 1) return fail(SMJP_E_INVALID, "dense_tc must be -1 (auto), 0 or 1");
+        c->dense_tc = (int)value;
         return SMJP_OK;
     }
     if (!strcmp(key, "fast_cpb")) {
@@ -1773,8 +1785,33 @@ int smjp_pf_host(smjp_ctx_t* c, int C, const int64_t* obs_offs, const double* ob
 // ------------------------------------------------------------------------------------------------
 namespace {
 
+// forward pass on the tensor cores (dense_tc.cuh): tiles of 128 chains, longest grids first
+int dense_tc_forward(smjp_ctx* c, const DenseArgs& a, int64_t n_max) {
+    const size_t smem = sizeof(DenseTcSmem) + (size_t)a.Kobs * (TC_N + 1) * sizeof(float);
+    if (smem > c->smem_optin) return fail(SMJP_E_UNSUPPORTED, "dense_tc: %zu B of shared memory", smem);
+    int rc = c->d_tile.reserve(16);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(c->d_tile.p, 0, 16, c->stream));
+    const int32_t* order = nullptr;
+    if (a.C > TC_M && c->lpt_order && n_max > 0) {
+        rc = c->d_order.reserve((size_t)a.C * sizeof(int32_t));
+        if (rc) return rc;
+        chain_order_kernel<<<1, 1024, 0, c->stream>>>(a.C, a.w_offs, (int)n_max, (int32_t*)c->d_order.p);
+        CUDA_TRY(cudaGetLastError());
+        c->launches += 1;
+        order = (const int32_t*)c->d_order.p;
+    }
+    const int tiles = (a.C + TC_M - 1) / TC_M;
+    int grid = tiles < 2 * c->num_sms ? tiles : 2 * c->num_sms;
+    CUDA_TRY(cudaFuncSetAttribute(dense_tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dense_tc_forward_kernel<<<grid, TC_THREADS, smem, c->stream>>>(a, order, (int*)c->d_tile.p);
+    CUDA_TRY(cudaGetLastError());
+    c->launches += 1;
+    return SMJP_OK;
+}
+
 template <typename Real>
-int dense_launch(smjp_ctx* c, const DenseArgs& a) {
+int dense_launch(smjp_ctx* c, DenseArgs a, int64_t n_max = 0) {
     const int K = a.K, spl = (K + 31) / 32, warps = DENSE_WARPS;
     const DensePlan plan = dense_plan(K, a.Kobs, sizeof(Real));
     const size_t smem = plan.bytes;
@@ -1785,6 +1822,15 @@ int dense_launch(smjp_ctx* c, const DenseArgs& a) {
         CUDA_TRY(cudaEventCreate(&e0));
         CUDA_TRY(cudaEventCreate(&e1));
         CUDA_TRY(cudaEventRecord(e0, c->stream));
+    }
+    // many chains: the forward matvecs run as [128 chains x 64] x [64 x 64] products on the tensor cores (3xTF32)
+    const bool tc = sizeof(Real) == 4 && K <= TC_N &&
+                    (c->dense_tc == 1 || (c->dense_tc == -1 && K >= 32 && a.C >= 32768));
+    c->last_dense_tc = tc ? 1 : 0;
+    if (tc) {
+        const int rct = dense_tc_forward(c, a, n_max);
+        if (rct) return rct;
+        a.fwd_done = 1;
     }
 #define DENSE_CASE(n)                                                                                       \
     case n:                                                                                                 \
@@ -1861,7 +1907,9 @@ int smjp_ffbs_dense_dev(smjp_ctx_t* c, int C, const int64_t* w_offs, const doubl
     a.time_in_state = time_in_state;
     a.jumps = jumps;
     a.status = status;
-    return precision == SMJP_F64 ? dense_launch<double>(c, a) : dense_launch<float>(c, a);
+    const int64_t n_max = c->dense_nmax_hint;  // set by smjp_sweep_dense_dev (tile ordering of the tensor-core forward)
+    c->dense_nmax_hint = 0;
+    return precision == SMJP_F64 ? dense_launch<double>(c, a, n_max) : dense_launch<float>(c, a, n_max);
 }
 
 int smjp_sweep_dense_dev(smjp_ctx_t* c, int C, const int64_t* p_offs, const int32_t* path_v,
@@ -1879,6 +1927,7 @@ int smjp_sweep_dense_dev(smjp_ctx_t* c, int C, const int64_t* p_offs, const int3
                     (long long)capacity);
     rc = smjp_candidates_fill_dev(c, C, p_offs, path_v, path_t, path_len, seed, sweep, mode, w_offs, soff, W);
     if (rc) return rc;
+    c->dense_nmax_hint = *n_max_host;
     return smjp_ffbs_dense_dev(c, C, w_offs, W, obs_offs, obs_t, obs_y, nullptr, nullptr, seed, sweep, precision,
                                nullptr, path_v_out, path_t_out, path_len_out, time_in_state, jumps, status,
                                *total_w_host);

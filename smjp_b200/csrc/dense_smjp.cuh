@@ -43,6 +43,7 @@ struct DenseArgs {
     double* time_in_state;
     int32_t* jumps;
     int32_t* status;
+    int fwd_done;           // the message rows (and status / logZ) were produced by dense_tc.cuh: backward pass only
 };
 
 // shared-memory plan: Bs [Kr][KV] (rows = source state, zero padded), optional BT [K][KV] (B transposed, for
@@ -157,8 +158,8 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32, 1) dense_smjp_kernel(const D
         // The row kept in shared memory and HBM is r_i = z_i m_i (normalised by the PREVIOUS step's sum only):
         // sum(r_i) is exactly the reference's normaliser z_i, and its warp reduction overlaps the next matvec.
         Real iz = 1;  // 1 / sum(r_{i-1})
-        int flag = 0, dbase = 0;
-        for (int i0 = 0; i0 < n && !flag; i0 += 32) {
+        int flag = a.fwd_done ? a.status[c] : 0, dbase = 0;
+        for (int i0 = 0; i0 < n && !flag && !a.fwd_done; i0 += 32) {
             const int il = i0 + lane;
             const bool live = il < n;
             const double wc_l = W[min(il, n)], wn_l = W[min(il + 1, n)];

@@ -160,3 +160,42 @@ def test_dense_sweep_k64_runs_and_is_seed_reproducible(engine):
     for c in range(C):
         assert np.array_equal(runs[0][0][c], runs[1][0][c]) and np.array_equal(runs[0][1][c], runs[1][1][c])
         assert runs[0][1][c][0] == 0.0 and runs[0][1][c][-1] == t_end and np.all(np.diff(runs[0][1][c]) > 0)
+
+
+@pytest.mark.parametrize("K,C", [(64, 300), (40, 150), (64, 1)])
+def test_tensor_core_forward_matches_oracle_and_the_warp_kernel(engine, K, C):
+    """dense_tc.cuh: the forward matvecs of 128 chains at a time as [128 x 64] x [64 x 64] tcgen05 products (3xTF32,
+    A operand in tensor memory).  Ragged tile (C is no multiple of 128), chains of different lengths in one tile, padded
+    states (K = 40): per-step log normalisers against the fp64 oracle within the fp32 tolerance, and the same sampled
+    paths as the warp-per-chain kernel for (nearly) every chain (same uniforms, fp32 messages differing at the 1e-6
+    level)."""
+    rng = np.random.default_rng(K + C)
+    omega, t_end = 2.0, 9.0
+    scale = rng.uniform(0.5 * K / 8, 2.0 * K / 8, (K, K))   # leaving rates of order 8 per unit time
+    emis = O.emission_matrix(K)
+    engine.set_model(np.ones((K, K)), scale, omega, emis, 1.0, t_end)
+    Ws, ots, oys, us, uj = [], [], [], [], []
+    for c in range(C):
+        n = int(rng.integers(20, 90))
+        W = np.concatenate([[0.0], np.sort(rng.uniform(0, t_end, n - 1)), [t_end]])
+        D = int(rng.integers(0, 25))
+        Ws.append(W); ots.append(np.sort(rng.uniform(0, t_end, D))); oys.append(rng.integers(0, K, D))
+        us.append(rng.uniform(size=n)); uj.append(rng.uniform(size=n))
+    out = {}
+    for tc in (1, 0):
+        engine.set_option("dense_tc", tc)
+        try:
+            out[tc] = engine.ffbs_dense(Ws, ots, oys, u_state=us, u_jump=uj, precision="f32")
+            assert engine.lib.smjp_ctx_get_stat(engine.ctx, b"dense_tc") == tc
+        finally:
+            engine.set_option("dense_tc", -1)
+    r, w = out[1], out[0]
+    assert np.all(r["status"] == 0) and np.all(w["status"] == 0)
+    same = 0
+    for c in range(C):
+        if c < 12:
+            o = O.dense_ffbs_collapsed(Ws[c], ots[c], oys[c], scale, omega, emis, 1.0, t_end, us[c], uj[c])
+            assert np.abs(r["logZ"][c] - o["logZ"]).max() < 2e-4
+        assert np.abs(r["logZ"][c] - w["logZ"][c]).max() < 1e-4
+        same += int(np.array_equal(r["V"][c], w["V"][c]) and np.array_equal(r["T"][c], w["T"][c]))
+    assert same >= C - max(1, C // 50), (same, C)
