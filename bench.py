@@ -321,6 +321,88 @@ def k10_block(local, steps, peak, peak_src, chains=K10_CHAINS, chain_base=0, pre
     return out
 
 
+PF_N = 65536      # BASELINE configs[2]: 65536 particles per chain, 5-state gamma-hazard sMJP, systematic resampling
+PF_K = 5
+PF_T = 10.0
+
+
+def pf_block(rank, world, local, dev, runs_per_gpu, peak, peak_src, reps=2, family="gamma"):
+    """BASELINE configs[2] as stated: bootstrap particle filter (pmcmc.py:224-310) with GAMMA holding-time hazards
+    (shape ~ U(0.6, 3) seed 3, scale 1), K = 5, T = 10, D = 99 observations, 65536 particles per filter run, systematic
+    resampling; `runs_per_gpu` filter runs in flight per GPU through the device-pointer entry point smjp_pf_dev.  With
+    N > 1 GPUs every rank owns its runs and the log-normalisers are gathered over NCCL (gather_lognorm) inside the
+    timed region.  Metric: particle-steps/s (N * D per run); roofline on SURVEY 8(d)'s 68 B per particle-step."""
+    import torch
+    import torch.distributed as dist
+    from smjp_b200.distributed import gather_lognorm
+    from smjp_b200.engine import Engine, pf_dev
+    rng = np.random.default_rng(3)
+    shape = rng.uniform(0.6, 3.0, (PF_K, PF_K))
+    emis = np.ones((PF_K, PF_K)) + 9 * np.eye(PF_K)
+    emis /= emis.sum(axis=1, keepdims=True)
+    eng = Engine(local)
+    eng.set_model(shape, np.ones((PF_K, PF_K)), OMEGA, emis, 1.0, PF_T)
+    eng.set_option("chain_base", rank * runs_per_gpu)
+    obs_t = np.arange(OBS_DT, PF_T, OBS_DT)
+    D = len(obs_t)
+    y = rng.integers(0, PF_K, D)
+    C = runs_per_gpu
+    t = torch
+    d_offs = t.arange(C + 1, dtype=t.int64, device=dev) * D
+    d_ot = t.from_numpy(np.tile(obs_t, C)).to(dev)
+    d_oy = t.from_numpy(np.tile(y, C).astype(np.int32)).to(dev)
+    d_pi0 = t.full((PF_K,), 1.0 / PF_K, dtype=t.float64, device=dev)
+    cap = 256
+    d_po = t.arange(C + 1, dtype=t.int64, device=dev) * cap
+    d_pv = t.zeros(C * cap, dtype=t.int32, device=dev)
+    d_pt = t.zeros(C * cap, dtype=t.float64, device=dev)
+    d_pl = t.zeros(C, dtype=t.int32, device=dev)
+    d_st = t.zeros(C, dtype=t.int32, device=dev)
+    d_ll = t.zeros(C, dtype=t.float64, device=dev)
+
+    def run(seed):
+        pf_dev(eng, C, d_offs, d_ot, d_oy, d_pi0, PF_N, seed, d_ll, d_po, d_pv, d_pt, d_pl, d_st, D, resampler="systematic",
+               family=family)
+        return gather_lognorm(d_ll) if world > 1 else d_ll
+
+    run(SEED + 40)
+    t.cuda.synchronize()
+    eng.set_option("time_kernels", 1)
+    eng.kernel_time("pf")
+    e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    e0.record()
+    for r in range(reps):
+        ll = run(SEED + 41 + r)
+    e1.record()
+    t.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    k_ms, k_cnt = eng.kernel_time("pf")
+    eng.set_option("time_kernels", 0)
+    bad = int((d_st != 0).sum().item())
+    cs = int(eng.lib.smjp_ctx_get_stat(eng.ctx, b"pf_cluster"))
+    if world > 1:
+        st = t.tensor([ms, float(bad)], dtype=t.float64, device=dev)
+        mx = st.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        ms, bad = float(mx[0]), int(mx[1])
+    ll_h = ll.cpu().numpy()
+    eng.close()
+    steps_total = float(PF_N) * D * C * world * reps
+    k_s = k_ms / max(k_cnt, 1) / 1e3
+    ach = 68.0 * PF_N * D * C / k_s / 1e9
+    return {"workload": "cfg3: particle filter, %d particles/run, K=5 %s hazards (shape~U(0.6,3) seed 3), T=10, D=%d, systematic "
+                        "resampling, %d runs in flight per GPU" % (PF_N, family.upper(), D, C),
+            "value": steps_total / (ms / 1e3), "unit": "particle-steps/s", "ms_per_call": ms / reps, "n_gpus": world,
+            "failed_runs": bad, "cluster_size": cs,
+            "loglik_mean": float(ll_h.mean()), "loglik_std_over_runs": float(ll_h.std()), "logliks_gathered": int(ll_h.shape[0]),
+            "collective": "gather_lognorm: NCCL all_gather of [runs] log-normalisers, inside the timed region" if world > 1 else "none (1 GPU)",
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
+                         "kernel": "pf_kernel", "kernel_ms_avg": k_ms / max(k_cnt, 1), "algorithmic_bytes_per_launch": 68.0 * PF_N * D * C,
+                         "bytes_per_particle_step": 68, "traffic": None}}
+
+
 CFG5_CHAINS = 65536  # BASELINE configs[4]: 65536 chains, 10-state sMJP, SPLIT over the GPUs of the run
 
 
@@ -520,6 +602,15 @@ def run_ours(args):
         e_wall = max(time.perf_counter() - t0, 1e-9)
         assert int(np.count_nonzero(ps.status[:C])) == 0
 
+    peak, peak_src = measured_peak()
+    pf = None
+    if not args.no_pf:
+        # as BASELINE states it (gamma holding times: incomplete-gamma inversion per draw), and the same filter with the
+        # reference's own Weibull hazards (distributions.py:296-304) for comparison
+        pf = {"gamma_runs_8": pf_block(rank, world, local, dev, 8, peak, peak_src),
+              "gamma_runs_64": pf_block(rank, world, local, dev, 64, peak, peak_src, reps=1),
+              "weibull_runs_8": pf_block(rank, world, local, dev, 8, peak, peak_src, reps=3, family="weibull"),
+              "weibull_runs_128": pf_block(rank, world, local, dev, 128, peak, peak_src, reps=3, family="weibull")}
     cfg5 = None if args.no_cfg5 else cfg5_block(rank, world, local, dev, max(3, min(args.steps, 5)), barrier, bool(args.gather_overlap))
 
     # ---- reduce over ranks: time = max, work = sum ----
@@ -601,6 +692,7 @@ def run_ours(args):
                        "bytes_per_gather": gather.bytes_per_gather, "gather_ms_avg": gather_ms,
                        "rows_gathered": int(all_tis.shape[0]), "time_in_state_checksum": float(all_tis.sum().item())},
         "cfg5": cfg5,
+        "pf": pf,
         "e2e": {"value": e_ss / e_wall, "unit": UNIT, "h2d_bytes_per_step": h2d // max(e2e_steps, 1),
                 "d2h_bytes_per_step": d2h // max(e2e_steps, 1), "steps": e2e_steps,
                 "api": "smjp_sweep_host (pinned host buffers in/out; H2D of paths + observations and D2H of the grid inside the timed call, new paths / metrics / status written by the kernels straight into the pinned output buffers)"},
@@ -707,6 +799,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (kernel experiments)")
     ap.add_argument("--gather-overlap", type=int, default=1, dest="gather_overlap",
                     help="1: the per-sweep NCCL gather runs on a side stream under the next sweep; 0: ordered between sweeps")
+    ap.add_argument("--no-pf", action="store_true", dest="no_pf", help="skip the cfg3 particle-filter block")
     ap.add_argument("--no-cfg5", action="store_true", dest="no_cfg5", help="skip the cfg5 strong-scaling block")
     ap.add_argument("--threads", type=int, default=0, help="threads per CTA of the FFBS kernel (0 = auto)")
     ap.add_argument("--item-k3", type=int, default=0, help="experiment: item-parallel kernel for K=3")

@@ -242,6 +242,14 @@ int smjp_hmm_dense_host(smjp_ctx_t* ctx, int C, int S, const int64_t* t_offs, co
                         const double* uniforms, uint64_t seed, int precision, void* alpha_hat, double* logc,
                         double* loglik, int32_t* states, int32_t* status);
 
+/* The same on DEVICE pointers, asynchronous on the context's stream (HiddenMarkovModel.likelihood / backward_sampling,
+ * hidden_markov_model.py:213-313, :88-202, for batches that are already resident).  logc / loglik are required here;
+ * sweep keys the Philox stream of the backward draws when uniforms is NULL. */
+int smjp_hmm_dense_dev(smjp_ctx_t* ctx, int C, int S, const int64_t* t_offs, const double* P, int p_steps,
+                       const double* E, const double* emis, int Kobs, const int32_t* y, const double* pi0,
+                       const double* uniforms, uint64_t seed, uint32_t sweep, int precision, void* alpha_hat,
+                       double* logc, double* loglik, int32_t* states, int32_t* status);
+
 /*
  * Bootstrap particle filter, one filter run of N particles per chain.  Replaces smjp_smc
  * (pmcmc.py:224-310) with the two reference defects removed.  Uses the model of
@@ -253,6 +261,16 @@ int smjp_hmm_dense_host(smjp_ctx_t* ctx, int C, int S, const int64_t* t_offs, co
 int smjp_pf_host(smjp_ctx_t* ctx, int C, const int64_t* obs_offs, const double* obs_t, const int32_t* obs_y,
                  const double* pi0, int N, uint64_t seed, int resampler, double* logZ, double* loglik,
                  const int64_t* p_offs, int32_t* path_v, double* path_t, int32_t* path_len, int32_t* status);
+
+/*
+ * The same filter on DEVICE pointers, asynchronous on the context's stream (pmcmc over many chains stays resident:
+ * nothing is staged, nothing synchronises).  max_obs_per_chain bounds obs_offs[c+1] - obs_offs[c] (workspace
+ * sizing); logZ may be NULL.  Replaces smjp_smc (pmcmc.py:224-310) like smjp_pf_host.
+ */
+int smjp_pf_dev(smjp_ctx_t* ctx, int C, const int64_t* obs_offs, const double* obs_t, const int32_t* obs_y,
+                const double* pi0, int N, uint64_t seed, int resampler, int64_t max_obs_per_chain, double* logZ,
+                double* loglik, const int64_t* p_offs, int32_t* path_v, double* path_t, int32_t* path_len,
+                int32_t* status);
 
 /*
  * FFBS on the dense K-state path: the shape == 1 collapse of the sMJP, K <= 128.

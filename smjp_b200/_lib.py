@@ -61,6 +61,10 @@ SIGNATURES = {
                                             c_i64p, c_i64p]),
     "smjp_shape_mle_dev": (ctypes.c_int, [P, ctypes.c_int, ctypes.c_int, P, P, P, P, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                           P, P, P, P, P]),
+    "smjp_pf_dev": (ctypes.c_int, [P, ctypes.c_int, P, P, P, P, ctypes.c_int, ctypes.c_uint64, ctypes.c_int, ctypes.c_int64, P, P,
+                                   P, P, P, P, P]),
+    "smjp_hmm_dense_dev": (ctypes.c_int, [P, ctypes.c_int, ctypes.c_int, P, P, ctypes.c_int, P, P, ctypes.c_int, P, P, P,
+                                          ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int, P, P, P, P, P]),
     "smjp_pf_host": (ctypes.c_int, [P, ctypes.c_int, P, P, P, P, ctypes.c_int, ctypes.c_uint64, ctypes.c_int, P, P,
                                     P, P, P, P, P]),
 }

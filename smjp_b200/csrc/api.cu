@@ -118,7 +118,7 @@ struct smjp_ctx {
     int fast_ring = 0;    // its ring slots of `threads` grid points (0 = auto: ~384 grid points)
     int fast_ways = 0;    // grid pairs in flight per thread (0 = auto; 1, 2, 4)
     int dense_tc = -1;    // tensor-core forward of the dense K-state path (dense_tc.cuh): -1 auto (fp32, 32 <= K <= 64, >= 32768 chains), 0, 1
-    DevBuf d_tile;
+    DevBuf d_tile, d_pfws;
     int last_dense_tc = 0;
     int64_t dense_nmax_hint = 0;
     int fast_cpb = 0;     // chains per CTA, one warp each (0 = auto; 1..11) -- 32-thread groups only
@@ -224,6 +224,7 @@ void smjp_ctx_destroy(smjp_ctx_t* c) {
     c->d_failed.release();
     c->d_live.release();
     c->d_tile.release();
+    c->d_pfws.release();
     c->d_in.release();
     c->d_out.release();
     c->h_in.release();
@@ -1529,6 +1530,41 @@ int hmm_launch(smjp_ctx* c, const HmmArgs& a) {
 
 extern "C" {
 
+int smjp_hmm_dense_dev(smjp_ctx_t* c, int C, int S, const int64_t* t_offs, const double* P, int p_steps,
+                       const double* E, const double* emis, int Kobs, const int32_t* y, const double* pi0,
+                       const double* uniforms, uint64_t seed, uint32_t sweep, int precision, void* alpha_hat,
+                       double* logc, double* loglik, int32_t* states, int32_t* status) {
+    if (!c) return fail(SMJP_E_INVALID, "null context");
+    if (C <= 0) return C == 0 ? SMJP_OK : fail(SMJP_E_INVALID, "C < 0");
+    if (S < 1 || S > 128) return fail(SMJP_E_UNSUPPORTED, "dense HMM kernel supports 1 <= S <= 128 (S=%d)", S);
+    if (!t_offs || !P || !pi0 || !alpha_hat || !logc || !loglik || !status) return fail(SMJP_E_INVALID, "null required pointer");
+    if (!E && (!emis || !y || Kobs < 1)) return fail(SMJP_E_INVALID, "need dense E or an emission table with symbols");
+    if (precision != SMJP_F64 && precision != SMJP_F32) return fail(SMJP_E_INVALID, "bad precision");
+    CUDA_TRY(cudaSetDevice(c->device));
+    HmmArgs a;
+    memset(&a, 0, sizeof a);
+    a.C = C;
+    a.S = S;
+    a.t_offs = t_offs;
+    a.P = P;
+    a.p_steps = p_steps > 0 ? p_steps : 0;
+    a.E = E;
+    a.emis = E ? nullptr : emis;
+    a.y = E ? nullptr : y;
+    a.Kobs = Kobs;
+    a.pi0 = pi0;
+    a.uniforms = uniforms;
+    a.seed = seed;
+    a.sweep = sweep;
+    a.chain_base = c->chain_base;
+    a.alpha_hat = alpha_hat;
+    a.logc = logc;
+    a.loglik = loglik;
+    a.states = states;
+    a.status = status;
+    return precision == SMJP_F64 ? hmm_launch<double>(c, a) : hmm_launch<float>(c, a);
+}
+
 int smjp_hmm_dense_host(smjp_ctx_t* c, int C, int S, const int64_t* t_offs, const double* P, int p_steps,
                         const double* E, const double* emis, int Kobs, const int32_t* y, const double* pi0,
                         const double* uniforms, uint64_t seed, int precision, void* alpha_hat, double* logc,
@@ -1614,80 +1650,26 @@ int smjp_hmm_dense_host(smjp_ctx_t* c, int C, int S, const int64_t* t_offs, cons
     return SMJP_OK;
 }
 
-int smjp_pf_host(smjp_ctx_t* c, int C, const int64_t* obs_offs, const double* obs_t, const int32_t* obs_y,
-                 const double* pi0, int N, uint64_t seed, int resampler, double* logZ, double* loglik,
-                 const int64_t* p_offs, int32_t* path_v, double* path_t, int32_t* path_len, int32_t* status) {
-    int rc = model_ready(c);
-    if (rc) return rc;
-    if (C <= 0) return C == 0 ? SMJP_OK : fail(SMJP_E_INVALID, "C < 0");
-    if (N < 1 || N > (1 << 24)) return fail(SMJP_E_INVALID, "N=%d outside [1, 2^24]", N);
-    if (resampler != SMJP_RESAMPLE_MULTINOMIAL && resampler != SMJP_RESAMPLE_SYSTEMATIC)
-        return fail(SMJP_E_INVALID, "bad resampler");
-    if (!obs_offs || !pi0 || !loglik || !p_offs || !path_v || !path_t || !path_len || !status)
-        return fail(SMJP_E_INVALID, "null required pointer");
-    if (obs_offs[0] != 0 || p_offs[0] != 0) return fail(SMJP_E_INVALID, "offsets must start at 0");
+}  // extern "C"
+
+namespace {
+
+// workspaces + launch of the particle filter; the caller has set the input / output pointers of `a` (device memory)
+int pf_launch(smjp_ctx* c, PfArgs a, int C, int N, int64_t Dmax, uint64_t seed, int resampler) {
     const int K = c->K;
-    const int64_t total_o = obs_offs[C], total_p = p_offs[C];
-    int64_t Dmax = 0;
-    for (int i = 0; i < C; ++i) {
-        const int64_t D = obs_offs[i + 1] - obs_offs[i];
-        if (D < 0) return fail(SMJP_E_INVALID, "obs_offs not monotone");
-        if (D > Dmax) Dmax = D;
-        if (p_offs[i + 1] - p_offs[i] < 2) return fail(SMJP_E_INVALID, "path window of chain %d smaller than 2", i);
-        for (int64_t d = obs_offs[i]; d < obs_offs[i + 1]; ++d) {
-            if (obs_y[d] < 0 || obs_y[d] >= c->Kobs) return fail(SMJP_E_INVALID, "observation symbol outside [0,Kobs)");
-            if (d > obs_offs[i] && !(obs_t[d] >= obs_t[d - 1])) return fail(SMJP_E_INVALID, "observation times not sorted");
-        }
-    }
-    double ptot = 0;
-    for (int s = 0; s < K; ++s) {
-        if (!(pi0[s] >= 0)) return fail(SMJP_E_INVALID, "pi0[%d] negative", s);
-        ptot += pi0[s];
-    }
-    if (!(ptot > 0)) return fail(SMJP_E_INVALID, "pi0 has no mass");
-    CUDA_TRY(cudaSetDevice(c->device));
+    const int64_t Dw = Dmax > 0 ? Dmax : 1;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += smjp::align_up(bytes, 16); return o; };
-    const size_t o_oo = take((C + 1) * 8), o_ot = take(total_o * 8), o_oy = take(total_o * 4);
-    const size_t o_po = take((C + 1) * 8), o_pi = take(K * 8);
-    const size_t in_bytes = off;
-    rc = c->h_in.reserve(in_bytes);
-    if (rc) return rc;
-    rc = c->d_in.reserve(in_bytes);
-    if (rc) return rc;
-    char* h = (char*)c->h_in.p;
-    memcpy(h + o_oo, obs_offs, (C + 1) * 8);
-    if (total_o) {
-        memcpy(h + o_ot, obs_t, total_o * 8);
-        memcpy(h + o_oy, obs_y, total_o * 4);
-    }
-    memcpy(h + o_po, p_offs, (C + 1) * 8);
-    memcpy(h + o_pi, pi0, K * 8);
-    CUDA_TRY(cudaMemcpyAsync(c->d_in.p, h, in_bytes, cudaMemcpyHostToDevice, c->stream));
-    // outputs + workspaces
-    off = 0;
-    const size_t o_st = take(C * 4), o_pl = take(C * 4), o_ll = take(C * 8), o_lz = take(total_o * 8 + 8);
-    const size_t o_pv = take(total_p * 4), o_pt = take(total_p * 8);
-    const size_t out_bytes = off;
     const size_t o_wv = take((size_t)C * 2 * N * 4), o_wl = take((size_t)C * 2 * N * 8), o_cdf = take((size_t)C * N * 8);
-    const size_t o_anc = take((size_t)C * (Dmax > 0 ? Dmax : 1) * N * 4), o_line = take((size_t)C * (Dmax > 0 ? Dmax : 1) * 4);
-    rc = c->d_out.reserve(off);
+    const size_t o_anc = take((size_t)C * Dw * N * 4), o_line = take((size_t)C * Dw * 4), o_lz = take((size_t)C * Dw * 8 + 8);
+    int rc = c->d_pfws.reserve(off);
     if (rc) return rc;
-    rc = c->h_out.reserve(out_bytes);
-    if (rc) return rc;
-    char* d = (char*)c->d_in.p;
-    char* o = (char*)c->d_out.p;
-    PfArgs a;
-    memset(&a, 0, sizeof a);
+    char* o = (char*)c->d_pfws.p;
     a.C = C;
     a.N = N;
     a.K = K;
     a.Kobs = c->Kobs;
-    a.obs_offs = (const int64_t*)(d + o_oo);
-    a.obs_t = (const double*)(d + o_ot);
-    a.obs_y = (const int32_t*)(d + o_oy);
     a.model = (const double*)c->d_model.p;
-    a.pi0 = (const double*)(d + o_pi);
     a.t_end = c->t_end;
     a.seed = seed;
     a.chain_base = c->chain_base;
@@ -1699,16 +1681,10 @@ int smjp_pf_host(smjp_ctx_t* c, int C, const int64_t* obs_offs, const double* ob
     a.pl = (double*)(o + o_wl);
     a.cdf = (double*)(o + o_cdf);
     a.anc = (int32_t*)(o + o_anc);
-    a.anc_stride = (int64_t)(Dmax > 0 ? Dmax : 1) * N;
+    a.anc_stride = Dw * N;
     a.lineage = (int32_t*)(o + o_line);
-    a.lineage_stride = Dmax > 0 ? Dmax : 1;
-    a.logZ = (double*)(o + o_lz);
-    a.loglik = (double*)(o + o_ll);
-    a.p_offs = (const int64_t*)(d + o_po);
-    a.path_v = (int32_t*)(o + o_pv);
-    a.path_t = (double*)(o + o_pt);
-    a.path_len = (int32_t*)(o + o_pl);
-    a.status = (int32_t*)(o + o_st);
+    a.lineage_stride = Dw;
+    if (!a.logZ) a.logZ = (double*)(o + o_lz);  // (per observation, ragged by obs_offs: never more than C * Dmax entries)
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c->time_kernels) {
         CUDA_TRY(cudaEventCreate(&e0));
@@ -1766,6 +1742,119 @@ int smjp_pf_host(smjp_ctx_t* c, int C, const int64_t* obs_offs, const double* ob
         c->pf_events.emplace_back(e0, e1);
     }
     c->launches += 1;
+    return SMJP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int smjp_pf_dev(smjp_ctx_t* c, int C, const int64_t* obs_offs, const double* obs_t, const int32_t* obs_y,
+                const double* pi0, int N, uint64_t seed, int resampler, int64_t max_obs_per_chain, double* logZ,
+                double* loglik, const int64_t* p_offs, int32_t* path_v, double* path_t, int32_t* path_len,
+                int32_t* status) {
+    int rc = model_ready(c);
+    if (rc) return rc;
+    if (C <= 0) return C == 0 ? SMJP_OK : fail(SMJP_E_INVALID, "C < 0");
+    if (N < 1 || N > (1 << 24)) return fail(SMJP_E_INVALID, "N=%d outside [1, 2^24]", N);
+    if (resampler != SMJP_RESAMPLE_MULTINOMIAL && resampler != SMJP_RESAMPLE_SYSTEMATIC)
+        return fail(SMJP_E_INVALID, "bad resampler");
+    if (max_obs_per_chain < 0) return fail(SMJP_E_INVALID, "max_obs_per_chain < 0");
+    if (!obs_offs || !pi0 || !loglik || !p_offs || !path_v || !path_t || !path_len || !status)
+        return fail(SMJP_E_INVALID, "null required pointer");
+    CUDA_TRY(cudaSetDevice(c->device));
+    PfArgs a;
+    memset(&a, 0, sizeof a);
+    a.obs_offs = obs_offs;
+    a.obs_t = obs_t;
+    a.obs_y = obs_y;
+    a.pi0 = pi0;
+    a.logZ = logZ;
+    a.loglik = loglik;
+    a.p_offs = p_offs;
+    a.path_v = path_v;
+    a.path_t = path_t;
+    a.path_len = path_len;
+    a.status = status;
+    return pf_launch(c, a, C, N, max_obs_per_chain, seed, resampler);
+}
+
+int smjp_pf_host(smjp_ctx_t* c, int C, const int64_t* obs_offs, const double* obs_t, const int32_t* obs_y,
+                 const double* pi0, int N, uint64_t seed, int resampler, double* logZ, double* loglik,
+                 const int64_t* p_offs, int32_t* path_v, double* path_t, int32_t* path_len, int32_t* status) {
+    int rc = model_ready(c);
+    if (rc) return rc;
+    if (C <= 0) return C == 0 ? SMJP_OK : fail(SMJP_E_INVALID, "C < 0");
+    if (N < 1 || N > (1 << 24)) return fail(SMJP_E_INVALID, "N=%d outside [1, 2^24]", N);
+    if (resampler != SMJP_RESAMPLE_MULTINOMIAL && resampler != SMJP_RESAMPLE_SYSTEMATIC)
+        return fail(SMJP_E_INVALID, "bad resampler");
+    if (!obs_offs || !pi0 || !loglik || !p_offs || !path_v || !path_t || !path_len || !status)
+        return fail(SMJP_E_INVALID, "null required pointer");
+    if (obs_offs[0] != 0 || p_offs[0] != 0) return fail(SMJP_E_INVALID, "offsets must start at 0");
+    const int K = c->K;
+    const int64_t total_o = obs_offs[C], total_p = p_offs[C];
+    int64_t Dmax = 0;
+    for (int i = 0; i < C; ++i) {
+        const int64_t D = obs_offs[i + 1] - obs_offs[i];
+        if (D < 0) return fail(SMJP_E_INVALID, "obs_offs not monotone");
+        if (D > Dmax) Dmax = D;
+        if (p_offs[i + 1] - p_offs[i] < 2) return fail(SMJP_E_INVALID, "path window of chain %d smaller than 2", i);
+        for (int64_t d = obs_offs[i]; d < obs_offs[i + 1]; ++d) {
+            if (obs_y[d] < 0 || obs_y[d] >= c->Kobs) return fail(SMJP_E_INVALID, "observation symbol outside [0,Kobs)");
+            if (d > obs_offs[i] && !(obs_t[d] >= obs_t[d - 1])) return fail(SMJP_E_INVALID, "observation times not sorted");
+        }
+    }
+    double ptot = 0;
+    for (int s = 0; s < K; ++s) {
+        if (!(pi0[s] >= 0)) return fail(SMJP_E_INVALID, "pi0[%d] negative", s);
+        ptot += pi0[s];
+    }
+    if (!(ptot > 0)) return fail(SMJP_E_INVALID, "pi0 has no mass");
+    CUDA_TRY(cudaSetDevice(c->device));
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += smjp::align_up(bytes, 16); return o; };
+    const size_t o_oo = take((C + 1) * 8), o_ot = take(total_o * 8), o_oy = take(total_o * 4);
+    const size_t o_po = take((C + 1) * 8), o_pi = take(K * 8);
+    const size_t in_bytes = off;
+    rc = c->h_in.reserve(in_bytes);
+    if (rc) return rc;
+    rc = c->d_in.reserve(in_bytes);
+    if (rc) return rc;
+    char* h = (char*)c->h_in.p;
+    memcpy(h + o_oo, obs_offs, (C + 1) * 8);
+    if (total_o) {
+        memcpy(h + o_ot, obs_t, total_o * 8);
+        memcpy(h + o_oy, obs_y, total_o * 4);
+    }
+    memcpy(h + o_po, p_offs, (C + 1) * 8);
+    memcpy(h + o_pi, pi0, K * 8);
+    CUDA_TRY(cudaMemcpyAsync(c->d_in.p, h, in_bytes, cudaMemcpyHostToDevice, c->stream));
+    // outputs + workspaces
+    off = 0;
+    const size_t o_st = take(C * 4), o_pl = take(C * 4), o_ll = take(C * 8), o_lz = take(total_o * 8 + 8);
+    const size_t o_pv = take(total_p * 4), o_pt = take(total_p * 8);
+    const size_t out_bytes = off;
+    rc = c->d_out.reserve(off);
+    if (rc) return rc;
+    rc = c->h_out.reserve(out_bytes);
+    if (rc) return rc;
+    char* d = (char*)c->d_in.p;
+    char* o = (char*)c->d_out.p;
+    PfArgs a;
+    memset(&a, 0, sizeof a);
+    a.obs_offs = (const int64_t*)(d + o_oo);
+    a.obs_t = (const double*)(d + o_ot);
+    a.obs_y = (const int32_t*)(d + o_oy);
+    a.pi0 = (const double*)(d + o_pi);
+    a.logZ = (double*)(o + o_lz);
+    a.loglik = (double*)(o + o_ll);
+    a.p_offs = (const int64_t*)(d + o_po);
+    a.path_v = (int32_t*)(o + o_pv);
+    a.path_t = (double*)(o + o_pt);
+    a.path_len = (int32_t*)(o + o_pl);
+    a.status = (int32_t*)(o + o_st);
+    rc = pf_launch(c, a, C, N, Dmax, seed, resampler);
+    if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(c->h_out.p, o, out_bytes, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     char* ho = (char*)c->h_out.p;

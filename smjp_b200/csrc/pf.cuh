@@ -67,9 +67,10 @@ struct PfArgs {
 // upper incomplete gamma function (series / continued fraction, inverse by Halley steps from a
 // Wilson-Hilferty start).  Twin: oracle cond_gamma (scipy.special.gammaincc / gammainccinv).
 // ------------------------------------------------------------------------------------------------
-__device__ inline double igamc(double a, double x) {
+// lga = lgamma(a): a model constant, tabulated once per filter run (it was recomputed ~10 times per draw)
+__device__ inline double igamc(double a, double x, double lga) {
     if (!(x > 0.0)) return 1.0;
-    const double lax = a * log(x) - x - lgamma(a);
+    const double lax = a * log(x) - x - lga;
     if (lax < -745.0) return x < a + 1.0 ? 1.0 : 0.0;
     const double ax = exp(lax);
     if (x < a + 1.0) {  // P(a,x) by series
@@ -99,21 +100,21 @@ __device__ inline double igamc(double a, double x) {
     return ax * h;
 }
 
-__device__ inline double igamci(double a, double q) {  // x with Q(a, x) = q
+__device__ inline double igamci(double a, double q, double lga) {  // x with Q(a, x) = q
     if (q >= 1.0) return 0.0;
     if (!(q > 0.0)) return INFINITY;
     const double t = -normcdfinv(q), d = 1.0 / (9.0 * a), y = 1.0 - d + t * sqrt(d);
     double x = a * y * y * y;
     if (x <= 0.0 || a < 1.0) {
         const double p = 1.0 - q;
-        const double x0 = exp((log(fmax(p, 1e-300)) + lgamma(a + 1.0)) / a);
+        const double x0 = exp((log(fmax(p, 1e-300)) + lga + log(a)) / a);  // lgamma(a + 1) = lgamma(a) + log a
         if (x <= 0.0) x = x0;
         else if (p < 0.5) x = x0;
         else x = fmax(x, x0);
     }
     for (int it = 0; it < 60; ++it) {
-        const double f = igamc(a, x) - q;
-        const double fp = -exp((a - 1.0) * log(x) - x - lgamma(a));
+        const double f = igamc(a, x, lga) - q;
+        const double fp = -exp((a - 1.0) * log(x) - x - lga);
         if (fp == 0.0) break;
         double dx = f / fp;
         const double den = 1.0 - 0.5 * dx * ((a - 1.0) / x - 1.0);
@@ -136,6 +137,7 @@ struct PfMath {
     const double* scale;  // lambda / theta                        [K*K] global
     const double* rk;     // 1/k: shared-memory cache, or null -> divide
     const double* l2lam;  // log2(lambda): shared-memory cache, or null -> c2 / k
+    const double* lga;    // gamma family: lgamma(a), shared-memory cache, or null -> lgamma()
 };
 
 // One round of competing risks for a particle in state v that has held for `hold`: K conditional holding-time
@@ -164,7 +166,8 @@ __device__ __forceinline__ double pf_round(const PfArgs& a, const PfMath& m, uin
         double key;  // gamma: tau itself; Weibull: log2 tau
         if (gamma) {
             const double k = m.shape[t], lam = m.scale[t];
-            key = lam * igamci(k, (1.0 - u) * igamc(k, hold / lam));
+            const double lga = m.lga ? m.lga[t] : lgamma(k);
+            key = lam * igamci(k, (1.0 - u) * igamc(k, hold / lam, lga), lga);
         } else {
             const double k = m.shape[t];
             const double hk = l2h == -INFINITY ? 0.0 : m.ex2(S * (k * l2h - m.c2[t]));  // (hold/lambda)^k
@@ -223,6 +226,7 @@ __global__ void __launch_bounds__(B) pf_kernel(const PfArgs a) {
     __shared__ double s_off[PF_MAXW];   // their exclusive prefix within the CTA
     __shared__ double s_rk[PF_RK];
     __shared__ double s_l2lam[PF_RK];
+    __shared__ double s_lga[PF_RK];
     __shared__ double s_tab[Exp2<double>::TAB];
     __shared__ double2 s_ltab[Exp2<double>::LTAB];
     __shared__ double s_total;          // this CTA's weight total, read by the whole cluster
@@ -245,6 +249,7 @@ __global__ void __launch_bounds__(B) pf_kernel(const PfArgs a) {
         for (int t = tid; t < K * K; t += B) {
             s_rk[t] = 1.0 / a.model[t];
             s_l2lam[t] = a.model[K * K + t] / a.model[t];
+            s_lga[t] = lgamma(a.model[t]);
         }
     PfMath m;
     m.ex2.tab = s_tab;
@@ -254,6 +259,7 @@ __global__ void __launch_bounds__(B) pf_kernel(const PfArgs a) {
     m.scale = a.model + 2 * K * K + K * a.Kobs;
     m.rk = K * K <= PF_RK ? s_rk : nullptr;
     m.l2lam = K * K <= PF_RK ? s_l2lam : nullptr;
+    m.lga = K * K <= PF_RK ? s_lga : nullptr;
     __syncthreads();
     for (int c = cluster_id; c < a.C; c += n_clusters) {
         const uint32_t chain = a.chain_base + (uint32_t)c;

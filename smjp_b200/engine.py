@@ -242,6 +242,21 @@ class Engine:
                                      _ptr(time_in_state), _ptr(jumps), _ptr(status), int(n_max), int(total_w)))
 
 
+def pf_dev(eng, C, obs_offs, obs_t, obs_y, pi0, N, seed, loglik, p_offs, path_v, path_t, path_len, status,
+           max_obs_per_chain, resampler="systematic", family="weibull", logZ=None, extend=False):
+    """Bootstrap particle filter (smjp_smc, pmcmc.py:224-310) on DEVICE tensors (torch), asynchronous on the context's
+    stream: nothing is staged and nothing synchronises, so pmcmc over many chains stays resident."""
+    res = {"multinomial": _lib.RESAMPLE_MULTINOMIAL, "systematic": _lib.RESAMPLE_SYSTEMATIC}[resampler]
+    eng.set_option("pf_extend", int(bool(extend)))
+    eng.set_option("hazard_family", {"weibull": 0, "gamma": 1}[family])
+    try:
+        check(eng.lib.smjp_pf_dev(eng.ctx, int(C), _ptr(obs_offs), _ptr(obs_t), _ptr(obs_y), _ptr(pi0), int(N),
+                                  int(seed) & 0xFFFFFFFFFFFFFFFF, res, int(max_obs_per_chain), _ptr(logZ), _ptr(loglik),
+                                  _ptr(p_offs), _ptr(path_v), _ptr(path_t), _ptr(path_len), _ptr(status)))
+    finally:
+        eng.set_option("hazard_family", 0)
+
+
 def _pack_paths(V, T):
     lens = [len(v) for v in V]
     if any(len(t) != l for t, l in zip(T, lens)):

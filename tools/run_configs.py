@@ -39,7 +39,7 @@ def cfg1():
             "state_steps_per_sec": ss / dt, "reference_measured_sweeps_per_sec": 1.04, "note": "latency-bound: 2 host calls per sweep"}
 
 
-def cfg3(N=65536, C=8, cluster=0, threads=0):
+def cfg3(N=65536, C=8, cluster=0, threads=0, family="gamma"):
     """pmcmc particle filter: 65536 particles per chain, 5-state sMJP, systematic resampling"""
     import torch
     from smjp_b200.engine import Engine, pf_host
@@ -51,16 +51,16 @@ def cfg3(N=65536, C=8, cluster=0, threads=0):
     y = rng.integers(0, K, len(obs_t))
     eng.set_option("pf_cluster", cluster)
     eng.set_option("pf_threads", threads)
-    pf_host(eng, obs_t, y, np.ones(K) / K, N, seed=1, C=C)
+    pf_host(eng, obs_t, y, np.ones(K) / K, N, seed=1, C=C, family=family)
     torch.cuda.synchronize()
     eng.set_option("time_kernels", 1)
     t0 = time.perf_counter()
-    r = pf_host(eng, obs_t, y, np.ones(K) / K, N, seed=2, C=C)
+    r = pf_host(eng, obs_t, y, np.ones(K) / K, N, seed=2, C=C, family=family)
     dt = time.perf_counter() - t0
     kms, _ = eng.kernel_time("pf")
     cs = eng.lib.smjp_ctx_get_stat(eng.ctx, b"pf_cluster")
     eng.close()
-    return {"config": "cfg3 particle filter N=%d, K=5 Weibull hazards, D=%d, %d filter runs, systematic" % (N, len(obs_t), C),
+    return {"config": "cfg3 particle filter N=%d, K=5 %s hazards, D=%d, %d filter runs, systematic" % (N, family, len(obs_t), C),
             "cluster": cs, "threads": threads,
             "particle_steps_per_sec": N * len(obs_t) * C / dt, "seconds": dt, "kernel_ms": kms,
             "kernel_particle_steps_per_sec": N * len(obs_t) * C / (kms / 1e3), "loglik_spread": float(np.ptp(r["loglik"])),
