@@ -208,3 +208,51 @@ def test_particle_filter_cluster_sizes_agree(engine, cs):
     assert np.allclose(r["loglik"], ref["loglik"], rtol=0, atol=1e-10)
     for c in range(3):
         assert np.array_equal(r["V"][c], ref["V"][c]) and np.array_equal(r["T"][c], ref["T"][c])
+
+
+@pytest.mark.parametrize("family", ["weibull", "gamma"])
+def test_particle_filter_at_cfg3_scale_reproduces_the_exact_mjp_likelihood(engine, family):
+    """Statistical anchor at BASELINE configs[2]'s scale: N = 65536 particles, K = 5, systematic resampling, cluster
+    launch (the runs are spread over several CTAs each).  With exponential holding times (Weibull shape 1 == gamma
+    shape 1) the sMJP is a Markov jump process and log p(y) is exact: pi0' prod_d [expm(Q dt_d) diag(P(y_d | .))] 1.
+    The filter's log-normaliser (pmcmc.py:294-297, summed) must reproduce it -- for BOTH hazard families, through the
+    host and the device-pointer entry points."""
+    import torch
+    from scipy.linalg import expm
+    from smjp_b200.engine import pf_dev, pf_host
+    rng = np.random.default_rng(65536)
+    K, t_end, N, C = 5, 10.0, 65536, 6
+    scale = rng.uniform(1.0, 4.0, (K, K))
+    emis = O.emission_matrix(K)
+    engine.set_model(np.ones((K, K)), scale, 2.0, emis, 1.0, t_end)
+    obs_t = np.arange(0.4, t_end, 0.4)
+    y = rng.integers(0, K, len(obs_t))
+    pi0 = np.array([0.1, 0.3, 0.2, 0.25, 0.15])
+    Q = 1.0 / scale
+    np.fill_diagonal(Q, 0.0)            # self-jumps do not move the state
+    Q -= np.diag(Q.sum(axis=1))
+    a, ll, t_prev = pi0.copy(), 0.0, 0.0
+    for t, s in zip(obs_t, y):
+        a = (a @ expm(Q * (t - t_prev))) * emis[:, s]
+        ll += np.log(a.sum())
+        a /= a.sum()
+        t_prev = t
+    r = pf_host(engine, obs_t, y, pi0, N, seed=11, C=C, family=family)
+    assert np.all(r["status"] == 0)
+    assert engine.lib.smjp_ctx_get_stat(engine.ctx, b"pf_cluster") > 1        # the cluster path
+    assert np.abs(r["loglik"] - ll).max() < 0.15, (r["loglik"], ll)            # sd of one estimate ~ 0.035 at this N
+    assert abs(r["loglik"].mean() - ll) < 0.06                                  # sd of the mean of 6 ~ 0.015
+    # device-pointer entry point: same runs, same numbers
+    dev = torch.device("cuda", engine.device)
+    D = len(obs_t)
+    d = lambda x, dt: torch.from_numpy(np.ascontiguousarray(x, dtype=dt)).to(dev)
+    cap = 256
+    out = dict(ll=torch.zeros(C, dtype=torch.float64, device=dev), pv=torch.zeros(C * cap, dtype=torch.int32, device=dev),
+               pt=torch.zeros(C * cap, dtype=torch.float64, device=dev), pl=torch.zeros(C, dtype=torch.int32, device=dev),
+               st=torch.zeros(C, dtype=torch.int32, device=dev))
+    pf_dev(engine, C, d(np.arange(C + 1) * D, np.int64), d(np.tile(obs_t, C), np.float64), d(np.tile(y, C), np.int32),
+           d(pi0, np.float64), N, 11, out["ll"], d(np.arange(C + 1) * cap, np.int64), out["pv"], out["pt"], out["pl"], out["st"], D,
+           family=family)
+    engine.sync()
+    assert np.array_equal(out["ll"].cpu().numpy(), r["loglik"])
+    assert int(out["st"].abs().sum().item()) == 0
