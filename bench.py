@@ -214,6 +214,39 @@ def cpu_sample(n_chains, sweeps, t_end, procs):
     return ss, gs, wall
 
 
+def time_unmodified_reference(budget_s=12.0):
+    """The UNMODIFIED reference (oracle/_ref = a copy of /root/reference's pure-Python sources, imported behind
+    oracle/ref_shim.py) on cfg1 = main.py's default model (experiments.py:154-222): the loop body of raoteh.py:58-59
+    (candidates + smjp_ffbs), one core -- BASELINE.md section 3 item 1.  ~1 sweep/s, so a handful of sweeps."""
+    try:
+        from oracle import ref_shim
+        if not ref_shim.reference_available():
+            return {"unavailable": "oracle/_ref is missing (run `make -C oracle` where /root/reference exists)"}
+        ref = ref_shim.load_reference()
+        shape = SHAPE
+        model = ref_shim.build_reference_model(ref, [1, 2, 3], shape, np.ones((3, 3)), 2, 2.0, np.arange(0.1, 2.0, 0.1),
+                                               [1, 1, 1, 1, 1, 1, 2, 2, 2, 1, 1, 1, 1, 3, 3, 2, 1, 1, 3], 1.0)
+        np.random.seed(SEED % (2 ** 31))
+        with ref_shim.quiet():
+            V, T = ref.smjp.sample_smjp_trajectory_prior(model.hazard_A, model.pi_0, [1, 2, 3], 2.0)
+        ss = gs = 0.0
+        sweeps = 0
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < budget_s and sweeps < 200:
+            with ref_shim.quiet():
+                W = ref.smjp.sample_smjp_event_times(model.pp_A_hat, V, T, 2.0)
+                V, T, _ = ref.smjp.smjp_ffbs(W, model.data, [1, 2, 3], model.hazard_A, model.hazard_B, model.emission, 2.0, "bench")
+            n = len(W) - 1
+            ss += 3 * n * (n + 1) / 2
+            gs += n
+            sweeps += 1
+        dt = time.perf_counter() - t0
+        return {"kind": "reference", "value": ss / dt, "unit": UNIT, "cores": 1, "sweeps_per_sec": sweeps / dt, "grid_steps_per_sec": gs / dt,
+                "sample": "%d sweeps of cfg1 (main.py default: K=3, T=2, 19 observations, n~11), unmodified gauenk/smjp via oracle/ref_shim.py" % sweeps}
+    except Exception as e:  # the port's line must still be printed
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port; the Python reference itself cannot
     travel to the GPU box) on all host cores, on a bounded sample of the same workload per step."""
@@ -243,6 +276,8 @@ def run_reference(args):
                              "sample": "%d full-size cfg2 chains (T=100, n~500) x %d sweeps per step, NumPy oracle, "
                                        "%d processes" % (sample_chains, SWEEPS_PER_REF_STEP, procs)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            # beside the port: the unmodified Python reference itself, on the only configuration it finishes (cfg1)
+            "reference_unmodified": time_unmodified_reference(),
             "chain_sweeps_per_sec": sample_chains * SWEEPS_PER_REF_STEP * args.steps / wall, "grid_steps_per_sec": tot_gs / wall}
     print(json.dumps(line), flush=True)
 

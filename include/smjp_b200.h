@@ -42,6 +42,7 @@ extern "C" {
 #define SMJP_ST_GRID_NOT_INCREASING 1 /* smjp_utils.py:398-399 "We can not have time_p >= time_c" */
 #define SMJP_ST_DEGENERATE 2          /* zero / non-finite normaliser (hidden_markov_model.py:170-185) */
 #define SMJP_ST_OVERFLOW 4            /* an output or workspace capacity was too small */
+#define SMJP_ST_BAD_INPUT 8           /* an observation symbol outside [0, Kobs) (checked on the device: the kernels never index the emission table out of bounds) */
 
 /* message precision */
 #define SMJP_F64 0

@@ -1,9 +1,10 @@
 """TEST INFRASTRUCTURE ONLY -- import shim for the *unmodified* reference (gauenk/smjp).
 
-Used in THIS container only (the reference tree at /root/reference does not exist on the GPU
-box) by ``oracle/gen_golden.py`` to produce the committed fixtures under ``tests/golden/`` and by
-``tests/test_oracle_vs_reference.py`` (auto-skipped when the tree is absent).  Nothing in the
-product package ``smjp_b200/`` imports this module.
+Used by ``oracle/gen_golden*.py`` (in the authoring container, where /root/reference exists) to produce the
+committed fixtures under ``tests/golden/``, and by ``bench.py --impl reference`` to time the unmodified
+reference beside the NumPy port: ``make -C oracle`` copies the reference's (pure-Python) sources into the
+git-ignored ``oracle/_ref/``, which travels to the GPU box with the snapshot.  Nothing in the product
+package ``smjp_b200/`` imports this module.
 
 What the shim does, without touching a single reference source line:
   * restores the numpy-1 aliases the reference uses (np.int, np.float, np.infty, np.math);
@@ -24,7 +25,9 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("SMJP_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REFERENCE_ROOT = os.environ.get("SMJP_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isfile("/root/reference/pkg/fast_hmm.py") else os.path.join(_HERE, "_ref"))
 
 
 def reference_available():

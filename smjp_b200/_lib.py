@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libsmjp_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 SMJP_F64, SMJP_F32 = 0, 1
-ST_GRID_NOT_INCREASING, ST_DEGENERATE, ST_OVERFLOW = 1, 2, 4
+ST_GRID_NOT_INCREASING, ST_DEGENERATE, ST_OVERFLOW, ST_BAD_INPUT = 1, 2, 4, 8
 CAND_REFERENCE, CAND_EXACT = 0, 1
 RESAMPLE_MULTINOMIAL, RESAMPLE_SYSTEMATIC = 0, 1
 

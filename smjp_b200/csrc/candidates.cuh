@@ -56,6 +56,7 @@ struct CandArgs {
 __device__ __forceinline__ int sojourn_events(const CandArgs& a, int c, int q, int v, double t0, double tau,
                                               double* out) {
     const int K = a.K;
+    v = min(max(v, 0), K - 1);  // a state index outside [0, K) (caller's paths) never indexes the model out of bounds
     const double* shape = a.model;
     const double* scale = a.model + 2 * K * K + K * a.Kobs;
     const double* crep = scale + K * K;  // class representative / class sum of lambda^-k (smjp_set_model)

@@ -402,7 +402,11 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
                 for (int v = 0; v < K; ++v) f[v] = a.obs_product ? (Real)1 : (Real)0;
                 int cnt = 0;
                 for (int d = lo; d < D && ot[d] <= wn; ++d, ++cnt) {
-                    const int y = oy[d];
+                    int y = oy[d];
+                    if ((unsigned)y >= (unsigned)Kobs) {  // never index the emission table out of bounds
+                        y = 0;
+                        atomicOr(&s_flag, 2);
+                    }
 #pragma unroll
                     for (int v = 0; v < K; ++v) {
                         const Real pe = (Real)emis[v * Kobs + y];
@@ -418,7 +422,7 @@ __global__ void __launch_bounds__(B, MINB) ffbs_kernel(const FfbsArgs a) {
         __syncthreads();
         if (s_flag) {
             if (tid == 0) {
-                a.status[c] = SMJP_ST_GRID_NOT_INCREASING;
+                a.status[c] = ((s_flag & 1) ? SMJP_ST_GRID_NOT_INCREASING : 0) | ((s_flag & 2) ? SMJP_ST_BAD_INPUT : 0);
                 a.path_len[c] = 0;
             }
             continue;

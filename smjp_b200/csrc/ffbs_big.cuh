@@ -129,7 +129,12 @@ __global__ void __launch_bounds__(B) ffbs_big_kernel(const FfbsArgs a) {
                 for (int v = 0; v < K; ++v) {
                     Real f = a.obs_product ? (Real)1 : (Real)0;
                     for (int d = 0; d < cnt; ++d) {
-                        const Real pe = (Real)emis[v * Kobs + oy[lo + d]];
+                        int y = oy[lo + d];
+                        if ((unsigned)y >= (unsigned)Kobs) {  // never index the emission table out of bounds
+                            y = 0;
+                            atomicOr(&s_flag, 2);
+                        }
+                        const Real pe = (Real)emis[v * Kobs + y];
                         f = a.obs_product ? f * pe : f + pe;
                     }
                     obsf[i * K + v] = (cnt == 0 || power == (Real)0) ? (Real)1 : (power == (Real)1 ? f : M::pow(f, power));
@@ -139,7 +144,7 @@ __global__ void __launch_bounds__(B) ffbs_big_kernel(const FfbsArgs a) {
         __syncthreads();
         if (s_flag) {
             if (tid == 0) {
-                a.status[c] = SMJP_ST_GRID_NOT_INCREASING;
+                a.status[c] = ((s_flag & 1) ? SMJP_ST_GRID_NOT_INCREASING : 0) | ((s_flag & 2) ? SMJP_ST_BAD_INPUT : 0);
                 a.path_len[c] = 0;
             }
             continue;

@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(32, MINB) ffbs_fastk_kernel(const FfbsArgs a) 
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(FULL, dmin, o));
         // ---- observation factor per interval (as in ffbs.cuh) ----
+        int badsym = 0;
         {
             const int64_t o0 = a.obs_offs[c];
             const int D = (int)(a.obs_offs[c + 1] - o0);
@@ -148,7 +149,11 @@ __global__ void __launch_bounds__(32, MINB) ffbs_fastk_kernel(const FfbsArgs a) 
                 for (int s = 0; s < K; ++s) f[s] = a.obs_product ? (Real)1 : (Real)0;
                 int cnt = 0;
                 for (int d = lo; d < D && ot[d] <= wn; ++d, ++cnt) {
-                    const int y = oy[d];
+                    int y = oy[d];
+                    if ((unsigned)y >= (unsigned)Kobs) {  // never index the emission table out of bounds
+                        y = 0;
+                        badsym = 1;
+                    }
 #pragma unroll
                     for (int s = 0; s < K; ++s) {
                         const Real pe = (Real)emis[s * Kobs + y];
@@ -162,9 +167,10 @@ __global__ void __launch_bounds__(32, MINB) ffbs_fastk_kernel(const FfbsArgs a) 
             }
         }
         __syncwarp();
-        if (bad) {
+        badsym = __any_sync(FULL, badsym);
+        if (bad || badsym) {
             if (lane == 0) {
-                a.status[c] = SMJP_ST_GRID_NOT_INCREASING;
+                a.status[c] = (bad ? SMJP_ST_GRID_NOT_INCREASING : 0) | (badsym ? SMJP_ST_BAD_INPUT : 0);
                 a.path_len[c] = 0;
             }
             continue;

@@ -121,7 +121,11 @@ __global__ void __launch_bounds__(FFBS_WARPS * 32, (sizeof(Real) == 4 && K <= 3 
                 for (int v = 0; v < K; ++v) f[v] = a.obs_product ? (Real)1 : (Real)0;
                 int cnt = 0;
                 for (int d = lo; d < D && ot[d] <= wn; ++d, ++cnt) {
-                    const int y = oy[d];
+                    int y = oy[d];
+                    if ((unsigned)y >= (unsigned)Kobs) {  // never index the emission table out of bounds
+                        y = 0;
+                        bad |= 2;
+                    }
 #pragma unroll
                     for (int v = 0; v < K; ++v) {
                         const Real pe = (Real)emis[v * Kobs + y];
@@ -135,8 +139,9 @@ __global__ void __launch_bounds__(FFBS_WARPS * 32, (sizeof(Real) == 4 && K <= 3 
             }
         }
         if (__any_sync(FULL, bad)) {
+            const int grid_bad = __any_sync(FULL, bad & 1), sym_bad = __any_sync(FULL, bad & 2);
             if (lane == 0) {
-                a.status[c] = SMJP_ST_GRID_NOT_INCREASING;
+                a.status[c] = (grid_bad ? SMJP_ST_GRID_NOT_INCREASING : 0) | (sym_bad ? SMJP_ST_BAD_INPUT : 0);
                 a.path_len[c] = 0;
             }
             continue;

@@ -521,6 +521,8 @@ def shape_mle_host(eng, V, T, K, pooled=True, grid=0.001, grid_max=5.0):
 def raise_for_status(status):
     """Per-chain status bits -> the exceptions the reference raises at the same conditions."""
     status = np.asarray(status)
+    if np.any(status & _lib.ST_BAD_INPUT):
+        raise ValueError("observation symbol outside [0, Kobs)")
     if np.any(status & _lib.ST_GRID_NOT_INCREASING):
         raise ValueError("We can not have time_p >= time_c")  # smjp_utils.py:398-399
     if np.any(status & _lib.ST_DEGENERATE):

@@ -50,9 +50,21 @@ def likelihood_and_decoding_hmm(*args, **kwargs):
 def backward_sampling_hmm(*args, **kwargs):
     """backward sampling (fast_hmm.py:104-191).  Returns (samples [1, n] dense indices a = v*n + j,
     t_samples = [aug_state_space[samples]]).  The forward messages are recomputed on the device (the
-    fused kernel costs less than uploading `alphas`); `uniforms=` / `seed=` make the draw reproducible."""
+    fused kernel costs less than uploading `alphas`); when `alphas` is given it is checked against them and a
+    mismatch raises ValueError.  `uniforms=` / `seed=` make the draw reproducible."""
     opts = {k: kwargs.pop(k) for k in ("precision", "engine", "uniforms", "seed") if k in kwargs}
-    r, n, K = _run(kwargs, False, **opts)
+    alphas = kwargs.get("alphas")
+    r, n, K = _run(kwargs, alphas is not None, **opts)
+    if alphas is not None:
+        # The reference samples from whatever `alphas` it is handed (fast_hmm.py:41-59).  The engine recomputes the
+        # forward pass inside the same kernel, so messages that are NOT the ones likelihood() returns for this model
+        # (a caller that edited them) cannot be honoured: refuse loudly instead of silently sampling something else.
+        mine = triangular_to_dense(r["messages"][0], n, K).astype(np.float64)
+        given = np.exp(np.asarray(alphas, dtype=np.float64))
+        tol = 1e-9 if opts.get("precision", "f64") in ("f64", "fp64", "float64") else 1e-4
+        if given.shape != mine.shape or not np.allclose(given, mine, rtol=tol, atol=tol * 1e-3):
+            raise ValueError("backward_sampling(alphas=...): the messages differ from this model's forward pass; the CUDA "
+                             "engine samples from its own forward messages and cannot use edited ones")
     samples = r["aug_idx"][0].astype(np.int64)[None, :]
     aug = np.asarray(kwargs["pi"].state_space)
     return samples, [aug[samples[0]]]

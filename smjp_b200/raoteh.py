@@ -75,10 +75,32 @@ def update_parameters(hazard_A, hazard_B, poisson_proc_A_hat, poisson_proc_B, th
     poisson_proc_B.update_parameters({"shape": hazard_A.shape_mat, "scale": tilde})
 
 
+def _is_number(x):
+    try:
+        float(x)
+        return True
+    except (TypeError, ValueError):
+        return False
+
+
+def _a_hat_is_scaled_hazard(hazard_A, hazard_B, poisson_process_A_hat):
+    """True when the candidate process is (omega - 1) * hazard_A (experiments.py:177-205): same shapes, scale
+    lambda / (omega - 1)^(1/k) -- the engine's sweep draws candidates from exactly that process"""
+    try:
+        omega = float(hazard_B.omega)
+        kA = np.asarray(hazard_A.shape_mat, dtype=np.float64)
+        kP = np.asarray(poisson_process_A_hat.mean_function_params["shape"], dtype=np.float64)
+        lP = np.asarray(poisson_process_A_hat.mean_function_params["scale"], dtype=np.float64)
+        want = create_upperbound_scale(kA, hazard_A.scale_mat, omega - 1.0)
+        return kA.shape == kP.shape and np.allclose(kA, kP, rtol=1e-12, atol=0) and np.allclose(lP, want, rtol=1e-9, atol=0)
+    except Exception:
+        return False
+
+
 def raoteh(inference, number_of_samples, save_iter, state_space, time_final, emission,
            data, pi_0, hazard_A, hazard_B, poisson_process_A_hat, poisson_process_B,
            uuid_str, omega, obs_times, filename, load_file, *, seed=None, verbose=False, save=True,
-           candidate_mode="reference", precision="f64", obs_combine="sum"):
+           candidate_mode="reference", precision="f64", obs_combine="sum", fused_sweep=True):
     """Returns (aggregate {'W','T','V','prob'[,'theta'][,'prior']}, uuid_str, omega)."""
     inference_error_checking(inference)
     if load_file:
@@ -93,13 +115,37 @@ def raoteh(inference, number_of_samples, save_iter, state_space, time_final, emi
         aggregate["prior"] = {"W": [], "T": [], "V": []}
     if "data" in inference:
         aggregate["data"] = []
+    # One fused host call per iteration (smjp_sweep_host: candidates -> FFBS in one launch sequence, model uploaded
+    # once) whenever the A_hat process IS (omega - 1) * hazard_A, as experiments.py:177-205 builds it; otherwise -- or
+    # with 'data' inference, which changes the observations every iteration -- the two reference calls are made.
+    from .engine import raise_for_status, sweep_host
+    from .smjp_utils import (enumerate_state_space, load_model, observation_arrays, state_index)
+    eng = runtime.get_engine()
+    states = list(state_space)
+    fused = fused_sweep and "data" not in inference and _a_hat_is_scaled_hazard(hazard_A, hazard_B, poisson_process_A_hat)
+    if fused:
+        load_model(eng, states, hazard_A, hazard_B, emission, time_final, obs_combine)
+        obs_t, obs_y = observation_arrays(data, states)
+        Vi, Ta = state_index(states, list(V)), np.asarray(T, dtype=np.float64)
+        labels = np.asarray([float(x) for x in states]) if all(_is_number(x) for x in states) else np.asarray(states, dtype=object)
     for i in range(number_of_samples):
         if "data" in inference:
             data = sample_data_posterior(V, T, state_space, emission, obs_times)
             aggregate["data"].append(data)
-        W = sample_smjp_event_times(poisson_process_A_hat, V, T, time_final, mode=candidate_mode)
-        V, T, prob = smjp_ffbs(W, data, state_space, hazard_A, hazard_B, emission, time_final,
-                               "raoteh_{}_{}".format(uuid_str, i), precision=precision, obs_combine=obs_combine)
+        if fused:
+            r = sweep_host(eng, [Vi], [Ta], obs_t, obs_y, runtime.next_seed(), sweep=i, mode=candidate_mode, precision=precision)
+            raise_for_status(r["status"])
+            Wa = r["W"][0]
+            W = Wa.tolist()
+            Vi, Ta = r["V"][0], r["T"][0]
+            V = labels[Vi]  # float64 labels for numeric state spaces (smjp_utils.py:328)
+            T, prob = Ta, 1.0
+            # side effect of the reference (:278): augmented states = states x grid[:-1], state-major
+            emission.augmented_state_space = np.column_stack([np.repeat(labels, len(Wa) - 1), np.tile(Wa[:-1], len(states))])
+        else:
+            W = sample_smjp_event_times(poisson_process_A_hat, V, T, time_final, mode=candidate_mode)
+            V, T, prob = smjp_ffbs(W, data, state_space, hazard_A, hazard_B, emission, time_final,
+                                   "raoteh_{}_{}".format(uuid_str, i), precision=precision, obs_combine=obs_combine)
         aggregate["W"].append(W)
         aggregate["V"].append(V)
         aggregate["T"].append(T)
@@ -108,10 +154,14 @@ def raoteh(inference, number_of_samples, save_iter, state_space, time_final, emi
             theta = sample_smjp_parameters(data, V, T, state_space)
             aggregate["theta"].append(theta)
             update_parameters(hazard_A, hazard_B, poisson_process_A_hat, poisson_process_B, theta)
+            if fused:  # the hazards changed in place: upload them (raoteh.py:74-78 re-reads them every sweep)
+                load_model(eng, states, hazard_A, hazard_B, emission, time_final, obs_combine)
         if "prior" in inference:
             _V, _T = sample_smjp_trajectory_prior(hazard_A, pi_0, state_space, time_final)
             aggregate["prior"]["V"].append(_V)
             aggregate["prior"]["T"].append(_T)
+            if fused:  # the prior sampler loaded its own model into the engine
+                load_model(eng, states, hazard_A, hazard_B, emission, time_final, obs_combine)
         if verbose:
             print("i = {}  |W| = {}  |T| = {}".format(i, len(W), len(T)))
         if save and (i % save_iter) == 0 and i > 0:

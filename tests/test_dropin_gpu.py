@@ -57,6 +57,10 @@ def test_fast_hmm_class_api():
     assert np.array_equal(np.isfinite(la), fin) and np.abs(la[fin] - ref[fin]).max() < 1e-11
     samples, t_samples = hmm.backward_sampling(alphas=la, uniforms=g["uniforms"])
     assert np.array_equal(samples[0], g["samples"]) and np.array_equal(t_samples[0], aug[g["samples"]])
+    edited = la.copy()
+    edited[3] = edited[2]           # legal in the reference (fast_hmm.py:41-59 samples from what it is given)
+    with pytest.raises(ValueError):  # here: refused loudly, never silently replaced by the engine's own messages
+        hmm.backward_sampling(alphas=edited, uniforms=g["uniforms"])
     with pytest.raises(TypeError):
         fast_HiddenMarkovModel([], emission=lambda *a: 0, transition=lambda *a: 0, data=data, state_alphabet=aug,
                                pi_0=pi_0, time_grid=list(g["W"])).likelihood()
@@ -189,3 +193,38 @@ def test_raoteh_batch_matches_single_chain_posterior():
                         seed=99, burn_in=15, candidate_mode="exact")
     for s in range(3):
         assert stats.ks_2samp(out["time_in_state"][-1][:, s], out2["time_in_state"][-1][:, s]).pvalue > 1e-3
+
+
+def test_raoteh_fused_sweep_equals_the_two_call_path_in_distribution():
+    """raoteh() makes ONE host call per iteration (smjp_sweep_host: candidates + FFBS, model uploaded once) when the
+    candidate process is (omega - 1) * hazard_A; fused_sweep=False makes the reference's two calls (raoteh.py:58-59).
+    Same posterior (time in state), reproducible by seed, grids contain the previous jump times, 'parameters' and
+    'prior' inference keep working (the hazards change in place every iteration)."""
+    import experiments
+    from smjp_b200 import mcmc_utils
+    from smjp_b200.raoteh import raoteh
+    n = 1200
+    out = {}
+    for fused in (True, False):
+        m = experiments.build_experiment_2_model()
+        rt, _, _ = raoteh(["trajectory"], n, 300, m["state_space"], m["time_final"], m["emission"], m["data"], m["pi_0"],
+                          m["hazard_A"], m["hazard_B"], m["poisson_process_A_hat"], m["poisson_process_B"], "u", m["omega"],
+                          m["obs_times"], None, False, seed=5, save=False, fused_sweep=fused)
+        assert len(rt["W"]) == n and all(p == 1.0 for p in rt["prob"])
+        assert all(T[0] == 0.0 and T[-1] == 2.0 and len(V) == len(T) and V.dtype == np.float64 for V, T in zip(rt["V"], rt["T"]))
+        assert all(set(np.asarray(rt["T"][i])[:-1]).issubset(set(rt["W"][i + 1])) for i in range(0, n - 1, 97))
+        out[fused] = mcmc_utils.compute_evaluation_chain_metrics({"V": rt["V"][100:], "T": rt["T"][100:]}, m["state_space"])[0]
+    for s in [1, 2, 3]:
+        assert abs(np.mean(out[True][s]) - np.mean(out[False][s])) < 0.08
+    m = experiments.build_experiment_2_model()
+    a1, _, _ = raoteh(["trajectory"], 30, 300, m["state_space"], 2.0, m["emission"], m["data"], m["pi_0"], m["hazard_A"], m["hazard_B"],
+                      m["poisson_process_A_hat"], m["poisson_process_B"], "u", 2, m["obs_times"], None, False, seed=9, save=False)
+    m = experiments.build_experiment_2_model()
+    a2, _, _ = raoteh(["trajectory"], 30, 300, m["state_space"], 2.0, m["emission"], m["data"], m["pi_0"], m["hazard_A"], m["hazard_B"],
+                      m["poisson_process_A_hat"], m["poisson_process_B"], "u", 2, m["obs_times"], None, False, seed=9, save=False)
+    assert all(np.array_equal(x, y) for x, y in zip(a1["T"], a2["T"]))
+    m = experiments.build_experiment_2_model()
+    a3, _, _ = raoteh(["trajectory", "parameters", "prior"], 25, 300, m["state_space"], 2.0, m["emission"], m["data"], m["pi_0"],
+                      m["hazard_A"], m["hazard_B"], m["poisson_process_A_hat"], m["poisson_process_B"], "u", 2, m["obs_times"], None,
+                      False, seed=10, save=False)
+    assert len(a3["theta"]) == 25 and len(a3["prior"]["V"]) == 25 and all(T[-1] == 2.0 for T in a3["T"])

@@ -313,3 +313,34 @@ def test_empty_batch_and_observations_on_grid_points(engine):
     # the shared observation really is counted twice: dropping it from either side changes logZ of both intervals
     r2 = engine.ffbs_host([W], ot[1:], oy[1:], uniforms=[u], precision="f64")
     assert abs(r2["logZ"][0][0] - r["logZ"][0][0]) > 1e-6 and abs(r2["logZ"][0][1] - r["logZ"][0][1]) > 1e-6
+
+
+@pytest.mark.parametrize("K,precision", [(3, "f64"), (3, "f32"), (6, "f64"), (12, "f64")])
+def test_observation_symbol_out_of_range_is_flagged_on_the_device(engine, K, precision):
+    """the device entry points cannot afford a host pass over the observations: every kernel checks the symbol before it
+    indexes the emission table and flags the chain (SMJP_ST_BAD_INPUT -> ValueError); the other chains are unaffected"""
+    import torch
+    from smjp_b200.engine import raise_for_status
+    rng = np.random.default_rng(K)
+    t_end, n = 5.0, 40
+    shape, scale, W, obs_t, obs_y = random_problem(rng, K, t_end, n, 30)
+    engine.set_model(shape, scale, 2.0, O.emission_matrix(K), 1.0, t_end)
+    dev = torch.device("cuda", engine.device)
+    C = 3
+    d = lambda x, dt: torch.from_numpy(np.ascontiguousarray(x, dtype=dt)).to(dev)
+    ys = np.tile(obs_y, C).astype(np.int32)
+    ys[len(obs_y) + 7] = K + 5      # chain 1 carries a bad symbol
+    tot = C * (n + 1)
+    out = dict(pv=torch.zeros(tot, dtype=torch.int32, device=dev), pt=torch.zeros(tot, dtype=torch.float64, device=dev),
+               pl=torch.zeros(C, dtype=torch.int32, device=dev), st=torch.zeros(C, dtype=torch.int32, device=dev))
+    for scratch in (True, False):
+        msgs = None if scratch else torch.zeros(C * K * n * (n + 1) // 2, dtype=torch.float64 if precision == "f64" else torch.float32, device=dev)
+        moffs = None if scratch else d(np.arange(C + 1) * (K * n * (n + 1) // 2), np.int64)
+        engine.ffbs_dev(C, d(np.arange(C + 1) * (n + 1), np.int64), d(np.tile(W, C), np.float64), d(np.arange(C + 1) * len(obs_t), np.int64),
+                        d(np.tile(obs_t, C), np.float64), d(ys, np.int32), out["pv"], out["pt"], out["pl"], out["st"], n, tot,
+                        seed=3, precision=precision, messages=msgs, msg_offs=moffs)
+        engine.sync()
+        st = out["st"].cpu().numpy()
+        assert st[0] == 0 and st[2] == 0 and (st[1] & 8) and out["pl"].cpu().numpy()[1] == 0
+        with pytest.raises(ValueError):
+            raise_for_status(st)
