@@ -72,7 +72,7 @@ int smjp_ctx_sync(smjp_ctx_t* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t smjp_ctx_launch_count(smjp_ctx_t* ctx);
 /* launch geometry of the last FFBS kernel: "ffbs_grid", "ffbs_threads", "ffbs_smem"; "num_sms"; "pf_cluster";
- * "ffbs_live_pairs": grid pairs (i, j) inside the live window that the K <= 3 FFBS kernel processed since the
+ * "ffbs_live_pairs": grid pairs (i, j) inside the live window that the FFBS kernels (K <= 10) processed since the
  * last query (synchronises; the nominal count is n(n+1)/2 per chain); "spec_launches" / "spec_misses": speculative
  * sweep launches and how many of them had to be repeated (option "speculate") */
 int64_t smjp_ctx_get_stat(smjp_ctx_t* ctx, const char* key);
@@ -274,7 +274,7 @@ int smjp_pf_dev(smjp_ctx_t* ctx, int C, const int64_t* obs_offs, const double* o
                 int32_t* status);
 
 /*
- * FFBS on the dense K-state path: the shape == 1 collapse of the sMJP, K <= 128.
+ * FFBS on the dense K-state path: the shape == 1 collapse of the sMJP, K <= 64 (smjp_set_model).
  * Same inputs and path outputs as smjp_ffbs_dev; requires every Weibull shape of the model to be 1
  * (SMJP_E_INVALID otherwise).  m_i ~ e_i o (m_{i-1} B) with the constant
  * B = (1 - 1/omega) I + diag(1/(omega A_v)) A; the backward pass draws the state with u_state[] and,

@@ -58,6 +58,7 @@ class DeviceChains:
         """sample_smjp_trajectory_prior for every chain (raoteh.py:25)."""
         t = self.torch
         pi0 = np.ascontiguousarray(pi0, dtype=np.float64)
+        self.eng.set_option("chain_base", self.chain_base)  # the engine is shared: another DeviceChains may have set its own
         cap = cap_per_chain or 64
         while True:
             p = self._alloc_paths(cap * self.C)
@@ -88,6 +89,7 @@ class DeviceChains:
     def simulate_observations(self, seed):
         """y_d ~ emis[v(t_d)] from the current paths (sample_data_posterior, smjp_utils.py:350-364)."""
         p = self.cur
+        self.eng.set_option("chain_base", self.chain_base)
         check(self.eng.lib.smjp_simulate_obs_dev(self.eng.ctx, self.C, _ptr(p["offs"]), _ptr(p["v"]), _ptr(p["t"]),
                                                  _ptr(p["len"]), _ptr(self.obs_offs), _ptr(self.obs_t),
                                                  int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(self.obs_y)))
@@ -106,9 +108,10 @@ class DeviceChains:
     # ------------------------------------------------------------------------------------------
     def sweep(self, seed, sweep=None, mode="reference", precision="f64", dense=False):
         """One Gibbs sweep of every chain (raoteh.py:58-59).  Asynchronous after one size read-back.
-        dense=True runs the K-state collapse (shape == 1 models only, any K <= 128)."""
+        dense=True runs the K-state collapse (shape == 1 models only; K <= 64, the limit of smjp_set_model)."""
         t = self.torch
         sweep = self.sweeps_done if sweep is None else sweep
+        self.eng.set_option("chain_base", self.chain_base)
         cur = self.cur
         if self.cap == 0:  # first sweep: size from the live path entries, grow on demand
             self.cap = int(cur["len"].sum().item()) * 3 + 1024

@@ -1,5 +1,5 @@
 // FFBS for the shape == 1 collapse of the sMJP (a Markov jump process with self-jumps): the K-state dense
-// path of SURVEY.md Appendix A.5, one warp per chain, any K <= 128.
+// path of SURVEY.md Appendix A.5, one warp per chain (the kernel handles K <= 128; smjp_set_model admits K <= 64).
 //
 // With every Weibull shape equal to 1 the hazards A_vs = 1/lambda_vs are constant, the emission of the
 // augmented filter does not depend on l, and m_i(v) = sum_l alpha_i(v,l) obeys

@@ -179,7 +179,7 @@ class Engine:
         return out
 
     def ffbs_dense(self, W, obs_t, obs_y, u_state=None, u_jump=None, seed=0, sweep=0, precision="f64"):
-        """FFBS of a shape == 1 model on its K-state collapse (smjp_ffbs_dense_dev; any K <= 128).
+        """FFBS of a shape == 1 model on its K-state collapse (smjp_ffbs_dense_dev; K <= 64).
         Host lists in, host lists out (staged through torch device tensors); uniforms per grid interval."""
         import torch as t
         if self.K is None:

@@ -36,7 +36,7 @@ def cfg1():
     dt = time.perf_counter() - t0
     ss = sum(3 * (len(w) - 1) * len(w) / 2 for w in agg["W"])
     return {"config": "cfg1 main.py default, 1 chain through the drop-in raoteh()", "sweeps_per_sec": n / dt,
-            "state_steps_per_sec": ss / dt, "reference_measured_sweeps_per_sec": 1.04, "note": "latency-bound: 2 host calls per sweep"}
+            "state_steps_per_sec": ss / dt, "reference_measured_sweeps_per_sec": 1.04, "note": "latency-bound: one fused host call per sweep (smjp_sweep_host)"}
 
 
 def cfg3(N=65536, C=8, cluster=0, threads=0, family="gamma"):
