@@ -553,13 +553,29 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
     a.use_item = item_kernel;  // thread per (v, j) for larger state spaces, thread per j for K <= 3
     int threads;
     size_t smem;
+    int big_slots = 0;
     if (big) {
+        // the chain state (2 K reals per live grid point) sits in a ring of slots of `threads` grid points: as many
+        // slots as shared memory holds (never more than the whole grid needs).  Exported messages need them all.
+        const size_t budget = c->smem_optin - 6 * 1024;  // the kernel's static shared memory (2^x / log2 tables)
+        auto slots_that_fit = [&](int th) {
+            const size_t fixed = ffbs_big_smem_bytes<Real>(K, 0, th), per = 2 * smjp::align_up((size_t)K * th * sizeof(Real), 16);
+            const int full = ffbs_nslot((int)n_max, th);
+            const int fit = fixed >= budget ? 0 : (int)((budget - fixed) / per);
+            return fit < full ? fit : full;
+        };
         threads = 128;
-        smem = ffbs_big_smem_bytes<Real>(K, (int)n_max, threads);
-        if (smem > c->smem_optin) {
+        big_slots = slots_that_fit(128);
+        // 64-thread slots waste less of the ring (the window is covered in finer steps) and leave room for more of them
+        if (big_slots < ffbs_nslot((int)n_max, 128) && slots_that_fit(64) * 64 > big_slots * 128) {
             threads = 64;
-            smem = ffbs_big_smem_bytes<Real>(K, (int)n_max, threads);
+            big_slots = slots_that_fit(64);
         }
+        if (big_slots < 1 || (a.messages && big_slots < ffbs_nslot((int)n_max, threads)))
+            return fail(SMJP_E_UNSUPPORTED,
+                        "K=%d, grid of %lld intervals: %s does not fit in shared memory", K, (long long)n_max,
+                        a.messages ? "the whole chain state (exported messages need every grid point)" : "one ring slot of chain state");
+        smem = ffbs_big_smem_bytes<Real>(K, big_slots, threads);
         // hazard parameters in the kernel's precision
         const double S = sizeof(Real) == 8 ? 256.0 : 1.0;  // Exp2<Real>::SCALE
         std::vector<Real> hp((size_t)3 * K * K);
@@ -725,7 +741,7 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
     const int regions_per_cta = use_warp ? FFBS_WARPS : use_fast ? fast_cpb : 1;  // scratch regions: one per chain in flight
     if (grid > (a.C + regions_per_cta - 1) / regions_per_cta) grid = (a.C + regions_per_cta - 1) / regions_per_cta;
     a.ncap = (int)n_max;
-    a.nslot = use_warp ? ring : use_fast ? fast_ns : item_kernel ? ffbs_item_nslot(K, (int)n_max, threads) : ffbs_nslot((int)n_max, threads);
+    a.nslot = big ? big_slots : use_warp ? ring : use_fast ? fast_ns : item_kernel ? ffbs_item_nslot(K, (int)n_max, threads) : ffbs_nslot((int)n_max, threads);
     if (use_fast && fastk) a.lay = ffbs_fastk_layout<Real>(K, fast_ns, (int)n_max);
     else if (!item_kernel && !big) a.lay = use_fast ? ffbs_fast_layout<Real>(K, fast_ns, (int)n_max, threads) : ffbs_layout<Real>(K, (int)n_max, threads);
     a.window_eps = c->window_log2 < 0 ? std::ldexp(1.0, c->window_log2) : 0.0;
@@ -769,6 +785,10 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
             a.obsf_stride = per;
         } else if (use_fast) {  // + the window start of every row (ints), see ffbs_fast.cuh
             per += ((int64_t)(n_max + 2) * 4 + (int64_t)sizeof(Real) - 1) / (int64_t)sizeof(Real);
+            per = (per + 3) / 4 * 4;
+            a.obsf_stride = per;
+        } else if (big) {  // + window starts [n + 1] and the sojourn list [2][n + 1] (ints), see ffbs_big.cuh
+            per += ((int64_t)3 * (n_max + 2) * 4 + (int64_t)sizeof(Real) - 1) / (int64_t)sizeof(Real);
             per = (per + 3) / 4 * 4;
             a.obsf_stride = per;
         }

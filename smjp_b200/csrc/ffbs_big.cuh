@@ -7,19 +7,23 @@
 // thread t owns grid points j = t, t+B, ... and its K hazards kE[s] and K accumulators Jp[s] sit in shared
 // memory columns ([s][B+1], conflict free), the hazard parameters are read from global memory through L1
 // (every lane reads the same (v,s) entry), and the per-step reduction sums the columns row by row.  The chain
-// state is 2 K reals per grid point, so a chain must satisfy 2 K n sizeof(real) + 2 K (B+1) sizeof(real)
-// < 227 KB: K = 64 allows n ~ 140 (fp64) / 280 (fp32), K = 16 n ~ 800 / 1600 -- BASELINE configs[3]'s
-// "sMJP path at K = 64 on a reduced horizon".  Scratch rows hold g (see ffbs.cuh, Backward).
+// state is 2 K reals per LIVE grid point (ffbs.cuh, "Live window": exact zeros are dropped; window_eps > 0 also
+// drops states below that fraction of the row sum) and sits in a RING of `nslot` slots of B grid points -- as many
+// as shared memory holds: K = 64 keeps a window of ~128 (fp64) / ~256 (fp32) grid points whatever the length of
+// the grid (the first version held the whole grid: n <= 140 / 280).  The grid, the window start of every row and
+// the sojourn list stay in global memory (L2).  A window that outgrows the ring ends the chain with
+// SMJP_ST_OVERFLOW (the caller prunes: option window_log2).  Exported messages need the whole triangle and keep the
+// old limit.  Scratch rows hold g (see ffbs.cuh, Backward).
 #pragma once
 #include "ffbs.cuh"
 
 namespace smjp {
 
+// shared memory for a ring of `slots` slots (ffbs_nslot(ncap, threads) slots hold the whole grid)
 template <typename Real>
-__host__ __device__ inline size_t ffbs_big_smem_bytes(int K, int ncap, int threads) {
-    const size_t state = (size_t)ffbs_nslot(ncap, threads) * K * threads;
+__host__ __device__ inline size_t ffbs_big_smem_bytes(int K, int slots, int threads) {
+    const size_t state = (size_t)slots * K * threads;
     size_t b = 0;
-    b += align_up((size_t)(ncap + 1) * sizeof(double), 16);       // W
     b += align_up((size_t)threads * sizeof(double), 16);          // backward uniforms
     b += align_up((size_t)(threads / 32 + 1) * sizeof(double), 16);  // scan totals
     b += 2 * align_up(state * sizeof(Real), 16);                  // message, H_v
@@ -37,18 +41,17 @@ __global__ void __launch_bounds__(B) ffbs_big_kernel(const FfbsArgs a) {
     if (a.guard && (a.guard[0] > a.guard_nmax || a.guard[1] > a.guard_total)) return;  // mis-speculated geometry
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int K = a.K, ncap = a.ncap, Kobs = a.Kobs;
-    const size_t state = (size_t)a.nslot * K * B;
+    const int NS = a.nslot;  // ring slots of B grid points
+    const size_t state = (size_t)NS * K * B;
 
     unsigned char* sp = smem_raw;
-    double* Wd = (double*)sp;
-    sp += align_up((size_t)(ncap + 1) * sizeof(double), 16);
     double* ubuf = (double*)sp;
     sp += align_up((size_t)B * sizeof(double), 16);
     Acc* scan_s = (Acc*)sp;
     sp += align_up((size_t)(NW + 1) * sizeof(double), 16);
-    Real* st_a = (Real*)sp;  // forward: unnormalised message [slot][v][B]; backward: weights [K][len]
+    Real* st_a = (Real*)sp;  // forward: unnormalised message, ring [slot][v][B]; backward: weights [K][window]
     sp += align_up(state * sizeof(Real), 16);
-    Real* st_h = (Real*)sp;  // forward: H_v(tau) [slot][v][B]; backward: sojourn list (int pairs)
+    Real* st_h = (Real*)sp;  // forward: H_v(tau), ring [slot][v][B]
     sp += align_up(state * sizeof(Real), 16);
     Real* Jp_s = (Real*)sp;  // [K][B+1] this step's inflow contributions, one column per thread
     sp += align_up((size_t)K * BP * sizeof(Real), 16);
@@ -58,9 +61,9 @@ __global__ void __launch_bounds__(B) ffbs_big_kernel(const FfbsArgs a) {
     Real* of_s = J_s + K;    // [K] observation factors of the current step
     Real* red_s = of_s + K;  // [K+1] column sums, red_s[K] = Z
     Real* Zp_s = red_s + K + 1;  // [B]
-    int* soj = (int*)st_h;
 
     __shared__ int s_chain, s_sel, s_flag, s_found;
+    __shared__ int s_jmin[2 * NW];
     __shared__ double s_tab[Exp2<Real>::TAB ? Exp2<Real>::TAB : 1];
     __shared__ double2 s_ltab[Exp2<Real>::LTAB ? Exp2<Real>::LTAB : 1];
     for (int t = tid; t < Exp2<Real>::TAB; t += B) s_tab[t] = exp2_table_entry(t);
@@ -82,8 +85,13 @@ __global__ void __launch_bounds__(B) ffbs_big_kernel(const FfbsArgs a) {
     const Real omega_r = (Real)a.omega;
     const Real om_l2e = (Real)(a.omega * SMJP_LOG2E * (double)Exp2<Real>::SCALE);
     const Real power = (Real)a.power;
-    Real* obsf = (Real*)a.obsf_scratch + (int64_t)blockIdx.x * ncap * K;
+    // per-CTA global scratch: observation factors [ncap][K], window start of every row [ncap + 1], sojourn list
+    // [2][ncap + 1]
+    Real* obsf = (Real*)a.obsf_scratch + (int64_t)blockIdx.x * a.obsf_stride;
+    int* jlo_arr = (int*)(obsf + (int64_t)ncap * K);
+    int* soj = jlo_arr + (ncap + 1);
     const bool exporting = a.messages != nullptr;
+    const Real weps = (Real)a.window_eps;
 
     while (true) {
         __syncthreads();
@@ -105,8 +113,7 @@ __global__ void __launch_bounds__(B) ffbs_big_kernel(const FfbsArgs a) {
             }
             continue;
         }
-        for (int t = tid; t <= n; t += B) Wd[t] = a.W[w0 + t];
-        __syncthreads();
+        const double* Wd = a.W + w0;  // the grid stays in global memory (L1 / L2)
         {
             int bad = 0;
             for (int t = tid; t < n; t += B) bad |= !(Wd[t + 1] > Wd[t]);
@@ -162,6 +169,9 @@ __global__ void __launch_bounds__(B) ffbs_big_kernel(const FfbsArgs a) {
         int i_final = n;
         while (i_final > 0 && np_isclose(a.t_end, Wd[i_final])) --i_final;
         Real* row_base = msg;  // start of row i-1 (row r holds K*(r+1) values)
+        int j_lo = 0, ms_lo = 0;  // first live grid point (ffbs.cuh, "Live window"); ring slot of its slot
+        bool overflow = false;
+        unsigned long long live = 0;
         __syncthreads();
         for (int i = 0; i < n; ++i) {
             const double wn = Wd[i + 1];
@@ -169,12 +179,35 @@ __global__ void __launch_bounds__(B) ffbs_big_kernel(const FfbsArgs a) {
             for (int s = 0; s < K; ++s) Jp_s[s * BP + tid] = 0;
             Real Zp = 0;
             const int mi = i / B, ti = i - mi * B;
-            for (int m = 0; m <= mi; ++m) {
+            const int m_lo = j_lo / B, t_lo = j_lo - m_lo * B;
+            if (mi - m_lo >= NS) {  // the window outgrew the ring (block-uniform)
+                overflow = true;
+                break;
+            }
+            if (tid == 0) jlo_arr[i] = j_lo;
+            live += (unsigned long long)(i - j_lo + 1);
+            const bool judge = !exporting && (i & 3) == 0;  // the window start is re-examined every fourth step
+            if (judge) {
+                int mylive = 0x7fffffff;
+                const int j0 = m_lo * B + tid;
+                if (j0 >= j_lo && j0 < i) {
+                    const Real thr = weps > (Real)0 ? weps / invZ_prev : (Real)0;
+                    const Real* q = st_a + (size_t)ms_lo * K * B + tid;
+                    bool alive = false;
+                    for (int v = 0; v < K; ++v) alive = alive || q[v * B] > thr;
+                    if (alive) mylive = j0;
+                }
+                mylive = __reduce_min_sync(0xffffffffu, mylive);
+                if (lane == 0) s_jmin[(i & 1) * NW + wid] = mylive;
+            }
+            int ms = ms_lo;
+            for (int m = m_lo; m <= mi; ++m, ms = (ms + 1 == NS ? 0 : ms + 1)) {
                 const bool diag = m == mi && tid == ti;
                 if (m == mi && tid > ti) break;
+                if (m == m_lo && tid < t_lo) continue;
                 const int j = m * B + tid;
-                Real* pa = st_a + (size_t)m * K * B + tid;
-                Real* ph = st_h + (size_t)m * K * B + tid;
+                Real* pa = st_a + (size_t)ms * K * B + tid;
+                Real* ph = st_h + (size_t)ms * K * B + tid;
                 const Real tau = (Real)(wn - Wd[j]);
                 const Real L2 = ex2.log2(tau);
                 for (int v = 0; v < K; ++v) {
@@ -226,11 +259,19 @@ __global__ void __launch_bounds__(B) ffbs_big_kernel(const FfbsArgs a) {
             }
             if (a.logZ && tid == 0) a.logZ[w0 + i] = log((double)Z);
             if (i > 0) row_base += (int64_t)K * i;
+            if (judge) {
+                int jl = 0x7fffffff;
+                for (int w = 0; w < NW; ++w) jl = min(jl, s_jmin[(i & 1) * NW + w]);
+                const int j_new = max(j_lo, min(jl, min((m_lo + 1) * B, i)));  // the states of step i itself are not judged yet
+                if (j_new / B != m_lo) ms_lo = ms_lo + 1 == NS ? 0 : ms_lo + 1;
+                j_lo = j_new;
+            }
             __syncthreads();
         }
-        if (degenerate) {  // block-uniform
+        if (a.live_pairs && tid == 0) atomicAdd(a.live_pairs, live);
+        if (degenerate || overflow) {  // block-uniform
             if (tid == 0) {
-                a.status[c] = SMJP_ST_DEGENERATE;
+                a.status[c] = overflow ? SMJP_ST_OVERFLOW : SMJP_ST_DEGENERATE;
                 a.path_len[c] = 0;
             }
             continue;
@@ -250,6 +291,8 @@ __global__ void __launch_bounds__(B) ffbs_big_kernel(const FfbsArgs a) {
         while (true) {
             const int len = cur + 1;
             const Real* row = msg + (int64_t)K * cur * (cur + 1) / 2;
+            const int lo = exporting ? 0 : jlo_arr[cur];  // live window of this row: entries below lo were never written
+            const int wl = len - lo;
             if (!a.uniforms && (u_hi < 0 || cur <= u_hi - B)) {
                 if (cur - tid >= 0)
                     ubuf[tid] = philox_u01(a.seed, TAG_BACKWARD, (uint64_t)(cur - tid), 0u, a.sweep,
@@ -257,11 +300,14 @@ __global__ void __launch_bounds__(B) ffbs_big_kernel(const FfbsArgs a) {
                 u_hi = cur;
             }
             if (vplus < 0) {  // a_{n-1} ~ alpha_{n-1}  (fast_hmm.py:124-125); g = alpha on the last row
-                for (int t = tid; t < K * len; t += B) wbuf[t] = row[t];
+                for (int t = tid; t < K * wl; t += B) {
+                    const int v = t / wl, jj = t - v * wl;
+                    wbuf[t] = row[(int64_t)v * len + lo + jj];
+                }
             } else {
                 const double wn = Wd[cur + 1];
                 const bool grow = !exporting && cur < i_final;  // the row holds g: one hazard per entry
-                for (int j = tid; j < len; j += B) {
+                for (int j = lo + tid; j < len; j += B) {
                     const Real L2 = ex2.log2((Real)(wn - Wd[j]));
                     for (int v = 0; v < K; ++v) {
                         const Real hto = ex2(pkm1[v * K + vplus] * L2 - pc2p[v * K + vplus]);
@@ -271,12 +317,12 @@ __global__ void __launch_bounds__(B) ffbs_big_kernel(const FfbsArgs a) {
                             for (int s = 0; s < K; ++s) dsum += ex2(pkm1[v * K + s] * L2 - pc2p[v * K + s]);
                             r = dsum > (Real)0 ? hto * M::rcp(dsum) : (Real)0;
                         }
-                        wbuf[v * len + j] = row[(int64_t)v * len + j] * r;
+                        wbuf[v * wl + (j - lo)] = row[(int64_t)v * len + j] * r;
                     }
                 }
             }
             __syncthreads();
-            const int L = K * len;
+            const int L = K * wl;
             const int q = (L + B - 1) / B;
             const int beg = min(tid * q, L), end = min(beg + q, L);
             Acc loc = 0;
@@ -328,7 +374,7 @@ __global__ void __launch_bounds__(B) ffbs_big_kernel(const FfbsArgs a) {
                 if (tid == 0) s_flag = 0;
             }
             const int idx = s_sel;
-            const int v = idx / len, j = idx - v * len;
+            const int v = idx / wl, j = lo + idx - v * wl;
             if (a.aug_idx)
                 for (int t = j + tid; t <= cur; t += B) a.aug_idx[w0 + t] = v * n + j;
             __syncthreads();  // everyone has read s_sel and the weights before they are overwritten

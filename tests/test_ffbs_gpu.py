@@ -149,7 +149,7 @@ def test_large_state_space_kernel_matches_oracle(engine, K, n, D, prec):
 
 
 def test_large_state_space_sweeps_and_capacity_error(engine):
-    """Rao-Teh sweeps at K = 12 through DeviceChains; a grid whose state does not fit on chip is refused"""
+    """Rao-Teh sweeps at K = 12 through DeviceChains; exported messages of a grid whose state does not fit on chip are refused"""
     from smjp_b200._lib import EngineError
     from smjp_b200.chains import DeviceChains
     rng = np.random.default_rng(5)
@@ -166,8 +166,12 @@ def test_large_state_space_sweeps_and_capacity_error(engine):
     K = 64
     engine.set_model(np.full((K, K), 1.5), np.ones((K, K)), 2.0, O.emission_matrix(K), 1.0, 1.0)
     W = np.linspace(0.0, 1.0, 2001)
-    with pytest.raises((EngineError, RuntimeError, ValueError)):
-        engine.ffbs_host([W], np.zeros(0), np.zeros(0, np.int32), uniforms=[np.full(2000, 0.5)])
+    # scratch mode: the chain state lives in a ring over the live window, so the length of the grid is no limit any
+    # more; a window that outgrows the ring would end the chain with SMJP_ST_OVERFLOW, never with wrong numbers
+    r = engine.ffbs_host([W], np.zeros(0), np.zeros(0, np.int32), uniforms=[np.full(2000, 0.5)])
+    assert r["status"][0] in (0, 4)
+    with pytest.raises((EngineError, RuntimeError, ValueError)):  # exported messages need the whole triangle on chip
+        engine.ffbs_host([W], np.zeros(0), np.zeros(0, np.int32), uniforms=[np.full(2000, 0.5)], want_messages=True)
 
 
 def test_ragged_batch_and_philox_backward(engine):
@@ -344,3 +348,60 @@ def test_observation_symbol_out_of_range_is_flagged_on_the_device(engine, K, pre
         assert st[0] == 0 and st[2] == 0 and (st[1] & 8) and out["pl"].cpu().numpy()[1] == 0
         with pytest.raises(ValueError):
             raise_for_status(st)
+
+
+def _long_grid_case(K, n, seed):
+    rng = np.random.default_rng(seed)
+    t_end = n / 4.0
+    # total leaving rate ~ 4 per unit time, grid spacing 1/4: a state loses ~2^-4 per grid step (thinning 1/2 x survival),
+    # so the exact fp64 window is ~270 grid points and the 2^-70 one ~20
+    shape = rng.uniform(0.6, 3.0, (K, K)); scale = rng.uniform(0.15 * K, 0.35 * K, (K, K))
+    W = np.concatenate([[0.0], np.sort(rng.uniform(0, t_end, n - 1)), [t_end]])
+    obs_t = np.arange(0.25, t_end, 0.25); obs_y = rng.integers(0, K, len(obs_t))
+    return shape, scale, W, obs_t, obs_y, t_end, rng.uniform(size=n)
+
+
+def test_large_state_space_long_grid_exact_window(engine):
+    """ffbs_big.cuh keeps the chain state of the LIVE window in a ring (it used to hold the whole grid: K = 24 stopped
+    near n = 500): K = 24, n = 700, exact fp64 window, scratch mode -- oracle parity, and the window really opened"""
+    K, n = 24, 700
+    shape, scale, W, obs_t, obs_y, t_end, u = _long_grid_case(K, n, 1)
+    emis = O.emission_matrix(K)
+    engine.set_model(shape, scale, 2.0, emis, 1.0, t_end)
+    engine.lib.smjp_ctx_get_stat(engine.ctx, b"ffbs_live_pairs")
+    r = engine.ffbs_host([W], obs_t, obs_y, uniforms=[u], precision="f64")
+    live = engine.lib.smjp_ctx_get_stat(engine.ctx, b"ffbs_live_pairs")
+    ora = O.ffbs(W, obs_t, obs_y, shape, scale, 2.0, emis, 1.0, t_end, u)
+    assert r["status"][0] == 0
+    assert np.array_equal(r["aug_idx"][0], ora["samples"])
+    assert np.array_equal(r["V"][0], ora["V"]) and np.array_equal(r["T"][0], ora["T"])
+    assert np.abs(r["logZ"][0] - ora["logZ"]).max() < 1e-10
+    assert live < 0.8 * n * (n + 1) / 2
+    with pytest.raises(Exception):  # exported messages need the whole triangle on chip: refused, as before
+        engine.ffbs_host([W], obs_t, obs_y, uniforms=[u], precision="f64", want_messages=True)
+
+
+def test_k64_long_grid_pruned_window_against_the_exact_oracle(engine):
+    """BASELINE configs[3]'s general-shape sMJP at K = 64 on a LONG grid (n = 520; the first version stopped at 140):
+    the exact fp64 window (hundreds of grid points: a state loses about the thinning factor 1/2 per grid step relative
+    to the row) does not fit the ring at K = 64 (two slots of 64 grid points), the pruned one (states below 2^-40 of the
+    row sum dropped, SURVEY 7 hard part 2) does: same path as the exact oracle, log Z within 1e-9; without pruning the
+    chain is refused (SMJP_ST_OVERFLOW), never silently truncated; fp32's exact window fits its five slots"""
+    from smjp_b200._lib import ST_OVERFLOW
+    K, n = 64, 520
+    shape, scale, W, obs_t, obs_y, t_end, u = _long_grid_case(K, n, 2)
+    emis = O.emission_matrix(K)
+    engine.set_model(shape, scale, 2.0, emis, 1.0, t_end)
+    ora = O.ffbs(W, obs_t, obs_y, shape, scale, 2.0, emis, 1.0, t_end, u)
+    raw = engine.ffbs_host([W], obs_t, obs_y, uniforms=[u], precision="f64")
+    assert raw["status"][0] & ST_OVERFLOW
+    engine.set_option("window_log2", -40)
+    try:
+        r = engine.ffbs_host([W], obs_t, obs_y, uniforms=[u], precision="f64")
+    finally:
+        engine.set_option("window_log2", 0)
+    assert r["status"][0] == 0
+    assert np.array_equal(r["V"][0], ora["V"]) and np.array_equal(r["T"][0], ora["T"])
+    assert np.abs(r["logZ"][0] - ora["logZ"]).max() < 1e-9
+    r32 = engine.ffbs_host([W], obs_t, obs_y, uniforms=[u], precision="f32")
+    assert r32["status"][0] == 0 and np.abs(r32["logZ"][0] - ora["logZ"]).max() < 5e-4

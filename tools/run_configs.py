@@ -101,8 +101,10 @@ def cfg4(C=1024, K=64, T=2000.0, sweeps=3):
     return {"config": "cfg4 dense K=%d exponential sMJP, %d chains, T=%g, Rao-Teh sweeps (candidates + dense FFBS)" % (K, C, T), **out}
 
 
-def cfg4b(C=1024, K=64, T=40.0, sweeps=2):
-    """K=64 sMJP with GENERAL Weibull shapes on a reduced horizon (the (v,l) path, run-time-K kernel)"""
+def cfg4b(C=1024, K=64, T=1000.0, sweeps=1):
+    """K=64 sMJP with GENERAL Weibull shapes over the long horizon of BASELINE configs[3] (the (v,l) path, run-time-K
+    kernel ffbs_big.cuh with the chain state of the live window in a ring): fp32 with the exact window, fp64 with states
+    below 2^-40 of the row sum dropped (the exact fp64 window does not fit on chip at K = 64)"""
     import torch
     from smjp_b200.chains import DeviceChains
     from smjp_b200.engine import Engine
@@ -111,23 +113,28 @@ def cfg4b(C=1024, K=64, T=40.0, sweeps=2):
     eng.set_model(rng.uniform(0.6, 3.0, (K, K)), rng.uniform(0.7 * K, 1.3 * K, (K, K)), 2.0, emission(K), 1.0, T)
     obs_t = np.arange(0.5, T, 1.0)
     out = {}
-    for prec in ("f64", "f32"):
-        ch = DeviceChains(eng, C, obs_t).init_prior(np.ones(K) / K, seed=1, honour_scale=True, cap_per_chain=512)
+    for prec, wl in (("f32", 0), ("f64", -40)):
+        eng.set_option("window_log2", wl)
+        ch = DeviceChains(eng, C, obs_t).init_prior(np.ones(K) / K, seed=1, honour_scale=True, cap_per_chain=int(4 * T) + 64)
         ch.simulate_observations(seed=2)
-        ch.init_prior(np.ones(K) / K, seed=3, honour_scale=True, cap_per_chain=512)
-        for sw in range(2):
-            ch.sweep(seed=4, sweep=sw, precision=prec, mode="exact")
+        ch.init_prior(np.ones(K) / K, seed=3, honour_scale=True, cap_per_chain=int(4 * T) + 64)
+        ch.sweep(seed=4, sweep=0, precision=prec, mode="exact")
         torch.cuda.synchronize()
+        eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_live_pairs")
         t0 = time.perf_counter()
         for sw in range(sweeps):
-            ch.sweep(seed=4, sweep=2 + sw, precision=prec, mode="exact")
+            ch.sweep(seed=4, sweep=1 + sw, precision=prec, mode="exact")
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        live = float(eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_live_pairs"))
         s, g = ch.state_steps_last_sweep()
-        out[prec] = {"ms_per_sweep": 1e3 * dt / sweeps, "mean_n": g / C, "state_steps_per_sec": s * sweeps / dt,
-                     "failed": int((ch.status != 0).sum().item())}
+        out[prec] = {"window": "exact" if wl == 0 else "pruned 2^%d" % wl, "ms_per_sweep": 1e3 * dt / sweeps, "mean_n": g / C,
+                     "nominal_state_steps_per_sec": s * sweeps / dt, "retained_state_steps_per_sec": K * live / dt,
+                     "live_fraction": K * live / max(s * sweeps, 1.0), "failed": int((ch.status != 0).sum().item())}
+        del ch
+    eng.set_option("window_log2", 0)
     eng.close()
-    return {"config": "cfg4b K=%d general-shape sMJP on a reduced horizon T=%g, %d chains (ffbs_big kernel)" % (K, T, C), **out}
+    return {"config": "cfg4b K=%d general-shape sMJP, T=%g, %d chains (ffbs_big kernel, state ring over the live window)" % (K, T, C), **out}
 
 
 def cfg5(C=16384, T=20.0, sweeps=4, threads=0):
