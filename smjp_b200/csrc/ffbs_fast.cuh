@@ -89,6 +89,52 @@ __device__ __forceinline__ void named_bar(int id, bool sync, int nthreads) {  //
 #undef SMJP_BAR_CASE
 }
 
+// ---- TMA 1-D bulk copy (cp.async.bulk) of a chain's observation slice into shared memory, completion on an mbarrier ----
+// The slice is staged in the (still unused) state ring while the warp validates the grid, so that the per-interval
+// binary searches and symbol reads of the prologue hit shared memory instead of L2.  Source, destination and size must
+// be multiples of 16 bytes: the copy starts at the 16-byte boundary below the slice and ends at the one above it.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// plan of the staged slice: element offsets of the 16-byte aligned windows around [o0, o0 + D)
+struct ObsStage {
+    int64_t t0, y0;      // first element copied (obs_t: even, obs_y: multiple of 4)
+    uint32_t bt, by;     // bytes copied
+    int dt, dy;          // position of element o0 inside the copies
+};
+__device__ __forceinline__ ObsStage obs_stage_plan(int64_t o0, int D) {
+    ObsStage p;
+    p.dt = (int)(o0 & 1);
+    p.dy = (int)(o0 & 3);
+    p.t0 = o0 - p.dt;
+    p.y0 = o0 - p.dy;
+    p.bt = (uint32_t)(((D + p.dt + 1) & ~1) * 8);
+    p.by = (uint32_t)(((D + p.dy + 3) & ~3) * 4);
+    return p;
+}
+
 // log2 of a positive NORMAL double (the prologue's range check guarantees it): Exp2<double>::log2 without the
 // special-case branch and without the int -> double conversion (exponent through the 2^52 trick)
 template <typename Real>
@@ -158,6 +204,7 @@ __global__ void __launch_bounds__(B * CPB, MINB) ffbs_fast_kernel(const FfbsArgs
     __shared__ int s_jmin_a[CPB][2 * NW];
     __shared__ int s_flag_a[CPB];
     __shared__ unsigned long long s_dmin_a[CPB];
+    __shared__ __align__(8) unsigned long long s_obar_a[CPB];  // completion of the observation bulk copy
     __shared__ double s_tab[Exp2<Real>::TAB ? Exp2<Real>::TAB : 1];
     __shared__ double2 s_ltab[Exp2<Real>::LTAB ? Exp2<Real>::LTAB : 1];
     int& s_chain = s_chain_a[cw];
@@ -167,6 +214,9 @@ __global__ void __launch_bounds__(B * CPB, MINB) ffbs_fast_kernel(const FfbsArgs
     int* s_jmin = s_jmin_a[cw];
     int& s_flag = s_flag_a[cw];
     unsigned long long& s_dmin = s_dmin_a[cw];
+    unsigned long long* s_obar = &s_obar_a[cw];
+    uint32_t obs_parity = 0;
+    if (tid == 0) mbar_init(s_obar, 1);
 
     for (int t = tid; t < K * K; t += B) {
         const double k = a.model[t];
@@ -194,6 +244,7 @@ __global__ void __launch_bounds__(B * CPB, MINB) ffbs_fast_kernel(const FfbsArgs
     // back once per backward draw: L2)
     Real* obsf = (Real*)a.obsf_scratch + (int64_t)region * a.obsf_stride;
     int* jlo_arr = (int*)(obsf + (int64_t)ncap * K);
+    const int64_t obs_total = a.obs_offs[a.C];  // entries of obs_t / obs_y: the aligned bulk copies stay inside them
     if (CPB > 1) __syncthreads();  // the tables; from here on the warps of the CTA go their own ways
 
     while (true) {
@@ -217,7 +268,22 @@ __global__ void __launch_bounds__(B * CPB, MINB) ffbs_fast_kernel(const FfbsArgs
             }
             continue;
         }
-        // ---- stage the grid, validate it (smjp_utils.py:398-399), smallest gap ----
+        // ---- observations: TMA bulk copy of the chain's slice into the (idle) state ring, under the grid validation ----
+        const int64_t o0 = a.obs_offs[c];
+        const int D = (int)(a.obs_offs[c + 1] - o0);
+        const ObsStage os = obs_stage_plan(o0, D);
+        const bool staged = D > 0 && (size_t)os.bt + os.by <= 2 * (size_t)NS * K * B * sizeof(Real) &&
+                            os.t0 + (int64_t)(os.bt / 8) <= obs_total && os.y0 + (int64_t)(os.by / 4) <= obs_total &&
+                            ((reinterpret_cast<uintptr_t>(a.obs_t) | reinterpret_cast<uintptr_t>(a.obs_y)) & 15) == 0;
+        double* so_t = (double*)st_a;                         // st_a and st_h are contiguous
+        int32_t* so_y = (int32_t*)((char*)st_a + os.bt);
+        if (staged && tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the ring was last written by ordinary stores
+            mbar_expect_tx(s_obar, os.bt + os.by);
+            bulk_g2s(so_t, a.obs_t + os.t0, os.bt, s_obar);
+            bulk_g2s(so_y, a.obs_y + os.y0, os.by, s_obar);
+        }
+        // ---- validate the grid (smjp_utils.py:398-399), smallest gap ----
         const double* Wg = a.W + w0;  // the grid stays in global memory (L2); only the window's times go on chip
         {
             int bad = 0;
@@ -232,10 +298,12 @@ __global__ void __launch_bounds__(B * CPB, MINB) ffbs_fast_kernel(const FfbsArgs
         }
         // ---- observation factor per interval: (sum_{x in [W[i],W[i+1]]} P(x|v))^power (as in ffbs.cuh) ----
         {
-            const int64_t o0 = a.obs_offs[c];
-            const int D = (int)(a.obs_offs[c + 1] - o0);
-            const double* ot = a.obs_t + o0;
-            const int32_t* oy = a.obs_y + o0;
+            if (staged) {
+                mbar_wait(s_obar, obs_parity);
+                obs_parity ^= 1u;
+            }
+            const double* ot = staged ? so_t + os.dt : a.obs_t + o0;
+            const int32_t* oy = staged ? so_y + os.dy : a.obs_y + o0;
             for (int i = tid; i < n; i += B) {
                 const double wc = Wg[i], wn = Wg[i + 1];
                 int lo = 0, hi = D;  // first d with ot[d] >= wc

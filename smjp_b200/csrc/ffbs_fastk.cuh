@@ -65,6 +65,9 @@ __global__ void __launch_bounds__(32, MINB) ffbs_fastk_kernel(const FfbsArgs a) 
 
     __shared__ double s_tab[Exp2<Real>::TAB ? Exp2<Real>::TAB : 1];
     __shared__ double2 s_ltab[Exp2<Real>::LTAB ? Exp2<Real>::LTAB : 1];
+    __shared__ __align__(8) unsigned long long s_obar;  // completion of the observation bulk copy (ffbs_fast.cuh)
+    uint32_t obs_parity = 0;
+    if (lane == 0) mbar_init(&s_obar, 1);
     for (int t = lane; t < K * K; t += 32) {
         const double k = a.model[t];
         srk[t] = (Real)(1.0 / k);
@@ -97,6 +100,7 @@ __global__ void __launch_bounds__(32, MINB) ffbs_fastk_kernel(const FfbsArgs a) 
     const int region = blockIdx.x;
     Real* obsf = (Real*)a.obsf_scratch + (int64_t)region * a.obsf_stride;
     int* jlo_arr = (int*)(obsf + (int64_t)ncap * K);
+    const int64_t obs_total = a.obs_offs[a.C];
 
     while (true) {
         int c;
@@ -119,6 +123,21 @@ __global__ void __launch_bounds__(32, MINB) ffbs_fastk_kernel(const FfbsArgs a) 
             continue;
         }
         const double* Wg = a.W + w0;
+        // ---- observations: TMA bulk copy of the chain's slice into the (idle) state ring, under the grid validation ----
+        const int64_t o0 = a.obs_offs[c];
+        const int D = (int)(a.obs_offs[c + 1] - o0);
+        const ObsStage os = obs_stage_plan(o0, D);
+        const bool staged = D > 0 && (size_t)os.bt + os.by <= 2 * (size_t)NS * IT * sizeof(Real) &&
+                            os.t0 + (int64_t)(os.bt / 8) <= obs_total && os.y0 + (int64_t)(os.by / 4) <= obs_total &&
+                            ((reinterpret_cast<uintptr_t>(a.obs_t) | reinterpret_cast<uintptr_t>(a.obs_y)) & 15) == 0;
+        double* so_t = (double*)st_a;  // st_a and st_h are contiguous
+        int32_t* so_y = (int32_t*)((char*)st_a + os.bt);
+        if (staged && lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&s_obar, os.bt + os.by);
+            bulk_g2s(so_t, a.obs_t + os.t0, os.bt, &s_obar);
+            bulk_g2s(so_y, a.obs_y + os.y0, os.by, &s_obar);
+        }
         // ---- validate the grid (smjp_utils.py:398-399), smallest gap ----
         int bad = 0;
         double dmin = INFINITY;
@@ -133,10 +152,12 @@ __global__ void __launch_bounds__(32, MINB) ffbs_fastk_kernel(const FfbsArgs a) 
         // ---- observation factor per interval (as in ffbs.cuh) ----
         int badsym = 0;
         {
-            const int64_t o0 = a.obs_offs[c];
-            const int D = (int)(a.obs_offs[c + 1] - o0);
-            const double* ot = a.obs_t + o0;
-            const int32_t* oy = a.obs_y + o0;
+            if (staged) {
+                mbar_wait(&s_obar, obs_parity);
+                obs_parity ^= 1u;
+            }
+            const double* ot = staged ? so_t + os.dt : a.obs_t + o0;
+            const int32_t* oy = staged ? so_y + os.dy : a.obs_y + o0;
             for (int i = lane; i < n; i += 32) {
                 const double wc = Wg[i], wn = Wg[i + 1];
                 int lo = 0, hi = D;
