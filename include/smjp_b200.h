@@ -183,7 +183,8 @@ int smjp_simulate_obs_dev(smjp_ctx_t* ctx, int C, const int64_t* p_offs, const i
  * (smjp_utils.py:194-210) + PoissonProcess.sample (:61-99) with the A_hat = (omega-1)*A process.
  * Two passes over the same counter-based draws:
  *   count: writes w_offs[C+1] (device), soff[] (device scratch, int32, same windows as the path
- *          arrays) and returns n_max / total_w to the HOST (synchronises the stream);
+ *          arrays: entry q of a chain's window = the grid index of jump q, entry path_len-1 = the
+ *          end point's) and returns n_max / total_w to the HOST (synchronises the stream);
  *   fill:  writes W[total_w] (device).
  */
 int smjp_candidates_count_dev(smjp_ctx_t* ctx, int C, const int64_t* p_offs, const int32_t* path_v,

@@ -1169,7 +1169,7 @@ int cand_count_enqueue(smjp_ctx* c, int C, const int64_t* p_offs, const int32_t*
     CandArgs a = make_cand_args(c, C, p_offs, path_v, path_t, path_len, seed, sweep);
     a.soff = soff;
     a.w_len = (int64_t*)c->d_wlen.p;
-    int grid = C < c->num_sms * 16 ? C : c->num_sms * 16;
+    int grid = (C + 3) / 4 < c->num_sms * 16 ? (C + 3) / 4 : c->num_sms * 16;  // a warp per chain, 4 per CTA
     cand_count_kernel<<<grid, 128, 0, c->stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     chain_scan_kernel<<<1, 1024, 0, c->stream>>>(C, (const int64_t*)c->d_wlen.p, w_offs, (int64_t*)c->d_stats.p);
@@ -1222,7 +1222,7 @@ int smjp_candidates_fill_dev(smjp_ctx_t* c, int C, const int64_t* p_offs, const 
     a.soff = const_cast<int32_t*>(soff);
     a.w_offs = w_offs;
     a.W = W;
-    int grid = C < c->num_sms * 16 ? C : c->num_sms * 16;
+    int grid = (C + 3) / 4 < c->num_sms * 16 ? (C + 3) / 4 : c->num_sms * 16;
     cand_fill_kernel<<<grid, 128, 0, c->stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     c->launches += 1;

@@ -52,83 +52,83 @@ struct CandArgs {
     int64_t guard_total;
 };
 
-// number of thinned events of sojourn q of chain c (all targets), optionally emitting them
-__device__ __forceinline__ int sojourn_events(const CandArgs& a, int c, int q, int v, double t0, double tau,
-                                              double* out) {
+// Thinned events of ONE (sojourn q, target class s) item of chain c: their number, optionally written (unsorted) to out
+__device__ __forceinline__ int target_events(const CandArgs& a, int c, int q, int v, int s, double tau, double t0,
+                                             double* out) {
     const int K = a.K;
     v = min(max(v, 0), K - 1);  // a state index outside [0, K) (caller's paths) never indexes the model out of bounds
     const double* shape = a.model;
     const double* scale = a.model + 2 * K * K + K * a.Kobs;
     const double* crep = scale + K * K;  // class representative / class sum of lambda^-k (smjp_set_model)
     const double* csum = crep + K * K;
-    int total = 0;
-    for (int s = 0; s < K; ++s) {
-        if ((int)crep[v * K + s] != s) continue;  // merged into an earlier target of the same shape
-        const double k = shape[v * K + s];
-        bool alone = true;
-        for (int u = s + 1; u < K; ++u) alone = alone && (int)crep[v * K + u] != s;
-        const double mu = alone ? (a.omega - 1.0) * pow(tau / scale[v * K + s], k)
-                                : (a.omega - 1.0) * pow(tau, k) * csum[v * K + s];
-        int m = (int)ceil(mu / SMJP_POISSON_CHUNK);
-        if (m < 1) m = 1;
-        const uint32_t aa = (uint32_t)(q * K + s);
-        int N = 0;
-        for (int cc = 0; cc < m; ++cc)
-            N += poisson_inv(mu / m, philox_u01(a.seed, TAG_CANDIDATES, (uint64_t)cc, aa, a.sweep,
-                                                a.chain_base + (uint32_t)c));
-        if (out) {
-            const double F = -expm1(-pow(tau, k));
-            for (int d = 0; d < N; ++d) {
-                const double u = philox_u01(a.seed, TAG_CANDIDATES, (uint64_t)(m + d), aa, a.sweep,
-                                            a.chain_base + (uint32_t)c);
-                double x = (a.mode == SMJP_CAND_REFERENCE) ? pow(-log1p(-u * F), 1.0 / k)
-                                                           : tau * pow(u, 1.0 / k);
-                x = fmin(x, tau);
-                // insertion into the sorted run out[0 .. total+d)
-                int pos = total + d;
-                const double val = t0 + x;
-                while (pos > 0 && out[pos - 1] > val) {
-                    out[pos] = out[pos - 1];
-                    --pos;
-                }
-                out[pos] = val;
-            }
+    if ((int)crep[v * K + s] != s) return 0;  // merged into an earlier target of the same shape (or s == v)
+    const double k = shape[v * K + s];
+    bool alone = true;
+    for (int u = s + 1; u < K; ++u) alone = alone && (int)crep[v * K + u] != s;
+    const double mu = alone ? (a.omega - 1.0) * pow(tau / scale[v * K + s], k)
+                            : (a.omega - 1.0) * pow(tau, k) * csum[v * K + s];
+    int m = (int)ceil(mu / SMJP_POISSON_CHUNK);
+    if (m < 1) m = 1;
+    const uint32_t aa = (uint32_t)(q * K + s);
+    int N = 0;
+    for (int cc = 0; cc < m; ++cc)
+        N += poisson_inv(mu / m, philox_u01(a.seed, TAG_CANDIDATES, (uint64_t)cc, aa, a.sweep,
+                                            a.chain_base + (uint32_t)c));
+    if (out && N > 0) {
+        const double F = (a.mode == SMJP_CAND_REFERENCE) ? -expm1(-pow(tau, k)) : 0.0;
+        const double rk = 1.0 / k;
+        for (int d = 0; d < N; ++d) {
+            const double u = philox_u01(a.seed, TAG_CANDIDATES, (uint64_t)(m + d), aa, a.sweep,
+                                        a.chain_base + (uint32_t)c);
+            double x = (a.mode == SMJP_CAND_REFERENCE) ? pow(-log1p(-u * F), rk) : tau * pow(u, rk);
+            out[d] = t0 + fmin(x, tau);
         }
-        total += N;
     }
-    return total;
+    return N;
 }
 
-// one CTA per chain: per-sojourn counts -> offsets inside the chain's grid, chain grid length
+// One WARP per chain, one LANE per (sojourn, target) item -- the serial chain of a lane is one Poisson draw and its
+// events, not K of them (a thread per sojourn spent its time in K back-to-back fp64 pow/exp chains).  Items are
+// ordered sojourn-major, so the exclusive prefix of the counts + the number of earlier sojourns (one grid point each,
+// the jump time) is the item's position in the chain's grid.
+struct CandItem {
+    int q, s, v;
+    double t0, tau;
+    bool valid;
+};
+__device__ __forceinline__ CandItem cand_item(const CandArgs& a, int64_t p0, int nsoj, int i) {
+    CandItem it;
+    it.q = i / a.K;
+    it.s = i - it.q * a.K;
+    it.valid = it.q < nsoj;
+    it.v = 0; it.t0 = 0.0; it.tau = 0.0;
+    if (it.valid) {
+        it.v = a.path_v[p0 + it.q];
+        it.t0 = a.path_t[p0 + it.q];
+        it.tau = a.path_t[p0 + it.q + 1] - it.t0;
+    }
+    return it;
+}
+
 __global__ void cand_count_kernel(const CandArgs a) {
-    __shared__ int s_warp[33];
-    __shared__ int s_carry;
-    const int tid = threadIdx.x, B = blockDim.x, lane = tid & 31, wid = tid >> 5, NW = B >> 5;
-    for (int c = blockIdx.x; c < a.C; c += gridDim.x) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, NW = blockDim.x >> 5;
+    for (int c = blockIdx.x * NW + wid; c < a.C; c += gridDim.x * NW) {
         const int64_t p0 = a.p_offs[c];
         const int plen = a.path_len[c];
         const int nsoj = plen - 1;
-        if (tid == 0) s_carry = 0;
-        __syncthreads();
-        for (int base = 0; base < nsoj; base += B) {
-            const int q = base + tid;
-            int cnt = 0;
-            if (q < nsoj) {
-                const double t0 = a.path_t[p0 + q], t1 = a.path_t[p0 + q + 1];
-                cnt = 1 + sojourn_events(a, c, q, a.path_v[p0 + q], t0, t1 - t0, nullptr);
-            }
-            int incl = warp_inclusive_scan(cnt, lane);
-            if (lane == 31) s_warp[wid] = incl;
-            __syncthreads();
-            int off = s_carry;
-            for (int w = 0; w < wid; ++w) off += s_warp[w];
-            if (q < nsoj) a.soff[p0 + q] = off + incl - cnt;
-            __syncthreads();
-            if (tid == B - 1) s_carry = off + incl;
-            __syncthreads();
+        const int items = nsoj * a.K;
+        int carry = 0;
+        for (int base = 0; base < items; base += 32) {
+            const CandItem it = cand_item(a, p0, nsoj, base + lane);
+            const int cnt = it.valid ? target_events(a, c, it.q, it.v, it.s, it.tau, it.t0, nullptr) : 0;
+            const int incl = warp_inclusive_scan(cnt, lane);
+            if (it.valid && it.s == 0) a.soff[p0 + it.q] = carry + incl - cnt + it.q;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
         }
-        if (tid == 0) a.w_len[c] = (plen >= 2) ? (int64_t)s_carry + 1 : 0;  // + the end point
-        __syncthreads();
+        if (lane == 0) {
+            if (plen >= 2) a.soff[p0 + nsoj] = carry + nsoj;                 // the end point's slot
+            a.w_len[c] = (plen >= 2) ? (int64_t)carry + nsoj + 1 : 0;  // + the end point
+        }
     }
 }
 
@@ -164,21 +164,44 @@ __global__ void chain_scan_kernel(int C, const int64_t* len, int64_t* offs, int6
     }
 }
 
-// thread per sojourn: W[base] = T[q]; W[base+1 ..] = sorted thinned events
+// warp per chain.  Phase 1, lane per (sojourn, target): W[soff[q]] = T[q], the item's events behind it, unsorted.
+// Phase 2, lane per sojourn: insertion sort of the sojourn's few events (they came target by target).
 __global__ void cand_fill_kernel(const CandArgs a) {
     if (a.guard && a.guard[1] > a.guard_total) return;
-    const int tid = threadIdx.x, B = blockDim.x;
-    for (int c = blockIdx.x; c < a.C; c += gridDim.x) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, NW = blockDim.x >> 5;
+    for (int c = blockIdx.x * NW + wid; c < a.C; c += gridDim.x * NW) {
         const int64_t p0 = a.p_offs[c], w0 = a.w_offs[c];
         const int plen = a.path_len[c];
         const int nsoj = plen - 1;
-        for (int q = tid; q < nsoj; q += B) {
-            const double t0 = a.path_t[p0 + q], t1 = a.path_t[p0 + q + 1];
-            double* out = a.W + w0 + a.soff[p0 + q];
-            out[0] = t0;
-            sojourn_events(a, c, q, a.path_v[p0 + q], t0, t1 - t0, out + 1);
+        const int items = nsoj * a.K;
+        double* Wc = a.W + w0;
+        int carry = 0;
+        for (int base = 0; base < items; base += 32) {
+            const CandItem it = cand_item(a, p0, nsoj, base + lane);
+            // the count is redrawn (same Philox counters) rather than kept in HBM; the events go straight to their slot
+            const int cnt = it.valid ? target_events(a, c, it.q, it.v, it.s, it.tau, it.t0, nullptr) : 0;
+            const int incl = warp_inclusive_scan(cnt, lane);
+            const int pos = carry + incl - cnt + it.q;  // slot of T[q] if s == 0; events of the item start at pos + 1
+            if (it.valid) {
+                if (it.s == 0) Wc[pos] = it.t0;
+                if (cnt > 0) target_events(a, c, it.q, it.v, it.s, it.tau, it.t0, Wc + pos + 1);
+            }
+            carry += __shfl_sync(0xffffffffu, incl, 31);
         }
-        if (tid == 0 && plen >= 2) a.W[a.w_offs[c + 1] - 1] = a.path_t[p0 + plen - 1];
+        if (lane == 0 && plen >= 2) Wc[carry + nsoj] = a.path_t[p0 + plen - 1];
+        __syncwarp();
+        for (int q = lane; q < nsoj; q += 32) {
+            const int lo = a.soff[p0 + q] + 1, hi = a.soff[p0 + q + 1];
+            for (int i = lo + 1; i < hi; ++i) {
+                const double val = Wc[i];
+                int pos = i;
+                while (pos > lo && Wc[pos - 1] > val) {
+                    Wc[pos] = Wc[pos - 1];
+                    --pos;
+                }
+                Wc[pos] = val;
+            }
+        }
     }
 }
 

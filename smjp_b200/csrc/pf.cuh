@@ -67,40 +67,52 @@ struct PfArgs {
 // upper incomplete gamma function (series / continued fraction, inverse by Halley steps from a
 // Wilson-Hilferty start).  Twin: oracle cond_gamma (scipy.special.gammaincc / gammainccinv).
 // ------------------------------------------------------------------------------------------------
-// lga = lgamma(a): a model constant, tabulated once per filter run (it was recomputed ~10 times per draw)
-__device__ inline double igamc(double a, double x, double lga) {
+// lga = lgamma(a): a model constant, tabulated once per filter run (it was recomputed ~10 times per draw).
+// Both expansions run WITHOUT a division per term (an fp64 division is ~30 instructions, the term itself 3): the
+// series sum is carried as a fraction P/D, the continued fraction by its forward recurrence A_i/B_i with the
+// convergence test cross-multiplied; each ends in one division.
+// e: the table-driven fp64 2^x / log2 of ffbs.cuh (libdevice log + exp were a fifth of the filter's instructions);
+// ax_out (optional) receives x^a e^-x / Gamma(a) = x * pdf(x), which the inverse's Newton step needs anyway.
+__device__ inline double igamc(const Exp2<double>& e, double a, double x, double lga, double* ax_out = nullptr) {
+    constexpr double S = Exp2<double>::SCALE, L2E = 1.4426950408889634;
+    if (ax_out) *ax_out = 0.0;
     if (!(x > 0.0)) return 1.0;
-    const double lax = a * log(x) - x - lga;
-    if (lax < -745.0) return x < a + 1.0 ? 1.0 : 0.0;
-    const double ax = exp(lax);
-    if (x < a + 1.0) {  // P(a,x) by series
-        double r = a, c = 1.0, ans = 1.0;
-        for (int it = 0; it < 500; ++it) {
+    const double lax2 = fma(a, e.log2(x), -(x + lga) * L2E);  // log2 of x^a e^-x / Gamma(a)
+    if (lax2 < -1020.0) return x < a + 1.0 ? 1.0 : 0.0;
+    const double ax = e(S * lax2);
+    if (ax_out) *ax_out = ax;
+    if (x < a + 1.0) {  // P(a,x) by series: sum_n x^n / ((a+1)...(a+n)) = P_n / D_n
+        double r = a, N = 1.0, P = 1.0, D = 1.0;
+        for (int it = 0; it < 512; it += 2) {
             r += 1.0;
-            c *= x / r;
-            ans += c;
-            if (c <= 1e-17 * ans) break;
+            N *= x;
+            P = fma(P, r, N);
+            D *= r;
+            r += 1.0;
+            N *= x;
+            P = fma(P, r, N);
+            D *= r;
+            if (N <= 1e-17 * P) break;
+            if ((it & 30) == 30 && D > 1e100) { N *= 1e-100; P *= 1e-100; D *= 1e-100; }  // 32 terms grow D by < 1e90
         }
-        return 1.0 - ans * ax / a;
+        return 1.0 - (P * ax) / (D * a);
     }
-    const double tiny = 1e-300;  // Q(a,x) by continued fraction (modified Lentz)
-    double b = x + 1.0 - a, c = 1.0 / tiny, d = 1.0 / b, h = d;
+    // Q(a,x) = ax / (b_0 + a_1/(b_1 + a_2/(b_2 + ...))), a_i = -i (i - a), b_i = x + 1 - a + 2 i
+    double b = x + 1.0 - a;
+    double A1 = 1.0, B1 = 0.0, A0 = b, B0 = 1.0;  // (A_{i-2}, B_{i-2}), (A_{i-1}, B_{i-1})
     for (int i = 1; i < 500; ++i) {
         const double an = -(double)i * ((double)i - a);
         b += 2.0;
-        d = an * d + b;
-        if (fabs(d) < tiny) d = tiny;
-        c = b + an / c;
-        if (fabs(c) < tiny) c = tiny;
-        d = 1.0 / d;
-        const double delta = d * c;
-        h *= delta;
-        if (fabs(delta - 1.0) < 1e-16) break;
+        const double A = fma(b, A0, an * A1), B = fma(b, B0, an * B1);
+        const double cross = fabs(fma(A, B0, -(A0 * B)));  // |f_i - f_{i-1}| * |B B0|
+        A1 = A0; B1 = B0; A0 = A; B0 = B;
+        if (cross <= 1e-16 * fabs(A * B1)) break;
+        if ((i & 15) == 15 && (fabs(A0) > 1e100 || fabs(B0) > 1e100)) { A0 *= 1e-100; B0 *= 1e-100; A1 *= 1e-100; B1 *= 1e-100; }
     }
-    return ax * h;
+    return ax * (B0 / A0);
 }
 
-__device__ inline double igamci(double a, double q, double lga) {  // x with Q(a, x) = q
+__device__ inline double igamci(const Exp2<double>& e, double a, double q, double lga) {  // x with Q(a, x) = q
     if (q >= 1.0) return 0.0;
     if (!(q > 0.0)) return INFINITY;
     const double t = -normcdfinv(q), d = 1.0 / (9.0 * a), y = 1.0 - d + t * sqrt(d);
@@ -113,8 +125,9 @@ __device__ inline double igamci(double a, double q, double lga) {  // x with Q(a
         else x = fmax(x, x0);
     }
     for (int it = 0; it < 60; ++it) {
-        const double f = igamc(a, x, lga) - q;
-        const double fp = -exp((a - 1.0) * log(x) - x - lga);
+        double ax;
+        const double f = igamc(e, a, x, lga, &ax) - q;
+        const double fp = -ax / x;
         if (fp == 0.0) break;
         double dx = f / fp;
         const double den = 1.0 - 0.5 * dx * ((a - 1.0) / x - 1.0);
@@ -122,6 +135,37 @@ __device__ inline double igamci(double a, double q, double lga) {  // x with Q(a
         double xn = x - dx;
         if (!(xn > 0.0)) xn = 0.5 * x;
         const bool done = fabs(xn - x) <= 1e-15 * xn;
+        x = xn;
+        if (done) break;
+    }
+    return x;
+}
+
+// The same inverse when the root is known to lie in [lo, hi] with Q(lo) = qlo > q > Q(hi) = qhi (the holding time
+// of a particle that jumps before its next observation: an interval one observation spacing wide).  Secant start,
+// Halley steps kept inside the bracket: 2-3 evaluations of Q instead of the ~6 of the global search.
+__device__ inline double igamci_bracketed(const Exp2<double>& e, double a, double q, double lga, double lo, double hi,
+                                          double qlo, double qhi) {
+    double x = lo + (qlo - q) / (qlo - qhi) * (hi - lo);
+    if (!(x > lo && x < hi)) x = 0.5 * (lo + hi);
+    for (int it = 0; it < 60; ++it) {
+        double ax;
+        const double f = igamc(e, a, x, lga, &ax) - q;
+        if (f > 0.0) lo = x; else hi = x;  // Q decreases: Q(x) > q puts the root above x
+        const double fp = -ax / x;
+        double xn, tol = 1e-15;
+        if (fp == 0.0 || !isfinite(fp)) {
+            xn = 0.5 * (lo + hi);
+        } else {
+            double dx = f / fp;
+            const double den = 1.0 - 0.5 * dx * ((a - 1.0) / x - 1.0);
+            // Halley converges cubically (Newton quadratically): after a step of relative size 1e-6 (1e-9) the next
+            // one is below the rounding of x and its evaluation of Q is saved; a bisection step promises nothing
+            if (den > 0.2) { dx /= den; tol = 1e-6; } else tol = 1e-9;
+            xn = x - dx;
+            if (!(xn > lo && xn < hi)) { xn = 0.5 * (lo + hi); tol = 1e-15; }
+        }
+        const bool done = fabs(xn - x) <= tol * xn || !(hi > lo);
         x = xn;
         if (done) break;
     }
@@ -145,14 +189,21 @@ struct PfMath {
 // in cancellation-free form; 1-u is exact for a 53-bit uniform) is compared in the log2 domain,
 // log2 tau_s = log2 lambda + log2(e_s)/k, so that only the winner is exponentiated.  Uniform r = it*K + s of
 // stream (seed, TAG_PF_PROPAGATE, slot, d, chain), two per Philox block.
+//
+// Gamma: the caller only needs the smallest draw if it falls before the next observation, `hnext` after the sojourn
+// began.  tau_s < hnext  <=>  (1-u) Q(a, hold/theta) > Q(a, hnext/theta), so two evaluations of Q decide a target and
+// the inverse is taken only for the (few) targets that do jump, inside the bracket [hold, hnext]; a round without a
+// jump returns +inf.  The draws are those of the full inversion (oracle cond_gamma) wherever both are exact.
 __device__ __forceinline__ double pf_round(const PfArgs& a, const PfMath& m, uint32_t chain, uint32_t d, uint32_t slot,
-                                           int it, int v, double hold, int& arg) {
+                                           int it, int v, double hold, double hnext, int& arg) {
     constexpr double S = Exp2<double>::SCALE;
     const int K = a.K;
     const bool gamma = a.family == SMJP_HAZARD_GAMMA;
     const double l2h = (!gamma && hold > 0.0) ? m.ex2.log2(hold) : -INFINITY;
     double best = INFINITY;
     arg = 0;
+    int ncand = 0;                            // gamma: targets that jump before hnext
+    double c_q = 0.0, c_qlo = 1.0, c_qhi = 0.0;  // the first of them, not yet inverted
     Philox4 blk;
     uint32_t blk_idx = 0xFFFFFFFFu;
     for (int s = 0; s < K; ++s) {
@@ -167,7 +218,26 @@ __device__ __forceinline__ double pf_round(const PfArgs& a, const PfMath& m, uin
         if (gamma) {
             const double k = m.shape[t], lam = m.scale[t];
             const double lga = m.lga ? m.lga[t] : lgamma(k);
-            key = lam * igamci(k, (1.0 - u) * igamc(k, hold / lam, lga), lga);
+            const double xlo = hold / lam, xhi = hnext / lam;
+            const double qlo = igamc(m.ex2, k, xlo, lga), qhi = igamc(m.ex2, k, xhi, lga);
+            const double q = (1.0 - u) * qlo;
+            key = INFINITY;
+            if (q > qhi) {
+                // the inverse is deferred: nearly always ONE target jumps, and it is then inverted after the loop,
+                // where the jumping lanes of the warp run the iteration together instead of target by target
+                if (ncand == 0) {
+                    ncand = 1; arg = s;
+                    c_q = q; c_qlo = qlo; c_qhi = qhi;
+                } else {
+                    if (ncand == 1) {
+                        const int t1 = v * K + arg;
+                        const double k1 = m.shape[t1], lam1 = m.scale[t1];
+                        best = lam1 * igamci_bracketed(m.ex2, k1, c_q, m.lga ? m.lga[t1] : lgamma(k1), hold / lam1, hnext / lam1, c_qlo, c_qhi);
+                    }
+                    ncand = 2;
+                    key = lam * igamci_bracketed(m.ex2, k, q, lga, xlo, xhi, qlo, qhi);
+                }
+            }
         } else {
             const double k = m.shape[t];
             const double hk = l2h == -INFINITY ? 0.0 : m.ex2(S * (k * l2h - m.c2[t]));  // (hold/lambda)^k
@@ -178,6 +248,11 @@ __device__ __forceinline__ double pf_round(const PfArgs& a, const PfMath& m, uin
         }
         if (key < best) { best = key; arg = s; }
     }
+    if (ncand == 1) {
+        const int t1 = v * K + arg;
+        const double k1 = m.shape[t1], lam1 = m.scale[t1];
+        best = lam1 * igamci_bracketed(m.ex2, k1, c_q, m.lga ? m.lga[t1] : lgamma(k1), hold / lam1, hnext / lam1, c_qlo, c_qhi);
+    }
     return gamma ? best : (best == -INFINITY ? 0.0 : m.ex2(S * best));
 }
 
@@ -187,7 +262,7 @@ __device__ __forceinline__ int pf_propagate(const PfArgs& a, const PfMath& m, ui
                                             double* out_t, int out_cap, int* out_n) {
     for (int it = 0; it < a.max_iters; ++it) {
         int arg;
-        const double w_next = l + pf_round(a, m, chain, d, slot, it, v, t_cur - l, arg);
+        const double w_next = l + pf_round(a, m, chain, d, slot, it, v, t_cur - l, t_obs - l, arg);
         if (w_next >= t_obs) return 0;
         t_cur = w_next;
         l = w_next;
@@ -328,7 +403,7 @@ __global__ void __launch_bounds__(B) pf_kernel(const PfArgs a) {
                     if (!__any_sync(0xffffffffu, have)) break;
                     if (have) {
                         int arg;
-                        const double w_next = l + pf_round(a, m, chain, (uint32_t)d, (uint32_t)p, it, v, t_cur - l, arg);
+                        const double w_next = l + pf_round(a, m, chain, (uint32_t)d, (uint32_t)p, it, v, t_cur - l, t_obs - l, arg);
                         bool fin = w_next >= t_obs;
                         if (!fin) {
                             t_cur = w_next;
