@@ -215,8 +215,8 @@ def cpu_sample(n_chains, sweeps, t_end, procs):
 
 
 def time_unmodified_reference(budget_s=12.0):
-    """The UNMODIFIED reference (oracle/_ref = a copy of /root/reference's pure-Python sources, imported behind
-    oracle/ref_shim.py) on cfg1 = main.py's default model (experiments.py:154-222): the loop body of raoteh.py:58-59
+    """The UNMODIFIED reference (oracle/_ref = the bytecode `make -C oracle` compiles from /root/reference's
+    pure-Python modules, imported sourceless behind oracle/ref_shim.py) on cfg1 = main.py's default model (experiments.py:154-222): the loop body of raoteh.py:58-59
     (candidates + smjp_ffbs), one core -- BASELINE.md section 3 item 1.  ~1 sweep/s, so a handful of sweeps."""
     try:
         from oracle import ref_shim

@@ -2,8 +2,9 @@
 
 Used by ``oracle/gen_golden*.py`` (in the authoring container, where /root/reference exists) to produce the
 committed fixtures under ``tests/golden/``, and by ``bench.py --impl reference`` to time the unmodified
-reference beside the NumPy port: ``make -C oracle`` copies the reference's (pure-Python) sources into the
-git-ignored ``oracle/_ref/``, which travels to the GPU box with the snapshot.  Nothing in the product
+reference beside the NumPy port: ``make -C oracle`` byte-compiles the reference's (pure-Python) modules from
+where they lie under /root/reference into the git-ignored ``oracle/_ref/pkg/*.pyc`` (bytecode only, no source is
+copied), which travels to the GPU box with the snapshot and is imported sourceless.  Nothing in the product
 package ``smjp_b200/`` imports this module.
 
 What the shim does, without touching a single reference source line:
@@ -31,7 +32,8 @@ REFERENCE_ROOT = os.environ.get("SMJP_REFERENCE_ROOT") or (
 
 
 def reference_available():
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "pkg", "fast_hmm.py"))
+    """the sources (/root/reference) or their bytecode (oracle/_ref/pkg/*.pyc, `make -C oracle`; imported sourceless)"""
+    return any(os.path.isfile(os.path.join(REFERENCE_ROOT, "pkg", "fast_hmm" + ext)) for ext in (".py", ".pyc"))
 
 
 class _EasyDict(dict):
