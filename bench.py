@@ -161,6 +161,30 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+FFBS_KERNEL_NAMES = {0: "ffbs_kernel", 1: "ffbs_item_kernel", 2: "ffbs_big_kernel", 3: "ffbs_warp_kernel",
+                     4: "ffbs_fast_kernel", 5: "ffbs_fastk_kernel"}  # smjp_ctx_get_stat("ffbs_kernel")
+
+
+def captured_traffic(traffic, key, kernel):
+    """DRAM bytes per launch from the committed ncu capture -- only when it is a capture of the kernel that ran"""
+    t = ((traffic or {}).get(key) or {})
+    return t.get("dram_bytes_per_launch") if str(t.get("kernel", "")).startswith(kernel + "<") else None
+
+
+def ceilings_from_capture(t):
+    """The compute ceilings of a kernel from its committed ncu --set full capture (profiles/roofline_traffic.json):
+    the launch cannot be shorter than its duration x the busiest pipe's utilisation; `ceiling_over_measured` is
+    that fraction -- 1.0 would mean the kernel sits on its arithmetic / issue ceiling."""
+    if not t or "issue_active_pct" not in t:
+        return None
+    busiest = max(float(t["issue_active_pct"]), float(t.get("pipe_active_pct_ncu", 0.0)))
+    return {"pipe": t.get("pipe"), "pipe_active_pct_ncu": t.get("pipe_active_pct_ncu"),
+            "issue_active_pct_ncu": t["issue_active_pct"], "thread_inst_per_pair": t.get("pipe_thread_inst_per_pair"),
+            "warp_inst_per_pair_all_pipes": t.get("warp_inst_per_warp_pair"),
+            "kernel_ms_at_ceiling_ncu": float(t["gpu_time_ms"]) * busiest / 100.0, "ceiling_over_measured": busiest / 100.0,
+            "source": "profiles/roofline_traffic.json (ncu --set full)"}
+
+
 def ncu_traffic():
     """per-launch DRAM bytes of the FFBS kernel from the committed ncu --set full capture, if any"""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -342,13 +366,18 @@ def k10_block(local, steps, peak, peak_src, chains=K10_CHAINS, chain_base=0, pre
             nominal += algorithmic_bytes(n, D, esz, K10_K)
             tail += float(np.sum(40.0 * n + 12 * D))
         kid = int(eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_kernel"))
+        cap = ((ncu_traffic() or {}).get("k10_" + prec) or {})
+        # the committed capture describes ffbs_fastk_kernel on this very workload (16384 chains); not other kernels / sizes
+        on_captured_kernel = bool(cap) and names.get(kid) == "ffbs_fastk_kernel" and chains == K10_CHAINS
         out[prec] = {"value": ss / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
                      "chain_sweeps_per_sec": chains * steps / (ms / 1e3), "mean_grid_intervals": gs / (chains * steps),
                      "failed_chains": int((ch.status != 0).sum().item()),
                      "chains_redone_by_rescue_pass_last_launch": int(eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_rescued")),
                      "roofline": roofline_block("%s<%s,10>" % (names.get(kid, "kernel %d" % kid), "double" if prec == "f64" else "float"),
                                                 2 * esz * K10_K * lp + tail, nominal, k_cnt, k_ms, peak, peak_src,
-                                                K10_K * lp / max(ss, 1.0), None, kernel_share_of_step=k_ms / ms,
+                                                K10_K * lp / max(ss, 1.0), cap.get("dram_bytes_per_launch") if on_captured_kernel else None,
+                                                compute=ceilings_from_capture(cap) if on_captured_kernel else None,
+                                                kernel_share_of_step=k_ms / ms,
                                                 grid=int(eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_grid")),
                                                 smem=int(eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_smem")))}
         del ch
@@ -693,12 +722,13 @@ def run_ours(args):
                 "issue_active_pct_ncu": t.get("issue_active_pct"), "source": "profiles/roofline_traffic.json (ncu --set full)"}
 
     clk = sampler.summary()
+    kernel_main = FFBS_KERNEL_NAMES.get(int(eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_kernel")), "ffbs_item_kernel")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": prec, "data": "synthetic",
         "config": {"workload": workload_name(C), "chains_total": C * world, "parallelism": "chains sharded x%d" % world,
-                   "l2": "no flush needed: the message stream of one sweep (%.1f GB/GPU nominal, 17 GB of measured DRAM traffic in fp64 "
+                   "l2": "no flush needed: the message stream of one sweep (%.1f GB/GPU nominal, 15 GB of measured DRAM traffic in fp64 "
                          "with the live window) exceeds the 126 MB L2 a hundredfold" % (alg_bytes / args.steps / 1e9),
                    "mean_grid_intervals": gs / (C * world * args.steps), "candidates": "reference (Q5)"},
         "chain_sweeps_per_sec": C * world * args.steps / secs, "grid_steps_per_sec": gs / secs,
@@ -707,9 +737,8 @@ def run_ours(args):
                    "ring_boost": int(eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_fast_boost_f64"))},
         "clocks": clk,
         "roofline": roofline_block(
-            "%s<%s,3>" % ({0: "ffbs_kernel", 3: "ffbs_warp_kernel", 4: "ffbs_fast_kernel"}.get(eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_kernel"), "ffbs_item_kernel"),
-                          "double" if prec == "f64" else "float"), ret_bytes, alg_bytes, k_cnt, k_ms, peak, peak_src,
-            live_frac, ((traffic or {}).get(prec) or {}).get("dram_bytes_per_launch"),
+            "%s<%s,3>" % (kernel_main, "double" if prec == "f64" else "float"), ret_bytes, alg_bytes, k_cnt, k_ms, peak, peak_src,
+            live_frac, captured_traffic(traffic, prec, kernel_main),
             grid=eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_grid"), threads=eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_threads"),
             smem=eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_smem"), kernel_share_of_step=k_ms / ms,
             # the kernel skips grid points whose states have underflowed to EXACT zeros (results unchanged to the
@@ -765,12 +794,13 @@ def run_ours(args):
             b32 += algorithmic_bytes(n, D, 4)
             r32 += float(np.sum(40.0 * n + 12 * D))
         r32 += 2 * 4 * K * lp32
+        kernel32 = FFBS_KERNEL_NAMES.get(int(eng.lib.smjp_ctx_get_stat(eng.ctx, b"ffbs_kernel")), "ffbs_item_kernel")
         line["f32"] = {"value": ss32 / (ms32 / 1e3), "unit": UNIT, "ms_per_step": ms32 / args.steps,
                        "chain_sweeps_per_sec": C * args.steps / (ms32 / 1e3),
                        "failed_chains": int((ch.status != 0).sum().item()),
                        "roofline": roofline_block(
-                           "ffbs_warp_kernel<float,3> (auto) / ffbs_kernel<float,3>", r32, b32, c32, k32, peak, peak_src,
-                           K * lp32 / max(ss32, 1.0), ((traffic or {}).get("f32") or {}).get("dram_bytes_per_launch"),
+                           kernel32 + "<float,3>", r32, b32, c32, k32, peak, peak_src,
+                           K * lp32 / max(ss32, 1.0), captured_traffic(traffic, "f32", kernel32),
                            compute=compute_ceiling("f32", ss32 / K / max(c32, 1), k32 / max(c32, 1) / 1e3, clk.get("sm_mhz"))),
                        "tolerance": "messages within 1e-4 of the reference (tests/test_ffbs_gpu.py)"}
     if world == 1 and prec == "f64" and not args.no_alt and args.window_log2 == 0:
