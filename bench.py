@@ -390,7 +390,7 @@ PF_K = 5
 PF_T = 10.0
 
 
-def pf_block(rank, world, local, dev, runs_per_gpu, peak, peak_src, reps=2, family="gamma"):
+def pf_block(rank, world, local, dev, runs_per_gpu, peak, peak_src, reps=2, family="gamma", opts=None):
     """BASELINE configs[2] as stated: bootstrap particle filter (pmcmc.py:224-310) with GAMMA holding-time hazards
     (shape ~ U(0.6, 3) seed 3, scale 1), K = 5, T = 10, D = 99 observations, 65536 particles per filter run, systematic
     resampling; `runs_per_gpu` filter runs in flight per GPU through the device-pointer entry point smjp_pf_dev.  With
@@ -407,6 +407,8 @@ def pf_block(rank, world, local, dev, runs_per_gpu, peak, peak_src, reps=2, fami
     eng = Engine(local)
     eng.set_model(shape, np.ones((PF_K, PF_K)), OMEGA, emis, 1.0, PF_T)
     eng.set_option("chain_base", rank * runs_per_gpu)
+    for k, v in (opts or {}).items():  # kernel experiments (tools/pf_probe.py)
+        eng.set_option(k, v)
     obs_t = np.arange(OBS_DT, PF_T, OBS_DT)
     D = len(obs_t)
     y = rng.integers(0, PF_K, D)
