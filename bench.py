@@ -588,8 +588,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    from smjp_b200.distributed import SummaryGather
+    # posterior summaries of ALL chains on every rank, every sweep, inside the timed region: one NCCL all-gather of
+    # [C, 2K] doubles per sweep on a side stream, overlapped with the next sweep (mcmc_utils.py:40-56 per chain).
+    # A warm-up step is a timed step: it gathers too (NCCL sets its channels up on the first call of a communicator)
+    gather = SummaryGather(C * world, K, rank, world, dev, overlap=bool(args.gather_overlap))
     for sw in range(args.warmup):
         ch.sweep(seed=SEED, sweep=sw, precision=prec)
+        gather.launch(ch.time_in_state, ch.jumps)
+    gather.result()
+    gather.reset_counters()
     # the collector is kept out of the timed regions: a generation-2 pass of a process with torch loaded was
     # seen to add 5-50 ms to a single step
     gc.collect()
@@ -601,10 +609,6 @@ def run_ours(args):
     launches0 = eng.launch_count
     spec0 = [eng.lib.smjp_ctx_get_stat(eng.ctx, k) for k in (b"spec_launches", b"spec_misses")]
     sampler = ClockSampler(local)
-    from smjp_b200.distributed import SummaryGather
-    # posterior summaries of ALL chains on every rank, every sweep, inside the timed region: one NCCL all-gather of
-    # [C, 2K] doubles per sweep on a side stream, overlapped with the next sweep (mcmc_utils.py:40-56 per chain)
-    gather = SummaryGather(C * world, K, rank, world, dev, overlap=bool(args.gather_overlap))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ss = gs = 0.0
     alg_bytes = tail_bytes = 0.0

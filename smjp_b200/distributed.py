@@ -76,6 +76,11 @@ class SummaryGather:
         self.launched = 0
         self.bytes_per_gather = self.world * self.m * 2 * self.K * 8 if self.world > 1 else 0
 
+    def reset_counters(self):
+        """forget the gathers launched so far (warm-up) in `launched` / gather_ms(); call after result()"""
+        self.timing = []
+        self.launched = 0
+
     def launch(self, time_in_state, jumps):
         """enqueue a gather of the current summaries; returns at once"""
         t = self.torch
