@@ -765,7 +765,9 @@ def run_ours(args):
         "pf": pf,
         "e2e": {"value": e_ss / e_wall, "unit": UNIT, "h2d_bytes_per_step": h2d // max(e2e_steps, 1),
                 "d2h_bytes_per_step": d2h // max(e2e_steps, 1), "steps": e2e_steps,
-                "api": "smjp_sweep_host (pinned host buffers in/out; H2D of paths + observations and D2H of the grid inside the timed call, new paths / metrics / status written by the kernels straight into the pinned output buffers)"},
+                "api": "smjp_sweep_host (pinned host buffers in/out, all PCIe traffic inside the timed call: the paths' entries in use are pulled by a gather kernel, each chain's observation slice is read in place by the FFBS kernel's bulk copies (TMA) when the chain starts, the grid is copied back under the FFBS kernel, new paths / metrics / status are written by the kernels straight into the pinned output buffers)",
+                "inputs_read_in_place": {"observations": bool(eng.lib.smjp_ctx_get_stat(eng.ctx, b"obs_in_place")),
+                                         "paths_gathered": bool(eng.lib.smjp_ctx_get_stat(eng.ctx, b"paths_gathered"))}},
     }
     if world == 1 and prec == "f64" and not args.no_alt:
         # the same workload in the engine's fp32 mode (north_star: messages within 1e-4), reported beside the

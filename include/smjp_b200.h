@@ -102,7 +102,18 @@ int64_t smjp_ctx_get_stat(smjp_ctx_t* ctx, const char* key);
  *        "obs_product" (0 = observations that share a grid interval are summed, as the reference does
  *        (smjp_utils.py:496-499); 1 = multiplied, the proper likelihood);
  *        "chain_base" (global index of chain 0 of this context's batches: keeps the Philox streams of
- *        chains sharded over several GPUs distinct and independent of the sharding) */
+ *        chains sharded over several GPUs distinct and independent of the sharding);
+ *        "ffbs_fast" (-1 auto (default), 0, 1: the warp-per-chain sweep kernels ffbs_fast.cuh (K <= 3, fp64, exact
+ *        window) and ffbs_fastk.cuh (4 <= K <= 10) with "fast_ring" / "fast_ways" / "fast_cpb" (0 = auto) as their
+ *        geometry; chains they cannot finish go to the rescue pass, so results never depend on them);
+ *        "dense_tc" (-1 auto (default: >= 32768 chains, 32 <= K <= 64, fp32), 0, 1: tensor-core forward pass of the
+ *        dense shape == 1 path);
+ *        "obs_zero_copy" (-1 auto (default), 0, 1: smjp_sweep_host with PINNED input arrays lets the FFBS kernel's bulk
+ *        copies read each chain's observations in place and a gather kernel pull only the path entries in use,
+ *        instead of uploading both first; stats "obs_in_place" / "paths_gathered" say what the last call did.
+ *        Results never depend on it).
+ * More stats: "ffbs_kernel" (which FFBS kernel the last launch used: 0 ffbs.cuh, 1 ffbs_item, 2 ffbs_big, 3 ffbs_warp,
+ * 4 ffbs_fast, 5 ffbs_fastk), "ffbs_rescued", "ffbs_fast_boost_f64" / "_f32", "dense_tc". */
 int smjp_ctx_set_option(smjp_ctx_t* ctx, const char* key, int64_t value);
 /* With option "time_kernels" = 1 every launch of the named kernel ("ffbs", "hmm", "pf") is bracketed by CUDA events
  * on the launching stream; this returns and resets their summed duration and count (synchronises). */

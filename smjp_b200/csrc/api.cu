@@ -121,6 +121,7 @@ struct smjp_ctx {
     DevBuf d_tile, d_pfws;
     int last_dense_tc = 0;
     int64_t dense_nmax_hint = 0;
+    int obs_zero_copy = -1;  // smjp_sweep_host: FFBS reads pinned observations in place (-1 auto, 0 off, 1 on)
     int fast_cpb = 0;     // chains per CTA, one warp each (0 = auto; 1..11) -- 32-thread groups only
     int fast_boost[2] = {0, 0};  // extra ring slots learnt from rescue counts, per precision
     int fast_off[2] = {0, 0};    // kept overflowing: ffbs.cuh from now on
@@ -139,6 +140,8 @@ struct smjp_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_obs = nullptr, ev_fill = nullptr;
     bool wait_obs = false;        // the next FFBS launch must wait for ev_obs
+    bool obs_in_place = false;    // last smjp_sweep_host: the kernels read the caller's pinned observations (stat)
+    bool paths_gathered = false;  // last stage_paths: a kernel pulled the paths' used entries out of pinned memory (stat)
     double* w_copy_dst = nullptr;  // pinned host destination of the grid, copied right after cand_fill
     PinBuf h_in, h_out;
     int ffbs_threads = 0;  // 0 = auto
@@ -269,6 +272,8 @@ int64_t smjp_ctx_get_stat(smjp_ctx_t* c, const char* key) {
     if (!strcmp(key, "ffbs_fast_boost_f32")) return c->fast_boost[1] + 100 * c->fast_off[1];
     if (!strcmp(key, "ffbs_fast_boost_f64")) return c->fast_boost[0] + 100 * c->fast_off[0];
     if (!strcmp(key, "dense_tc")) return c->last_dense_tc;
+    if (!strcmp(key, "obs_in_place")) return c->obs_in_place ? 1 : 0;
+    if (!strcmp(key, "paths_gathered")) return c->paths_gathered ? 1 : 0;
     if (!strcmp(key, "ffbs_kernel")) return c->last_kernel;  // 0 ffbs.cuh, 1 ffbs_item, 2 ffbs_big, 3 ffbs_warp, 4 ffbs_fast, 5 ffbs_fastk
     if (!strcmp(key, "spec_launches")) return c->spec_launches;
     if (!strcmp(key, "spec_misses")) return c->spec_misses;
@@ -351,6 +356,11 @@ int smjp_ctx_set_option(smjp_ctx_t* c, const char* key, int64_t value) {
     if (!strcmp(key, "dense_tc")) {
         if (value < -1 || value > 1) return fail(SMJP_E_INVALID, "dense_tc must be -1 (auto), 0 or 1");
         c->dense_tc = (int)value;
+        return SMJP_OK;
+    }
+    if (!strcmp(key, "obs_zero_copy")) {
+        if (value < -1 || value > 1) return fail(SMJP_E_INVALID, "obs_zero_copy must be -1 (auto), 0 or 1");
+        c->obs_zero_copy = (int)value;
         return SMJP_OK;
     }
     if (!strcmp(key, "fast_cpb")) {
@@ -1328,13 +1338,17 @@ struct StagedPaths {
 
 int stage_paths(smjp_ctx* c, int C, const int64_t* p_offs, const int32_t* path_v, const double* path_t,
                 const int32_t* path_len, const int64_t* obs_offs, const double* obs_t, const int32_t* obs_y,
-                StagedPaths* out, bool obs_on_copy_stream = false) {
+                StagedPaths* out, bool obs_on_copy_stream = false, const double* obs_t_mapped = nullptr,
+                const int32_t* obs_y_mapped = nullptr, const int32_t* path_v_mapped = nullptr,
+                const double* path_t_mapped = nullptr) {
     if (p_offs[0] != 0) return fail(SMJP_E_INVALID, "offsets must start at 0");
     const int64_t total_p = p_offs[C];
+    int64_t used_p = 0;
     for (int i = 0; i < C; ++i) {
         if (p_offs[i + 1] < p_offs[i]) return fail(SMJP_E_INVALID, "p_offs not monotone");
         if (path_len[i] < 2 || path_len[i] > p_offs[i + 1] - p_offs[i])
             return fail(SMJP_E_INVALID, "chain %d: path_len %d outside [2, window]", i, path_len[i]);
+        used_p += path_len[i];
     }
     const int64_t total_o = obs_offs ? obs_offs[C] : 0;
     size_t off = 0;
@@ -1377,17 +1391,32 @@ int stage_paths(smjp_ctx* c, int C, const int64_t* p_offs, const int32_t* path_v
         return bytes ? cudaMemcpyAsync(dd + o, src, bytes, cudaMemcpyHostToDevice, c->stream) : cudaSuccess;
     };
     CUDA_TRY(put(o_po, p_offs, (C + 1) * 8));
-    CUDA_TRY(put(o_pv, path_v, total_p * 4));
-    CUDA_TRY(put(o_pt, path_t, total_p * 8));
     CUDA_TRY(put(o_pl, path_len, C * 4));
+    if (path_v_mapped && path_t_mapped && used_p * 10 < total_p * 7) {
+        // sparse windows in pinned memory (a sweep's output windows are grid-sized, its paths a fraction of that): a
+        // kernel pulls only the entries in use over PCIe (cfg2: 5 MB instead of 26 MB)
+        int grid = (C + 7) / 8 < c->num_sms * 8 ? (C + 7) / 8 : c->num_sms * 8;
+        smjp::path_gather_kernel<<<grid, 256, 0, c->stream>>>(C, (const int64_t*)(dd + o_po), (const int32_t*)(dd + o_pl),
+                                                               path_v_mapped, path_t_mapped, (int32_t*)(dd + o_pv),
+                                                               (double*)(dd + o_pt));
+        CUDA_TRY(cudaGetLastError());
+        c->launches += 1;
+        c->paths_gathered = true;
+    } else {
+        CUDA_TRY(put(o_pv, path_v, total_p * 4));
+        CUDA_TRY(put(o_pt, path_t, total_p * 8));
+        c->paths_gathered = false;
+    }
     if (obs_offs) {
         cudaStream_t os = obs_on_copy_stream ? c->copy_stream : c->stream;
         auto puto = [&](size_t o, const void* src, size_t bytes) -> cudaError_t {
             return bytes ? cudaMemcpyAsync(dd + o, src, bytes, cudaMemcpyHostToDevice, os) : cudaSuccess;
         };
         CUDA_TRY(puto(o_oo, obs_offs, (C + 1) * 8));
-        CUDA_TRY(puto(o_ot, obs_t, total_o * 8));
-        CUDA_TRY(puto(o_oy, obs_y, total_o * 4));
+        if (!obs_t_mapped) {
+            CUDA_TRY(puto(o_ot, obs_t, total_o * 8));
+            CUDA_TRY(puto(o_oy, obs_y, total_o * 4));
+        }
         if (obs_on_copy_stream) {
             CUDA_TRY(cudaEventRecord(c->ev_obs, c->copy_stream));
             c->wait_obs = true;
@@ -1399,8 +1428,8 @@ int stage_paths(smjp_ctx* c, int C, const int64_t* p_offs, const int32_t* path_v
     out->path_t = (const double*)(d + o_pt);
     out->path_len = (const int32_t*)(d + o_pl);
     out->obs_offs = (const int64_t*)(d + o_oo);
-    out->obs_t = (const double*)(d + o_ot);
-    out->obs_y = (const int32_t*)(d + o_oy);
+    out->obs_t = obs_t_mapped ? obs_t_mapped : (const double*)(d + o_ot);
+    out->obs_y = obs_t_mapped ? obs_y_mapped : (const int32_t*)(d + o_oy);
     return SMJP_OK;
 }
 
@@ -1486,9 +1515,36 @@ int smjp_sweep_host(smjp_ctx_t* c, int C, const int64_t* p_offs, const int32_t* 
     int32_t* m_jm = (int32_t*)mapped(jumps);
     const bool w_pinned = mapped(W) != nullptr;
     const bool in_pinned = mapped((void*)obs_t) != nullptr || !obs_t;
+    // Zero-copy observations.  The sweep kernels ffbs_fast.cuh / ffbs_fastk.cuh fetch a chain's observation slice with
+    // ONE bulk-async copy per array (TMA) when the chain starts; when the caller's arrays are pinned that copy can read
+    // them in place over PCIe -- 12 KB per chain spread over the whole kernel -- instead of waiting for a 49 MB
+    // (cfg2) upload before the kernel may start.  Only when those kernels will run (exact window, K <= 10, fp64 or
+    // K >= 4, not switched off by rescue counts) and every slice fits their staging area; anything else uploads.
+    const double* obs_t_m = nullptr;
+    const int32_t* obs_y_m = nullptr;
+    if (c->obs_zero_copy != 0 && obs_t && obs_y && obs_offs[C] > 0) {
+        const int pidx = precision == SMJP_F64 ? 0 : 1;
+        const bool fast_kernels = c->ffbs_fast != 0 && c->window_log2 == 0 && c->f32_rescue && K <= 10 &&
+                                  (precision == SMJP_F64 || K >= 4) && !c->fast_off[pidx] && c->ffbs_warp != 1;
+        int64_t dmax = 0;
+        for (int i = 0; i < C; ++i) dmax = std::max(dmax, obs_offs[i + 1] - obs_offs[i]);
+        const size_t esz = precision == SMJP_F64 ? 8 : 4;
+        // smallest staging area those kernels have: the state ring (api.cu, ffbs launcher: ring sizes)
+        const size_t ring_bytes = K <= 3 ? (size_t)2 * 10 * K * 32 * esz : (size_t)2 * (96 / (32 / K)) * (32 / K) * K * esz;
+        const bool fits = (size_t)dmax * 12 + 64 <= ring_bytes;
+        if ((c->obs_zero_copy == 1 || fast_kernels) && fits) {
+            obs_t_m = (const double*)mapped((void*)obs_t);
+            obs_y_m = (const int32_t*)mapped((void*)obs_y);
+            if (!obs_t_m || !obs_y_m || (((uintptr_t)obs_t_m | (uintptr_t)obs_y_m) & 15)) obs_t_m = nullptr, obs_y_m = nullptr;
+        }
+    }
     StagedPaths sp;
-    rc = stage_paths(c, C, p_offs, path_v, path_t, path_len, obs_offs, obs_t, obs_y, &sp, in_pinned);
+    const bool gather_ok = c->obs_zero_copy != 0;  // (one switch for both in-place reads of pinned input)
+    rc = stage_paths(c, C, p_offs, path_v, path_t, path_len, obs_offs, obs_t, obs_y, &sp, in_pinned, obs_t_m, obs_y_m,
+                     gather_ok ? (const int32_t*)mapped((void*)path_v) : nullptr,
+                     gather_ok ? (const double*)mapped((void*)path_t) : nullptr);
     if (rc) return rc;
+    c->obs_in_place = obs_t_m != nullptr;
     rc = c->d_soff.reserve((size_t)p_offs[C] * 4 + 16);
     if (rc) return rc;
     // output staging: fixed part sized by `capacity`

@@ -213,6 +213,21 @@ __global__ void cand_fill_kernel(const CandArgs a) {
     }
 }
 
+// Host paths in pinned (device-mapped) memory -> device staging, entries in use only: warp per chain, coalesced reads
+// over PCIe.  (smjp_sweep_host: the windows of a sweep's output are grid-sized, the paths a fraction of that.)
+__global__ void path_gather_kernel(int C, const int64_t* p_offs, const int32_t* path_len, const int32_t* src_v,
+                                   const double* src_t, int32_t* dst_v, double* dst_t) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, NW = blockDim.x >> 5;
+    for (int c = blockIdx.x * NW + wid; c < C; c += gridDim.x * NW) {
+        const int64_t p0 = p_offs[c];
+        const int plen = path_len[c];
+        for (int q = lane; q < plen; q += 32) {
+            dst_t[p0 + q] = src_t[p0 + q];
+            dst_v[p0 + q] = src_v[p0 + q];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // prior trajectories: thread per chain (sequential competing risks)
 // ------------------------------------------------------------------------------------------------

@@ -369,7 +369,12 @@ class PackedSweep:
         return self
 
     def h2d_bytes(self):
-        live = int(self.in_offs[self.C])
+        """bytes that cross PCIe towards the device in the next run(): path entries (the windows as a whole when they
+        are copied, the entries in use when the library's gather kernel pulls them out of these pinned buffers -- stat
+        `paths_gathered` of the previous run), path lengths and offsets, the observations (uploaded, or read in place
+        by the FFBS kernel's bulk copies: same bytes either way)"""
+        gathered = bool(self.eng.lib.smjp_ctx_get_stat(self.eng.ctx, b"paths_gathered"))
+        live = int(self.in_len[: self.C].sum()) if gathered else int(self.in_offs[self.C])
         return live * 12 + self.C * 12 + 8 + (self.C + 1) * 8 + len(self.obs_t) * 12
 
     def d2h_bytes(self):

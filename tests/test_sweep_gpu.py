@@ -273,6 +273,50 @@ def _packed_sweep_case(engine):
         V, T = r["V"], r["T"]
 
 
+@pytest.mark.parametrize("K,precision", [(3, "f64"), (5, "f32")])
+def test_pinned_inputs_read_in_place_change_no_result(engine, K, precision):
+    """smjp_sweep_host with pinned buffers: the FFBS kernel's bulk copies read each chain's observations straight out of
+    the caller's memory and a gather kernel pulls only the path entries in use (option obs_zero_copy, default auto);
+    the same sweeps with both switched off (everything uploaded first) give the same bits."""
+    from smjp_b200.engine import PackedSweep, ragged_offsets
+    rng = np.random.default_rng(K)
+    shape = SHAPE3 if K == 3 else rng.uniform(0.6, 3.0, (K, K))
+    t_end = 30.0
+    emis = O.emission_matrix(K)
+    engine.set_model(shape, np.ones((K, K)), 2.0, emis, 1.0, t_end)
+    obs_t = np.arange(0.1, t_end, 0.1)
+    C = 40
+    V, T, Y = [], [], []
+    for c in range(C):
+        v, w = O.prior_path(shape, np.ones((K, K)), np.ones(K) / K, t_end, seed=1, chain=c)
+        V.append(v); T.append(w); Y.append(O.simulate_observations(v, w, obs_t, emis, seed=2, chain=c))
+    out = {}
+    try:
+        for mode in (-1, 0):
+            engine.set_option("obs_zero_copy", mode)
+            ps = PackedSweep(engine, C, ragged_offsets([len(obs_t)] * C), np.tile(obs_t, C), np.concatenate(Y), 40000)
+            ps.set_paths(V, T)
+            seen = []
+            for sw in range(4):
+                ps.run(7, sw, precision=precision)
+                seen.append((int(engine.lib.smjp_ctx_get_stat(engine.ctx, b"obs_in_place")),
+                             int(engine.lib.smjp_ctx_get_stat(engine.ctx, b"paths_gathered"))))
+                assert not np.any(ps.status[:C])
+                ps.swap()
+            out[mode] = (ps.in_offs[: C + 1].copy(), ps.in_v[: ps.in_offs[C]].copy(), ps.in_t[: ps.in_offs[C]].copy(),
+                         ps.in_len[:C].copy(), ps.W[: ps.total_w].copy(), seen)
+    finally:
+        engine.set_option("obs_zero_copy", -1)
+    assert all(s == (0, 0) for s in out[0][5])
+    assert all(s[0] == 1 for s in out[-1][5]) and any(s[1] == 1 for s in out[-1][5])
+    lens = out[0][3]
+    assert np.array_equal(out[0][0], out[-1][0]) and np.array_equal(lens, out[-1][3]) and np.array_equal(out[0][4], out[-1][4])
+    for c in range(C):
+        lo = out[0][0][c]
+        assert np.array_equal(out[0][1][lo: lo + lens[c]], out[-1][1][lo: lo + lens[c]])
+        assert np.array_equal(out[0][2][lo: lo + lens[c]], out[-1][2][lo: lo + lens[c]])
+
+
 def test_fp32_sweeps_leave_no_failed_chain(engine):
     """1.2e7 fp32 backward draws (4096 chains x 24 sweeps): none may lose its path.  Regression for a draw whose
     target fell between the inclusive scan value of the last thread holding weights and the warp total (a
