@@ -794,7 +794,8 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
             per = (per + 3) / 4 * 4;  // keeps every region 16-byte aligned
             a.obsf_stride = per;
         } else if (use_fast) {  // + the window start of every row (ints), see ffbs_fast.cuh
-            per += ((int64_t)(n_max + 2) * 4 + (int64_t)sizeof(Real) - 1) / (int64_t)sizeof(Real);
+            per += ffbs_fast_jlo_elems<Real>(n_max);
+            if (fastk) per += 3 * K * K;  // + the hazard tables the backward pass reads (ffbs_fastk.cuh)
             per = (per + 3) / 4 * 4;
             a.obsf_stride = per;
         } else if (big) {  // + window starts [n + 1] and the sojourn list [2][n + 1] (ints), see ffbs_big.cuh

@@ -37,6 +37,12 @@ namespace smjp {
 
 #define PC(w, t) (sizeof(Real) == 8 ? (Real)a.pc_d[w][t] : (Real)a.pc_f[w][t])  // as in ffbs.cuh (K <= 3)
 
+// elements of Real that hold the window starts [ncap + 2] (ints) inside a scratch region (api.cu sizes it the same way)
+template <typename Real>
+__host__ __device__ inline int64_t ffbs_fast_jlo_elems(int64_t ncap) {
+    return ((ncap + 2) * 4 + (int64_t)sizeof(Real) - 1) / (int64_t)sizeof(Real);
+}
+
 constexpr int FAST_RS = 8;   // steps between block-wide synchronisations (renormalisation, window judgement)
 constexpr int FAST_RR = 16;  // ring of partial-sum slots (> RS + the steps a warp can be ahead)
 

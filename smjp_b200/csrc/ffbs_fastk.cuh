@@ -28,10 +28,16 @@ __host__ __device__ inline FfbsLayout ffbs_fastk_layout(int K, int ring, int nca
     L.wd = (int)b;   b += align_up((size_t)ring * jps * sizeof(double), 16);          // grid times of the window (ring)
     L.ubuf = (int)b; b += align_up((size_t)32 * sizeof(double), 16);                  // backward uniforms
     L.scan = (int)b;                                                                  // (unused)
+    // Shared memory decides how many chains an SM holds (fp64, K = 10: 7 with a separate sojourn list and the hazard
+    // tables here, 8 without): the backward pass's sojourn list reuses the H ring, dead by then, when it fits, and the
+    // K x K hazard tables the backward pass reads live in the CTA's global scratch region (L1-resident, 2.4 KB).
+    const size_t soj = (size_t)2 * (ncap + 1) * sizeof(int);
     L.sta = (int)b;  b += align_up(state, 16);                                        // message ring; backward: weights
     L.sth = (int)b;  b += align_up(state, 16);                                        // H ring (contiguous with sta)
-    L.red = (int)b;  b += align_up((size_t)2 * (ncap + 1) * sizeof(int), 16);         // backward: sojourn list
-    L.par = (int)b;  b += align_up((size_t)(3 * K * K) * sizeof(Real), 16);           // hazard parameters
+    L.red = L.sth;                                                                    // backward: sojourn list
+    if (soj > state) { L.red = (int)b; b += align_up(soj, 16); }
+    L.par = (int)b;                                                                   // hazard tables: fp32 only
+    if (sizeof(Real) == 4) b += align_up((size_t)(3 * K * K) * sizeof(Real), 16);     // (fp32 is register-bound: 16 chains either way)
     L.jlo = (int)b;
     L.total = (int)b;
     return L;
@@ -59,7 +65,12 @@ __global__ void __launch_bounds__(32, MINB) ffbs_fastk_kernel(const FfbsArgs a) 
     Real* st_a = (Real*)(smem_raw + a.lay.sta);       // [slot][IT]
     Real* st_h = (Real*)(smem_raw + a.lay.sth);
     int* soj = (int*)(smem_raw + a.lay.red);
-    Real* srk = (Real*)(smem_raw + a.lay.par);
+    const int region = blockIdx.x;
+    Real* obsf = (Real*)a.obsf_scratch + (int64_t)region * a.obsf_stride;
+    int* jlo_arr = (int*)(obsf + (int64_t)ncap * K);
+    // hazard tables [3][K*K]: fp64 behind the window starts in global scratch, fp32 in shared memory; written once by
+    // this CTA (device arithmetic, like every kernel)
+    Real* srk = sizeof(Real) == 8 ? obsf + (int64_t)ncap * K + ffbs_fast_jlo_elems<Real>(ncap) : (Real*)(smem_raw + a.lay.par);
     Real* skm1 = srk + K * K;
     Real* sc2p = skm1 + K * K;
 
@@ -97,9 +108,6 @@ __global__ void __launch_bounds__(32, MINB) ffbs_fastk_kernel(const FfbsArgs a) 
     const Real om_l2e = (Real)(a.omega * SMJP_LOG2E * (double)Exp2<Real>::SCALE);
     const Real power = (Real)a.power;
     const Real weps = (Real)a.window_eps;
-    const int region = blockIdx.x;
-    Real* obsf = (Real*)a.obsf_scratch + (int64_t)region * a.obsf_stride;
-    int* jlo_arr = (int*)(obsf + (int64_t)ncap * K);
     const int64_t obs_total = a.obs_offs[a.C];
 
     while (true) {
