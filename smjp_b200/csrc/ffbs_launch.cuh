@@ -95,10 +95,15 @@ cudaError_t ffbs_fast_pick(const FfbsArgs& a, FfbsLaunch& L, bool query) {
 }
 inline int ffbs_fast_round_threads(int t) { return t <= 32 ? 32 : t <= 64 ? 64 : t <= 96 ? 96 : t <= 128 ? 128 : 256; }
 
+// resident warps per SM the fp32 kernel is compiled for.  Measured on the K = 10 shard (16384 chains), kernel ms:
+// 12 (145 registers): 8.49; 14 (122, still 16 resident): 7.37; 16 (120): 7.55; 18 (112): 9.36; 20 (96): 10.84
+#ifndef FASTK_MINB32
+#define FASTK_MINB32 14
+#endif
 // ---- 4 <= K <= 10, scratch mode: ffbs_fastk.cuh (one warp per chain, lane = (grid point, source state)) ----
 template <typename Real, int K, int WAYS>
 cudaError_t ffbs_fastk_do(const FfbsArgs& a, FfbsLaunch& L, bool query) {
-    constexpr int MINB = sizeof(Real) == 8 ? 8 : 16;  // <= 255 / <= 128 registers
+    constexpr int MINB = sizeof(Real) == 8 ? 8 : FASTK_MINB32;  // <= 255 / <= 144 registers
     auto kern = ffbs_fastk_kernel<Real, K, WAYS, MINB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
     if (e != cudaSuccess) return e;
