@@ -13,8 +13,8 @@ $NCU -k regex:ffbs_fast_kernel --launch-skip 3 -o $OUT/${TAG}_fast_f64 -f \
 # K = 10 block: fp64 then fp32 launches of ffbs_fastk_kernel
 $NCU -k regex:ffbs_fastk_kernel --launch-skip 2 -o $OUT/${TAG}_fastk_f64 -f python tools/k10_probe.py > $OUT/${TAG}_ncu2.log 2>&1
 $NCU -k "regex:ffbs_fastk_kernel<float" --launch-skip 2 -o $OUT/${TAG}_fastk_f32 -f python tools/k10_probe.py > $OUT/${TAG}_ncu3.log 2>&1
-# fp32 cfg2 block
-$NCU -k "regex:ffbs_fast_kernel<float" --launch-skip 2 -o $OUT/${TAG}_fast_f32 -f \
+# fp32 cfg2 block (K <= 3 in fp32 runs on ffbs_warp_kernel)
+$NCU -k "regex:ffbs_warp_kernel<float" --launch-skip 2 -o $OUT/${TAG}_warp_f32 -f \
   python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-cfg5 --no-pf > $OUT/${TAG}_ncu4.log 2>&1
 # launch list of the main loop
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches_mainloop.csv \
