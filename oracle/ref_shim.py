@@ -3,7 +3,7 @@
 Used by ``oracle/gen_golden*.py`` (in the authoring container, where /root/reference exists) to produce the
 committed fixtures under ``tests/golden/``, and by ``bench.py --impl reference`` to time the unmodified
 reference beside the NumPy port: ``make -C oracle`` byte-compiles the reference's (pure-Python) modules from
-where they lie under /root/reference into the git-ignored ``oracle/_ref/pkg/*.pyc`` (bytecode only, no source is
+where they lie under /root/reference into the git-ignored ``oracle/_ref/pkg/*.pycbin`` (bytecode only, no source is
 copied), which travels to the GPU box with the snapshot and is imported sourceless.  Nothing in the product
 package ``smjp_b200/`` imports this module.
 
@@ -31,9 +31,33 @@ REFERENCE_ROOT = os.environ.get("SMJP_REFERENCE_ROOT") or (
     "/root/reference" if os.path.isfile("/root/reference/pkg/fast_hmm.py") else os.path.join(_HERE, "_ref"))
 
 
+BYTECODE_EXT = ".pycbin"  # `make -C oracle`: py_compile output under a name snapshot tools do not filter out (*.pyc is)
+
+
 def reference_available():
-    """the sources (/root/reference) or their bytecode (oracle/_ref/pkg/*.pyc, `make -C oracle`; imported sourceless)"""
-    return any(os.path.isfile(os.path.join(REFERENCE_ROOT, "pkg", "fast_hmm" + ext)) for ext in (".py", ".pyc"))
+    """the sources (/root/reference) or their bytecode (oracle/_ref/pkg/*.pycbin, `make -C oracle`; imported sourceless)"""
+    return any(os.path.isfile(os.path.join(REFERENCE_ROOT, "pkg", "fast_hmm" + ext)) for ext in (".py", BYTECODE_EXT))
+
+
+class _BytecodeFinder:
+    """sys.meta_path finder for the byte-compiled reference: package `pkg` and its modules from <root>/pkg/*.pycbin"""
+
+    def __init__(self, root):
+        self.dir = os.path.join(root, "pkg")
+
+    def find_spec(self, fullname, path=None, target=None):
+        import importlib.machinery
+        import importlib.util
+        if fullname == "pkg":
+            f = os.path.join(self.dir, "__init__" + BYTECODE_EXT)
+            if os.path.isfile(f):
+                return importlib.util.spec_from_loader("pkg", importlib.machinery.SourcelessFileLoader("pkg", f),
+                                                       origin=f, is_package=True)
+        elif fullname.startswith("pkg.") and fullname.count(".") == 1:
+            f = os.path.join(self.dir, fullname[4:] + BYTECODE_EXT)
+            if os.path.isfile(f):
+                return importlib.util.spec_from_loader(fullname, importlib.machinery.SourcelessFileLoader(fullname, f), origin=f)
+        return None
 
 
 class _EasyDict(dict):
@@ -77,8 +101,11 @@ def _install_stubs():
                 stub = types.ModuleType(name)
                 stub.use = lambda *a, **k: None
                 sys.modules[name] = stub
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if os.path.isfile(os.path.join(REFERENCE_ROOT, "pkg", "fast_hmm.py")):
+        if REFERENCE_ROOT not in sys.path:
+            sys.path.insert(0, REFERENCE_ROOT)
+    elif not any(isinstance(f, _BytecodeFinder) for f in sys.meta_path):
+        sys.meta_path.insert(0, _BytecodeFinder(REFERENCE_ROOT))
 
 
 @contextlib.contextmanager
