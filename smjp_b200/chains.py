@@ -195,3 +195,137 @@ class DeviceChains:
         """live augmented state-steps K*n(n+1)/2 summed over chains (SURVEY.md 8d unit)"""
         n = (self.cur["offs"][1:] - self.cur["offs"][:-1] - 1).to(self.torch.float64)
         return float((self.K * n * (n + 1) / 2).sum().item()), float(n.sum().item())
+
+
+class InterleavedChains:
+    """The same batch of chains as `parts` sub-batches, each with its own engine context and CUDA stream.
+
+    Why: the sweep kernels are persistent -- a CTA pulls chains until the queue is empty -- so a launch ends in a tail
+    during which SMs drain (cfg2: 4096 chains over 1184 resident warps, ~8 % of the warp slots idle on average).  The
+    chains of a Gibbs sampler are independent, so sweep s+1 of one half of the batch needs nothing from sweep s of the
+    other half: with two sub-batches in flight on two streams the block scheduler fills the slots one kernel frees
+    with CTAs of the other's next kernel, and only the last launch of a run has a tail.  Chain c keeps its global
+    index (`chain_base`), so every path is bit-identical to the single-batch run (Philox streams are keyed by chain).
+
+    sweep() enqueues one sweep of every sub-batch and returns; join() makes the caller's stream wait for all of them.
+    The per-chain results (time_in_state, jumps, status) are gathered in global chain order by summaries()."""
+
+    def __init__(self, device_index, C, obs_t, model, parts=2, chain_base=0, options=None):
+        """model: (shape, scale, omega, emis, power, t_end) as for Engine.set_model; options: {name: value} for every engine"""
+        import torch
+        from .engine import Engine
+        self.torch = torch
+        self.C, self.S = int(C), int(parts)
+        self.dev = torch.device("cuda", int(device_index))
+        self.streams = [torch.cuda.Stream(self.dev) for _ in range(self.S)]
+        self.bounds = [(s * self.C // self.S, (s + 1) * self.C // self.S) for s in range(self.S)]
+        self.engines, self.parts = [], []
+        for s, (lo, hi) in enumerate(self.bounds):
+            with torch.cuda.stream(self.streams[s]):
+                eng = Engine(int(device_index), stream=self.streams[s].cuda_stream)
+                eng.set_model(*model)
+                for k, v in (options or {}).items():
+                    eng.set_option(k, v)
+                per = obs_t if (isinstance(obs_t, np.ndarray) and obs_t.ndim == 1 and obs_t.dtype != object) else list(obs_t)[lo:hi]
+                self.engines.append(eng)
+                self.parts.append(DeviceChains(eng, hi - lo, per, device=self.dev, chain_base=int(chain_base) + lo))
+        self.K = self.engines[0].K
+        self._tis = torch.zeros((2, self.C, self.K), dtype=torch.float64, device=self.dev)   # double-buffered snapshots
+        self._jumps = torch.zeros((2, self.C, self.K), dtype=torch.int32, device=self.dev)
+        self._snap = 0
+        self._released = None  # event: the previous snapshot buffer of this parity may be overwritten
+
+    def _each(self, fn):
+        for s, ch in enumerate(self.parts):
+            with self.torch.cuda.stream(self.streams[s]):
+                fn(ch)
+        return self
+
+    def set_option(self, key, value):
+        for e in self.engines:
+            e.set_option(key, value)
+        return self
+
+    def init_prior(self, pi0, seed, **kw):
+        return self._each(lambda ch: ch.init_prior(pi0, seed, **kw))
+
+    def simulate_observations(self, seed):
+        return self._each(lambda ch: ch.simulate_observations(seed))
+
+    def sweep(self, seed, sweep=None, mode="reference", precision="f64"):
+        """one Gibbs sweep of every chain: one enqueue per sub-batch, each on its own stream"""
+        return self._each(lambda ch: ch.sweep(seed, sweep=sweep, mode=mode, precision=precision))
+
+    def join(self, stream=None):
+        """the given (default: current) stream waits for everything enqueued on the sub-batch streams"""
+        t = self.torch
+        stream = t.cuda.current_stream(self.dev) if stream is None else stream
+        for s in self.streams:
+            ev = t.cuda.Event()
+            ev.record(s)
+            stream.wait_event(ev)
+        return self
+
+    def fork(self, stream=None):
+        """the sub-batch streams wait for what is enqueued on the given (default: current) stream"""
+        t = self.torch
+        stream = t.cuda.current_stream(self.dev) if stream is None else stream
+        ev = t.cuda.Event()
+        ev.record(stream)
+        for s in self.streams:
+            s.wait_event(ev)
+        return self
+
+    def summaries(self, release_after=None):
+        """(time_in_state [C, K] f64, jumps [C, K] i32) of the last sweep in global chain order: every sub-batch copies
+        its rows on its own stream into one of two snapshot buffers and the CURRENT stream waits for the copies --
+        no host synchronisation.  A buffer is reused two calls later; pass as `release_after` an event after which the
+        buffer handed out by the PREVIOUS call may be overwritten (e.g. recorded once its all-gather was staged)."""
+        t = self.torch
+        b = self._snap
+        self._snap ^= 1
+        if release_after is not None:
+            for s in self.streams:
+                s.wait_event(release_after)
+        cur = t.cuda.current_stream(self.dev)
+        for s, (ch, (lo, hi)) in enumerate(zip(self.parts, self.bounds)):
+            with t.cuda.stream(self.streams[s]):
+                self._tis[b, lo:hi].copy_(ch.time_in_state)
+                self._jumps[b, lo:hi].copy_(ch.jumps)
+                ev = t.cuda.Event()
+                ev.record(self.streams[s])
+            cur.wait_event(ev)
+        return self._tis[b], self._jumps[b]
+
+    @property
+    def status(self):
+        self.join()
+        return self.torch.cat([ch.status for ch in self.parts])
+
+    def grid_offsets(self):
+        """per sub-batch: the grid windows (offs [C_part + 1]) of the last sweep -- clones, on the sub-batch streams"""
+        out = []
+        for s, ch in enumerate(self.parts):
+            with self.torch.cuda.stream(self.streams[s]):
+                out.append(ch.cur["offs"].clone())
+        return out
+
+    def paths_host(self):
+        self.join()
+        self.torch.cuda.current_stream(self.dev).synchronize()
+        V, T = [], []
+        for ch in self.parts:
+            v, w = ch.paths_host()
+            V += v
+            T += w
+        return V, T
+
+    @property
+    def launch_count(self):
+        return sum(e.launch_count for e in self.engines)
+
+    def close(self):
+        self.join()
+        self.torch.cuda.current_stream(self.dev).synchronize()
+        for e in self.engines:
+            e.close()

@@ -70,7 +70,8 @@ class SummaryGather:
         self.cuda = self.device.type == "cuda"
         self.stage = torch.zeros((self.m, 2 * self.K), dtype=torch.float64, device=self.device)
         self.out = torch.zeros((self.world * self.m, 2 * self.K), dtype=torch.float64, device=self.device)
-        self.stream = torch.cuda.Stream(self.device) if self.cuda else None
+        # high priority: its staging copies and the collective must not queue behind persistent sweep kernels
+        self.stream = torch.cuda.Stream(self.device, priority=-1) if self.cuda else None
         self.work = None
         self.timing = []  # (start, end) CUDA events of every gather, on the side stream
         self.launched = 0

@@ -317,6 +317,38 @@ def test_pinned_inputs_read_in_place_change_no_result(engine, K, precision):
         assert np.array_equal(out[0][2][lo: lo + lens[c]], out[-1][2][lo: lo + lens[c]])
 
 
+@pytest.mark.parametrize("parts", [2, 3])
+def test_interleaved_sub_batches_equal_the_single_batch(engine, parts):
+    """InterleavedChains: the batch as sub-batches on their own streams and contexts (the next kernel of one fills the
+    tail of the other's persistent kernel) -- same chains, same global indices, same bits as one DeviceChains."""
+    from smjp_b200.chains import DeviceChains, InterleavedChains
+    import torch
+    K, T, C = 3, 40.0, 301
+    emis = O.emission_matrix(K)
+    model = (SHAPE3, np.ones((K, K)), 2.0, emis, 1.0, T)
+    obs_t = np.arange(0.1, T, 0.1)
+    engine.set_model(*model)
+    one = DeviceChains(engine, C, obs_t, chain_base=7).init_prior(np.ones(K) / K, seed=1).simulate_observations(seed=2)
+    one.init_prior(np.ones(K) / K, seed=3)
+    il = InterleavedChains(0, C, obs_t, model, parts=parts, chain_base=7)
+    il.init_prior(np.ones(K) / K, seed=1).simulate_observations(seed=2)
+    il.init_prior(np.ones(K) / K, seed=3)
+    try:
+        for sw in range(5):
+            one.sweep(seed=4, sweep=sw)
+            il.sweep(seed=4, sweep=sw)
+            tis, jm = il.summaries()
+            torch.cuda.synchronize()
+            assert torch.equal(tis, one.time_in_state) and torch.equal(jm, one.jumps)
+        assert int((il.status != 0).sum().item()) == 0
+        V1, T1 = one.paths_host()
+        V2, T2 = il.paths_host()
+        assert all(np.array_equal(a, b) for a, b in zip(V1, V2)) and all(np.array_equal(a, b) for a, b in zip(T1, T2))
+    finally:
+        il.close()
+        engine.set_option("chain_base", 0)
+
+
 def test_fp32_sweeps_leave_no_failed_chain(engine):
     """1.2e7 fp32 backward draws (4096 chains x 24 sweeps): none may lose its path.  Regression for a draw whose
     target fell between the inclusive scan value of the last thread holding weights and the warp total (a
