@@ -236,6 +236,19 @@ int smjp_sweep_host(smjp_ctx_t* ctx, int C, const int64_t* p_offs, const int32_t
                     int precision, int64_t capacity, int64_t* w_offs, double* W, int32_t* path_v_out,
                     double* path_t_out, int32_t* path_len_out, double* time_in_state, int32_t* jumps,
                     int32_t* status, int64_t* total_w);
+/* The same call in two halves, for callers that keep several batches in flight (one context per batch: while one
+ * batch's kernels run, the next batch's inputs are staged and its kernels queue up behind -- the sweep kernels are
+ * persistent, so the second batch also fills the slots the first one's tail leaves idle).  _begin returns as soon as
+ * this sweep's grid sizes are on the host (total_w is valid; SMJP_E_CAPACITY as above) with the kernels and copies
+ * still in flight; nothing in the output buffers may be read, and no input buffer changed, before _end has returned.
+ * smjp_sweep_host == _begin + _end.  Small pageable batches complete inside _begin. */
+int smjp_sweep_host_begin(smjp_ctx_t* ctx, int C, const int64_t* p_offs, const int32_t* path_v,
+                          const double* path_t, const int32_t* path_len, const int64_t* obs_offs,
+                          const double* obs_t, const int32_t* obs_y, uint64_t seed, uint32_t sweep, int mode,
+                          int precision, int64_t capacity, int64_t* w_offs, double* W, int32_t* path_v_out,
+                          double* path_t_out, int32_t* path_len_out, double* time_in_state, int32_t* jumps,
+                          int32_t* status, int64_t* total_w);
+int smjp_sweep_host_end(smjp_ctx_t* ctx);
 
 /*
  * Dense S-state HMM: scaled forward filter + backward sampler, chains batched (ragged step windows

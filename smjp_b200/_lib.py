@@ -52,6 +52,10 @@ SIGNATURES = {
     "smjp_sweep_host": (ctypes.c_int, [P, ctypes.c_int, P, P, P, P, P, P, P, ctypes.c_uint64, ctypes.c_uint32,
                                        ctypes.c_int, ctypes.c_int, ctypes.c_int64, P, P, P, P, P, P, P, P,
                                        c_i64p]),
+    "smjp_sweep_host_begin": (ctypes.c_int, [P, ctypes.c_int, P, P, P, P, P, P, P, ctypes.c_uint64, ctypes.c_uint32,
+                                             ctypes.c_int, ctypes.c_int, ctypes.c_int64, P, P, P, P, P, P, P, P,
+                                             c_i64p]),
+    "smjp_sweep_host_end": (ctypes.c_int, [P]),
     "smjp_hmm_dense_host": (ctypes.c_int, [P, ctypes.c_int, ctypes.c_int, P, P, ctypes.c_int, P, P, ctypes.c_int, P,
                                            P, P, ctypes.c_uint64, ctypes.c_int, P, P, P, P, P]),
     "smjp_ffbs_dense_dev": (ctypes.c_int, [P, ctypes.c_int, P, P, P, P, P, P, P, ctypes.c_uint64, ctypes.c_uint32,

@@ -140,6 +140,7 @@ struct smjp_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_obs = nullptr, ev_fill = nullptr;
     bool wait_obs = false;        // the next FFBS launch must wait for ev_obs
+    bool host_pending = false;    // smjp_sweep_host_begin returned with work in flight
     bool obs_in_place = false;    // last smjp_sweep_host: the kernels read the caller's pinned observations (stat)
     bool paths_gathered = false;  // last stage_paths: a kernel pulled the paths' used entries out of pinned memory (stat)
     double* w_copy_dst = nullptr;  // pinned host destination of the grid, copied right after cand_fill
@@ -1477,14 +1478,41 @@ int smjp_candidates_host(smjp_ctx_t* c, int C, const int64_t* p_offs, const int3
     return SMJP_OK;
 }
 
+int smjp_sweep_host_end(smjp_ctx_t* c) {
+    if (!c) return fail(SMJP_E_INVALID, "null context");
+    if (!c->host_pending) return SMJP_OK;
+    c->host_pending = false;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SMJP_OK;
+}
+
 int smjp_sweep_host(smjp_ctx_t* c, int C, const int64_t* p_offs, const int32_t* path_v,
                     const double* path_t, const int32_t* path_len, const int64_t* obs_offs,
                     const double* obs_t, const int32_t* obs_y, uint64_t seed, uint32_t sweep, int mode,
                     int precision, int64_t capacity, int64_t* w_offs, double* W, int32_t* path_v_out,
                     double* path_t_out, int32_t* path_len_out, double* time_in_state, int32_t* jumps,
                     int32_t* status, int64_t* total_w) {
+    int rc = smjp_sweep_host_begin(c, C, p_offs, path_v, path_t, path_len, obs_offs, obs_t, obs_y, seed, sweep, mode,
+                                   precision, capacity, w_offs, W, path_v_out, path_t_out, path_len_out, time_in_state,
+                                   jumps, status, total_w);
+    if (rc) return rc;
+    return smjp_sweep_host_end(c);
+}
+
+int smjp_sweep_host_begin(smjp_ctx_t* c, int C, const int64_t* p_offs, const int32_t* path_v,
+                          const double* path_t, const int32_t* path_len, const int64_t* obs_offs,
+                          const double* obs_t, const int32_t* obs_y, uint64_t seed, uint32_t sweep, int mode,
+                          int precision, int64_t capacity, int64_t* w_offs, double* W, int32_t* path_v_out,
+                          double* path_t_out, int32_t* path_len_out, double* time_in_state, int32_t* jumps,
+                          int32_t* status, int64_t* total_w) {
     int rc = model_ready(c);
     if (rc) return rc;
+    if (c->host_pending) {  // an earlier begin without its end: finish it first
+        rc = smjp_sweep_host_end(c);
+        if (rc) return rc;
+    }
     if (C <= 0) return fail(SMJP_E_INVALID, "C <= 0");
     if (!p_offs || !path_v || !path_t || !path_len || !obs_offs || !w_offs || !W || !path_v_out ||
         !path_t_out || !path_len_out || !status || !total_w)
@@ -1604,8 +1632,7 @@ int smjp_sweep_host(smjp_ctx_t* c, int C, const int64_t* p_offs, const int32_t* 
     if (!w_pinned) CUDA_TRY(get(W, o_W, tw * 8));
     if (!m_pv) CUDA_TRY(get(path_v_out, o_pv, tw * 4));
     if (!m_pt) CUDA_TRY(get(path_t_out, o_pt, tw * 8));
-    CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->host_pending = true;  // smjp_sweep_host_end waits for the kernels and the copies
     return SMJP_OK;
 }
 

@@ -338,10 +338,21 @@ class PackedSweep:
         return self
 
     def run(self, seed, sweep, mode="reference", precision="f64"):
+        """one sweep, synchronous: the outputs are valid on return"""
+        return self.begin(seed, sweep, mode, precision).end()
+
+    def end(self):
+        """wait for the sweep enqueued by begin(); the outputs are valid afterwards"""
+        check(self.eng.lib.smjp_sweep_host_end(self.eng.ctx))
+        return self
+
+    def begin(self, seed, sweep, mode="reference", precision="f64"):
+        """enqueue one sweep (smjp_sweep_host_begin) and return with its kernels and copies in flight: a caller with two
+        PackedSweeps (two engines) alternates begin / end so that one batch is staged while the other computes"""
         modes = {"reference": _lib.CAND_REFERENCE, "exact": _lib.CAND_EXACT}
         total = ctypes.c_int64(0)
         while True:
-            rc = self.eng.lib.smjp_sweep_host(
+            rc = self.eng.lib.smjp_sweep_host_begin(
                 self.eng.ctx, self.C, _ptr(self.in_offs), _ptr(self.in_v), _ptr(self.in_t), _ptr(self.in_len),
                 _ptr(self.obs_offs), _ptr(self.obs_t), _ptr(self.obs_y), int(seed) & 0xFFFFFFFFFFFFFFFF, int(sweep),
                 modes[mode], PRECISIONS[precision], self.cap, _ptr(self.w_offs), _ptr(self.W), _ptr(self.out_v),

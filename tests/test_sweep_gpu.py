@@ -317,6 +317,56 @@ def test_pinned_inputs_read_in_place_change_no_result(engine, K, precision):
         assert np.array_equal(out[0][2][lo: lo + lens[c]], out[-1][2][lo: lo + lens[c]])
 
 
+def test_two_host_batches_in_flight_equal_the_synchronous_call(engine):
+    """smjp_sweep_host_begin / _end: two half-batches on two contexts, one staged while the other computes, give the
+    bits of one synchronous smjp_sweep_host call over all chains."""
+    from smjp_b200.engine import Engine, PackedSweep, ragged_offsets
+    import torch
+    K, t_end, C = 3, 30.0, 48
+    emis = O.emission_matrix(K)
+    model = (SHAPE3, np.ones((K, K)), 2.0, emis, 1.0, t_end)
+    engine.set_model(*model)
+    obs_t = np.arange(0.1, t_end, 0.1)
+    V, T, Y = [], [], []
+    for c in range(C):
+        v, w = O.prior_path(SHAPE3, np.ones((K, K)), np.ones(K) / K, t_end, seed=1, chain=c)
+        V.append(v); T.append(w); Y.append(O.simulate_observations(v, w, obs_t, emis, seed=2, chain=c))
+    full = PackedSweep(engine, C, ragged_offsets([len(obs_t)] * C), np.tile(obs_t, C), np.concatenate(Y), 40000)
+    full.set_paths(V, T)
+    halves = []
+    for lo, hi in ((0, 20), (20, C)):
+        st = torch.cuda.Stream()
+        eh = Engine(0, stream=st.cuda_stream)
+        eh.set_model(*model)
+        eh.set_option("chain_base", lo)
+        ph = PackedSweep(eh, hi - lo, ragged_offsets([len(obs_t)] * (hi - lo)), np.tile(obs_t, hi - lo), np.concatenate(Y[lo:hi]), 20000)
+        ph.set_paths(V[lo:hi], T[lo:hi])
+        halves.append((lo, hi, st, eh, ph))
+    try:
+        for _, _, _, _, ph in halves:
+            ph.begin(9, 0)
+        for sw in range(4):
+            full.run(9, sw)
+            for lo, hi, _, _, ph in halves:
+                ph.end()
+                assert not np.any(ph.status[: ph.C])
+                for c in range(lo, hi):
+                    a, b = full.w_offs[c], ph.w_offs[c - lo]
+                    n = full.w_offs[c + 1] - a
+                    assert n == ph.w_offs[c - lo + 1] - b and np.array_equal(full.W[a: a + n], ph.W[b: b + n])
+                    m = full.out_len[c]
+                    assert m == ph.out_len[c - lo]
+                    assert np.array_equal(full.out_v[a: a + m], ph.out_v[b: b + m]) and np.array_equal(full.out_t[a: a + m], ph.out_t[b: b + m])
+                assert np.array_equal(full.jumps[lo * K: hi * K], ph.jumps[: ph.C * K])
+                ph.swap()
+                if sw < 3:
+                    ph.begin(9, sw + 1)
+            full.swap()
+    finally:
+        for _, _, _, eh, _ in halves:
+            eh.close()
+
+
 @pytest.mark.parametrize("parts", [2, 3])
 def test_interleaved_sub_batches_equal_the_single_batch(engine, parts):
     """InterleavedChains: the batch as sub-batches on their own streams and contexts (the next kernel of one fills the
