@@ -810,10 +810,12 @@ def run_ours(args):
     if not args.no_pf:
         # as BASELINE states it (gamma holding times: incomplete-gamma inversion per draw), and the same filter with the
         # reference's own Weibull hazards (distributions.py:296-304) for comparison
+        # "many runs in flight" = one filter run per SM (a run is one cluster; at this size one CTA of 1024 threads)
+        sms = torch.cuda.get_device_properties(local).multi_processor_count
         pf = {"gamma_runs_8": pf_block(rank, world, local, dev, 8, peak, peak_src),
-              "gamma_runs_64": pf_block(rank, world, local, dev, 64, peak, peak_src, reps=1),
+              "gamma_runs_%d" % sms: pf_block(rank, world, local, dev, sms, peak, peak_src, reps=1),
               "weibull_runs_8": pf_block(rank, world, local, dev, 8, peak, peak_src, reps=3, family="weibull"),
-              "weibull_runs_128": pf_block(rank, world, local, dev, 128, peak, peak_src, reps=3, family="weibull")}
+              "weibull_runs_%d" % sms: pf_block(rank, world, local, dev, sms, peak, peak_src, reps=3, family="weibull")}
     cfg5 = None if args.no_cfg5 else cfg5_block(rank, world, local, dev, max(3, min(args.steps, 5)), barrier, bool(args.gather_overlap))
 
     # ---- reduce over ranks: time = max, work = sum ----
