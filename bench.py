@@ -472,17 +472,19 @@ def pf_block(rank, world, local, dev, runs_per_gpu, peak, peak_src, reps=2, fami
 CFG5_CHAINS = 65536  # BASELINE configs[4]: 65536 chains, 10-state sMJP, SPLIT over the GPUs of the run
 
 
-def cfg5_block(rank, world, local, dev, steps, barrier, overlap=False):
+def cfg5_block(rank, world, local, dev, steps, barrier, overlap=False, interleave=1):
     """BASELINE configs[4] as stated: 65536 chains of the 10-state sMJP (k10_model, T = 20) split over the N ranks of
     this run (contiguous ranges, Philox streams keyed by the GLOBAL chain index), Rao-Teh sweeps with the NCCL
     all-gather of the posterior jump-count / holding-time summaries ([65536, 2K] doubles, mcmc_utils.py:40-56) once per
     sweep INSIDE the timed loop, on a side stream under the next sweep.  STRONG scaling: the total work is fixed.
     Rank 0 returns the block; `summaries_sha1` of the gathered summaries after the last sweep is the same at every N
-    (sharded == unsharded, bit for bit)."""
+    (sharded == unsharded, bit for bit).  interleave > 1: every rank runs its chains as that many sub-batches on their
+    own streams (InterleavedChains): the candidate kernels of one sub-batch -- a tenth of an fp32 sweep at K = 10 -- run
+    under the FFBS kernel of another.  Same chains, same bits: the SHA-1 does not change."""
     import hashlib
     import torch
     import torch.distributed as dist
-    from smjp_b200.chains import DeviceChains
+    from smjp_b200.chains import DeviceChains, InterleavedChains
     from smjp_b200.distributed import SummaryGather, shard_range
     from smjp_b200.engine import Engine
     shape, emis = k10_model()
@@ -490,28 +492,49 @@ def cfg5_block(rank, world, local, dev, steps, barrier, overlap=False):
     C = hi - lo
     obs_t = np.arange(OBS_DT, K10_T, OBS_DT)
     out = {"workload": "cfg5: %d chains total, K=10 Weibull sMJP, T=20, D=%d obs, split over %d GPU(s)" % (CFG5_CHAINS, len(obs_t), world),
-           "scaling": "strong", "n_gpus": world, "chains_per_gpu": C, "unit": UNIT}
+           "scaling": "strong", "n_gpus": world, "chains_per_gpu": C, "unit": UNIT, "sub_batches_per_gpu": int(interleave)}
+    model = (shape, np.ones((K10_K, K10_K)), OMEGA, emis, 1.0, K10_T)
     eng = Engine(local)
-    eng.set_model(shape, np.ones((K10_K, K10_K)), OMEGA, emis, 1.0, K10_T)
+    eng.set_model(*model)
+    cur_stream = torch.cuda.current_stream(dev)
     for prec in ("f64", "f32"):
-        ch = DeviceChains(eng, C, obs_t, chain_base=lo)
+        if interleave > 1:
+            ch = InterleavedChains(local, C, obs_t, model, parts=interleave, chain_base=lo)
+        else:
+            ch = DeviceChains(eng, C, obs_t, chain_base=lo)
         ch.init_prior(np.ones(K10_K) / K10_K, seed=SEED + 31).simulate_observations(seed=SEED + 32)
         ch.init_prior(np.ones(K10_K) / K10_K, seed=SEED + 33)
         gather = SummaryGather(CFG5_CHAINS, K10_K, rank, world, dev, overlap=overlap)
-        for sw in range(3):
+        release = [None]
+
+        def one_sweep(sw):
             ch.sweep(seed=SEED + 34, sweep=sw, precision=prec)
+            if interleave > 1:
+                t_, j_ = ch.summaries(release[0])
+                gather.launch(t_, j_)
+                release[0] = torch.cuda.Event()
+                release[0].record(cur_stream)
+                return ch.grid_offsets()
             gather.launch(ch.time_in_state, ch.jumps)
+            return [ch.cur["offs"].clone()]
+
+        for sw in range(3):
+            one_sweep(sw)
         gather.result()
         gather.timing.clear()
+        if interleave > 1:
+            ch.join()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         snaps = []
         e0.record()
+        if interleave > 1:
+            ch.fork()
         for sw in range(steps):
-            ch.sweep(seed=SEED + 34, sweep=3 + sw, precision=prec)
-            gather.launch(ch.time_in_state, ch.jumps)
-            snaps.append(ch.cur["offs"].clone())
+            snaps += one_sweep(3 + sw)
         tis, jm = gather.result()
+        if interleave > 1:
+            ch.join()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -537,6 +560,8 @@ def cfg5_block(rank, world, local, dev, steps, barrier, overlap=False):
                                     "backend": "nccl" if world > 1 else None, "per_sweep": True, "inside_timed_region": True,
                                     "bytes_per_gather": gather.bytes_per_gather, "gather_ms_avg": gather.gather_ms()},
                      "summaries_sha1": h}
+        if interleave > 1:
+            ch.close()
         del ch, gather
     eng.close()
     return out if rank == 0 else None
@@ -816,7 +841,8 @@ def run_ours(args):
               "gamma_runs_%d" % sms: pf_block(rank, world, local, dev, sms, peak, peak_src, reps=1),
               "weibull_runs_8": pf_block(rank, world, local, dev, 8, peak, peak_src, reps=3, family="weibull"),
               "weibull_runs_%d" % sms: pf_block(rank, world, local, dev, sms, peak, peak_src, reps=3, family="weibull")}
-    cfg5 = None if args.no_cfg5 else cfg5_block(rank, world, local, dev, max(3, min(args.steps, 5)), barrier, bool(args.gather_overlap))
+    cfg5 = None if args.no_cfg5 else cfg5_block(rank, world, local, dev, max(3, min(args.steps, 5)), barrier, bool(args.gather_overlap),
+                                                   interleave=args.interleave)
 
     # ---- reduce over ranks: time = max, work = sum ----
     ss_rank0 = ss  # this rank's own state-steps (the kernel figures below are rank 0's)
