@@ -1,6 +1,6 @@
 """Latency of the host-buffer entry points on a single tiny chain (cfg1 scale): where does a sweep's time go?"""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from oracle import smjp_oracle as O
 from smjp_b200.engine import Engine, candidates_host, sweep_host
