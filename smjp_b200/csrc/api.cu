@@ -122,6 +122,7 @@ struct smjp_ctx {
     int last_dense_tc = 0;
     int64_t dense_nmax_hint = 0;
     int obs_zero_copy = -1;  // smjp_sweep_host: FFBS reads pinned observations in place (-1 auto, 0 off, 1 on)
+    int cand_R = 1;       // candidate kernels: item slots per sojourn (most target classes of a row, smjp_set_model)
     int fast_cpb = 0;     // chains per CTA, one warp each (0 = auto; 1..11) -- 32-thread groups only
     int fast_boost[2] = {0, 0};  // extra ring slots learnt from rescue counts, per precision
     int fast_off[2] = {0, 0};    // kept overflowing: ffbs.cuh from now on
@@ -466,8 +467,9 @@ int smjp_set_model(smjp_ctx_t* c, int K, int Kobs, const double* shape, const do
     // device layout: shape[K*K], c2[K*K] = k*log2(lambda), emis[K*Kobs], scale[K*K], then for the candidate
     // sampler crep[K*K] and csum[K*K]: targets of one row that share a shape form a class (thinned events of
     // equal-shape Weibull hazards superpose into one Poisson process with the same position density);
-    // crep = first target of the class, csum = sum over the class of lambda^-k (at the representative)
-    c->h_model.assign((size_t)5 * K * K + (size_t)K * Kobs, 0.0);
+    // crep = first target of the class, csum = sum over the class of lambda^-k (at the representative), replist[K*K] =
+    // the class representatives of every row in order (-1 padded)
+    c->h_model.assign((size_t)6 * K * K + (size_t)K * Kobs, 0.0);
     for (int t = 0; t < K * K; ++t) {
         c->h_model[t] = shape[t];
         c->h_model[K * K + t] = shape[t] * std::log2(scale[t]);
@@ -484,6 +486,17 @@ int smjp_set_model(smjp_ctx_t* c, int K, int Kobs, const double* shape, const do
                 crep[v * K + s] = (double)r;
                 csum[v * K + r] += std::pow(scale[v * K + s], -shape[v * K + s]);
             }
+        // replist[v][r] = the r-th class representative of row v (-1 beyond the row's classes); cand_R = most classes
+        // of any row: the candidate kernels give every sojourn cand_R item slots
+        double* replist = csum + K * K;
+        c->cand_R = 1;
+        for (int v = 0; v < K; ++v) {
+            int nr = 0;
+            for (int s = 0; s < K; ++s)
+                if ((int)crep[v * K + s] == s) replist[v * K + nr++] = (double)s;
+            for (int r = nr; r < K; ++r) replist[v * K + r] = -1.0;
+            if (nr > c->cand_R) c->cand_R = nr;
+        }
     }
     for (int t = 0; t < K * Kobs; ++t) c->h_model[2 * K * K + t] = emis[t];
     int rc = c->d_model.reserve(c->h_model.size() * sizeof(double));
@@ -1076,6 +1089,7 @@ CandArgs make_cand_args(smjp_ctx* c, int C, const int64_t* p_offs, const int32_t
     a.chain_base = c->chain_base;
     a.guard = c->guard;
     a.guard_total = c->guard_total;
+    a.R = c->cand_R;
     return a;
 }
 

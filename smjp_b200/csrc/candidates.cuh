@@ -50,6 +50,7 @@ struct CandArgs {
     // not fit the caller's W (guard_total points) is not written
     const int64_t* guard;
     int64_t guard_total;
+    int R;  // item slots per sojourn = the largest number of target CLASSES of a row (smjp_set_model; 1 when shape == 1)
 };
 
 // Thinned events of ONE (sojourn q, target class s) item of chain c.  target_count draws their number N (m Poisson
@@ -61,10 +62,9 @@ __device__ __forceinline__ int target_count(const CandArgs& a, int c, int q, int
     const int K = a.K;
     v = min(max(v, 0), K - 1);  // a state index outside [0, K) (caller's paths) never indexes the model out of bounds
     const double* shape = a.model;
-    const double* crep = a.model + 3 * K * K + K * a.Kobs;  // class representative / class sum of lambda^-k (smjp_set_model)
-    const double* csum = crep + K * K;
+    const double* csum = a.model + 4 * K * K + K * a.Kobs;  // class sum of lambda^-k at the representative (smjp_set_model)
     m = 1; k = 1.0; tk = 0.0;
-    if ((int)crep[v * K + s] != s) return 0;  // merged into an earlier target of the same shape
+    if (s < 0) return 0;  // this row has fewer classes than slots
     k = shape[v * K + s];
     tk = exp2(k * l2tau);
     const double mu = (a.omega - 1.0) * tk * csum[v * K + s];
@@ -94,19 +94,23 @@ __device__ __forceinline__ void target_emit(const CandArgs& a, int c, int q, int
 // events, not K of them (a thread per sojourn spent its time in K back-to-back fp64 pow/exp chains).  Items are
 // ordered sojourn-major, so the exclusive prefix of the counts + the number of earlier sojourns (one grid point each,
 // the jump time) is the item's position in the chain's grid.
+// A sojourn has R item slots, slot r = the r-th target CLASS of its row (replist, smjp_set_model): models whose targets
+// share shapes (cfg4: shape == 1, one class per row) do not spend K lanes per sojourn on one Poisson draw.
 struct CandItem {
-    int q, s, v;
+    int q, r, s, v;  // sojourn, slot, target (class representative; -1: the row has fewer classes), state
     double t0, tau, l2tau;
     bool valid;
 };
 __device__ __forceinline__ CandItem cand_item(const CandArgs& a, int64_t p0, int nsoj, int i) {
     CandItem it;
-    it.q = i / a.K;
-    it.s = i - it.q * a.K;
+    it.q = i / a.R;
+    it.r = i - it.q * a.R;
     it.valid = it.q < nsoj;
-    it.v = 0; it.t0 = 0.0; it.tau = 0.0; it.l2tau = 0.0;
+    it.s = -1; it.v = 0; it.t0 = 0.0; it.tau = 0.0; it.l2tau = 0.0;
     if (it.valid) {
-        it.v = a.path_v[p0 + it.q];
+        const int K = a.K;
+        it.v = min(max(a.path_v[p0 + it.q], 0), K - 1);  // a state index outside [0, K) never indexes the model out of bounds
+        it.s = (int)a.model[5 * K * K + K * a.Kobs + it.v * K + it.r];
         it.t0 = a.path_t[p0 + it.q];
         it.tau = a.path_t[p0 + it.q + 1] - it.t0;
         it.l2tau = log2(it.tau);
@@ -120,7 +124,7 @@ __global__ void cand_count_kernel(const CandArgs a) {
         const int64_t p0 = a.p_offs[c];
         const int plen = a.path_len[c];
         const int nsoj = plen - 1;
-        const int items = nsoj * a.K;
+        const int items = nsoj * a.R;
         int carry = 0;
         for (int base = 0; base < items; base += 32) {
             const CandItem it = cand_item(a, p0, nsoj, base + lane);
@@ -128,7 +132,7 @@ __global__ void cand_count_kernel(const CandArgs a) {
             double k, tk;
             const int cnt = it.valid ? target_count(a, c, it.q, it.v, it.s, it.l2tau, m, k, tk) : 0;
             const int incl = warp_inclusive_scan(cnt, lane);
-            if (it.valid && it.s == 0) a.soff[p0 + it.q] = carry + incl - cnt + it.q;
+            if (it.valid && it.r == 0) a.soff[p0 + it.q] = carry + incl - cnt + it.q;
             carry += __shfl_sync(0xffffffffu, incl, 31);
         }
         if (lane == 0) {
@@ -179,7 +183,7 @@ __global__ void cand_fill_kernel(const CandArgs a) {
         const int64_t p0 = a.p_offs[c], w0 = a.w_offs[c];
         const int plen = a.path_len[c];
         const int nsoj = plen - 1;
-        const int items = nsoj * a.K;
+        const int items = nsoj * a.R;
         double* Wc = a.W + w0;
         int carry = 0;
         for (int base = 0; base < items; base += 32) {
@@ -191,7 +195,7 @@ __global__ void cand_fill_kernel(const CandArgs a) {
             const int incl = warp_inclusive_scan(cnt, lane);
             const int pos = carry + incl - cnt + it.q;  // slot of T[q] if s == 0; events of the item start at pos + 1
             if (it.valid) {
-                if (it.s == 0) Wc[pos] = it.t0;
+                if (it.r == 0) Wc[pos] = it.t0;
                 if (cnt > 0) target_emit(a, c, it.q, it.s, cnt, m, k, tk, it.tau, it.t0, Wc + pos + 1);
             }
             carry += __shfl_sync(0xffffffffu, incl, 31);
