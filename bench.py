@@ -842,7 +842,7 @@ def run_ours(args):
               "weibull_runs_8": pf_block(rank, world, local, dev, 8, peak, peak_src, reps=3, family="weibull"),
               "weibull_runs_%d" % sms: pf_block(rank, world, local, dev, sms, peak, peak_src, reps=3, family="weibull")}
     cfg5 = None if args.no_cfg5 else cfg5_block(rank, world, local, dev, max(3, min(args.steps, 5)), barrier, bool(args.gather_overlap),
-                                                   interleave=args.interleave)
+                                                   interleave=args.cfg5_interleave)
 
     # ---- reduce over ranks: time = max, work = sum ----
     ss_rank0 = ss  # this rank's own state-steps (the kernel figures below are rank 0's)
@@ -1052,6 +1052,9 @@ def main():
                     help="1: the per-sweep NCCL gather runs on a side stream under the next sweep; 0: ordered between sweeps")
     ap.add_argument("--interleave", type=int, default=2,
                     help="headline pass: sub-batches per GPU, each on its own stream (1 = the single-stream pass is the headline)")
+    ap.add_argument("--cfg5-interleave", type=int, default=1, dest="cfg5_interleave",
+                    help="sub-batches per GPU in the cfg5 block (measured within +-2 %% of 1 at every N: the shards have 7-55 chains "
+                         "per resident warp, the tail that interleaving hides is small, and at 8 GPUs half a shard no longer fills the GPU)")
     ap.add_argument("--no-pf", action="store_true", dest="no_pf", help="skip the cfg3 particle-filter block")
     ap.add_argument("--no-cfg5", action="store_true", dest="no_cfg5", help="skip the cfg5 strong-scaling block")
     ap.add_argument("--threads", type=int, default=0, help="threads per CTA of the FFBS kernel (0 = auto)")
