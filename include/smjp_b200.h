@@ -108,6 +108,10 @@ int64_t smjp_ctx_get_stat(smjp_ctx_t* ctx, const char* key);
  *        geometry; chains they cannot finish go to the rescue pass, so results never depend on them);
  *        "dense_tc" (-1 auto (default: >= 32768 chains, 32 <= K <= 64, fp32), 0, 1: tensor-core forward pass of the
  *        dense shape == 1 path);
+ *        "fast_split" (-1 auto (default), 0, 1: the K <= 3 sweep kernel as a forward-only and a backward-only launch
+ *        with a scratch region per chain instead of per resident chain; falls back to the fused kernel when the rows
+ *        of all chains would not fit in a third of the free device memory; stat "fast_split" says what the last
+ *        launch did.  Results never depend on it);
  *        "obs_zero_copy" (-1 auto (default), 0, 1: smjp_sweep_host with PINNED input arrays lets the FFBS kernel's bulk
  *        copies read each chain's observations in place and a gather kernel pull only the path entries in use,
  *        instead of uploading both first; stats "obs_in_place" / "paths_gathered" say what the last call did.

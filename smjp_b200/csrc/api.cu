@@ -122,6 +122,9 @@ struct smjp_ctx {
     int last_dense_tc = 0;
     int64_t dense_nmax_hint = 0;
     int obs_zero_copy = -1;  // smjp_sweep_host: FFBS reads pinned observations in place (-1 auto, 0 off, 1 on)
+    int fast_split = -1;  // K <= 3 sweep kernel as forward-only + backward-only launches (-1 auto, 0, 1)
+    int last_split = 0;
+    DevBuf d_fwdok;
     int cand_R = 1;       // candidate kernels: item slots per sojourn (most target classes of a row, smjp_set_model)
     int fast_cpb = 0;     // chains per CTA, one warp each (0 = auto; 1..11) -- 32-thread groups only
     int fast_boost[2] = {0, 0};  // extra ring slots learnt from rescue counts, per precision
@@ -227,6 +230,7 @@ void smjp_ctx_destroy(smjp_ctx_t* c) {
     c->d_dense_msg.release();
     c->d_big.release();
     c->d_failed.release();
+    c->d_fwdok.release();
     c->d_live.release();
     c->d_tile.release();
     c->d_pfws.release();
@@ -274,6 +278,7 @@ int64_t smjp_ctx_get_stat(smjp_ctx_t* c, const char* key) {
     if (!strcmp(key, "ffbs_fast_boost_f32")) return c->fast_boost[1] + 100 * c->fast_off[1];
     if (!strcmp(key, "ffbs_fast_boost_f64")) return c->fast_boost[0] + 100 * c->fast_off[0];
     if (!strcmp(key, "dense_tc")) return c->last_dense_tc;
+    if (!strcmp(key, "fast_split")) return c->last_split;
     if (!strcmp(key, "obs_in_place")) return c->obs_in_place ? 1 : 0;
     if (!strcmp(key, "paths_gathered")) return c->paths_gathered ? 1 : 0;
     if (!strcmp(key, "ffbs_kernel")) return c->last_kernel;  // 0 ffbs.cuh, 1 ffbs_item, 2 ffbs_big, 3 ffbs_warp, 4 ffbs_fast, 5 ffbs_fastk
@@ -358,6 +363,11 @@ int smjp_ctx_set_option(smjp_ctx_t* c, const char* key, int64_t value) {
     if (!strcmp(key, "dense_tc")) {
         if (value < -1 || value > 1) return fail(SMJP_E_INVALID, "dense_tc must be -1 (auto), 0 or 1");
         c->dense_tc = (int)value;
+        return SMJP_OK;
+    }
+    if (!strcmp(key, "fast_split")) {
+        if (value < -1 || value > 1) return fail(SMJP_E_INVALID, "fast_split must be -1 (auto), 0 or 1");
+        c->fast_split = (int)value;
         return SMJP_OK;
     }
     if (!strcmp(key, "obs_zero_copy")) {
@@ -764,6 +774,8 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
     int grid = c->num_sms * per_sm;
     const int regions_per_cta = use_warp ? FFBS_WARPS : use_fast ? fast_cpb : 1;  // scratch regions: one per chain in flight
     if (grid > (a.C + regions_per_cta - 1) / regions_per_cta) grid = (a.C + regions_per_cta - 1) / regions_per_cta;
+    // K <= 3 sweep kernel as two launches (ffbs_fast.cuh, PHASE 1 / 2): needs the rows of EVERY chain in scratch
+    bool split = use_fast && !fastk && threads == 32 && fast_cpb == 1 && fast_ways == 2 && c->fast_split != 0 && !a.messages;
     a.ncap = (int)n_max;
     a.nslot = big ? big_slots : use_warp ? ring : use_fast ? fast_ns : item_kernel ? ffbs_item_nslot(K, (int)n_max, threads) : ffbs_nslot((int)n_max, threads);
     if (use_fast && fastk) a.lay = ffbs_fastk_layout<Real>(K, fast_ns, (int)n_max);
@@ -778,6 +790,15 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
         c->ffbs_ncap_hint = hint;
         const int64_t stride = (int64_t)K * hint * (hint + 1) / 2;
         size_t bytes = (size_t)stride * sizeof(Real) * (size_t)grid * regions_per_cta;
+        if (split) {  // a region per chain: only while that stays a modest share of the device (cfg2: 14 GB)
+            const size_t all = (size_t)stride * sizeof(Real) * (size_t)a.C;
+            if (all > c->d_msg_scratch.cap) {
+                size_t free_b = 0, total_b = 0;
+                CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+                if (all > (free_b + c->d_msg_scratch.cap) / 3) split = false;
+            }
+            if (split) bytes = all;
+        }
         if (rescue && bytes < (size_t)stride * 8 * RESCUE_GRID) bytes = (size_t)stride * 8 * RESCUE_GRID;
         if (bytes > c->d_msg_scratch.cap) {  // (steady state: no growth, and no trip into the driver for the query)
             size_t free_b = 0, total_b = 0;
@@ -810,6 +831,7 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
         } else if (use_fast) {  // + the window start of every row (ints), see ffbs_fast.cuh
             per += ffbs_fast_jlo_elems<Real>(n_max);
             if (fastk) per += 3 * K * K;  // + the hazard tables the backward pass reads (ffbs_fastk.cuh)
+            if (split) per += (ffbs_fast_split_ints(n_max) * 4 + (int64_t)sizeof(Real) - 1) / (int64_t)sizeof(Real);  // + sojourn list
             per = (per + 3) / 4 * 4;
             a.obsf_stride = per;
         } else if (big) {  // + window starts [n + 1] and the sojourn list [2][n + 1] (ints), see ffbs_big.cuh
@@ -817,7 +839,7 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
             per = (per + 3) / 4 * 4;
             a.obsf_stride = per;
         }
-        size_t ob = (size_t)grid * regions_per_cta * per * sizeof(Real);
+        size_t ob = (size_t)(split ? a.C : grid * regions_per_cta) * per * sizeof(Real);
         if (rescue && ob < (size_t)RESCUE_GRID * n_max * K * 8) ob = (size_t)RESCUE_GRID * n_max * K * 8;
         rc = c->d_obsf.reserve(ob);
     }
@@ -831,8 +853,9 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
         CUDA_TRY(cudaMemsetAsync(c->d_live.p, 0, 8, c->stream));
     }
     a.live_pairs = (unsigned long long*)c->d_live.p;
-    CUDA_TRY(cudaMemsetAsync(c->d_queue.p, 0, 2 * sizeof(unsigned int), c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->d_queue.p, 0, 3 * sizeof(unsigned int), c->stream));
     a.queue = (unsigned int*)c->d_queue.p;
+    a.queue2 = a.queue + 2;  // (+ 1: the rescue pass)
     if (a.C > grid && c->lpt_order) {  // more chains than resident CTAs: start the long grids first
         rc = c->d_order.reserve((size_t)a.C * sizeof(int32_t));
         if (rc) return rc;
@@ -848,7 +871,30 @@ int ffbs_dev_impl(smjp_ctx* c, FfbsArgs& a, int64_t n_max) {
         CUDA_TRY(cudaEventRecord(e0, c->stream));
     }
     L.grid = grid;
+    if (split) {
+        rc = c->d_fwdok.reserve((size_t)a.C * sizeof(int32_t));
+        if (rc) return rc;
+        CUDA_TRY(cudaMemsetAsync(c->d_fwdok.p, 0, (size_t)a.C * sizeof(int32_t), c->stream));
+        a.fwd_ok = (int32_t*)c->d_fwdok.p;
+        a.fast_phase = 1;
+    }
     CUDA_TRY(use_warp ? ffbs_warp_call<Real>(a, L, false) : big ? ffbs_big_call<Real>(a, L, false) : ffbs_call<Real>(a, L, false));
+    if (split) {  // the backward pass of every chain: small shared memory, half the registers, twice the warps
+        FfbsArgs b = a;
+        b.fast_phase = 2;
+        b.lay = ffbs_fast_bwd_layout<Real>(K, fast_ns, threads);
+        FfbsLaunch B2 = L;
+        B2.smem = (size_t)b.lay.total;
+        B2.grid = 0;
+        CUDA_TRY(ffbs_call<Real>(b, B2, true));
+        if (B2.grid < 1) return fail(SMJP_E_UNSUPPORTED, "backward kernel cannot be resident (smem=%zu)", B2.smem);
+        B2.grid *= c->num_sms;
+        if (B2.grid > a.C) B2.grid = a.C;
+        CUDA_TRY(ffbs_call<Real>(b, B2, false));
+        c->launches += 1;
+        a.fast_phase = 0;
+    }
+    c->last_split = split ? 1 : 0;
     if (rescue) {
         // fp32 has ~38 orders of magnitude per grid step: a step over which every live state loses more than
         // that (or gains it) leaves a chain without a row sum.  Those chains -- rare, none on most sweeps --

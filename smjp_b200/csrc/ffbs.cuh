@@ -84,6 +84,9 @@ struct FfbsArgs {
     int use_fast;     // K <= 3, scratch mode: ffbs_fast.cuh (nslot = ring slots, lay = ffbs_fast_layout)
     int fast_ways;    // its grid pairs in flight per thread (1, 2 or 4)
     int fast_cpb;     // its chains per CTA (one warp each when > 1)
+    int fast_phase;   // 0: forward + backward in one kernel; 1 / 2: forward-only / backward-only launch (scratch per chain)
+    int32_t* fwd_ok;  // split kernels: [C] set by the forward kernel for chains whose backward pass may run
+    unsigned int* queue2;  // work counter of the backward kernel
     int obs_product;  // 0: observations sharing a grid interval are SUMMED (reference); 1: multiplied
     double omega, power, t_end;
     // speculative launch (smjp_sweep_dev): the kernel was sized for guard_nmax intervals and guard_total grid points

@@ -65,6 +65,27 @@ __host__ __device__ inline FfbsLayout ffbs_fast_layout(int K, int ring, int ncap
     return L;
 }
 
+// the backward-only kernel (PHASE 2): uniforms, the weights of one draw (K x window), the per-warp totals, the
+// hazard tables -- no state rings, no grid ring; the sojourn list lives in the chain's global scratch region
+template <typename Real>
+__host__ __device__ inline FfbsLayout ffbs_fast_bwd_layout(int K, int ring, int threads) {
+    FfbsLayout L;
+    size_t b = 0;
+    L.wd = (int)b;
+    L.ubuf = (int)b; b += align_up((size_t)threads * sizeof(double), 16);
+    L.scan = (int)b; b += align_up((size_t)(threads / 32 + 1) * sizeof(double), 16);
+    L.sta = (int)b;  b += align_up((size_t)ring * K * threads * sizeof(Real), 16);
+    L.sth = (int)b;
+    L.red = (int)b;  b += align_up((size_t)FAST_RR * (threads / 32) * (K + 1) * sizeof(Real), 16);
+    L.par = (int)b;  b += align_up((size_t)(4 * K * K) * sizeof(Real), 16);
+    L.jlo = (int)b;
+    L.total = (int)b;
+    return L;
+}
+// ints behind the observation factors of a chain's scratch region in split mode: window starts [ncap + 2], sojourn
+// list [2][ncap + 1]
+__host__ __device__ inline int64_t ffbs_fast_split_ints(int64_t ncap) { return 3 * ncap + 4; }
+
 // Named barriers with IMMEDIATE ids: with a run-time id ptxas reserves all 16 hardware barriers for the CTA, and an
 // SM has 64 of them -- 4 resident CTAs whatever the registers allow (measured: grid 592 instead of 740).  Ids 1..7.
 template <int ID>
@@ -171,7 +192,13 @@ struct FastLog2<float> {
 
 // B threads per chain, CPB chains per CTA (CPB > 1: one warp per chain, the warps of a CTA are independent and share
 // only the 2^x / log2 tables), WAYS grid pairs in flight per thread
-template <typename Real, int K, int B, int MINB, int WAYS, int CPB>
+//
+// PHASE 0: forward and backward of a chain in one go (scratch regions per resident chain).  PHASE 1 / 2: the same code as
+// TWO kernels -- forward pass of every chain (rows, window starts and observation factors in a scratch region PER
+// CHAIN), then the backward pass of every chain.  The forward pass is FP64-pipe bound and needs ~230 registers; the
+// backward pass is a chain of dependent draws (latency bound) and needs half of them: on its own it runs with twice
+// the resident warps, and the forward kernel no longer shares its SMs with warps that wait on L2.
+template <typename Real, int K, int B, int MINB, int WAYS, int CPB, int PHASE = 0>
 __global__ void __launch_bounds__(B * CPB, MINB) ffbs_fast_kernel(const FfbsArgs a) {
     using M = Math<Real>;
     using Acc = typename ScanAcc<Real>::type;
@@ -180,13 +207,14 @@ __global__ void __launch_bounds__(B * CPB, MINB) ffbs_fast_kernel(const FfbsArgs
     constexpr int RS = FAST_RS, RR = FAST_RR;
     static_assert(RS == 8 && RR >= 2 * RS, "named barrier ids 1..7 and the partial-sum ring assume RS = 8");
     static_assert(CPB == 1 || B == 32, "several chains per CTA: one warp each");
+    static_assert(PHASE == 0 || (B == 32 && CPB == 1), "split kernels: one warp per chain");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (a.guard && (a.guard[0] > a.guard_nmax || a.guard[1] > a.guard_total)) return;  // mis-speculated geometry
     const int cw = CPB > 1 ? (int)threadIdx.x / B : 0;                  // chain slot of this thread within the CTA
     const int tid = CPB > 1 ? (int)threadIdx.x % B : (int)threadIdx.x;  // thread index within the chain's group
     const int lane = tid & 31, wid = tid >> 5;
     const int ncap = a.ncap, Kobs = a.Kobs, NS = a.nslot;  // nslot = ring slots of B grid points
-    const int region = blockIdx.x * CPB + cw;              // scratch region (messages, observation factors)
+    const int region0 = blockIdx.x * CPB + cw;             // scratch region (messages, observation factors): per resident chain
     auto sync_chain = [&]() {  // every thread working on this chain
         if (CPB > 1) __syncwarp();
         else __syncthreads();
@@ -202,7 +230,7 @@ __global__ void __launch_bounds__(B * CPB, MINB) ffbs_fast_kernel(const FfbsArgs
     Real* skm1 = srk + K * K;
     Real* sc2p = skm1 + K * K;
     Real* sk = sc2p + K * K;
-    int* soj = (int*)st_h;
+    int* soj = (int*)st_h;  // (PHASE 2: re-pointed to the chain's global scratch region)
 
     __shared__ int s_chain_a[CPB];
     __shared__ int s_sel_a[CPB], s_selv_a[CPB];
@@ -248,15 +276,13 @@ __global__ void __launch_bounds__(B * CPB, MINB) ffbs_fast_kernel(const FfbsArgs
     const Real weps = (Real)a.window_eps;
     // per-region global scratch: observation factors [ncap][K], then the window start of every row [ncap + 1] (read
     // back once per backward draw: L2)
-    Real* obsf = (Real*)a.obsf_scratch + (int64_t)region * a.obsf_stride;
-    int* jlo_arr = (int*)(obsf + (int64_t)ncap * K);
     const int64_t obs_total = a.obs_offs[a.C];  // entries of obs_t / obs_y: the aligned bulk copies stay inside them
     if (CPB > 1) __syncthreads();  // the tables; from here on the warps of the CTA go their own ways
 
     while (true) {
         sync_chain();
         if (tid == 0) {
-            unsigned int q = atomicAdd(a.queue, 1u);
+            unsigned int q = atomicAdd(PHASE == 2 ? a.queue2 : a.queue, 1u);
             const unsigned limit = a.C_dev ? (unsigned)*a.C_dev : (unsigned)a.C;
             s_chain = (q < limit) ? (a.order ? a.order[q] : (int)q) : -1;
             s_flag = 0;
@@ -265,6 +291,7 @@ __global__ void __launch_bounds__(B * CPB, MINB) ffbs_fast_kernel(const FfbsArgs
         sync_chain();
         const int c = s_chain;
         if (c < 0) break;
+        if (PHASE == 2 && !a.fwd_ok[c]) continue;  // the forward kernel has set this chain's status
         const int64_t w0 = a.w_offs[c];
         const int n = (int)(a.w_offs[c + 1] - w0) - 1;
         if (n < 1 || n > ncap) {
@@ -274,6 +301,17 @@ __global__ void __launch_bounds__(B * CPB, MINB) ffbs_fast_kernel(const FfbsArgs
             }
             continue;
         }
+        // scratch region: of this resident chain (fused kernel) or of chain c itself (split kernels)
+        const int64_t region = PHASE == 0 ? region0 : c;
+        Real* obsf = (Real*)a.obsf_scratch + region * a.obsf_stride;
+        int* jlo_arr = (int*)(obsf + (int64_t)ncap * K);
+        if (PHASE == 2) soj = jlo_arr + (ncap + 2);  // the sojourn list: behind the window starts, not in shared memory
+        const double* Wg = a.W + w0;  // the grid stays in global memory (L2); only the window's times go on chip
+        Real* msg = (Real*)a.msg_scratch + region * a.msg_scratch_stride;
+        int i_final = n;  // rows from i_final on have no B_v factor in the emission (smjp_utils.py:544)
+        while (i_final > 0 && np_isclose(a.t_end, Wg[i_final])) --i_final;
+        bool degenerate = false;
+        if constexpr (PHASE != 2) {
         // ---- observations: TMA bulk copy of the chain's slice into the (idle) state ring, under the grid validation ----
         const int64_t o0 = a.obs_offs[c];
         const int D = (int)(a.obs_offs[c + 1] - o0);
@@ -290,7 +328,6 @@ __global__ void __launch_bounds__(B * CPB, MINB) ffbs_fast_kernel(const FfbsArgs
             bulk_g2s(so_y, a.obs_y + os.y0, os.by, s_obar);
         }
         // ---- validate the grid (smjp_utils.py:398-399), smallest gap ----
-        const double* Wg = a.W + w0;  // the grid stays in global memory (L2); only the window's times go on chip
         {
             int bad = 0;
             double dmin = INFINITY;
@@ -368,12 +405,9 @@ __global__ void __launch_bounds__(B * CPB, MINB) ffbs_fast_kernel(const FfbsArgs
             }
         }
 
-        Real* msg = (Real*)a.msg_scratch + (int64_t)region * a.msg_scratch_stride;
 
         // =========================== forward ===========================
-        int i_final = n;  // rows from i_final on have no B_v factor in the emission (smjp_utils.py:544)
-        while (i_final > 0 && np_isclose(a.t_end, Wg[i_final])) --i_final;
-        bool degenerate = false, overflow = false;
+        bool overflow = false;
         int j_lo = 0, ms_lo = 0;  // first live grid point; ring slot of its slot m_lo = j_lo / B
         unsigned long long live = 0;
         Real sc = om1;            // (Omega - 1) * renormalisation factor of the coming step
@@ -648,6 +682,12 @@ __global__ void __launch_bounds__(B * CPB, MINB) ffbs_fast_kernel(const FfbsArgs
                 sync_chain();
             }
         }
+        if (PHASE == 1) {  // forward kernel: the backward kernel takes the chain from here
+            __threadfence();
+            if (tid == 0) a.fwd_ok[c] = 1;
+            continue;
+        }
+        }  // PHASE != 2
         if (tid == 0) s_found[0] = s_found[1] = 0;
         sync_chain();
 

@@ -52,9 +52,9 @@ cudaError_t ffbs_pick(const FfbsArgs& a, FfbsLaunch& L, bool query) {
 }
 
 // ---- K <= 3, scratch mode: ffbs_fast.cuh (deferred normalisation, split barriers, state ring, WAYS pairs in flight) ----
-template <typename Real, int K, int B, int MINB, int WAYS, int CPB = 1>
+template <typename Real, int K, int B, int MINB, int WAYS, int CPB = 1, int PHASE = 0>
 cudaError_t ffbs_fast_do(const FfbsArgs& a, FfbsLaunch& L, bool query) {
-    auto kern = ffbs_fast_kernel<Real, K, B, MINB, WAYS, CPB>;
+    auto kern = ffbs_fast_kernel<Real, K, B, MINB, WAYS, CPB, PHASE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
     if (e != cudaSuccess) return e;
     // the driver's default carve-out can stop short of what the registers allow: ask for all of it
@@ -65,6 +65,9 @@ cudaError_t ffbs_fast_do(const FfbsArgs& a, FfbsLaunch& L, bool query) {
     return cudaGetLastError();
 }
 
+#ifndef FAST_BWD_MINB
+#define FAST_BWD_MINB 16  // resident warps per SM the backward-only kernel is compiled for (<= 128 registers)
+#endif
 // (threads per chain, ways, chains per CTA) the kernel is instantiated for
 inline bool ffbs_fast_has_variant(int threads, int ways, int cpb) {
     if (threads == 32) return (ways == 2 && (cpb == 1 || cpb == 2 || cpb == 5 || cpb == 9)) || (cpb == 1 && (ways == 1 || ways == 3 || ways == 4));
@@ -82,6 +85,9 @@ cudaError_t ffbs_fast_pick(const FfbsArgs& a, FfbsLaunch& L, bool query) {
             if (w == 2 && cpb == 2) return ffbs_fast_do<Real, K, 32, 5, 2, 2>(a, L, query);   // 10 chains/SM, <= 200
             if (w == 4) return ffbs_fast_do<Real, K, 32, 7, 4>(a, L, query);
             if (w == 3) return ffbs_fast_do<Real, K, 32, 8, 3>(a, L, query);
+            // split kernels (FfbsArgs::fast_phase): forward as the fused kernel, backward compiled for twice the warps
+            if (w == 2 && cpb == 1 && a.fast_phase == 1) return ffbs_fast_do<Real, K, 32, 8, 2, 1, 1>(a, L, query);
+            if (w == 2 && cpb == 1 && a.fast_phase == 2) return ffbs_fast_do<Real, K, 32, FAST_BWD_MINB, 2, 1, 2>(a, L, query);
             if (w == 2) return ffbs_fast_do<Real, K, 32, 8, 2>(a, L, query);                  // 8 chains/SM, <= 256
             return ffbs_fast_do<Real, K, 32, D ? 16 : 32, 1>(a, L, query);
         case 64:
