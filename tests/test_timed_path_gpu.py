@@ -154,6 +154,23 @@ def test_cfg2_scratch_mode_fp64_equals_oracle(engine, cfg2_case, threads, warp, 
     assert live < 1.1 * exact, (exact, live)
 
 
+@pytest.mark.parametrize("split", [0, 1])
+def test_cfg2_fast_kernel_fused_and_split_launches_equal_oracle(engine, cfg2_case, split):
+    """the K <= 3 sweep kernel as ONE launch (forward + backward per chain) and as TWO (forward of every chain, then
+    backward of every chain, scratch region per chain): the stat says which ran, both give the oracle's paths"""
+    g = cfg2_case
+    engine.set_model(SHAPE3, g["scale"], 2.0, g["emis"], 1.0, g["t_end"])
+    engine.set_option("fast_split", split)
+    try:
+        r = engine.ffbs_host(g["Ws"], [g["obs_t"]] * g["C"], g["Ys"], seed=SEED_BACK, sweep=7, precision="f64")
+        assert kernel_used(engine) == "ffbs_fast_kernel"
+        assert int(engine.lib.smjp_ctx_get_stat(engine.ctx, b"fast_split")) == split
+        assert int(engine.lib.smjp_ctx_get_stat(engine.ctx, b"ffbs_rescued")) == 0
+    finally:
+        engine.set_option("fast_split", -1)
+    assert_exact_parity(r, g["oras"], g["K"])
+
+
 def test_fast_kernel_ring_overflow_and_range_go_to_the_rescue_pass(engine, cfg2_case):
     """results never depend on the ring size: with one ring slot (128 grid points, the cfg2 window needs ~250) every
     chain overflows and is redone by the rescue pass (ffbs.cuh) -- same paths; a grid with a 1e-300 gap leaves the
