@@ -692,7 +692,11 @@ __global__ void __launch_bounds__(B * CPB, MINB) ffbs_fast_kernel(const FfbsArgs
         sync_chain();
 
         // =========================== backward (as in ffbs.cuh, scratch rows) ===========================
-        Real* wbuf = st_a;  // [K][wl] weights of the current draw, each entry written and read by its own thread only
+        // weights of the current draw, each entry written and read by its own thread only: entry t of thread's run of state
+        // v at [(v q + t) B + tid] -- a thread's run is contiguous in j, so [v][j - lo] put the lanes of a warp 8 banks
+        // apart (q ~ 12 doubles) and every store and walk load was an 8-way bank conflict (ncu r03g: short scoreboard
+        // 2.9 stalled warps per issue in the backward-only kernel)
+        Real* wbuf = st_a;
         int cur = n - 1, vplus = -1, cnt = 0, u_hi = -1;
         // One warp per chain: a draw is a chain of dependent L2 round trips (window start of the row -> row entries and
         // grid times -> weights).  The window start and the right grid time of the NEXT draw's row are fetched one draw
@@ -799,7 +803,7 @@ __global__ void __launch_bounds__(B * CPB, MINB) ffbs_fast_kernel(const FfbsArgs
 #pragma unroll
                             for (int v = 0; v < K; ++v) {
                                 loc[v] += (Acc)w[u][v];
-                                wbuf[v * wl + (j0 + u - lo)] = w[u][v];
+                                wbuf[(v * q + (j0 + u - jb)) * B + tid] = w[u][v];
                             }
                         }
                     }
@@ -811,7 +815,7 @@ __global__ void __launch_bounds__(B * CPB, MINB) ffbs_fast_kernel(const FfbsArgs
 #pragma unroll
                     for (int v = 0; v < K; ++v) {
                         loc[v] += (Acc)w[v];
-                        wbuf[v * wl + (j - lo)] = w[v];
+                        wbuf[(v * q + (j - jb)) * B + tid] = w[v];
                     }
                 }
             }
@@ -875,7 +879,7 @@ __global__ void __launch_bounds__(B * CPB, MINB) ffbs_fast_kernel(const FfbsArgs
                     Acc acc = excl;
                     int sel = -1, lastpos = jb;
                     for (int j = jb; j < je; ++j) {
-                        const Acc wv = (Acc)wbuf[vs * wl + (j - lo)];
+                        const Acc wv = (Acc)wbuf[(vs * q + (j - jb)) * B + tid];
                         if (wv > (Acc)0) lastpos = j;
                         acc += wv;
                         if (acc > target) { sel = j; break; }
@@ -896,7 +900,7 @@ __global__ void __launch_bounds__(B * CPB, MINB) ffbs_fast_kernel(const FfbsArgs
                     const int vf = (key - 1) / B;
                     int lastpos = jb;
                     for (int j = jb; j < je; ++j)
-                        if ((Acc)wbuf[vf * wl + (j - lo)] > (Acc)0) lastpos = j;
+                        if ((Acc)wbuf[(vf * q + (j - jb)) * B + tid] > (Acc)0) lastpos = j;
                     s_sel = lastpos;
                     s_selv = vf;
                 }
